@@ -1,0 +1,171 @@
+/*
+ * sw_b200.h -- C ABI of the B200-native score-only Smith-Waterman engine
+ *              (libsw_b200.so, built from smith-waterman-fpga-module_b200/csrc/).
+ *
+ * This is the drop-in boundary for the reference's hot path: the systolic
+ * scoring datapath (SW_ProcessingElement_v1 -> ScoringModule_v1_1 ->
+ * ScoreBank_v2) and the CAPI job/MMIO/DMA shell that reaches it.  Each entry
+ * point cites the reference interface it replaces; paths are relative to the
+ * reference checkout.  Plain C types only (no torch / CUDA types).
+ *
+ * Operator surface that is kept (ScoreBank_v2.v:31-44):
+ *   load penalties once -> load a query -> stream targets -> collect one
+ *   max local-alignment score per (query, target).
+ * Sequences are 2-bit packed exactly as the reference host packs them
+ * (aligner_Header.c:14-47): A=10 C=01 G=11 T=00, base k in byte k/4 at bit
+ * 2*(k%4), anything else packs as 00.
+ *
+ * Threading: a handle is not re-entrant (the reference host is strictly
+ * single-threaded, main_test.c:214-537); distinct handles are independent.
+ * Every call returns 0 (SW_OK) or a negative SW_E* code.  There is no CPU
+ * fallback: without a usable CUDA device sw_init fails with SW_ENODEV.
+ */
+#ifndef SW_B200_H_
+#define SW_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (replace the WED error bitfield, main_test.c:64-100) ---- */
+#define SW_OK          0
+#define SW_EINVAL     -1   /* bad argument / unsupported parameter set          */
+#define SW_ENOMEM     -2   /* host or device allocation failed                  */
+#define SW_ECUDA      -3   /* CUDA runtime error, see sw_last_cuda_error()      */
+#define SW_ENODEV     -4   /* no CUDA device / requested GPU id not present     */
+#define SW_ESTATE     -5   /* call out of order (e.g. fetch before score_batch) */
+#define SW_ETIMEOUT   -6   /* sw_fetch timed out (the host's -t option)         */
+#define SW_ECAPACITY  -7   /* caller's score buffer too small                   */
+#define SW_EIO        -8   /* file could not be read / written                  */
+#define SW_EAGAIN     -9   /* a batch is already in flight (the bank's `full`)  */
+
+/* The `penalties` bus + SCORE_WIDTH parameter.
+ * Replaces: ScoreBank_v2.v:34,161 (ld_penalties, penalties[4*W]),
+ *           SW_ProcessingElement_v1.0.v:15 (SCORE_WIDTH),
+ *           defaults ScoreBank_v1_tb.sv:16-19. */
+typedef struct sw_params {
+    int16_t match;        /* default   5 */
+    int16_t mismatch;     /* default  -4 */
+    int16_t gap_open;     /* default -12 */
+    int16_t gap_extend;   /* default  -4  (first gap residue costs open+extend) */
+    int32_t score_width;  /* 0 = exact integers (default); 12 = RTL-faithful
+                             12-bit biased machine: M wraps to 0 above 2047   */
+} sw_params_t;
+
+typedef struct sw_handle sw_handle_t;
+
+/* Fills *p with the reference defaults (5/-4/-12/-4, exact width). */
+void sw_default_params(sw_params_t *p);
+
+/* Replaces: cxl_afu_open_dev + cxl_afu_attach (main_test.c:342,370) and the
+ * ld_penalties cycle (ScoreBank_v1_tb.sv:175-181).  gpu_ids == NULL with
+ * n_gpus == 0 means "device 0".  One stream set + pinned staging per GPU. */
+int sw_init(sw_handle_t **h, const sw_params_t *p, const int *gpu_ids, int n_gpus);
+
+/* Replaces: cxl_afu_free (main_test.c:533). */
+void sw_destroy(sw_handle_t *h);
+
+/* Replaces: the type-01 record / ld_q (ScoreBank_v2.v:162,181-182;
+ * ScoringModule_v1.1.v:121-126).  Queries are copied and replicated to every
+ * GPU.  packed + off[i] is the first byte of query i, len[i] its base count. */
+int sw_set_queries(sw_handle_t *h, const uint8_t *packed, const uint32_t *len,
+                   const uint64_t *off, int nq);
+
+/* Replaces: the stream of type-10 records with feeder / PrioEncoder arbitration
+ * (ScoreBank_v2.v:142-169, SM_Feeder2.v:104-205, PrioEncoder.v:18-21) and the
+ * DMA read of the sequence array (afu.v:383-398).  Subjects are length-bucketed,
+ * sharded over the handle's GPUs, copied H2D and scored against every query.
+ * Asynchronous with respect to the GPUs: returns once the work is enqueued; the
+ * caller's buffers may be reused as soon as it returns.  ids may be NULL
+ * (then id = input index); they are returned by sw_fetch_ids.  SW_EAGAIN while a
+ * previous batch has not been fetched. */
+int sw_score_batch(sw_handle_t *h, const uint8_t *packed, const uint32_t *len,
+                   const uint64_t *off, const uint64_t *ids, size_t ns);
+
+/* Replaces: the (IDs, results, vld) outputs (ScoreBank_v2.v:39-41), the WED
+ * status poll with timeout (main_test.c:422-477) and `*result-2048`
+ * (main_test.c:528).  Blocks until the batch is complete or timeout_ms elapses
+ * (timeout_ms < 0 = wait forever).  scores[iq * ns + is] = unbiased score of
+ * query iq against subject is, in INPUT order (deterministic, unlike the RTL's
+ * completion order).  cap = number of int32 the buffer holds. */
+int sw_fetch(sw_handle_t *h, int32_t *scores, size_t cap, int timeout_ms);
+
+/* ---- resident-database path (database stays in HBM between calls) ---------
+ * sw_load_db     = the H2D half of sw_score_batch (bucket, shard, upload).
+ * sw_score_db    = enqueue scoring of all current queries against the resident db.
+ * sw_wait        = block until enqueued work is done.
+ * sw_fetch_db    = D2H of the score matrix of the last sw_score_db.
+ * These replace nothing in the reference (its feeder holds two targets); they
+ * exist so that a database larger than one batch is not re-uploaded per query set. */
+int sw_load_db(sw_handle_t *h, const uint8_t *packed, const uint32_t *len,
+               const uint64_t *off, const uint64_t *ids, size_t ns);
+int sw_score_db(sw_handle_t *h);
+int sw_wait(sw_handle_t *h, int timeout_ms);
+int sw_fetch_db(sw_handle_t *h, int32_t *scores, size_t cap);
+
+/* Per-query best hit over the resident db, reduced on the GPU: the `max` /
+ * `vld_max` outputs ScoreBank_v2 declares but never drives (ScoreBank_v2.v:42-43).
+ * best_score[iq], best_index[iq] (input index of the first subject reaching it). */
+int sw_fetch_best(sw_handle_t *h, int32_t *best_score, uint64_t *best_index, int nq_cap);
+
+/* ---- introspection --------------------------------------------------------- */
+const char *sw_strerror(int code);
+int sw_last_cuda_error(const sw_handle_t *h);          /* cudaError_t as int */
+const char *sw_last_cuda_error_string(const sw_handle_t *h);
+/* Device time (CUDA events on the launching stream) of the scoring kernels of the
+ * last sw_score_db / sw_score_batch, max over the handle's GPUs, milliseconds. */
+double sw_last_kernel_ms(const sw_handle_t *h);
+/* Number of kernels this library launched since sw_init (all GPUs). */
+uint64_t sw_kernel_launches(const sw_handle_t *h);
+/* Cell updates (sum of qlen*tlen over all pairs) of the last scoring call. */
+uint64_t sw_last_cells(const sw_handle_t *h);
+/* Name of the kernel variant chosen for the last scoring call, e.g.
+ * "strip_s16x2_R50_G1"; static storage. */
+const char *sw_last_kernel_name(const sw_handle_t *h);
+/* Overrides the automatic kernel choice (testing / benchmarking):
+ * rows_per_lane in {0=auto, ...}, lanes_per_pair in {0=auto,1,2,4,8,16,32},
+ * force32 != 0 forces the 32-bit fallback kernel. */
+int sw_set_kernel_choice(sw_handle_t *h, int rows_per_lane, int lanes_per_pair, int force32);
+int sw_device_count(void);
+const char *sw_version(void);
+
+/* ---- pure-host helpers (file-level drop-in) -------------------------------- */
+/* Replaces: charTo2bit (aligner_Header.c:14-47).  out must hold (len+3)/4 bytes. */
+void sw_pack_2bit(const char *seq, size_t len, uint8_t *out);
+void sw_unpack_2bit(const uint8_t *packed, size_t len, char *out /* len+1 */);
+
+/* A set of sequences, packed.  Owned by the library; free with sw_seqset_free. */
+typedef struct sw_seqset {
+    size_t    n;
+    uint8_t  *packed;     /* concatenated 2-bit data, each record byte-aligned   */
+    uint32_t *len;        /* bases per record                                     */
+    uint64_t *off;        /* byte offset of each record in packed                 */
+    char    **name;       /* record names without the leading '>'                 */
+    size_t    packed_bytes;
+} sw_seqset_t;
+
+/* Replaces: the testbench FASTA parser (ScoreBank_v1_tb.sv:184-216): `>name`
+ * then sequence; wrapped sequence lines are concatenated.  A file with no '>'
+ * line is read like main_test.c:304,310 does: first whitespace token = the
+ * sequence, name "seq0". */
+int sw_read_fasta(const char *path, sw_seqset_t **out);
+void sw_seqset_free(sw_seqset_t *s);
+
+/* Replaces: Display_results (ScoreBank_v1_tb.sv:271-285), one line per subject,
+ * "@%6dns: %10s score: \t%11d" with the name prefixed by '>'.  The engine has no
+ * simulation clock: time_ns[i] is printed if given, else 0. */
+int sw_write_out_txt(FILE *f, const sw_seqset_t *db, const int32_t *scores,
+                     const uint64_t *time_ns);
+/* ssearch36 -R style rows (data/score500.txt:1-3): score is the 6th field. */
+int sw_write_ssearch_R(FILE *f, const char *query_file, const char *db_file,
+                       const sw_seqset_t *query, const sw_seqset_t *db,
+                       const int32_t *scores);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SW_B200_H_ */
