@@ -94,6 +94,11 @@ int sw_score_batch(sw_handle_t *h, const uint8_t *packed, const uint32_t *len,
  * completion order).  cap = number of int32 the buffer holds. */
 int sw_fetch(sw_handle_t *h, int32_t *scores, size_t cap, int timeout_ms);
 
+/* Replaces: the 48-bit ID that travels with every target record and comes back next to
+ * its score (ScoreBank_v2.v:26-28,40; fifo.v:36-64).  ids[is] = the id given to
+ * sw_score_batch / sw_load_db for subject is (or is itself when ids was NULL). */
+int sw_fetch_ids(sw_handle_t *h, uint64_t *ids, size_t cap);
+
 /* ---- resident-database path (database stays in HBM between calls) ---------
  * sw_load_db     = the H2D half of sw_score_batch (bucket, shard, upload).
  * sw_score_db    = enqueue scoring of all current queries against the resident db.
@@ -130,6 +135,9 @@ const char *sw_last_kernel_name(const sw_handle_t *h);
  * rows_per_lane in {0=auto, ...}, lanes_per_pair in {0=auto,1,2,4,8,16,32},
  * force32 != 0 forces the 32-bit fallback kernel. */
 int sw_set_kernel_choice(sw_handle_t *h, int rows_per_lane, int lanes_per_pair, int force32);
+/* arith: -1 = automatic, 0 = packed signed 16-bit (DPX), 1 = packed fp16 (exact while the
+ * largest possible score is <= 2048; rejected with SW_EINVAL otherwise). */
+int sw_set_arith(sw_handle_t *h, int arith);
 int sw_device_count(void);
 const char *sw_version(void);
 

@@ -1,0 +1,224 @@
+"""B200-native score-only Smith-Waterman engine -- Python plumbing over the C ABI.
+
+The product is ``libsw_b200.so`` (hand-written CUDA for sm_100a behind the C ABI of
+``include/sw_b200.h``).  This module only binds it with ctypes so that tests and
+``bench.py`` can drive it; it contains no scoring code and no CPU fallback: if the
+library is missing or no B200 is visible, construction raises.
+
+Operator surface mirrored (reference: ScoreBank/ScoreBank_v2.v:31-44 and
+capi_sample_aligner/software-C,C++/src/main_test.c:290-528):
+    Engine(match, mismatch, gap_open, gap_extend)   <- ld_penalties / penalties bus
+    Engine.set_queries(...)                          <- type-01 record, ld_q
+    Engine.score_batch(...)                          <- stream of type-10 records
+    Engine.fetch(timeout_ms)                         <- (IDs, results, vld) + WED poll, result-2048
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .seqio import pack_sequences, random_packed_db  # noqa: F401
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsw_b200.so")
+
+SW_OK, SW_EINVAL, SW_ENOMEM, SW_ECUDA, SW_ENODEV = 0, -1, -2, -3, -4
+SW_ESTATE, SW_ETIMEOUT, SW_ECAPACITY, SW_EIO, SW_EAGAIN = -5, -6, -7, -8, -9
+
+
+class SwParams(C.Structure):
+    _fields_ = [("match", C.c_int16), ("mismatch", C.c_int16), ("gap_open", C.c_int16),
+                ("gap_extend", C.c_int16), ("score_width", C.c_int32)]
+
+
+class SwError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"sw_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libsw_b200.so (built by ``__graft_entry__.build()`` / csrc/Makefile)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a). "
+                          "There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, sz, i32 = C.c_void_p, C.c_uint64, C.c_size_t, C.c_int
+    L.sw_default_params.argtypes = [C.POINTER(SwParams)]
+    L.sw_default_params.restype = None
+    L.sw_init.argtypes = [C.POINTER(vp), C.POINTER(SwParams), C.POINTER(C.c_int), i32]
+    L.sw_destroy.argtypes = [vp]
+    L.sw_destroy.restype = None
+    L.sw_set_queries.argtypes = [vp, vp, vp, vp, i32]
+    L.sw_score_batch.argtypes = [vp, vp, vp, vp, vp, sz]
+    L.sw_fetch.argtypes = [vp, vp, sz, i32]
+    L.sw_fetch_ids.argtypes = [vp, vp, sz]
+    L.sw_load_db.argtypes = [vp, vp, vp, vp, vp, sz]
+    L.sw_score_db.argtypes = [vp]
+    L.sw_wait.argtypes = [vp, i32]
+    L.sw_fetch_db.argtypes = [vp, vp, sz]
+    L.sw_fetch_best.argtypes = [vp, vp, vp, i32]
+    L.sw_strerror.argtypes = [i32]
+    L.sw_strerror.restype = C.c_char_p
+    L.sw_last_cuda_error.argtypes = [vp]
+    L.sw_last_cuda_error_string.argtypes = [vp]
+    L.sw_last_cuda_error_string.restype = C.c_char_p
+    L.sw_last_kernel_ms.argtypes = [vp]
+    L.sw_last_kernel_ms.restype = C.c_double
+    L.sw_kernel_launches.argtypes = [vp]
+    L.sw_kernel_launches.restype = u64
+    L.sw_last_cells.argtypes = [vp]
+    L.sw_last_cells.restype = u64
+    L.sw_last_kernel_name.argtypes = [vp]
+    L.sw_last_kernel_name.restype = C.c_char_p
+    L.sw_set_kernel_choice.argtypes = [vp, i32, i32, i32]
+    L.sw_set_arith.argtypes = [vp, i32]
+    L.sw_device_count.restype = i32
+    L.sw_version.restype = C.c_char_p
+    L.sw_pack_2bit.argtypes = [C.c_char_p, sz, vp]
+    L.sw_pack_2bit.restype = None
+    L.sw_unpack_2bit.argtypes = [vp, sz, C.c_char_p]
+    L.sw_unpack_2bit.restype = None
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class Engine:
+    """One handle = one control thread; not re-entrant (like the reference host)."""
+
+    def __init__(self, match=5, mismatch=-4, gap_open=-12, gap_extend=-4, score_width=0, gpu_ids=None):
+        self.lib = load_library()
+        self.h = C.c_void_p()
+        p = SwParams(match, mismatch, gap_open, gap_extend, score_width)
+        if gpu_ids is None:
+            rc = self.lib.sw_init(C.byref(self.h), C.byref(p), None, 0)
+        else:
+            arr = (C.c_int * len(gpu_ids))(*gpu_ids)
+            rc = self.lib.sw_init(C.byref(self.h), C.byref(p), arr, len(gpu_ids))
+        if rc != SW_OK:
+            self.h = C.c_void_p()
+            raise SwError(rc, self.lib.sw_strerror(rc).decode())
+        self.nq = 0
+        self.ns = 0
+
+    # -- plumbing ---------------------------------------------------------------------
+    def _check(self, rc):
+        if rc != SW_OK:
+            msg = self.lib.sw_strerror(rc).decode()
+            if rc == SW_ECUDA:
+                msg += " [" + self.lib.sw_last_cuda_error_string(self.h).decode() + "]"
+            raise SwError(rc, msg)
+
+    def close(self):
+        if self.h:
+            self.lib.sw_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @staticmethod
+    def _as_packed(seqs):
+        if isinstance(seqs, tuple):
+            packed, ln, off = seqs
+            return (np.ascontiguousarray(packed, dtype=np.uint8), np.ascontiguousarray(ln, dtype=np.uint32),
+                    np.ascontiguousarray(off, dtype=np.uint64))
+        return pack_sequences(seqs)
+
+    # -- operator surface ---------------------------------------------------------------
+    def set_queries(self, queries):
+        packed, ln, off = self._as_packed(queries)
+        self._check(self.lib.sw_set_queries(self.h, _ptr(packed), _ptr(ln), _ptr(off), len(ln)))
+        self.nq = len(ln)
+
+    def score_batch(self, subjects, ids=None):
+        packed, ln, off = self._as_packed(subjects)
+        ids_a = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint64)
+        self._check(self.lib.sw_score_batch(self.h, _ptr(packed), _ptr(ln), _ptr(off), _ptr(ids_a), len(ln)))
+        self.ns = len(ln)
+
+    def fetch(self, timeout_ms=-1, out=None):
+        if out is None:
+            out = np.empty((self.nq, self.ns), dtype=np.int32)
+        self._check(self.lib.sw_fetch(self.h, _ptr(out), out.size, timeout_ms))
+        return out
+
+    def fetch_ids(self):
+        ids = np.empty(self.ns, dtype=np.uint64)
+        self._check(self.lib.sw_fetch_ids(self.h, _ptr(ids), ids.size))
+        return ids
+
+    def score(self, queries, subjects, timeout_ms=-1):
+        """Convenience: full score matrix [nq, ns]."""
+        self.set_queries(queries)
+        self.score_batch(subjects)
+        return self.fetch(timeout_ms)
+
+    # -- resident database ---------------------------------------------------------------
+    def load_db(self, subjects, ids=None):
+        packed, ln, off = self._as_packed(subjects)
+        ids_a = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint64)
+        self._check(self.lib.sw_load_db(self.h, _ptr(packed), _ptr(ln), _ptr(off), _ptr(ids_a), len(ln)))
+        self.ns = len(ln)
+
+    def score_db(self):
+        self._check(self.lib.sw_score_db(self.h))
+
+    def wait(self, timeout_ms=-1):
+        self._check(self.lib.sw_wait(self.h, timeout_ms))
+
+    def fetch_db(self, out=None):
+        if out is None:
+            out = np.empty((self.nq, self.ns), dtype=np.int32)
+        self._check(self.lib.sw_fetch_db(self.h, _ptr(out), out.size))
+        return out
+
+    def fetch_best(self):
+        bs = np.empty(self.nq, dtype=np.int32)
+        bi = np.empty(self.nq, dtype=np.uint64)
+        self._check(self.lib.sw_fetch_best(self.h, _ptr(bs), _ptr(bi), self.nq))
+        return bs, bi
+
+    # -- introspection -------------------------------------------------------------------
+    def set_kernel_choice(self, rows_per_lane=0, lanes_per_pair=0, force32=False, arith=-1):
+        self._check(self.lib.sw_set_kernel_choice(self.h, rows_per_lane, lanes_per_pair, int(force32)))
+        self._check(self.lib.sw_set_arith(self.h, arith))
+
+    @property
+    def last_kernel_ms(self):
+        return float(self.lib.sw_last_kernel_ms(self.h))
+
+    @property
+    def kernel_launches(self):
+        return int(self.lib.sw_kernel_launches(self.h))
+
+    @property
+    def last_cells(self):
+        return int(self.lib.sw_last_cells(self.h))
+
+    @property
+    def last_kernel_name(self):
+        return self.lib.sw_last_kernel_name(self.h).decode()
+
+
+def device_count():
+    return int(load_library().sw_device_count())

@@ -1,0 +1,735 @@
+/*
+ * sw_api.cu -- host side of libsw_b200.so: the C ABI declared in include/sw_b200.h.
+ *
+ * Replaces the reference's job path (main_test.c:290-477: build sequence records, attach the
+ * AFU, poll the WED) and the bank-level dispatch (ScoreBank_v2.v:142-169 + PrioEncoder.v +
+ * SM_Feeder2.v): subjects are length-sorted and paired on the host (the "first free module"
+ * arbitration becomes a length-bucketed work queue drained by persistent blocks), sharded
+ * over the handle's GPUs as contiguous input ranges, and moved with cudaMemcpyAsync from
+ * pinned staging on per-GPU streams.  No CPU scoring path exists in this library.
+ */
+#include "../../include/sw_b200.h"
+#include "sw_kernels.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap && p) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes ? bytes : 16;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct QueryChunk { int q0, q1; cudaEvent_t done; };
+
+struct GpuCtx {
+    int dev = 0;
+    int num_sms = 0;
+    cudaStream_t st_compute = nullptr, st_copy = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_upload = nullptr;
+    // queries
+    DevBuf d_qpacked, d_qoff, d_qlen;
+    // database shard
+    size_t s0 = 0, s1 = 0;            // global subject range [s0, s1)
+    DevBuf d_raw, d_off, d_len, d_pair_subj, d_pair_len, d_tile_woff, d_tp;
+    uint32_t npairs = 0, max_len = 0;
+    uint64_t sum_len = 0;
+    PinnedBuf h_stage_a, h_stage_b, h_stage_c, h_stage_d;
+    // scoring
+    DevBuf d_out, d_bnd, d_counters, d_scratch32, d_best_score, d_best_index;
+    std::vector<QueryChunk> chunks;
+    bool scored = false;
+};
+
+}  // namespace
+
+struct sw_handle {
+    sw_params_t params;
+    std::vector<GpuCtx> gpus;
+    // host copy of the queries
+    std::vector<uint8_t> q_packed;
+    std::vector<uint32_t> q_off, q_len;
+    uint32_t q_max_len = 0;
+    uint64_t q_sum_len = 0;
+    // database
+    size_t ns = 0;
+    bool db_loaded = false;
+    bool batch_in_flight = false;
+    std::vector<uint64_t> ids;
+    bool have_ids = false;
+    // bookkeeping
+    int last_cuda = 0;
+    uint64_t launches = 0;
+    uint64_t last_cells = 0;
+    double last_ms = 0.0;
+    const char *last_kernel = "none";
+    int force_R = 0, force_G = 0, force32 = 0, force_arith = -1;
+};
+
+namespace {
+
+const int kMaxCounters = 4096;
+
+#define SW_CUDA(h, call)                                                        \
+    do {                                                                        \
+        cudaError_t e__ = (call);                                               \
+        if (e__ != cudaSuccess) { (h)->last_cuda = (int)e__; return SW_ECUDA; } \
+    } while (0)
+
+int validate_params(const sw_params_t *p)
+{
+    if (p->match <= 0 || p->match > 255) return SW_EINVAL;
+    if (p->mismatch > p->match || p->mismatch < -255) return SW_EINVAL;
+    if (p->gap_extend > 0 || p->gap_extend < -255) return SW_EINVAL;
+    const int goe = (int)p->gap_open + (int)p->gap_extend;
+    if (goe > 0 || p->gap_open < -2040) return SW_EINVAL;
+    if (p->score_width != 0) {
+        if (p->score_width < 6 || p->score_width > 15) return SW_EINVAL;
+        const int half = 1 << (p->score_width - 1);
+        /* keep every intermediate of the W-bit machine inside its range except the
+           M overflow the mode exists to reproduce */
+        if (p->match >= half || goe + p->gap_extend < -half || p->mismatch < -half) return SW_EINVAL;
+    }
+    return SW_OK;
+}
+
+void free_gpu(GpuCtx &g)
+{
+    cudaSetDevice(g.dev);
+    for (auto &c : g.chunks) if (c.done) cudaEventDestroy(c.done);
+    g.chunks.clear();
+    DevBuf *bufs[] = {&g.d_qpacked, &g.d_qoff, &g.d_qlen, &g.d_raw, &g.d_off, &g.d_len, &g.d_pair_subj,
+                      &g.d_pair_len, &g.d_tile_woff, &g.d_tp, &g.d_out, &g.d_bnd, &g.d_counters,
+                      &g.d_scratch32, &g.d_best_score, &g.d_best_index};
+    for (DevBuf *b : bufs) b->release();
+    g.h_stage_a.release(); g.h_stage_b.release(); g.h_stage_c.release(); g.h_stage_d.release();
+    if (g.ev_start) cudaEventDestroy(g.ev_start);
+    if (g.ev_stop) cudaEventDestroy(g.ev_stop);
+    if (g.ev_upload) cudaEventDestroy(g.ev_upload);
+    if (g.st_compute) cudaStreamDestroy(g.st_compute);
+    if (g.st_copy) cudaStreamDestroy(g.st_copy);
+}
+
+int upload_queries(sw_handle *h, GpuCtx &g)
+{
+    SW_CUDA(h, cudaSetDevice(g.dev));
+    const size_t nq = h->q_len.size();
+    SW_CUDA(h, g.d_qpacked.reserve(h->q_packed.size() + 16));
+    SW_CUDA(h, g.d_qoff.reserve(nq * sizeof(uint32_t)));
+    SW_CUDA(h, g.d_qlen.reserve(nq * sizeof(uint32_t)));
+    // the compute stream orders these copies before any later kernel
+    SW_CUDA(h, cudaMemcpyAsync(g.d_qpacked.p, h->q_packed.data(), h->q_packed.size(), cudaMemcpyHostToDevice, g.st_compute));
+    SW_CUDA(h, cudaMemcpyAsync(g.d_qoff.p, h->q_off.data(), nq * sizeof(uint32_t), cudaMemcpyHostToDevice, g.st_compute));
+    SW_CUDA(h, cudaMemcpyAsync(g.d_qlen.p, h->q_len.data(), nq * sizeof(uint32_t), cudaMemcpyHostToDevice, g.st_compute));
+    SW_CUDA(h, cudaStreamSynchronize(g.st_compute));
+    return SW_OK;
+}
+
+// Length-sorts the shard's subjects, pairs equal lengths, lays out 32-pair tiles, uploads.
+int load_shard(sw_handle *h, GpuCtx &g, const uint8_t *packed, const uint32_t *len, const uint64_t *off)
+{
+    SW_CUDA(h, cudaSetDevice(g.dev));
+    const size_t n = g.s1 - g.s0;
+    g.npairs = 0; g.max_len = 0; g.sum_len = 0; g.scored = false;
+    if (n == 0) return SW_OK;
+    if (n >= 0xFFFFFFF0ull) return SW_EINVAL;
+    const uint32_t *ln = len + g.s0;
+    const uint64_t *of = off + g.s0;
+
+    uint64_t bmin = ~0ull, bmax = 0;
+    uint32_t maxlen = 0;
+    uint64_t sum = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const uint64_t b = (ln[i] + 3ull) >> 2;
+        if (ln[i] == 0) continue;
+        bmin = std::min(bmin, of[i]);
+        bmax = std::max(bmax, of[i] + b);
+        maxlen = std::max(maxlen, ln[i]);
+        sum += ln[i];
+    }
+    g.max_len = maxlen; g.sum_len = sum;
+    if (maxlen == 0) return SW_OK;
+
+    // --- order by length (counting sort when the range is small, else comparison sort)
+    SW_CUDA(h, g.h_stage_a.reserve((n + 64) * 2 * sizeof(uint32_t)));      // pair_subj
+    SW_CUDA(h, g.h_stage_b.reserve((n + 64) * sizeof(uint32_t)));          // pair_len
+    std::vector<uint32_t> order;
+    order.reserve(n);
+    if (maxlen <= (1u << 22)) {
+        std::vector<uint32_t> start((size_t)maxlen + 2, 0);
+        for (size_t i = 0; i < n; ++i) start[ln[i] + 1]++;
+        for (size_t l = 1; l < start.size(); ++l) start[l] += start[l - 1];
+        order.resize(n);
+        for (size_t i = 0; i < n; ++i) order[start[ln[i]]++] = (uint32_t)i;
+    } else {
+        order.resize(n);
+        for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ln[a] < ln[b]; });
+    }
+    // --- pair equal lengths; an odd one out is paired with itself (high lane unused)
+    uint32_t *pair_subj = (uint32_t *)g.h_stage_a.p;
+    uint32_t *pair_len = (uint32_t *)g.h_stage_b.p;
+    size_t np = 0, i = 0;
+    while (i < n && ln[order[i]] == 0) ++i;           // empty subjects score 0 (output is pre-zeroed)
+    while (i < n) {
+        const uint32_t a = order[i];
+        if (i + 1 < n && ln[order[i + 1]] == ln[a]) {
+            pair_subj[2 * np] = a; pair_subj[2 * np + 1] = order[i + 1];
+            i += 2;
+        } else {
+            pair_subj[2 * np] = a; pair_subj[2 * np + 1] = SW_NO_SUBJECT;
+            i += 1;
+        }
+        pair_len[np] = ln[a];
+        ++np;
+    }
+    const size_t ntiles = (np + 31) / 32;
+    for (size_t p = np; p < ntiles * 32; ++p) {
+        pair_subj[2 * p] = SW_NO_SUBJECT; pair_subj[2 * p + 1] = SW_NO_SUBJECT; pair_len[p] = 0;
+    }
+    SW_CUDA(h, g.h_stage_c.reserve((ntiles + 1) * sizeof(uint64_t)));
+    uint64_t *tile_woff = (uint64_t *)g.h_stage_c.p;
+    uint64_t w = 0;
+    for (size_t t = 0; t < ntiles; ++t) {
+        tile_woff[t] = w;
+        const size_t last = std::min(np, (t + 1) * 32) - 1;     // lengths ascend: last valid pair is longest
+        w += 32ull * ((pair_len[last] + 7) / 8);
+    }
+    tile_woff[ntiles] = w;
+    g.npairs = (uint32_t)np;
+
+    // --- local byte offsets
+    SW_CUDA(h, g.h_stage_d.reserve(n * sizeof(uint64_t)));
+    uint64_t *loc_off = (uint64_t *)g.h_stage_d.p;
+    for (size_t k = 0; k < n; ++k) loc_off[k] = ln[k] ? of[k] - bmin : 0;
+
+    // --- device buffers + uploads (copy stream), then the code-stream build (compute stream)
+    const size_t raw_bytes = bmax - bmin;
+    SW_CUDA(h, g.d_raw.reserve(raw_bytes + 16));
+    SW_CUDA(h, g.d_off.reserve(n * sizeof(uint64_t)));
+    SW_CUDA(h, g.d_len.reserve(n * sizeof(uint32_t)));
+    SW_CUDA(h, g.d_pair_subj.reserve(ntiles * 32 * 2 * sizeof(uint32_t)));
+    SW_CUDA(h, g.d_pair_len.reserve(ntiles * 32 * sizeof(uint32_t)));
+    SW_CUDA(h, g.d_tile_woff.reserve((ntiles + 1) * sizeof(uint64_t)));
+    SW_CUDA(h, g.d_tp.reserve((w + 32) * sizeof(uint32_t)));
+    cudaStream_t cs = g.st_copy;
+    SW_CUDA(h, cudaMemcpyAsync(g.d_raw.p, packed + bmin, raw_bytes, cudaMemcpyHostToDevice, cs));
+    SW_CUDA(h, cudaMemcpyAsync(g.d_len.p, ln, n * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+    SW_CUDA(h, cudaMemcpyAsync(g.d_off.p, loc_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, cs));
+    SW_CUDA(h, cudaMemcpyAsync(g.d_pair_subj.p, pair_subj, ntiles * 32 * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+    SW_CUDA(h, cudaMemcpyAsync(g.d_pair_len.p, pair_len, ntiles * 32 * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+    SW_CUDA(h, cudaMemcpyAsync(g.d_tile_woff.p, tile_woff, (ntiles + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, cs));
+    SW_CUDA(h, cudaEventRecord(g.ev_upload, cs));
+    SW_CUDA(h, cudaStreamWaitEvent(g.st_compute, g.ev_upload, 0));
+
+    SwDevDb db;
+    db.raw = g.d_raw.as<uint8_t>(); db.off = g.d_off.as<uint64_t>(); db.len = g.d_len.as<uint32_t>();
+    db.ns = (uint32_t)n; db.pair_subj = g.d_pair_subj.as<uint32_t>(); db.pair_len = g.d_pair_len.as<uint32_t>();
+    db.tile_woff = g.d_tile_woff.as<uint64_t>(); db.tp = g.d_tp.as<uint32_t>();
+    db.npairs = g.npairs; db.max_len = g.max_len;
+    SW_CUDA(h, sw_launch_build_tp(g.st_compute, db));
+    h->launches++;
+    return SW_OK;
+}
+
+SwDevDb dev_db(const GpuCtx &g)
+{
+    SwDevDb db;
+    db.raw = g.d_raw.as<uint8_t>(); db.off = g.d_off.as<uint64_t>(); db.len = g.d_len.as<uint32_t>();
+    db.ns = (uint32_t)(g.s1 - g.s0); db.pair_subj = g.d_pair_subj.as<uint32_t>();
+    db.pair_len = g.d_pair_len.as<uint32_t>(); db.tile_woff = g.d_tile_woff.as<uint64_t>();
+    db.tp = g.d_tp.as<uint32_t>(); db.npairs = g.npairs; db.max_len = g.max_len;
+    return db;
+}
+
+// Picks the strip variant: enough lanes to fill the GPU first, least padded rows second.
+int choose_variant(const sw_handle *h, const GpuCtx &g, uint32_t maxq)
+{
+    const int nv = sw_strip_variant_count();
+    const int want_arith = h->force_arith >= 0 ? h->force_arith : 0;
+    if (h->force_R || h->force_G) {
+        for (int i = 0; i < nv; ++i) {
+            const SwStripVariant *v = sw_strip_variant(i);
+            if (v->arith == want_arith && (!h->force_R || v->R == h->force_R) && (!h->force_G || v->G == h->force_G))
+                return i;
+        }
+        return -1;
+    }
+    const double fill = (double)g.num_sms * 256.0;        // lanes that keep every SM busy
+    int best = -1;
+    double best_cost = 0;
+    for (int i = 0; i < nv; ++i) {
+        const SwStripVariant *v = sw_strip_variant(i);
+        if (v->arith != want_arith) continue;
+        const int P = v->R * v->G;
+        const double rows = (double)((maxq + P - 1) / P) * P;
+        const double lanes = (double)g.npairs * v->G;
+        const double util = std::min(1.0, lanes / fill);
+        // time ~ padded rows per lane * (columns + pipeline fill) / utilisation
+        const double cols = (double)std::max<uint32_t>(g.max_len, 1);
+        const double cost = rows / v->G * (cols + v->G - 1) / cols / util * (v->G > 1 ? 1.03 : 1.0);
+        if (best < 0 || cost < best_cost) { best = i; best_cost = cost; }
+    }
+    return best;
+}
+
+int score_gpu(sw_handle *h, GpuCtx &g)
+{
+    SW_CUDA(h, cudaSetDevice(g.dev));
+    const int nq = (int)h->q_len.size();
+    const size_t n = g.s1 - g.s0;
+    for (auto &c : g.chunks) if (c.done) cudaEventDestroy(c.done);
+    g.chunks.clear();
+    g.scored = true;
+    if (n == 0 || nq == 0) return SW_OK;
+
+    SW_CUDA(h, g.d_out.reserve((size_t)nq * n * sizeof(int32_t)));
+    SW_CUDA(h, cudaMemsetAsync(g.d_out.p, 0, (size_t)nq * n * sizeof(int32_t), g.st_compute));
+    SW_CUDA(h, cudaEventRecord(g.ev_start, g.st_compute));
+    if (g.npairs == 0) {
+        SW_CUDA(h, cudaEventRecord(g.ev_stop, g.st_compute));
+        QueryChunk c{0, nq, nullptr};
+        SW_CUDA(h, cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+        SW_CUDA(h, cudaEventRecord(c.done, g.st_compute));
+        g.chunks.push_back(c);
+        return SW_OK;
+    }
+
+    SwScoring sc;
+    sc.match = h->params.match; sc.mismatch = h->params.mismatch;
+    sc.goe = (int)h->params.gap_open + (int)h->params.gap_extend; sc.ge = h->params.gap_extend;
+    sc.limit = h->params.score_width ? (1 << (h->params.score_width - 1)) - 1 : 0;
+
+    SwDevDb db = dev_db(g);
+    SwDevQueries dq;
+    dq.packed = g.d_qpacked.as<uint8_t>(); dq.off = g.d_qoff.as<uint32_t>(); dq.len = g.d_qlen.as<uint32_t>();
+    dq.nq = nq; dq.max_len = h->q_max_len;
+
+    // value range: exact s16 needs match * min(m, n) to stay clear of 32767
+    const uint64_t smax = (uint64_t)sc.match * std::min<uint64_t>(h->q_max_len, g.max_len);
+    const bool fits16 = sc.limit ? true : (smax + (uint64_t)sc.match < 32000ull);
+    const bool fitsf16 = !sc.limit && smax <= 2048ull;
+    int vidx = -1;
+    if (!h->force32 && fits16) {
+        if (h->force_arith == 1 && !fitsf16) return SW_EINVAL;
+        vidx = choose_variant(h, g, h->q_max_len);
+        if (vidx < 0 && (h->force_R || h->force_G)) return SW_EINVAL;
+    }
+
+    // query chunks: a handful of launches so that D2H of finished rows overlaps compute
+    const int nchunks = std::max(1, std::min(nq, 8));
+    SW_CUDA(h, g.d_counters.reserve(kMaxCounters * sizeof(unsigned)));
+    SW_CUDA(h, cudaMemsetAsync(g.d_counters.p, 0, kMaxCounters * sizeof(unsigned), g.st_compute));
+
+    int grid = 0, chunk_rows = 0;
+    if (vidx >= 0) {
+        const SwStripVariant *v = sw_strip_variant(vidx);
+        const int P = v->R * v->G;
+        const int need_rows = (int)((h->q_max_len + P - 1) / P) * P;
+        const int budget_rows = std::max(P, (768 / P) * P);
+        chunk_rows = std::min(need_rows, budget_rows);
+        int bps = 0;
+        SW_CUDA(h, sw_strip_occupancy(vidx, (size_t)chunk_rows * 64, &bps));
+        if (bps < 1) return SW_ECUDA;
+        const int ppb = v->block_threads / v->G;
+        const uint32_t npb = (g.npairs + ppb - 1) / ppb;
+        grid = (int)std::min<uint64_t>(npb, (uint64_t)g.num_sms * bps);
+        if (need_rows > P) {
+            const size_t bytes = (size_t)grid * g.max_len * ppb * sizeof(uint2);
+            SW_CUDA(h, g.d_bnd.reserve(bytes));
+        }
+        h->last_kernel = v->name;
+    } else {
+        const int threads_total = g.num_sms * 2 * 128;
+        SW_CUDA(h, g.d_scratch32.reserve((size_t)2 * std::max<uint32_t>(h->q_max_len, 1) * threads_total * sizeof(int32_t)));
+        h->last_kernel = "generic32";
+    }
+
+    for (int c = 0; c < nchunks; ++c) {
+        QueryChunk qc;
+        qc.q0 = (int)((long long)nq * c / nchunks);
+        qc.q1 = (int)((long long)nq * (c + 1) / nchunks);
+        qc.done = nullptr;
+        if (qc.q1 <= qc.q0) continue;
+        if (vidx >= 0) {
+            SW_CUDA(h, sw_launch_strip(vidx, g.st_compute, db, dq, qc.q0, qc.q1, sc, g.d_out.as<int32_t>(), n,
+                                       g.d_bnd.as<uint2>(), g.max_len, g.d_counters.as<unsigned>() + (c % kMaxCounters),
+                                       grid, chunk_rows));
+        } else {
+            SW_CUDA(h, sw_launch_generic32(g.st_compute, db, dq, qc.q0, qc.q1, sc, g.d_out.as<int32_t>(), n,
+                                           g.d_scratch32.as<int32_t>(), g.num_sms * 2 * 128));
+        }
+        h->launches++;
+        SW_CUDA(h, cudaEventCreateWithFlags(&qc.done, cudaEventDisableTiming));
+        SW_CUDA(h, cudaEventRecord(qc.done, g.st_compute));
+        g.chunks.push_back(qc);
+    }
+    SW_CUDA(h, cudaEventRecord(g.ev_stop, g.st_compute));
+    return SW_OK;
+}
+
+// waits for an event with a deadline; deadline_ms < 0 = forever
+int wait_event(sw_handle *h, cudaEvent_t ev, const std::chrono::steady_clock::time_point &t_end, bool forever)
+{
+    if (forever) { SW_CUDA(h, cudaEventSynchronize(ev)); return SW_OK; }
+    for (;;) {
+        cudaError_t e = cudaEventQuery(ev);
+        if (e == cudaSuccess) return SW_OK;
+        if (e != cudaErrorNotReady) { h->last_cuda = (int)e; return SW_ECUDA; }
+        if (std::chrono::steady_clock::now() >= t_end) return SW_ETIMEOUT;
+        std::this_thread::sleep_for(std::chrono::microseconds(50));
+    }
+}
+
+int copy_out(sw_handle *h, int32_t *scores, size_t cap, int timeout_ms)
+{
+    const size_t nq = h->q_len.size();
+    if (cap < nq * h->ns) return SW_ECAPACITY;
+    const bool forever = timeout_ms < 0;
+    const auto t_end = std::chrono::steady_clock::now() + std::chrono::milliseconds(forever ? 0 : timeout_ms);
+    size_t maxchunks = 0;
+    for (auto &g : h->gpus) maxchunks = std::max(maxchunks, g.chunks.size());
+    for (size_t c = 0; c < maxchunks; ++c) {
+        for (auto &g : h->gpus) {
+            if (c >= g.chunks.size()) continue;
+            const size_t n = g.s1 - g.s0;
+            if (n == 0) continue;
+            SW_CUDA(h, cudaSetDevice(g.dev));
+            const QueryChunk &qc = g.chunks[c];
+            int rc = wait_event(h, qc.done, t_end, forever);
+            if (rc != SW_OK) return rc;
+            SW_CUDA(h, cudaMemcpy2DAsync(scores + (size_t)qc.q0 * h->ns + g.s0, h->ns * sizeof(int32_t),
+                                         g.d_out.as<int32_t>() + (size_t)qc.q0 * n, n * sizeof(int32_t),
+                                         n * sizeof(int32_t), (size_t)(qc.q1 - qc.q0), cudaMemcpyDeviceToHost,
+                                         g.st_copy));
+        }
+    }
+    double ms_max = 0.0;
+    for (auto &g : h->gpus) {
+        SW_CUDA(h, cudaSetDevice(g.dev));
+        SW_CUDA(h, cudaStreamSynchronize(g.st_copy));
+        if (g.scored && (g.s1 > g.s0) && nq) {
+            SW_CUDA(h, cudaEventSynchronize(g.ev_stop));
+            float ms = 0.f;
+            SW_CUDA(h, cudaEventElapsedTime(&ms, g.ev_start, g.ev_stop));
+            ms_max = std::max(ms_max, (double)ms);
+        }
+    }
+    h->last_ms = ms_max;
+    return SW_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+void sw_default_params(sw_params_t *p)
+{
+    if (!p) return;
+    p->match = 5; p->mismatch = -4; p->gap_open = -12; p->gap_extend = -4; p->score_width = 0;
+}
+
+const char *sw_version(void) { return "sw_b200 0.1 (sm_100a)"; }
+
+int sw_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *sw_strerror(int code)
+{
+    switch (code) {
+        case SW_OK: return "ok";
+        case SW_EINVAL: return "invalid argument or unsupported parameter set";
+        case SW_ENOMEM: return "out of memory";
+        case SW_ECUDA: return "CUDA error (see sw_last_cuda_error)";
+        case SW_ENODEV: return "no usable CUDA device";
+        case SW_ESTATE: return "call out of order";
+        case SW_ETIMEOUT: return "timed out";
+        case SW_ECAPACITY: return "output buffer too small";
+        case SW_EIO: return "I/O error";
+        case SW_EAGAIN: return "a batch is already in flight";
+        default: return "unknown error";
+    }
+}
+
+int sw_init(sw_handle_t **out, const sw_params_t *p, const int *gpu_ids, int n_gpus)
+{
+    if (!out) return SW_EINVAL;
+    *out = nullptr;
+    sw_params_t prm;
+    if (p) prm = *p; else sw_default_params(&prm);
+    int rc = validate_params(&prm);
+    if (rc != SW_OK) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return SW_ENODEV; }
+    std::vector<int> ids;
+    if (!gpu_ids || n_gpus <= 0) ids.push_back(0);
+    else ids.assign(gpu_ids, gpu_ids + n_gpus);
+    for (int id : ids) if (id < 0 || id >= ndev) return SW_ENODEV;
+
+    sw_handle *h = new (std::nothrow) sw_handle();
+    if (!h) return SW_ENOMEM;
+    h->params = prm;
+    h->gpus.resize(ids.size());
+    for (size_t i = 0; i < ids.size(); ++i) {
+        GpuCtx &g = h->gpus[i];
+        g.dev = ids[i];
+        cudaError_t e = cudaSetDevice(g.dev);
+        cudaDeviceProp prop;
+        if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, g.dev);
+        if (e == cudaSuccess) {
+            g.num_sms = prop.multiProcessorCount;
+            if (prop.major < 10) e = cudaErrorInvalidDevice;      // sm_100a cubin only
+        }
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g.st_compute, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g.st_copy, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreate(&g.ev_start);
+        if (e == cudaSuccess) e = cudaEventCreate(&g.ev_stop);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g.ev_upload, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            for (auto &gg : h->gpus) free_gpu(gg);
+            delete h;
+            cudaGetLastError();
+            return e == cudaErrorInvalidDevice ? SW_ENODEV : SW_ECUDA;
+        }
+    }
+    *out = h;
+    return SW_OK;
+}
+
+void sw_destroy(sw_handle_t *h)
+{
+    if (!h) return;
+    for (auto &g : h->gpus) {
+        cudaSetDevice(g.dev);
+        cudaDeviceSynchronize();
+        free_gpu(g);
+    }
+    delete h;
+}
+
+int sw_set_queries(sw_handle_t *h, const uint8_t *packed, const uint32_t *len, const uint64_t *off, int nq)
+{
+    if (!h || nq < 0 || (nq > 0 && (!packed || !len || !off))) return SW_EINVAL;
+    if (h->batch_in_flight) return SW_EAGAIN;
+    h->q_packed.clear(); h->q_off.clear(); h->q_len.clear();
+    h->q_max_len = 0; h->q_sum_len = 0;
+    for (int i = 0; i < nq; ++i) {
+        const size_t bytes = ((size_t)len[i] + 3) / 4;
+        if (h->q_packed.size() + bytes > 0xFFFFFFF0ull) return SW_EINVAL;
+        h->q_off.push_back((uint32_t)h->q_packed.size());
+        h->q_len.push_back(len[i]);
+        h->q_packed.insert(h->q_packed.end(), packed + off[i], packed + off[i] + bytes);
+        h->q_max_len = std::max(h->q_max_len, len[i]);
+        h->q_sum_len += len[i];
+    }
+    h->q_packed.resize(h->q_packed.size() + 16, 0);
+    for (auto &g : h->gpus) {
+        int rc = upload_queries(h, g);
+        if (rc != SW_OK) return rc;
+        g.scored = false;
+    }
+    return SW_OK;
+}
+
+int sw_load_db(sw_handle_t *h, const uint8_t *packed, const uint32_t *len, const uint64_t *off,
+               const uint64_t *ids, size_t ns)
+{
+    if (!h || (ns > 0 && (!packed || !len || !off))) return SW_EINVAL;
+    if (h->batch_in_flight) return SW_EAGAIN;
+    h->ns = ns;
+    h->db_loaded = false;
+    h->have_ids = ids != nullptr;
+    if (ids) h->ids.assign(ids, ids + ns); else h->ids.clear();
+    // contiguous input ranges balanced by residue count (cells per query row)
+    const size_t ng = h->gpus.size();
+    uint64_t total = 0;
+    for (size_t s = 0; s < ns; ++s) total += len[s];
+    size_t s = 0;
+    uint64_t acc = 0;
+    for (size_t gi = 0; gi < ng; ++gi) {
+        GpuCtx &g = h->gpus[gi];
+        g.s0 = s;
+        const uint64_t target = (gi + 1 == ng) ? total : (total * (gi + 1)) / ng;
+        if (gi + 1 == ng) s = ns;
+        else while (s < ns && acc + len[s] / 2 < target) { acc += len[s]; ++s; }
+        g.s1 = s;
+    }
+    for (auto &g : h->gpus) {
+        int rc = load_shard(h, g, packed, len, off);
+        if (rc != SW_OK) return rc;
+    }
+    // caller's buffers must be reusable on return
+    for (auto &g : h->gpus) {
+        SW_CUDA(h, cudaSetDevice(g.dev));
+        SW_CUDA(h, cudaStreamSynchronize(g.st_copy));
+    }
+    h->db_loaded = true;
+    return SW_OK;
+}
+
+int sw_score_db(sw_handle_t *h)
+{
+    if (!h) return SW_EINVAL;
+    if (!h->db_loaded) return SW_ESTATE;
+    uint64_t db_len = 0;
+    for (auto &g : h->gpus) db_len += g.sum_len;
+    h->last_cells = db_len * h->q_sum_len;
+    for (auto &g : h->gpus) {
+        int rc = score_gpu(h, g);
+        if (rc != SW_OK) return rc;
+    }
+    return SW_OK;
+}
+
+int sw_wait(sw_handle_t *h, int timeout_ms)
+{
+    if (!h) return SW_EINVAL;
+    const bool forever = timeout_ms < 0;
+    const auto t_end = std::chrono::steady_clock::now() + std::chrono::milliseconds(forever ? 0 : timeout_ms);
+    double ms_max = 0.0;
+    for (auto &g : h->gpus) {
+        if (!g.scored || g.chunks.empty()) continue;
+        SW_CUDA(h, cudaSetDevice(g.dev));
+        int rc = wait_event(h, g.chunks.back().done, t_end, forever);
+        if (rc != SW_OK) return rc;
+        SW_CUDA(h, cudaEventSynchronize(g.ev_stop));
+        float ms = 0.f;
+        SW_CUDA(h, cudaEventElapsedTime(&ms, g.ev_start, g.ev_stop));
+        ms_max = std::max(ms_max, (double)ms);
+    }
+    h->last_ms = ms_max;
+    return SW_OK;
+}
+
+int sw_fetch_db(sw_handle_t *h, int32_t *scores, size_t cap)
+{
+    if (!h || !scores) return SW_EINVAL;
+    if (!h->db_loaded) return SW_ESTATE;
+    for (auto &g : h->gpus) if (!g.scored) return SW_ESTATE;
+    return copy_out(h, scores, cap, -1);
+}
+
+int sw_score_batch(sw_handle_t *h, const uint8_t *packed, const uint32_t *len, const uint64_t *off,
+                   const uint64_t *ids, size_t ns)
+{
+    if (!h) return SW_EINVAL;
+    if (h->batch_in_flight) return SW_EAGAIN;
+    int rc = sw_load_db(h, packed, len, off, ids, ns);
+    if (rc != SW_OK) return rc;
+    rc = sw_score_db(h);
+    if (rc != SW_OK) return rc;
+    h->batch_in_flight = true;
+    return SW_OK;
+}
+
+int sw_fetch(sw_handle_t *h, int32_t *scores, size_t cap, int timeout_ms)
+{
+    if (!h || (!scores && cap)) return SW_EINVAL;
+    if (!h->batch_in_flight) return SW_ESTATE;
+    int rc = copy_out(h, scores, cap, timeout_ms);
+    if (rc == SW_ETIMEOUT) return rc;          // batch stays in flight; fetch again later
+    h->batch_in_flight = false;
+    return rc;
+}
+
+int sw_fetch_ids(sw_handle_t *h, uint64_t *ids, size_t cap)
+{
+    if (!h || !ids) return SW_EINVAL;
+    if (cap < h->ns) return SW_ECAPACITY;
+    for (size_t s = 0; s < h->ns; ++s) ids[s] = h->have_ids ? h->ids[s] : (uint64_t)s;
+    return SW_OK;
+}
+
+int sw_fetch_best(sw_handle_t *h, int32_t *best_score, uint64_t *best_index, int nq_cap)
+{
+    if (!h || !best_score || !best_index) return SW_EINVAL;
+    const int nq = (int)h->q_len.size();
+    if (nq_cap < nq) return SW_ECAPACITY;
+    if (!h->db_loaded) return SW_ESTATE;
+    for (auto &g : h->gpus) if (!g.scored) return SW_ESTATE;
+    for (int q = 0; q < nq; ++q) { best_score[q] = 0; best_index[q] = 0; }
+    std::vector<int32_t> hs(nq);
+    std::vector<uint32_t> hi(nq);
+    bool first = true;
+    for (auto &g : h->gpus) {
+        const size_t n = g.s1 - g.s0;
+        if (n == 0 || nq == 0) continue;
+        SW_CUDA(h, cudaSetDevice(g.dev));
+        SW_CUDA(h, g.d_best_score.reserve(nq * sizeof(int32_t)));
+        SW_CUDA(h, g.d_best_index.reserve(nq * sizeof(uint32_t)));
+        SW_CUDA(h, sw_launch_best(g.st_compute, g.d_out.as<int32_t>(), n, (uint32_t)n, nq,
+                                  g.d_best_score.as<int32_t>(), g.d_best_index.as<uint32_t>()));
+        h->launches++;
+        SW_CUDA(h, cudaMemcpyAsync(hs.data(), g.d_best_score.p, nq * sizeof(int32_t), cudaMemcpyDeviceToHost, g.st_compute));
+        SW_CUDA(h, cudaMemcpyAsync(hi.data(), g.d_best_index.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, g.st_compute));
+        SW_CUDA(h, cudaStreamSynchronize(g.st_compute));
+        for (int q = 0; q < nq; ++q) {
+            if (first || hs[q] > best_score[q]) { best_score[q] = hs[q]; best_index[q] = g.s0 + hi[q]; }
+        }
+        first = false;
+    }
+    return SW_OK;
+}
+
+int sw_last_cuda_error(const sw_handle_t *h) { return h ? h->last_cuda : 0; }
+const char *sw_last_cuda_error_string(const sw_handle_t *h)
+{
+    return cudaGetErrorString((cudaError_t)(h ? h->last_cuda : 0));
+}
+double sw_last_kernel_ms(const sw_handle_t *h) { return h ? h->last_ms : 0.0; }
+uint64_t sw_kernel_launches(const sw_handle_t *h) { return h ? h->launches : 0; }
+uint64_t sw_last_cells(const sw_handle_t *h) { return h ? h->last_cells : 0; }
+const char *sw_last_kernel_name(const sw_handle_t *h) { return h ? h->last_kernel : "none"; }
+
+int sw_set_kernel_choice(sw_handle_t *h, int rows_per_lane, int lanes_per_pair, int force32)
+{
+    if (!h) return SW_EINVAL;
+    h->force_R = rows_per_lane; h->force_G = lanes_per_pair; h->force32 = force32;
+    return SW_OK;
+}
+
+int sw_set_arith(sw_handle_t *h, int arith)
+{
+    if (!h || arith < -1 || arith > 1) return SW_EINVAL;
+    h->force_arith = arith;
+    return SW_OK;
+}
+
+}  // extern "C"

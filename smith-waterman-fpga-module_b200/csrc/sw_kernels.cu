@@ -1,0 +1,515 @@
+/*
+ * sw_kernels.cu -- hand-written sm_100a kernels of the score-only Smith-Waterman engine.
+ *
+ * What is computed (reference: ScoreBank/SW_ProcessingElement_v1.0.v:119-129, 287-291,
+ * 411-420), per (query, subject) pair, i = query row, j = subject column:
+ *     M(i,j) = max(0, s(i,j) + H(i-1,j-1))          H = max(M, I)
+ *     I(i,j) = max(G(i-1,j), G(i,j-1))              G = max(M + go + ge, I + ge)
+ *     score  = max over all cells of H
+ * with H = 0 and G = max(go+ge, ge) on both boundaries.  G is "the gap value leaving a
+ * cell"; substituting it back gives exactly the RTL's M_open / I_extend form.
+ *
+ * How it is mapped to the GPU (replaces the systolic array of ScoringModule_v1.1.v and the
+ * two-way time sharing of each PE, SW_ProcessingElement_v1.0.v:25-27):
+ *   - two subjects of equal length share every 32-bit register (low / high 16-bit lane) --
+ *     the PE's toggle-0 / toggle-1 sequences;
+ *   - a lane keeps R consecutive query rows of H and G in registers and walks the subject
+ *     columns; per cell pair the arithmetic is 4.5 ALU-pipe + 1 FMA-pipe instructions
+ *     (VIADDMNMX.S16x2.RELU, VIMNMX.S16x2 x2, VIADDMNMX.S16x2, 1/2 VIMNMX3.S16x2; VIADD.16x2);
+ *   - G lanes of a warp form a systolic group over R*G rows: lane l is one column behind
+ *     lane l-1 and receives (H, G, column code) with __shfl_up_sync, exactly like
+ *     M_in / I_in / data_in travel from PE to PE;
+ *   - queries longer than R*G rows are processed in passes; the bottom row of a pass is kept
+ *     in an L2-resident scratch line per column and read back by lane 0 in the next pass;
+ *   - substitution scores come from a shared-memory query profile prof[row][16 column codes],
+ *     so that all lanes of a warp that sit on the same row hit 16 distinct banks.
+ */
+#include "sw_kernels.h"
+
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace {
+
+constexpr int kPadScoreS16 = -8192;   // profile value of padding rows: M becomes 0, nothing can grow
+constexpr int kPadScoreF16 = -2048;
+
+// ------------------------------------------------------------------------------------------
+// Arithmetic policies.  Both pack two independent lanes into one 32-bit register.
+// ------------------------------------------------------------------------------------------
+struct ArithS16 {
+    static constexpr int kPad = kPadScoreS16;
+    static __device__ __forceinline__ uint32_t pack(int lo, int hi) {
+        return (uint32_t)(lo & 0xFFFF) | ((uint32_t)(hi & 0xFFFF) << 16);
+    }
+    static __device__ __forceinline__ int extract(uint32_t v, int h) {
+        return (int)(int16_t)(h ? (v >> 16) : (v & 0xFFFF));
+    }
+    // max(a + b, 0): `zero` is an opaque register holding 0 (a literal makes ptxas emit a PRMT per use)
+    static __device__ __forceinline__ uint32_t add_relu(uint32_t a, uint32_t b, uint32_t zero) {
+        return __viaddmax_s16x2_relu(a, b, zero);
+    }
+    static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+    static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+    static __device__ __forceinline__ uint32_t addmax(uint32_t a, uint32_t b, uint32_t c) {
+        return __viaddmax_s16x2(a, b, c);   // max(a + b, c)
+    }
+    // values above `lim` restart at 0 (W-bit wrap-then-clamp, SW_ProcessingElement_v1.0.v:287-288)
+    static __device__ __forceinline__ uint32_t wrap_clamp(uint32_t m, uint32_t lim) {
+        return m & ~__vcmpgts2(m, lim);
+    }
+};
+
+struct ArithF16 {
+    static constexpr int kPad = kPadScoreF16;
+    static __device__ __forceinline__ uint32_t pack(int lo, int hi) {
+        __half2 h = __halves2half2(__int2half_rn(lo), __int2half_rn(hi));
+        return *reinterpret_cast<uint32_t *>(&h);
+    }
+    static __device__ __forceinline__ int extract(uint32_t v, int h) {
+        __half2 x = *reinterpret_cast<__half2 *>(&v);
+        return __half2int_rn(h ? __high2half(x) : __low2half(x));
+    }
+    static __device__ __forceinline__ uint32_t add_relu(uint32_t a, uint32_t b, uint32_t) {
+        uint32_t d;
+        const uint32_t one = 0x3C003C00u;
+        asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+        return d;
+    }
+    static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) {
+        uint32_t d;
+        asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+        return d;
+    }
+    static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+        uint32_t d;
+        asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+        return d;
+    }
+    static __device__ __forceinline__ uint32_t addmax(uint32_t a, uint32_t b, uint32_t c) {
+        return max2(add(a, b), c);
+    }
+    static __device__ __forceinline__ uint32_t wrap_clamp(uint32_t m, uint32_t) { return m; }
+};
+
+struct StripArgs {
+    const uint32_t *tp;
+    const uint64_t *tile_woff;
+    const uint32_t *pair_len;
+    const uint32_t *pair_subj;
+    uint32_t npairs;
+    uint32_t npb;              // pair blocks = ceil(npairs / pairs-per-block)
+    const uint8_t *qpacked;
+    const uint32_t *qoff;
+    const uint32_t *qlen;
+    int q0, q1;
+    int32_t *out;
+    size_t out_stride;
+    uint2 *bnd;
+    uint32_t bnd_cols;
+    unsigned *counter;
+    int chunk_rows;            // profile rows resident in shared memory (multiple of R*G)
+    int match, mismatch, goe, ge, limit;
+    uint32_t zero;             // always 0, but opaque to the compiler
+};
+
+// One column of a register strip.  H[r] / Gl[r] hold H and G of the previous column on entry
+// and of this column on exit.  hd_top = H(row0-1, c-1), g_top = G(row0-1, c).
+template <int R, class AR, bool W12>
+__device__ __forceinline__ void column_step(uint32_t (&H)[R], uint32_t (&Gl)[R], uint32_t &best,
+                                            uint32_t hd_top, uint32_t g_top, const uint32_t *prow,
+                                            uint32_t goe2, uint32_t ge2, uint32_t zero, uint32_t lim2)
+{
+    // M pass, bottom-up and in place: H[r] <- M(r, c) = relu(H(r-1, c-1) + s(r, c))
+#pragma unroll
+    for (int r = R - 1; r >= 1; --r) {
+        uint32_t m = AR::add_relu(H[r - 1], prow[r * 16], zero);
+        if (W12) m = AR::wrap_clamp(m, lim2);
+        H[r] = m;
+    }
+    {
+        uint32_t m = AR::add_relu(hd_top, prow[0], zero);
+        if (W12) m = AR::wrap_clamp(m, lim2);
+        H[0] = m;
+    }
+    // gap pass, top-down: the only serial chain of the column (I -> I+ge -> G)
+    uint32_t gu = g_top;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t i_ = AR::max2(Gl[r], gu);          // I = max(G_left, G_up)
+        const uint32_t j_ = AR::add(i_, ge2);             // I + ge            (FMA-side pipe)
+        gu = AR::addmax(H[r], goe2, j_);                  // G = max(M + goe, I + ge)
+        Gl[r] = gu;
+        H[r] = AR::max2(H[r], i_);                        // H = max(M, I)
+        best = AR::max2(best, H[r]);                      // ptxas pairs these into VIMNMX3
+    }
+}
+
+template <int R, int G, class AR, bool W12, int BT, int MINB>
+__global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
+{
+    extern __shared__ uint32_t s_prof[];
+    __shared__ unsigned s_work;
+    constexpr int P = R * G;
+    constexpr int PPB = BT / G;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+
+    const int lane = threadIdx.x & 31;
+    const int gl = (G == 1) ? 0 : (lane & (G - 1));
+    const int pslot = threadIdx.x / G;
+    const uint32_t zero = a.zero;
+    const uint32_t goe2 = AR::pack(a.goe, a.goe), ge2 = AR::pack(a.ge, a.ge);
+    const int gbv = a.goe > a.ge ? a.goe : a.ge;
+    const uint32_t gb2 = AR::pack(gbv, gbv);
+    const uint32_t lim2 = AR::pack(a.limit, a.limit);
+    uint2 *bnd = a.bnd + (size_t)blockIdx.x * a.bnd_cols * PPB + pslot;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_work = atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const unsigned pb = s_work;
+        if (pb >= a.npb) break;
+
+        const unsigned pair = pb * PPB + pslot;
+        const bool valid = pair < a.npairs;
+        const int ncols = valid ? (int)a.pair_len[pair] : 0;
+        const uint32_t *tpp = a.tp;
+        uint32_t subj_lo = SW_NO_SUBJECT, subj_hi = SW_NO_SUBJECT;
+        if (valid) {
+            tpp += a.tile_woff[pair >> 5] + (pair & 31);
+            subj_lo = a.pair_subj[2 * pair];
+            subj_hi = a.pair_subj[2 * pair + 1];
+        }
+        const int nsteps = __reduce_max_sync(FULL, ncols) + (G - 1);
+
+        for (int q = a.q0; q < a.q1; ++q) {
+            const int m = (int)a.qlen[q];
+            const uint8_t *qp = a.qpacked + a.qoff[q];
+            const int npass = (m + P - 1) / P;
+            uint32_t best = zero;
+
+            for (int pass = 0; pass < npass; ++pass) {
+                const int row_in_chunk = (pass * P) % a.chunk_rows;
+                if (row_in_chunk == 0) {
+                    // (re)build the query profile chunk: prof[row][code], code = t_lo | t_hi << 2
+                    __syncthreads();
+                    const int row0 = pass * P;
+                    for (int idx = threadIdx.x; idx < a.chunk_rows * 16; idx += BT) {
+                        const int i = row0 + (idx >> 4);
+                        const int code = idx & 15;
+                        int lo = AR::kPad, hi = AR::kPad;
+                        if (i < m) {
+                            const int qi = (qp[i >> 2] >> ((i & 3) * 2)) & 3;
+                            lo = (qi == (code & 3)) ? a.match : a.mismatch;   // v1.0.v:119
+                            hi = (qi == (code >> 2)) ? a.match : a.mismatch;
+                        }
+                        s_prof[idx] = AR::pack(lo, hi);
+                    }
+                    __syncthreads();
+                }
+                const uint32_t *prof_lane = s_prof + (row_in_chunk + gl * R) * 16;
+                const bool has_top = pass > 0;
+                const bool has_bottom = pass + 1 < npass;
+
+                uint32_t H[R], Gl[R];
+#pragma unroll
+                for (int r = 0; r < R; ++r) { H[r] = zero; Gl[r] = gb2; }
+
+                uint32_t wcur = 0, wnext = 0;
+                uint2 bcur = make_uint2(zero, gb2);          // (H, G) of the row above, column c
+                if (gl == 0 && ncols > 0) {
+                    wcur = __ldg(tpp);
+                    if (ncols > 8) wnext = __ldg(tpp + 32);
+                    if (has_top) bcur = __ldcg(bnd);
+                }
+                uint32_t pub_h = zero, pub_g = gb2, pub_t = 0;   // what the next lane will receive
+                uint32_t hd_top = zero;                          // H(row0-1, c-1)
+
+#pragma unroll 1
+                for (int t = 0; t < nsteps; ++t) {
+                    const int c = t - gl;
+                    uint32_t top_h, top_g, code;
+                    if (G > 1) {
+                        top_h = __shfl_up_sync(FULL, pub_h, 1, G);
+                        top_g = __shfl_up_sync(FULL, pub_g, 1, G);
+                        code = __shfl_up_sync(FULL, pub_t, 1, G);
+                    }
+                    if (G == 1 || gl == 0) {
+                        top_h = bcur.x;
+                        top_g = bcur.y;
+                        code = (wcur >> ((c & 7) * 4)) & 15u;
+                    }
+                    if (c >= 0 && c < ncols) {
+                        if (G == 1 || gl == 0) {
+                            if ((c & 7) == 7) {
+                                wcur = wnext;
+                                const int k = (c >> 3) + 2;
+                                if (k * 8 < ncols) wnext = __ldg(tpp + k * 32);
+                            }
+                            if (has_top && c + 1 < ncols) bcur = __ldcg(bnd + (size_t)(c + 1) * PPB);
+                        }
+                        column_step<R, AR, W12>(H, Gl, best, hd_top, top_g, prof_lane + code,
+                                                goe2, ge2, zero, lim2);
+                        hd_top = top_h;
+                        pub_h = H[R - 1];
+                        pub_g = Gl[R - 1];
+                        pub_t = code;
+                        if (has_bottom && gl == G - 1)
+                            __stcg(bnd + (size_t)c * PPB, make_uint2(pub_h, pub_g));
+                    }
+                }
+                if (has_bottom) __syncwarp();   // bottom row written by lane G-1, read by lane 0
+            }
+
+#pragma unroll
+            for (int o = G / 2; o >= 1; o >>= 1) best = AR::max2(best, __shfl_xor_sync(FULL, best, o));
+            if (gl == 0 && valid) {
+                int32_t *orow = a.out + (size_t)q * a.out_stride;
+                orow[subj_lo] = AR::extract(best, 0);
+                if (subj_hi != SW_NO_SUBJECT) orow[subj_hi] = AR::extract(best, 1);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Column-pair code stream builder: interleaves the 2-bit codes of the two members of a pair.
+// One thread per (pair, word); a word covers 8 columns.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread2(uint32_t x)
+{
+    // 16 bits = eight 2-bit groups  ->  eight 4-bit groups with the payload in the low 2 bits
+    x &= 0xFFFFu;
+    x = (x | (x << 8)) & 0x00FF00FFu;
+    x = (x | (x << 4)) & 0x0F0F0F0Fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    return x;
+}
+
+__device__ __forceinline__ uint32_t load16_bases(const uint8_t *rec, uint32_t len, uint32_t k)
+{
+    const uint32_t nbytes = (len + 3) >> 2;
+    const uint32_t b0 = 2 * k, b1 = 2 * k + 1;
+    uint32_t v = 0;
+    if (b0 < nbytes) v |= rec[b0];
+    if (b1 < nbytes) v |= (uint32_t)rec[b1] << 8;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) build_tp_kernel(const uint8_t *raw, const uint64_t *off,
+                                                      const uint32_t *len, const uint32_t *pair_subj,
+                                                      const uint32_t *pair_len, const uint64_t *tile_woff,
+                                                      uint32_t *tp, uint32_t ntiles)
+{
+    // one warp per tile: lane = pair slot, loop over words -> coalesced 128-byte stores
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (warp >= ntiles) return;
+    const uint64_t w0 = tile_woff[warp], w1 = tile_woff[warp + 1];
+    const uint32_t kmax = (uint32_t)((w1 - w0) >> 5);
+    const uint32_t pair = warp * 32 + lane;
+    const uint32_t slo = pair_subj[2 * pair], shi = pair_subj[2 * pair + 1];
+    const uint32_t n = pair_len[pair];
+    const uint8_t *rlo = (slo != SW_NO_SUBJECT) ? raw + off[slo] : nullptr;
+    const uint8_t *rhi = (shi != SW_NO_SUBJECT) ? raw + off[shi] : rlo;
+    for (uint32_t k = 0; k < kmax; ++k) {
+        uint32_t w = 0;
+        if (rlo != nullptr && k * 8 < n) {
+            const uint32_t a = load16_bases(rlo, n, k), b = load16_bases(rhi, n, k);
+            w = spread2(a) | (spread2(b) << 2);
+        }
+        tp[w0 + (uint64_t)k * 32 + lane] = w;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 32-bit fallback: one thread per (subject, query) job, H/G columns in global scratch laid
+// out [row][thread] so that a warp touches one 128-byte line per row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) generic32_kernel(const uint8_t *raw, const uint64_t *off,
+                                                       const uint32_t *len, uint32_t ns,
+                                                       const uint8_t *qpacked, const uint32_t *qoff,
+                                                       const uint32_t *qlen, int q0, int q1,
+                                                       int32_t *out, size_t out_stride, int32_t *scratch,
+                                                       uint32_t max_q, int match, int mismatch, int goe,
+                                                       int ge, int limit)
+{
+    const size_t nthreads = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int32_t *Hc = scratch + tid;                          // Hc[i * nthreads]
+    int32_t *Gc = scratch + (size_t)max_q * nthreads + tid;
+    const int gb = goe > ge ? goe : ge;
+    const size_t njobs = (size_t)ns * (size_t)(q1 - q0);
+    for (size_t job = tid; job < njobs; job += nthreads) {
+        const uint32_t s = (uint32_t)(job % ns);
+        const int q = q0 + (int)(job / ns);
+        const int m = (int)qlen[q], n = (int)len[s];
+        const uint8_t *qp = qpacked + qoff[q];
+        const uint8_t *tpk = raw + off[s];
+        for (int i = 0; i < m; ++i) { Hc[(size_t)i * nthreads] = 0; Gc[(size_t)i * nthreads] = gb; }
+        int best = 0;
+        for (int j = 0; j < n; ++j) {
+            const int tj = (tpk[j >> 2] >> ((j & 3) * 2)) & 3;
+            int hd = 0, gu = gb;
+            for (int i = 0; i < m; ++i) {
+                const int qi = (qp[i >> 2] >> ((i & 3) * 2)) & 3;
+                int mm = hd + (qi == tj ? match : mismatch);
+                mm = mm > 0 ? mm : 0;
+                if (limit && mm > limit) mm = 0;
+                const int gl_ = Gc[(size_t)i * nthreads];
+                const int ii = gl_ > gu ? gl_ : gu;
+                hd = Hc[(size_t)i * nthreads];
+                const int hn = mm > ii ? mm : ii;
+                const int a1 = mm + goe, a2 = ii + ge;
+                gu = a1 > a2 ? a1 : a2;
+                Gc[(size_t)i * nthreads] = gu;
+                Hc[(size_t)i * nthreads] = hn;
+                best = hn > best ? hn : best;
+            }
+        }
+        out[(size_t)q * out_stride + s] = best;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-query best hit (the bank's never-driven max / vld_max, ScoreBank_v2.v:42-43).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) best_kernel(const int32_t *scores, size_t stride, uint32_t ns,
+                                                    int32_t *best_score, uint32_t *best_index)
+{
+    const int q = blockIdx.x;
+    const int32_t *row = scores + (size_t)q * stride;
+    // key = (score << 32) | ~index : max key = highest score, lowest index
+    unsigned long long key = 0;
+    for (uint32_t s = threadIdx.x; s < ns; s += blockDim.x) {
+        const unsigned long long k = ((unsigned long long)(uint32_t)row[s] << 32) | (uint32_t)(~s);
+        key = k > key ? k : key;
+    }
+    __shared__ unsigned long long sk[32];
+    for (int o = 16; o >= 1; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+        key = other > key ? other : key;
+    }
+    if ((threadIdx.x & 31) == 0) sk[threadIdx.x >> 5] = key;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        key = (threadIdx.x < (blockDim.x >> 5)) ? sk[threadIdx.x] : 0ull;
+        for (int o = 16; o >= 1; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+            key = other > key ? other : key;
+        }
+        if (threadIdx.x == 0) {
+            best_score[q] = ns ? (int32_t)(key >> 32) : 0;
+            best_index[q] = ns ? ~(uint32_t)(key & 0xFFFFFFFFu) : 0u;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Variant table
+// ------------------------------------------------------------------------------------------
+constexpr int kBT = 128;
+
+typedef void (*StripFn)(const StripArgs);
+
+struct VariantEntry {
+    SwStripVariant info;
+    StripFn fn;        // exact arithmetic
+    StripFn fn_w12;    // W-bit wrap-then-clamp (s16 only)
+};
+
+#define SW_VARIANT_S16(R, G, MINB)                                                              \
+    { {R, G, 0, kBT, "strip_s16x2_R" #R "_G" #G},                                               \
+      sw_strip_kernel<R, G, ArithS16, false, kBT, MINB>, sw_strip_kernel<R, G, ArithS16, true, kBT, MINB> }
+#define SW_VARIANT_F16(R, G, MINB)                                                              \
+    { {R, G, 1, kBT, "strip_f16x2_R" #R "_G" #G},                                               \
+      sw_strip_kernel<R, G, ArithF16, false, kBT, MINB>, nullptr }
+
+const VariantEntry g_variants[] = {
+    SW_VARIANT_S16(32, 1, 4),
+    SW_VARIANT_S16(50, 1, 3),
+    SW_VARIANT_S16(64, 1, 2),
+    SW_VARIANT_S16(75, 2, 2),
+    SW_VARIANT_S16(38, 4, 3),
+    SW_VARIANT_S16(32, 4, 4),
+    SW_VARIANT_S16(32, 32, 4),
+    SW_VARIANT_F16(50, 1, 3),
+    SW_VARIANT_F16(38, 4, 3),
+};
+constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
+
+}  // namespace
+
+int sw_strip_variant_count(void) { return kNumVariants; }
+
+const SwStripVariant *sw_strip_variant(int idx)
+{
+    return (idx >= 0 && idx < kNumVariants) ? &g_variants[idx].info : nullptr;
+}
+
+cudaError_t sw_strip_occupancy(int idx, size_t smem_bytes, int *blocks_per_sm)
+{
+    if (idx < 0 || idx >= kNumVariants) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute((const void *)g_variants[idx].fn,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, (const void *)g_variants[idx].fn,
+                                                         g_variants[idx].info.block_threads, smem_bytes);
+}
+
+cudaError_t sw_launch_strip(int idx, cudaStream_t st, const SwDevDb &db, const SwDevQueries &q,
+                            int q0, int q1, const SwScoring &sc, int32_t *out, size_t out_stride,
+                            uint2 *bnd, uint32_t bnd_cols, unsigned *counter, int grid, int chunk_rows)
+{
+    if (idx < 0 || idx >= kNumVariants) return cudaErrorInvalidValue;
+    const VariantEntry &v = g_variants[idx];
+    StripFn fn = sc.limit ? v.fn_w12 : v.fn;
+    if (fn == nullptr) return cudaErrorInvalidValue;
+    const int ppb = v.info.block_threads / v.info.G;
+    StripArgs a;
+    a.tp = db.tp; a.tile_woff = db.tile_woff; a.pair_len = db.pair_len; a.pair_subj = db.pair_subj;
+    a.npairs = db.npairs; a.npb = (db.npairs + ppb - 1) / ppb;
+    a.qpacked = q.packed; a.qoff = q.off; a.qlen = q.len; a.q0 = q0; a.q1 = q1;
+    a.out = out; a.out_stride = out_stride; a.bnd = bnd; a.bnd_cols = bnd_cols; a.counter = counter;
+    a.chunk_rows = chunk_rows;
+    a.match = sc.match; a.mismatch = sc.mismatch; a.goe = sc.goe; a.ge = sc.ge; a.limit = sc.limit;
+    a.zero = 0;
+    const size_t smem = (size_t)chunk_rows * 16 * sizeof(uint32_t);
+    cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fn<<<grid, v.info.block_threads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t sw_launch_generic32(cudaStream_t st, const SwDevDb &db, const SwDevQueries &q, int q0, int q1,
+                                const SwScoring &sc, int32_t *out, size_t out_stride, int32_t *scratch,
+                                int threads_total)
+{
+    const int bt = 128;
+    const int grid = threads_total / bt;
+    if (grid <= 0) return cudaErrorInvalidValue;
+    generic32_kernel<<<grid, bt, 0, st>>>(db.raw, db.off, db.len, db.ns, q.packed, q.off, q.len, q0, q1, out,
+                                          out_stride, scratch, q.max_len, sc.match, sc.mismatch, sc.goe,
+                                          sc.ge, sc.limit);
+    return cudaGetLastError();
+}
+
+cudaError_t sw_launch_build_tp(cudaStream_t st, const SwDevDb &db)
+{
+    const uint32_t ntiles = (db.npairs + 31) / 32;
+    if (ntiles == 0) return cudaSuccess;
+    const int bt = 256;
+    const uint32_t grid = (ntiles * 32 + bt - 1) / bt;
+    build_tp_kernel<<<grid, bt, 0, st>>>(db.raw, db.off, db.len, db.pair_subj, db.pair_len, db.tile_woff,
+                                         db.tp, ntiles);
+    return cudaGetLastError();
+}
+
+cudaError_t sw_launch_best(cudaStream_t st, const int32_t *scores, size_t stride, uint32_t ns, int nq,
+                           int32_t *best_score, uint32_t *best_index)
+{
+    if (nq <= 0) return cudaSuccess;
+    best_kernel<<<nq, 1024, 0, st>>>(scores, stride, ns, best_score, best_index);
+    return cudaGetLastError();
+}

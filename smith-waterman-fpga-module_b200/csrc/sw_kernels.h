@@ -1,0 +1,82 @@
+/*
+ * sw_kernels.h -- host-side launch interface of the CUDA kernels (internal to
+ * libsw_b200.so; the public boundary is include/sw_b200.h).
+ */
+#ifndef SW_KERNELS_H_
+#define SW_KERNELS_H_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define SW_NO_SUBJECT 0xFFFFFFFFu
+
+/* Database shard resident in HBM.  Layout (DESIGN.md "data layout"):
+ *   raw/off/len   : the caller's 2-bit packed records, as uploaded
+ *   pair_subj     : [2*npairs] shard-local subject index of the low / high 16-bit
+ *                   lane of pair p (SW_NO_SUBJECT = lane unused)
+ *   pair_len      : [npairs] columns of the pair (both members have this length)
+ *   tp            : column-pair codes, 4 bit per column = t_lo | t_hi << 2, eight
+ *                   columns per 32-bit word, tiles of 32 pairs, word k of the 32
+ *                   pairs of a tile contiguous: tp[tile_woff[tile] + k*32 + slot]
+ */
+struct SwDevDb {
+    const uint8_t  *raw;
+    const uint64_t *off;
+    const uint32_t *len;
+    uint32_t        ns;
+    const uint32_t *pair_subj;
+    const uint32_t *pair_len;
+    const uint64_t *tile_woff;
+    uint32_t       *tp;
+    uint32_t        npairs;
+    uint32_t        max_len;
+};
+
+struct SwDevQueries {
+    const uint8_t  *packed;   /* 2-bit packed, each query byte aligned */
+    const uint32_t *off;      /* byte offset of each query             */
+    const uint32_t *len;
+    int             nq;
+    uint32_t        max_len;
+};
+
+struct SwScoring {
+    int match, mismatch, goe /* gap_open + gap_extend */, ge;
+    int limit;                /* 0 = exact; else 2^(W-1)-1: M above it restarts at 0 */
+};
+
+/* One strip-kernel variant = (rows per lane R, lanes per pair G, arithmetic). */
+struct SwStripVariant {
+    int R, G;
+    int arith;        /* 0 = packed s16 (DPX), 1 = packed f16 (exact while score <= 2048) */
+    int block_threads;
+    const char *name;
+};
+
+int sw_strip_variant_count(void);
+const SwStripVariant *sw_strip_variant(int idx);
+
+/* Resident blocks per SM of variant idx with smem_bytes of dynamic shared memory. */
+cudaError_t sw_strip_occupancy(int idx, size_t smem_bytes, int *blocks_per_sm);
+
+/* Scores queries [q0,q1) against all pairs of db.  out[(q)*out_stride + subj].
+ * bnd: scratch for pass boundaries, grid * bnd_cols * (block_threads/G) uint2.
+ * counter: zeroed device word (work queue).  chunk_rows: profile rows held in
+ * shared memory at once (multiple of R*G). */
+cudaError_t sw_launch_strip(int idx, cudaStream_t st, const SwDevDb &db, const SwDevQueries &q,
+                            int q0, int q1, const SwScoring &sc, int32_t *out, size_t out_stride,
+                            uint2 *bnd, uint32_t bnd_cols, unsigned *counter, int grid,
+                            int chunk_rows);
+
+/* 32-bit fallback: any length, any score range.  scratch: 2 * (q.max_len) * threads int32. */
+cudaError_t sw_launch_generic32(cudaStream_t st, const SwDevDb &db, const SwDevQueries &q,
+                                int q0, int q1, const SwScoring &sc, int32_t *out, size_t out_stride,
+                                int32_t *scratch, int threads_total);
+
+cudaError_t sw_launch_build_tp(cudaStream_t st, const SwDevDb &db);
+
+/* Per-query arg-max over subjects (first index reaching the max). */
+cudaError_t sw_launch_best(cudaStream_t st, const int32_t *scores, size_t stride, uint32_t ns,
+                           int nq, int32_t *best_score, uint32_t *best_index);
+
+#endif

@@ -1,0 +1,277 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libsw_b200.so via ctypes),
+against the golden vectors of the reference and against the CPU oracle on seeded inputs.
+Bit-exact is the bar (integer work)."""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _fasta(golden, name):
+    return golden["fasta"][name]
+
+
+def _rand(rng, n):
+    return "".join(rng.choice("ACGT") for _ in range(n))
+
+
+def _mutate(rng, s, psub=0.1, pindel=0.05):
+    out = []
+    for ch in s:
+        r = rng.random()
+        if r < pindel / 2:
+            continue
+        if r < pindel:
+            out.append(rng.choice("ACGT"))
+        out.append(rng.choice("ACGT") if rng.random() < psub else ch)
+    return "".join(out)
+
+
+def _oracle_matrix(oracle_mod, pkg, queries, subjects, **params):
+    o = oracle_mod.Oracle(**params)
+    qp, ql, qo = pkg.pack_sequences(queries)
+    tp, tl, to = pkg.pack_sequences(subjects)
+    out, _ = o.score_batch_packed(qp, ql, qo, tp, tl, to)
+    return out
+
+
+# every (rows per lane, lanes per pair, arith) variant the library instantiates + the 32-bit fallback
+VARIANTS = [(0, 0, False, -1), (32, 1, False, 0), (50, 1, False, 0), (64, 1, False, 0), (75, 2, False, 0),
+            (38, 4, False, 0), (32, 4, False, 0), (32, 32, False, 0), (50, 1, False, 1), (38, 4, False, 1),
+            (0, 0, True, -1)]
+
+
+def test_config2_data500_query100_bit_exact(golden, pkg):
+    """BASELINE config 2: data500.fa x query100.fa on one B200, bit-exact against both
+    data500.fa_query100.fa_out.txt (RTL) and score500.txt (ssearch36)."""
+    q = _fasta(golden, "query100.fa")[0][1]
+    db = _fasta(golden, "data500.fa")
+    names = [n for n, _ in db]
+    with pkg.Engine() as e:
+        sc = e.score([q], [s for _, s in db])
+        assert e.kernel_launches >= 2
+    got = dict(zip(names, sc[0].tolist()))
+    rtl = [s for s in golden["rtl"] if s["file"] == "data500.fa_query100.fa_out.txt"][0]
+    assert len(rtl["rows"]) == 499
+    for name, score, _t in rtl["rows"]:
+        assert got[name] == score, name
+    ss = [s for s in golden["ssearch"] if s["file"] == "score500.txt"][0]
+    for name, score in ss["rows"]:
+        assert got[name] == score, name
+
+
+@pytest.mark.parametrize("R,G,force32,arith", VARIANTS)
+def test_all_golden_sets_every_variant(golden, pkg, R, G, force32, arith):
+    """All 730 RTL pairs + 598 ssearch36 scores, through every kernel variant."""
+    n = 0
+    with pkg.Engine() as e:
+        e.set_kernel_choice(R, G, force32, arith)
+        for s in golden["rtl"] + golden["ssearch"]:
+            q = _fasta(golden, s["query"])[0][1]
+            db = _fasta(golden, s["db"])
+            sc = e.score([q], [x for _, x in db])
+            got = dict(zip([nm for nm, _ in db], sc[0].tolist()))
+            for row in s["rows"]:
+                assert got[row[0]] == row[1], (s["file"], row[0], e.last_kernel_name)
+                n += 1
+    assert n == 730 + 598
+
+
+def test_swalign_alt_params_and_capi(golden, pkg):
+    sw = golden["swalign"]
+    q = _fasta(golden, sw["query"])[0][1]
+    db = dict(_fasta(golden, sw["db"]))
+    with pkg.Engine(**sw["params"]) as e:
+        sc = e.score([q], [db[n] for n, _ in sw["rows"]])
+    assert sc[0].tolist() == [s for _, s in sw["rows"]]
+    c = golden["capi"]
+    with pkg.Engine(score_width=12) as e:
+        assert int(e.score([c["query"]], [c["library"]])[0, 0]) == c["result"]
+
+
+@pytest.mark.parametrize("R,G,force32,arith", VARIANTS)
+def test_random_mixed_lengths_vs_oracle(oracle_mod, pkg, R, G, force32, arith):
+    rng = random.Random(1000 + R * 7 + G)
+    queries = [_rand(rng, n) for n in (1, 37, 150, 151, 203)]
+    subjects = []
+    for _ in range(300):
+        base = rng.choice(queries)
+        if rng.random() < 0.5:
+            s = _mutate(rng, base, 0.08, 0.06)
+            a = rng.randint(0, max(0, len(s) - 1))
+            s = _rand(rng, rng.randint(0, 40)) + s[a:] + _rand(rng, rng.randint(0, 40))
+        else:
+            s = _rand(rng, rng.randint(1, 260))
+        subjects.append(s or "A")
+    subjects += ["", "A", "C", "ACGT" * 60, "T" * 150]
+    want = _oracle_matrix(oracle_mod, pkg, queries, subjects)
+    with pkg.Engine() as e:
+        e.set_kernel_choice(R, G, force32, arith)
+        got = e.score(queries, subjects)
+    np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("params", [(5, -4, -12, -4), (5, -4, -8, -4), (5, -4, -2, -1), (1, -3, -5, -2),
+                                    (2, -5, 0, -2), (5, -9, -3, -4), (3, 0, -1, 0)])
+def test_parameter_sets_vs_oracle(oracle_mod, pkg, params):
+    """Run-time loadable penalties (ScoreBank_v2.v:34,161), including the cheap-gap sets
+    where the PE recurrence differs from Gotoh."""
+    rng = random.Random(hash(params) & 0xFFFF)
+    queries = [_rand(rng, 90), _rand(rng, 150)]
+    subjects = [(_mutate(rng, rng.choice(queries), 0.15, 0.15) or "A") for _ in range(200)]
+    keys = dict(zip(("match", "mismatch", "gap_open", "gap_extend"), params))
+    want = _oracle_matrix(oracle_mod, pkg, queries, subjects, **keys)
+    for choice in [(0, 0, False, -1), (38, 4, False, 0), (0, 0, True, -1)]:
+        with pkg.Engine(*params) as e:
+            e.set_kernel_choice(*choice)
+            got = e.score(queries, subjects)
+        np.testing.assert_array_equal(got, want)
+
+
+def test_score_width_12_wrap_then_clamp(oracle_mod, pkg):
+    """identical sequences of length 400..900; 12-bit mode must
+    reproduce the RTL's wrap-to-zero, wide mode the true 5*L."""
+    rng = random.Random(1)
+    seqs = [_rand(rng, L) for L in (400, 409, 410, 411, 500, 900)]
+    noise = [_mutate(rng, s, 0.02, 0.01) for s in seqs]
+    for width in (0, 12):
+        o = oracle_mod.Oracle(score_width=width)
+        for choice in [(0, 0, False, -1), (50, 1, False, 0), (32, 32, False, 0), (0, 0, True, -1)]:
+            with pkg.Engine(score_width=width) as e:
+                e.set_kernel_choice(*choice)
+                got = e.score(seqs, seqs + noise)
+            for i, q in enumerate(seqs):
+                for j, t in enumerate(seqs + noise):
+                    assert got[i, j] == o.score(q, t), (width, choice, len(q), len(t))
+    with pkg.Engine() as e:
+        got = e.score(seqs, seqs)
+    assert [int(got[i, i]) for i in range(len(seqs))] == [5 * len(s) for s in seqs]
+
+
+def test_long_query_multi_pass_and_chunks(oracle_mod, pkg):
+    """Queries longer than one pass (R*G rows) and longer than one shared-memory profile
+    chunk; subjects long enough to exercise the pass-boundary scratch."""
+    rng = random.Random(77)
+    q1 = _rand(rng, 2500)
+    q2 = _rand(rng, 1030)
+    subjects = []
+    for _ in range(70):
+        a = rng.randint(0, 1800)
+        subjects.append(_mutate(rng, q1[a:a + rng.randint(50, 700)], 0.05, 0.03) or "A")
+    subjects += [_rand(rng, rng.randint(1, 900)) for _ in range(30)]
+    want = _oracle_matrix(oracle_mod, pkg, [q1, q2], subjects)
+    for choice in [(0, 0, False, -1), (32, 1, False, 0), (50, 1, False, 0), (75, 2, False, 0), (38, 4, False, 0),
+                   (32, 32, False, 0), (0, 0, True, -1)]:
+        with pkg.Engine() as e:
+            e.set_kernel_choice(*choice)
+            got = e.score([q1, q2], subjects)
+        np.testing.assert_array_equal(got, want, err_msg=str(choice))
+
+
+def test_scores_beyond_int16_use_32bit_path(oracle_mod, pkg):
+    rng = random.Random(5)
+    s = _rand(rng, 7000)                      # identical pair scores 35000 > 32767
+    t = _mutate(rng, s, 0.01, 0.005)
+    with pkg.Engine() as e:
+        got = e.score([s], [s, t, "ACGT"])
+        assert e.last_kernel_name == "generic32"
+    o = oracle_mod.Oracle()
+    assert got[0].tolist() == [35000, o.score(s, t), o.score(s, "ACGT")]
+
+
+def test_edge_cases(pkg):
+    with pkg.Engine() as e:
+        got = e.score(["A" * 50, "A", "ACGT"], ["T" * 50, "A", "C", "", "acgt", "ACGTNACGT"])
+    assert got[0].tolist() == [0, 5, 0, 0, 5, 5]
+    assert got[1].tolist() == [0, 5, 0, 0, 5, 5]
+    assert got[2].tolist() == [5, 5, 5, 0, 20, 20]
+    with pkg.Engine() as e:          # empty database, empty query set
+        e.set_queries(["ACGT"])
+        e.score_batch([])
+        assert e.fetch().shape == (1, 0)
+        e.set_queries([])
+        e.score_batch(["ACGT"])
+        assert e.fetch().shape == (0, 1)
+
+
+def test_large_synthetic_sample_vs_oracle(oracle_mod, pkg):
+    """Config 3 shape at reduced count: 150-nt reads, 8 queries, 40k subjects; the whole
+    matrix is compared (oracle needs a few seconds)."""
+    packed, ln, off = pkg.random_packed_db(40000, 150, seed=20160912)
+    qp, ql, qo = pkg.random_packed_db(8, 150, seed=7)
+    # plant homologs so that gaps are exercised
+    rng = np.random.default_rng(3)
+    nb = 38
+    db2 = packed[:40000 * nb].reshape(40000, nb).copy()
+    for k in range(0, 40000, 100):
+        db2[k] = qp[(k // 100 % 8) * nb:(k // 100 % 8 + 1) * nb]
+        db2[k, rng.integers(0, nb)] ^= np.uint8(rng.integers(1, 255))
+    db2[:, -1] &= np.uint8(0x0F)
+    flat = np.concatenate([db2.reshape(-1), np.zeros(16, np.uint8)])
+    o = oracle_mod.Oracle()
+    want, _ = o.score_batch_packed(qp, ql, qo, flat, ln, off)
+    with pkg.Engine() as e:
+        got = e.score((qp, ql, qo), (flat, ln, off))
+        assert e.last_cells == 8 * 150 * 40000 * 150
+    np.testing.assert_array_equal(got, want)
+    assert want.max() > 600          # the planted homologs are really there
+
+
+def test_resident_db_best_hit_and_ids(oracle_mod, pkg):
+    rng = random.Random(11)
+    queries = [_rand(rng, 120) for _ in range(3)]
+    subjects = [_rand(rng, rng.randint(30, 200)) for _ in range(500)]
+    subjects[137] = queries[1]
+    subjects[400] = queries[1]
+    want = _oracle_matrix(oracle_mod, pkg, queries, subjects)
+    with pkg.Engine() as e:
+        e.load_db(subjects, ids=np.arange(500, dtype=np.uint64) + 1000)
+        e.set_queries(queries)
+        e.score_db()
+        e.wait()
+        assert e.last_kernel_ms > 0
+        np.testing.assert_array_equal(e.fetch_db(), want)
+        bs, bi = e.fetch_best()
+        assert bs.tolist() == want.max(axis=1).tolist()
+        assert bi.tolist() == want.argmax(axis=1).tolist()
+        assert int(bi[1]) == 137 and int(bs[1]) == 600
+        assert e.fetch_ids()[5] == 1005
+        # new query set against the same resident database
+        e.set_queries(queries[:1])
+        e.score_db()
+        np.testing.assert_array_equal(e.fetch_db(), want[:1])
+
+
+def test_state_errors_and_timeout(pkg):
+    with pkg.Engine() as e:
+        with pytest.raises(pkg.SwError) as ei:
+            e.fetch()
+        assert ei.value.code == pkg.SW_ESTATE
+        e.set_queries(["ACGT" * 30])
+        e.score_batch(["ACGT" * 30] * 10)
+        with pytest.raises(pkg.SwError) as ei:
+            e.score_batch(["ACGT"])
+        assert ei.value.code == pkg.SW_EAGAIN          # the bank's `full`
+        out = e.fetch(timeout_ms=10000)
+        assert out[0].tolist() == [600] * 10
+    with pytest.raises(pkg.SwError) as ei:
+        pkg.Engine(gap_extend=3)
+    assert ei.value.code == pkg.SW_EINVAL
+    with pytest.raises(pkg.SwError) as ei:
+        pkg.Engine(gpu_ids=[99])
+    assert ei.value.code == pkg.SW_ENODEV
+
+
+def test_multi_gpu_handle_if_available(oracle_mod, pkg):
+    n = pkg.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    rng = random.Random(4)
+    queries = [_rand(rng, 150) for _ in range(4)]
+    subjects = [_rand(rng, rng.randint(1, 300)) for _ in range(3000)]
+    want = _oracle_matrix(oracle_mod, pkg, queries, subjects)
+    with pkg.Engine(gpu_ids=list(range(n))) as e:
+        got = e.score(queries, subjects)
+    np.testing.assert_array_equal(got, want)
