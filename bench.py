@@ -1,0 +1,309 @@
+#!/usr/bin/env python3
+"""bench.py -- GCUPS of the score-only Smith-Waterman hot path on B200.
+
+Workload (BASELINE.json configs[2], the configuration the metric is quoted on):
+synthetic iid-uniform 150-nt subjects (10 M per GPU, weak scaling) against 100 x 150-nt
+queries, penalties 5/-4/-12/-4, inter-task strip kernel.  One "step" = one pass of the
+hot path over the whole resident database shard for all queries.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our arm
+  python bench.py --impl reference [...]                         CPU arm (oracle port, all host threads)
+  torchrun --nproc-per-node N bench.py --gpus N ...              one rank per GPU, no collective on the data path
+
+Prints ONE JSON line (rank 0).  `value` = device-resident kernel throughput (CUDA events on
+the launching stream, max over ranks); `e2e` = the same metric through sw_score_batch /
+sw_fetch with pinned HOST buffers, H2D + D2H inside the timed region.
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+QLEN = 150
+TLEN = 150
+SEED = 20160912
+# measured with microbench/pipe_pairs.cu on this pool's B200 (profiles/r01_pipe_pairs_1024thr.json):
+# every packed-16-bit DPX / VIMNMX instruction issues at 64 thread-instructions / clock / SM
+R_INT = 64.0
+SM_COUNT = 148
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p = {"hbm_gbs": float(m["hbm_gbs"]), "sm_max_mhz": float(m["sm_max_mhz"]), "source": "measured"}
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU with nvidia-smi while a region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 7:
+                self.rows.append(f)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for f in self.rows:
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_inputs(pkg, n_subjects, n_queries, rank):
+    db = pkg.random_packed_db(n_subjects, TLEN, seed=SEED + 1000 * rank)
+    q = pkg.random_packed_db(n_queries, QLEN, seed=SEED - 1)
+    return q, db
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port of the PE recurrence (the reference ships no CPU scorer and its
+    RTL cannot be simulated here), all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    from oracle import oracle as om
+    om.build_oracle()
+    o = om.Oracle()
+    pkg_seq = importlib.import_module("smith-waterman-fpga-module_b200.seqio")
+    ns = args.ref_subjects
+    q = pkg_seq.random_packed_db(args.queries, QLEN, seed=SEED - 1)
+    db = pkg_seq.random_packed_db(ns, TLEN, seed=SEED)
+    cells = ns * TLEN * args.queries * QLEN
+    used = 1
+    for _ in range(max(args.warmup, 0)):
+        _, used = o.score_batch_packed(q[0], q[1], q[2], db[0][: (ns // 8) * 38 + 16], db[1][: ns // 8], db[2][: ns // 8])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        _, used = o.score_batch_packed(q[0], q[1], q[2], db[0], db[1], db[2])
+    dt = time.perf_counter() - t0
+    gcups = cells * args.steps / dt / 1e9
+    sample = f"first {ns} of the synthetic 150-nt subjects x {args.queries} queries per step ({cells:.3g} cells)"
+    line = {"impl": "reference", "metric": "GCUPS (score-only SW)", "value": gcups, "unit": "GCUPS",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "queries": args.queries, "query_len": QLEN,
+                       "subject_len": TLEN, "penalties": "5/-4/-12/-4"},
+            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": used, "kind": "port", "sample": sample},
+            "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return (f"configs[2]: synthetic {args.subjects} x {TLEN} nt subjects per GPU vs {args.queries} x {QLEN} nt "
+            f"queries, inter-task kernel")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--subjects", type=int, default=10_000_000, help="subjects per GPU")
+    ap.add_argument("--queries", type=int, default=100)
+    ap.add_argument("--ref-subjects", type=int, default=4000, help="subjects per step of the CPU arm")
+    ap.add_argument("--cpu-subjects", type=int, default=20000, help="subjects of the cpu_baseline sample")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--rows", type=int, default=0, help="force rows-per-lane of the strip kernel")
+    ap.add_argument("--lanes", type=int, default=0, help="force lanes-per-pair of the strip kernel")
+    ap.add_argument("--arith", type=int, default=-1, help="-1 auto, 0 s16x2, 1 f16x2")
+    ap.add_argument("--kernel", default="", help="force a strip-kernel variant by name")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this bench has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    pkg = importlib.import_module("smith-waterman-fpga-module_b200")
+    q, db = make_inputs(pkg, args.subjects, args.queries, rank)
+    eng = pkg.Engine(gpu_ids=[local_rank])
+    eng.set_kernel_choice(args.rows, args.lanes, False, args.arith)
+    if args.kernel:
+        eng.set_kernel_name(args.kernel)
+    eng.set_queries(q)
+
+    # ---- device-resident arm: database uploaded once, then K timed passes -------------------
+    eng.load_db(db)
+    for _ in range(args.warmup):
+        eng.score_db()
+        eng.wait()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.kernel_launches
+    kernel_ms = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        eng.score_db()
+        eng.wait()
+        kernel_ms.append(eng.last_kernel_ms)        # CUDA events on the library's compute stream
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.kernel_launches - launches0
+    cells_step = eng.last_cells
+    kname = eng.last_kernel_name
+    dev_s = max_over_ranks(sum(kernel_ms) / 1e3)
+    wall_s = max_over_ranks(wall)
+    gcups = cells_step * world * args.steps / dev_s / 1e9
+    # spot check: the timed output is the real thing (compare a slice with an independent launch)
+    chk = eng.fetch_db()
+    checksum = int(chk[:, :: max(1, args.subjects // 4096)].astype(np.int64).sum())
+
+    # ---- end-to-end arm: host buffers in, host scores out, every step -----------------------
+    e2e = None
+    if not args.no_e2e:
+        pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+        hp, hl, ho = pin(db[0]), pin(db[1]), pin(db[2])
+        out = torch.empty((args.queries, args.subjects), dtype=torch.int32, pin_memory=True).numpy()
+        eng.score_batch((hp, hl, ho)); eng.fetch(out=out)          # warm-up
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            eng.score_batch((hp, hl, ho))
+            eng.fetch(out=out)
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        assert np.array_equal(out, chk), "e2e scores differ from the resident-path scores"
+        e2e = {"value": cells_step * world * args.e2e_steps / e2e_s / 1e9, "unit": "GCUPS",
+               "h2d_bytes_per_step": int(hp.nbytes + hl.nbytes + ho.nbytes), "d2h_bytes_per_step": int(out.nbytes),
+               "ms_per_step": e2e_s / args.e2e_steps * 1e3, "steps": args.e2e_steps,
+               "api": "sw_score_batch + sw_fetch, pinned host buffers"}
+        del out
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample ---------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as om
+        om.build_oracle()
+        o = om.Oracle()
+        ns = min(args.cpu_subjects, args.subjects)
+        nb = (TLEN + 3) // 4
+        t0 = time.perf_counter()
+        ref, used = o.score_batch_packed(q[0], q[1], q[2], db[0][: ns * nb + 16], db[1][:ns], db[2][:ns])
+        dt = time.perf_counter() - t0
+        assert np.array_equal(ref, chk[:, :ns]), "GPU scores differ from the CPU oracle on the sample"
+        cpu = {"value": ns * TLEN * args.queries * QLEN / dt / 1e9, "unit": "GCUPS", "cores": used, "kind": "port",
+               "sample": f"first {ns} subjects x {args.queries} queries ({ns * TLEN * args.queries * QLEN:.3g} cells), "
+                         f"scalar int32 C oracle, OpenMP; scores equal to the GPU's"}
+
+    if rank == 0:
+        pk = peaks()
+        roof_gcups = SM_COUNT * pk["sm_max_mhz"] * 1e6 * R_INT * 2.0 / 6.0 / 1e9
+        per_gpu = gcups / world
+        # algorithmic HBM bytes per step and GPU: column-code stream once per query chunk (8 launches)
+        # + one int32 score per pair written once
+        algo_bytes = args.subjects * ((TLEN + 7) // 8 * 4 / 2 + 8) * 8 + args.subjects * args.queries * 4
+        line = {
+            "metric": "GCUPS (score-only SW)", "value": gcups, "unit": "GCUPS", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s16x2",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "queries": args.queries, "query_len": QLEN,
+                       "subject_len": TLEN, "subjects_per_gpu": args.subjects, "penalties": "5/-4/-12/-4",
+                       "kernel": kname, "l2": "inputs (code stream + 4 GB score matrix per GPU) larger than L2",
+                       "wall_ms_per_step": wall_s / args.steps * 1e3, "checksum": checksum},
+            "roofline": {"bound": "int_pipe", "achieved": per_gpu, "peak": roof_gcups, "unit": "GCUPS",
+                         "frac": per_gpu / roof_gcups,
+                         "peak_def": f"148 SM x {pk['sm_max_mhz']:.0f} MHz x R_int {R_INT:.0f} thread-instr/clk/SM "
+                                     f"(measured, profiles/r01_pipe_pairs_1024thr.json) x 2 cells / 6 instr (SURVEY 8d)",
+                         "traffic": None,
+                         "hbm": {"algorithmic_bytes_per_step": int(algo_bytes),
+                                 "achieved_gbs": algo_bytes / (dev_s / args.steps) / 1e9,
+                                 "peak_gbs": pk["hbm_gbs"], "peak_source": pk["source"],
+                                 "frac": algo_bytes / (dev_s / args.steps) / 1e9 / pk["hbm_gbs"]}},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

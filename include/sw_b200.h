@@ -138,6 +138,12 @@ int sw_set_kernel_choice(sw_handle_t *h, int rows_per_lane, int lanes_per_pair, 
 /* arith: -1 = automatic, 0 = packed signed 16-bit (DPX), 1 = packed fp16 (exact while the
  * largest possible score is <= 2048; rejected with SW_EINVAL otherwise). */
 int sw_set_arith(sw_handle_t *h, int arith);
+/* The strip-kernel variants compiled into the library, and forcing one by name
+ * (NULL or "" = back to automatic).  Names look like "strip_s16x2_R25x2_G1":
+ * 25 rows x 2 sub-strips per lane, 1 lane per subject pair. */
+int sw_kernel_variant_count(void);
+const char *sw_kernel_variant_name(int idx);
+int sw_set_kernel_name(sw_handle_t *h, const char *name);
 int sw_device_count(void);
 const char *sw_version(void);
 

@@ -79,6 +79,10 @@ def load_library():
     L.sw_last_kernel_name.restype = C.c_char_p
     L.sw_set_kernel_choice.argtypes = [vp, i32, i32, i32]
     L.sw_set_arith.argtypes = [vp, i32]
+    L.sw_kernel_variant_count.restype = i32
+    L.sw_kernel_variant_name.argtypes = [i32]
+    L.sw_kernel_variant_name.restype = C.c_char_p
+    L.sw_set_kernel_name.argtypes = [vp, C.c_char_p]
     L.sw_device_count.restype = i32
     L.sw_version.restype = C.c_char_p
     L.sw_pack_2bit.argtypes = [C.c_char_p, sz, vp]
@@ -203,6 +207,9 @@ class Engine:
         self._check(self.lib.sw_set_kernel_choice(self.h, rows_per_lane, lanes_per_pair, int(force32)))
         self._check(self.lib.sw_set_arith(self.h, arith))
 
+    def set_kernel_name(self, name):
+        self._check(self.lib.sw_set_kernel_name(self.h, name.encode() if name else None))
+
     @property
     def last_kernel_ms(self):
         return float(self.lib.sw_last_kernel_ms(self.h))
@@ -218,6 +225,11 @@ class Engine:
     @property
     def last_kernel_name(self):
         return self.lib.sw_last_kernel_name(self.h).decode()
+
+
+def kernel_variants():
+    L = load_library()
+    return [L.sw_kernel_variant_name(i).decode() for i in range(L.sw_kernel_variant_count())]
 
 
 def device_count():

@@ -96,6 +96,7 @@ struct sw_handle {
     double last_ms = 0.0;
     const char *last_kernel = "none";
     int force_R = 0, force_G = 0, force32 = 0, force_arith = -1;
+    int force_variant = -1;
 };
 
 namespace {
@@ -274,12 +275,30 @@ SwDevDb dev_db(const GpuCtx &g)
     return db;
 }
 
-// Picks the strip variant: enough lanes to fill the GPU first, least padded rows second.
-int choose_variant(const sw_handle *h, const GpuCtx &g, uint32_t maxq)
+// Measured steady-state speed of each variant in GCUPS over PADDED cells (150-nt reads,
+// profiles/r01_variant_sweep.txt); only the ratios matter for the choice below.
+double variant_speed(const SwStripVariant *v)
+{
+    struct { const char *name; double gcups; } tab[] = {
+        {"strip_s16x2_R32x1_G1", 6210}, {"strip_s16x2_R50x1_G1", 6345}, {"strip_s16x2_R25x2_G1", 6297},
+        {"strip_s16x2_R25x1_G2", 5690}, {"strip_s16x2_R64x1_G1", 5770}, {"strip_s16x2_R32x2_G1", 6360},
+        {"strip_s16x2_R75x1_G2", 5570}, {"strip_s16x2_R25x3_G2", 6100}, {"strip_s16x2_R38x1_G4", 5170},
+        {"strip_s16x2_R19x2_G4", 5000}, {"strip_s16x2_R32x1_G4", 5110}, {"strip_s16x2_R32x1_G32", 4050},
+        {"strip_s16x2_R16x2_G32", 4130}, {"strip_f16x2_R50x1_G1", 6380}, {"strip_f16x2_R25x2_G1", 6821},
+        {"strip_f16x2_R25x1_G2", 6195}, {"strip_f16x2_R38x1_G4", 5120}, {"strip_f16x2_R19x2_G4", 5100},
+    };
+    for (auto &t : tab) if (std::strcmp(t.name, v->name) == 0) return t.gcups;
+    return 5000.0;
+}
+
+// Picks the strip variant: least estimated time = padded rows x (columns + pipeline fill)
+// / measured speed / fraction of the GPU the pairs can keep busy.
+int choose_variant(const sw_handle *h, const GpuCtx &g, uint32_t maxq, bool allow_f16)
 {
     const int nv = sw_strip_variant_count();
-    const int want_arith = h->force_arith >= 0 ? h->force_arith : 0;
+    if (h->force_variant >= 0) return h->force_variant;
     if (h->force_R || h->force_G) {
+        const int want_arith = h->force_arith >= 0 ? h->force_arith : 0;
         for (int i = 0; i < nv; ++i) {
             const SwStripVariant *v = sw_strip_variant(i);
             if (v->arith == want_arith && (!h->force_R || v->R == h->force_R) && (!h->force_G || v->G == h->force_G))
@@ -287,19 +306,19 @@ int choose_variant(const sw_handle *h, const GpuCtx &g, uint32_t maxq)
         }
         return -1;
     }
-    const double fill = (double)g.num_sms * 256.0;        // lanes that keep every SM busy
     int best = -1;
     double best_cost = 0;
     for (int i = 0; i < nv; ++i) {
         const SwStripVariant *v = sw_strip_variant(i);
-        if (v->arith != want_arith) continue;
+        if (v->arith == 1 && !allow_f16) continue;
+        if (h->force_arith >= 0 && v->arith != h->force_arith) continue;
         const int P = v->R * v->G;
         const double rows = (double)((maxq + P - 1) / P) * P;
         const double lanes = (double)g.npairs * v->G;
+        const double fill = (double)g.num_sms * v->min_blocks * v->block_threads;
         const double util = std::min(1.0, lanes / fill);
-        // time ~ padded rows per lane * (columns + pipeline fill) / utilisation
         const double cols = (double)std::max<uint32_t>(g.max_len, 1);
-        const double cost = rows / v->G * (cols + v->G - 1) / cols / util * (v->G > 1 ? 1.03 : 1.0);
+        const double cost = rows * (cols + v->G * v->S - 1) / cols / variant_speed(v) / util;
         if (best < 0 || cost < best_cost) { best = i; best_cost = cost; }
     }
     return best;
@@ -344,8 +363,9 @@ int score_gpu(sw_handle *h, GpuCtx &g)
     int vidx = -1;
     if (!h->force32 && fits16) {
         if (h->force_arith == 1 && !fitsf16) return SW_EINVAL;
-        vidx = choose_variant(h, g, h->q_max_len);
+        vidx = choose_variant(h, g, h->q_max_len, fitsf16);
         if (vidx < 0 && (h->force_R || h->force_G)) return SW_EINVAL;
+        if (vidx >= 0 && sw_strip_variant(vidx)->arith == 1 && !fitsf16) return SW_EINVAL;
     }
 
     // query chunks: a handful of launches so that D2H of finished rows overlaps compute
@@ -723,6 +743,23 @@ int sw_set_kernel_choice(sw_handle_t *h, int rows_per_lane, int lanes_per_pair, 
     if (!h) return SW_EINVAL;
     h->force_R = rows_per_lane; h->force_G = lanes_per_pair; h->force32 = force32;
     return SW_OK;
+}
+
+int sw_kernel_variant_count(void) { return sw_strip_variant_count(); }
+
+const char *sw_kernel_variant_name(int idx)
+{
+    const SwStripVariant *v = sw_strip_variant(idx);
+    return v ? v->name : nullptr;
+}
+
+int sw_set_kernel_name(sw_handle_t *h, const char *name)
+{
+    if (!h) return SW_EINVAL;
+    if (!name || !*name) { h->force_variant = -1; return SW_OK; }
+    for (int i = 0; i < sw_strip_variant_count(); ++i)
+        if (std::strcmp(sw_strip_variant(i)->name, name) == 0) { h->force_variant = i; return SW_OK; }
+    return SW_EINVAL;
 }
 
 int sw_set_arith(sw_handle_t *h, int arith)

@@ -113,16 +113,16 @@ struct StripArgs {
     uint32_t zero;             // always 0, but opaque to the compiler
 };
 
-// One column of a register strip.  H[r] / Gl[r] hold H and G of the previous column on entry
-// and of this column on exit.  hd_top = H(row0-1, c-1), g_top = G(row0-1, c).
-template <int R, class AR, bool W12>
-__device__ __forceinline__ void column_step(uint32_t (&H)[R], uint32_t (&Gl)[R], uint32_t &best,
+// One column of one register sub-strip.  H[r] / Gl[r] hold H and G of the previous column on
+// entry and of this column on exit.  hd_top = H(row0-1, c-1), g_top = G(row0-1, c).
+template <int RS, class AR, bool W12>
+__device__ __forceinline__ void column_step(uint32_t (&H)[RS], uint32_t (&Gl)[RS], uint32_t &best,
                                             uint32_t hd_top, uint32_t g_top, const uint32_t *prow,
                                             uint32_t goe2, uint32_t ge2, uint32_t zero, uint32_t lim2)
 {
     // M pass, bottom-up and in place: H[r] <- M(r, c) = relu(H(r-1, c-1) + s(r, c))
 #pragma unroll
-    for (int r = R - 1; r >= 1; --r) {
+    for (int r = RS - 1; r >= 1; --r) {
         uint32_t m = AR::add_relu(H[r - 1], prow[r * 16], zero);
         if (W12) m = AR::wrap_clamp(m, lim2);
         H[r] = m;
@@ -135,7 +135,7 @@ __device__ __forceinline__ void column_step(uint32_t (&H)[R], uint32_t (&Gl)[R],
     // gap pass, top-down: the only serial chain of the column (I -> I+ge -> G)
     uint32_t gu = g_top;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
+    for (int r = 0; r < RS; ++r) {
         const uint32_t i_ = AR::max2(Gl[r], gu);          // I = max(G_left, G_up)
         const uint32_t j_ = AR::add(i_, ge2);             // I + ge            (FMA-side pipe)
         gu = AR::addmax(H[r], goe2, j_);                  // G = max(M + goe, I + ge)
@@ -145,11 +145,52 @@ __device__ __forceinline__ void column_step(uint32_t (&H)[R], uint32_t (&Gl)[R],
     }
 }
 
-template <int R, int G, class AR, bool W12, int BT, int MINB>
+// S sub-strips of one lane, each on its own column (sub-strip s is one column behind s-1):
+// S independent dependency chains in one basic block, so that a warp always has an
+// instruction whose operands are ready (the PE array's pipelining, inside one thread).
+template <int RS, int S, class AR, bool W12>
+__device__ __forceinline__ void column_step_multi(uint32_t (&H)[S][RS], uint32_t (&Gl)[S][RS], uint32_t &best,
+                                                  const uint32_t (&hd_top)[S], const uint32_t (&g_top)[S],
+                                                  const uint32_t *const (&prow)[S], uint32_t goe2,
+                                                  uint32_t ge2, uint32_t zero, uint32_t lim2)
+{
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+#pragma unroll
+        for (int r = RS - 1; r >= 1; --r) {
+            uint32_t m = AR::add_relu(H[s][r - 1], prow[s][r * 16], zero);
+            if (W12) m = AR::wrap_clamp(m, lim2);
+            H[s][r] = m;
+        }
+        uint32_t m = AR::add_relu(hd_top[s], prow[s][0], zero);
+        if (W12) m = AR::wrap_clamp(m, lim2);
+        H[s][0] = m;
+    }
+    uint32_t gu[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) gu[s] = g_top[s];
+#pragma unroll
+    for (int r = 0; r < RS; ++r) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const uint32_t i_ = AR::max2(Gl[s][r], gu[s]);
+            const uint32_t j_ = AR::add(i_, ge2);
+            gu[s] = AR::addmax(H[s][r], goe2, j_);
+            Gl[s][r] = gu[s];
+            H[s][r] = AR::max2(H[s][r], i_);
+            best = AR::max2(best, H[s][r]);
+        }
+    }
+}
+
+// RS rows per sub-strip, S sub-strips per lane, G lanes per pair: R = RS*S rows per lane,
+// P = R*G rows per pass.  Virtual PE v = lane_in_group*S + s works on column t - v at step t.
+template <int RS, int S, int G, class AR, bool W12, int BT, int MINB>
 __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
 {
     extern __shared__ uint32_t s_prof[];
     __shared__ unsigned s_work;
+    constexpr int R = RS * S;
     constexpr int P = R * G;
     constexpr int PPB = BT / G;
     constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -181,7 +222,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
             subj_lo = a.pair_subj[2 * pair];
             subj_hi = a.pair_subj[2 * pair + 1];
         }
-        const int nsteps = __reduce_max_sync(FULL, ncols) + (G - 1);
+        const int nsteps = __reduce_max_sync(FULL, ncols) + (G * S - 1);
 
         for (int q = a.q0; q < a.q1; ++q) {
             const int m = (int)a.qlen[q];
@@ -212,9 +253,11 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                 const bool has_top = pass > 0;
                 const bool has_bottom = pass + 1 < npass;
 
-                uint32_t H[R], Gl[R];
+                uint32_t H[S][RS], Gl[S][RS];
 #pragma unroll
-                for (int r = 0; r < R; ++r) { H[r] = zero; Gl[r] = gb2; }
+                for (int s = 0; s < S; ++s)
+#pragma unroll
+                    for (int r = 0; r < RS; ++r) { H[s][r] = zero; Gl[s][r] = gb2; }
 
                 uint32_t wcur = 0, wnext = 0;
                 uint2 bcur = make_uint2(zero, gb2);          // (H, G) of the row above, column c
@@ -223,41 +266,64 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                     if (ncols > 8) wnext = __ldg(tpp + 32);
                     if (has_top) bcur = __ldcg(bnd);
                 }
-                uint32_t pub_h = zero, pub_g = gb2, pub_t = 0;   // what the next lane will receive
-                uint32_t hd_top = zero;                          // H(row0-1, c-1)
+                // what each sub-strip hands to the next virtual PE (the next sub-strip, or for
+                // s = S-1 the next lane): bottom H, bottom G and the column code it just used
+                uint32_t pub_h[S], pub_g[S], pub_t[S], hd_top[S];
+#pragma unroll
+                for (int s = 0; s < S; ++s) { pub_h[s] = zero; pub_g[s] = gb2; pub_t[s] = 0; hd_top[s] = zero; }
 
 #pragma unroll 1
                 for (int t = 0; t < nsteps; ++t) {
-                    const int c = t - gl;
-                    uint32_t top_h, top_g, code;
+                    const int c0 = t - gl * S;                 // column of sub-strip 0
+                    uint32_t in_h[S], in_g[S], in_t[S];
                     if (G > 1) {
-                        top_h = __shfl_up_sync(FULL, pub_h, 1, G);
-                        top_g = __shfl_up_sync(FULL, pub_g, 1, G);
-                        code = __shfl_up_sync(FULL, pub_t, 1, G);
+                        in_h[0] = __shfl_up_sync(FULL, pub_h[S - 1], 1, G);
+                        in_g[0] = __shfl_up_sync(FULL, pub_g[S - 1], 1, G);
+                        in_t[0] = __shfl_up_sync(FULL, pub_t[S - 1], 1, G);
                     }
                     if (G == 1 || gl == 0) {
-                        top_h = bcur.x;
-                        top_g = bcur.y;
-                        code = (wcur >> ((c & 7) * 4)) & 15u;
+                        in_h[0] = bcur.x;
+                        in_g[0] = bcur.y;
+                        in_t[0] = (wcur >> ((c0 & 7) * 4)) & 15u;
                     }
-                    if (c >= 0 && c < ncols) {
-                        if (G == 1 || gl == 0) {
-                            if ((c & 7) == 7) {
-                                wcur = wnext;
-                                const int k = (c >> 3) + 2;
-                                if (k * 8 < ncols) wnext = __ldg(tpp + k * 32);
-                            }
-                            if (has_top && c + 1 < ncols) bcur = __ldcg(bnd + (size_t)(c + 1) * PPB);
+#pragma unroll
+                    for (int s = 1; s < S; ++s) { in_h[s] = pub_h[s - 1]; in_g[s] = pub_g[s - 1]; in_t[s] = pub_t[s - 1]; }
+
+                    const bool first_on = c0 >= 0 && c0 < ncols;
+                    const bool last_on = (c0 - (S - 1)) >= 0 && (c0 - (S - 1)) < ncols;
+                    if (first_on && (G == 1 || gl == 0)) {
+                        if ((c0 & 7) == 7) {
+                            wcur = wnext;
+                            const int k = (c0 >> 3) + 2;
+                            if (k * 8 < ncols) wnext = __ldg(tpp + k * 32);
                         }
-                        column_step<R, AR, W12>(H, Gl, best, hd_top, top_g, prof_lane + code,
-                                                goe2, ge2, zero, lim2);
-                        hd_top = top_h;
-                        pub_h = H[R - 1];
-                        pub_g = Gl[R - 1];
-                        pub_t = code;
-                        if (has_bottom && gl == G - 1)
-                            __stcg(bnd + (size_t)c * PPB, make_uint2(pub_h, pub_g));
+                        if (has_top && c0 + 1 < ncols) bcur = __ldcg(bnd + (size_t)(c0 + 1) * PPB);
                     }
+                    if (S > 1 && first_on && last_on) {
+                        // steady state: all sub-strips active, one basic block
+                        const uint32_t *prow[S];
+#pragma unroll
+                        for (int s = 0; s < S; ++s) prow[s] = prof_lane + s * RS * 16 + in_t[s];
+                        column_step_multi<RS, S, AR, W12>(H, Gl, best, hd_top, in_g, prow, goe2, ge2, zero, lim2);
+#pragma unroll
+                        for (int s = 0; s < S; ++s) {
+                            hd_top[s] = in_h[s];
+                            pub_h[s] = H[s][RS - 1]; pub_g[s] = Gl[s][RS - 1]; pub_t[s] = in_t[s];
+                        }
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < S; ++s) {
+                            const int c = c0 - s;
+                            if (c >= 0 && c < ncols) {
+                                column_step<RS, AR, W12>(H[s], Gl[s], best, hd_top[s], in_g[s],
+                                                         prof_lane + s * RS * 16 + in_t[s], goe2, ge2, zero, lim2);
+                                hd_top[s] = in_h[s];
+                                pub_h[s] = H[s][RS - 1]; pub_g[s] = Gl[s][RS - 1]; pub_t[s] = in_t[s];
+                            }
+                        }
+                    }
+                    if (has_bottom && gl == G - 1 && last_on)
+                        __stcg(bnd + (size_t)(c0 - (S - 1)) * PPB, make_uint2(pub_h[S - 1], pub_g[S - 1]));
                 }
                 if (has_bottom) __syncwarp();   // bottom row written by lane G-1, read by lane 0
             }
@@ -419,23 +485,32 @@ struct VariantEntry {
     StripFn fn_w12;    // W-bit wrap-then-clamp (s16 only)
 };
 
-#define SW_VARIANT_S16(R, G, MINB)                                                              \
-    { {R, G, 0, kBT, "strip_s16x2_R" #R "_G" #G},                                               \
-      sw_strip_kernel<R, G, ArithS16, false, kBT, MINB>, sw_strip_kernel<R, G, ArithS16, true, kBT, MINB> }
-#define SW_VARIANT_F16(R, G, MINB)                                                              \
-    { {R, G, 1, kBT, "strip_f16x2_R" #R "_G" #G},                                               \
-      sw_strip_kernel<R, G, ArithF16, false, kBT, MINB>, nullptr }
+#define SW_VARIANT_S16(RS, S, G, MINB)                                                          \
+    { {RS * S, G, 0, kBT, S, MINB, "strip_s16x2_R" #RS "x" #S "_G" #G},                         \
+      sw_strip_kernel<RS, S, G, ArithS16, false, kBT, MINB>, sw_strip_kernel<RS, S, G, ArithS16, true, kBT, MINB> }
+#define SW_VARIANT_F16(RS, S, G, MINB)                                                          \
+    { {RS * S, G, 1, kBT, S, MINB, "strip_f16x2_R" #RS "x" #S "_G" #G},                         \
+      sw_strip_kernel<RS, S, G, ArithF16, false, kBT, MINB>, nullptr }
 
 const VariantEntry g_variants[] = {
-    SW_VARIANT_S16(32, 1, 4),
-    SW_VARIANT_S16(50, 1, 3),
-    SW_VARIANT_S16(64, 1, 2),
-    SW_VARIANT_S16(75, 2, 2),
-    SW_VARIANT_S16(38, 4, 3),
-    SW_VARIANT_S16(32, 4, 4),
-    SW_VARIANT_S16(32, 32, 4),
-    SW_VARIANT_F16(50, 1, 3),
-    SW_VARIANT_F16(38, 4, 3),
+    SW_VARIANT_S16(32, 1, 1, 4),
+    SW_VARIANT_S16(50, 1, 1, 3),
+    SW_VARIANT_S16(25, 2, 1, 3),
+    SW_VARIANT_S16(25, 1, 2, 5),
+    SW_VARIANT_S16(64, 1, 1, 2),
+    SW_VARIANT_S16(32, 2, 1, 2),
+    SW_VARIANT_S16(75, 1, 2, 2),
+    SW_VARIANT_S16(25, 3, 2, 2),
+    SW_VARIANT_S16(38, 1, 4, 3),
+    SW_VARIANT_S16(19, 2, 4, 3),
+    SW_VARIANT_S16(32, 1, 4, 4),
+    SW_VARIANT_S16(32, 1, 32, 4),
+    SW_VARIANT_S16(16, 2, 32, 4),
+    SW_VARIANT_F16(50, 1, 1, 3),
+    SW_VARIANT_F16(25, 2, 1, 3),
+    SW_VARIANT_F16(25, 1, 2, 5),
+    SW_VARIANT_F16(38, 1, 4, 3),
+    SW_VARIANT_F16(19, 2, 4, 3),
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 

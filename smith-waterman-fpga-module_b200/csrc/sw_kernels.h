@@ -50,6 +50,8 @@ struct SwStripVariant {
     int R, G;
     int arith;        /* 0 = packed s16 (DPX), 1 = packed f16 (exact while score <= 2048) */
     int block_threads;
+    int S;            /* independent sub-strips per lane (R = RS * S) */
+    int min_blocks;   /* resident blocks per SM the kernel was compiled for */
     const char *name;
 };
 

@@ -37,10 +37,26 @@ def _oracle_matrix(oracle_mod, pkg, queries, subjects, **params):
     return out
 
 
-# every (rows per lane, lanes per pair, arith) variant the library instantiates + the 32-bit fallback
-VARIANTS = [(0, 0, False, -1), (32, 1, False, 0), (50, 1, False, 0), (64, 1, False, 0), (75, 2, False, 0),
-            (38, 4, False, 0), (32, 4, False, 0), (32, 32, False, 0), (50, 1, False, 1), (38, 4, False, 1),
-            (0, 0, True, -1)]
+# every strip-kernel variant the library instantiates (kept in sync by
+# tests/test_host_abi.py::test_variant_list_matches_library) + automatic choice + 32-bit fallback
+STRIP_VARIANTS = [
+    "strip_s16x2_R32x1_G1", "strip_s16x2_R50x1_G1", "strip_s16x2_R25x2_G1", "strip_s16x2_R25x1_G2",
+    "strip_s16x2_R64x1_G1", "strip_s16x2_R32x2_G1", "strip_s16x2_R75x1_G2", "strip_s16x2_R25x3_G2",
+    "strip_s16x2_R38x1_G4", "strip_s16x2_R19x2_G4", "strip_s16x2_R32x1_G4", "strip_s16x2_R32x1_G32",
+    "strip_s16x2_R16x2_G32", "strip_f16x2_R50x1_G1", "strip_f16x2_R25x2_G1", "strip_f16x2_R25x1_G2",
+    "strip_f16x2_R38x1_G4", "strip_f16x2_R19x2_G4",
+]
+S16_VARIANTS = [v for v in STRIP_VARIANTS if "s16x2" in v]
+VARIANTS = ["auto", "generic32"] + STRIP_VARIANTS
+
+
+def _choose(e, variant):
+    if variant == "auto":
+        return
+    if variant == "generic32":
+        e.set_kernel_choice(0, 0, True, -1)
+    else:
+        e.set_kernel_name(variant)
 
 
 def test_config2_data500_query100_bit_exact(golden, pkg):
@@ -62,12 +78,12 @@ def test_config2_data500_query100_bit_exact(golden, pkg):
         assert got[name] == score, name
 
 
-@pytest.mark.parametrize("R,G,force32,arith", VARIANTS)
-def test_all_golden_sets_every_variant(golden, pkg, R, G, force32, arith):
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_all_golden_sets_every_variant(golden, pkg, variant):
     """All 730 RTL pairs + 598 ssearch36 scores, through every kernel variant."""
     n = 0
     with pkg.Engine() as e:
-        e.set_kernel_choice(R, G, force32, arith)
+        _choose(e, variant)
         for s in golden["rtl"] + golden["ssearch"]:
             q = _fasta(golden, s["query"])[0][1]
             db = _fasta(golden, s["db"])
@@ -91,9 +107,9 @@ def test_swalign_alt_params_and_capi(golden, pkg):
         assert int(e.score([c["query"]], [c["library"]])[0, 0]) == c["result"]
 
 
-@pytest.mark.parametrize("R,G,force32,arith", VARIANTS)
-def test_random_mixed_lengths_vs_oracle(oracle_mod, pkg, R, G, force32, arith):
-    rng = random.Random(1000 + R * 7 + G)
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_random_mixed_lengths_vs_oracle(oracle_mod, pkg, variant):
+    rng = random.Random(1000 + VARIANTS.index(variant))
     queries = [_rand(rng, n) for n in (1, 37, 150, 151, 203)]
     subjects = []
     for _ in range(300):
@@ -108,7 +124,7 @@ def test_random_mixed_lengths_vs_oracle(oracle_mod, pkg, R, G, force32, arith):
     subjects += ["", "A", "C", "ACGT" * 60, "T" * 150]
     want = _oracle_matrix(oracle_mod, pkg, queries, subjects)
     with pkg.Engine() as e:
-        e.set_kernel_choice(R, G, force32, arith)
+        _choose(e, variant)
         got = e.score(queries, subjects)
     np.testing.assert_array_equal(got, want)
 
@@ -123,9 +139,9 @@ def test_parameter_sets_vs_oracle(oracle_mod, pkg, params):
     subjects = [(_mutate(rng, rng.choice(queries), 0.15, 0.15) or "A") for _ in range(200)]
     keys = dict(zip(("match", "mismatch", "gap_open", "gap_extend"), params))
     want = _oracle_matrix(oracle_mod, pkg, queries, subjects, **keys)
-    for choice in [(0, 0, False, -1), (38, 4, False, 0), (0, 0, True, -1)]:
+    for choice in ["auto", "strip_s16x2_R38x1_G4", "strip_s16x2_R25x2_G1", "generic32"]:
         with pkg.Engine(*params) as e:
-            e.set_kernel_choice(*choice)
+            _choose(e, choice)
             got = e.score(queries, subjects)
         np.testing.assert_array_equal(got, want)
 
@@ -138,9 +154,9 @@ def test_score_width_12_wrap_then_clamp(oracle_mod, pkg):
     noise = [_mutate(rng, s, 0.02, 0.01) for s in seqs]
     for width in (0, 12):
         o = oracle_mod.Oracle(score_width=width)
-        for choice in [(0, 0, False, -1), (50, 1, False, 0), (32, 32, False, 0), (0, 0, True, -1)]:
+        for choice in ["auto", "strip_s16x2_R50x1_G1", "strip_s16x2_R25x2_G1", "strip_s16x2_R16x2_G32", "generic32"]:
             with pkg.Engine(score_width=width) as e:
-                e.set_kernel_choice(*choice)
+                _choose(e, choice)
                 got = e.score(seqs, seqs + noise)
             for i, q in enumerate(seqs):
                 for j, t in enumerate(seqs + noise):
@@ -162,10 +178,9 @@ def test_long_query_multi_pass_and_chunks(oracle_mod, pkg):
         subjects.append(_mutate(rng, q1[a:a + rng.randint(50, 700)], 0.05, 0.03) or "A")
     subjects += [_rand(rng, rng.randint(1, 900)) for _ in range(30)]
     want = _oracle_matrix(oracle_mod, pkg, [q1, q2], subjects)
-    for choice in [(0, 0, False, -1), (32, 1, False, 0), (50, 1, False, 0), (75, 2, False, 0), (38, 4, False, 0),
-                   (32, 32, False, 0), (0, 0, True, -1)]:
+    for choice in ["auto", "generic32"] + S16_VARIANTS:
         with pkg.Engine() as e:
-            e.set_kernel_choice(*choice)
+            _choose(e, choice)
             got = e.score([q1, q2], subjects)
         np.testing.assert_array_equal(got, want, err_msg=str(choice))
 
