@@ -277,11 +277,17 @@ def main():
         per_gpu = gcups / world
         # algorithmic HBM bytes per step and GPU: column-code stream once per query chunk (8 launches)
         # + one int32 score per pair written once
+        arith = ("f16x2" if "f16x2" in kname else "s16x2+f16x2" if "hyb16" in kname else
+                 "s16x2" if "s16x2" in kname else "int32")
+        # ALU-pipe instructions per cell pair of the chosen kernel (DESIGN.md "roofline"): the other
+        # instructions of the recurrence run on the FMA-side pipe and overlap
+        alu_per_pair = {"f16x2": 3.5, "s16x2+f16x2": 3.5, "s16x2": 4.5, "int32": 12.0}[arith]
+        tight_gcups = SM_COUNT * pk["sm_max_mhz"] * 1e6 * R_INT * 2.0 / alu_per_pair / 1e9
         algo_bytes = args.subjects * ((TLEN + 7) // 8 * 4 / 2 + 8) * 8 + args.subjects * args.queries * 4
         line = {
             "metric": "GCUPS (score-only SW)", "value": gcups, "unit": "GCUPS", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "s16x2",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": arith,
             "data": "synthetic",
             "config": {"workload": workload_name(args), "queries": args.queries, "query_len": QLEN,
                        "subject_len": TLEN, "subjects_per_gpu": args.subjects, "penalties": "5/-4/-12/-4",
@@ -292,6 +298,9 @@ def main():
                          "peak_def": f"148 SM x {pk['sm_max_mhz']:.0f} MHz x R_int {R_INT:.0f} thread-instr/clk/SM "
                                      f"(measured, profiles/r01_pipe_pairs_1024thr.json) x 2 cells / 6 instr (SURVEY 8d)",
                          "traffic": None,
+                         "tight": {"peak": tight_gcups, "frac": per_gpu / tight_gcups,
+                                   "def": f"ALU-pipe bound of this kernel: {alu_per_pair} ALU-pipe instr per 2 cells, "
+                                          f"adds co-issue on the FMA-side pipe (profiles/r01_pipe_pairs_1024thr.json)"},
                          "hbm": {"algorithmic_bytes_per_step": int(algo_bytes),
                                  "achieved_gbs": algo_bytes / (dev_s / args.steps) / 1e9,
                                  "peak_gbs": pk["hbm_gbs"], "peak_source": pk["source"],

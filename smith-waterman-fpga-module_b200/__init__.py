@@ -20,7 +20,7 @@ import numpy as np
 from .seqio import pack_sequences, random_packed_db  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsw_b200.so")
+LIB_PATH = os.environ.get("SW_B200_LIB", os.path.join(_HERE, "libsw_b200.so"))   # override: A/B builds
 
 SW_OK, SW_EINVAL, SW_ENOMEM, SW_ECUDA, SW_ENODEV = 0, -1, -2, -3, -4
 SW_ESTATE, SW_ETIMEOUT, SW_ECAPACITY, SW_EIO, SW_EAGAIN = -5, -6, -7, -8, -9

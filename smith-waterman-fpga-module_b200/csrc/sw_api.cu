@@ -280,12 +280,16 @@ SwDevDb dev_db(const GpuCtx &g)
 double variant_speed(const SwStripVariant *v)
 {
     struct { const char *name; double gcups; } tab[] = {
-        {"strip_s16x2_R32x1_G1", 6210}, {"strip_s16x2_R50x1_G1", 6345}, {"strip_s16x2_R25x2_G1", 6297},
-        {"strip_s16x2_R25x1_G2", 5690}, {"strip_s16x2_R64x1_G1", 5770}, {"strip_s16x2_R32x2_G1", 6360},
-        {"strip_s16x2_R75x1_G2", 5570}, {"strip_s16x2_R25x3_G2", 6100}, {"strip_s16x2_R38x1_G4", 5170},
-        {"strip_s16x2_R19x2_G4", 5000}, {"strip_s16x2_R32x1_G4", 5110}, {"strip_s16x2_R32x1_G32", 4050},
-        {"strip_s16x2_R16x2_G32", 4130}, {"strip_f16x2_R50x1_G1", 6380}, {"strip_f16x2_R25x2_G1", 6821},
-        {"strip_f16x2_R25x1_G2", 6195}, {"strip_f16x2_R38x1_G4", 5120}, {"strip_f16x2_R19x2_G4", 5100},
+        {"strip_s16x2_R32x1_G1", 6210}, {"strip_s16x2_R50x1_G1", 6360}, {"strip_s16x2_R25x2_G1", 6580},
+        {"strip_s16x2_R25x1_G2", 5690}, {"strip_s16x2_R64x1_G1", 5770}, {"strip_s16x2_R32x2_G1", 6870},
+        {"strip_s16x2_R75x1_G2", 5570}, {"strip_s16x2_R25x3_G2", 6100}, {"strip_s16x2_R25x3_G1", 6740},
+        {"strip_s16x2_R38x2_G1", 6580}, {"strip_s16x2_R38x1_G4", 5170}, {"strip_s16x2_R19x2_G4", 5000},
+        {"strip_s16x2_R32x1_G4", 5110}, {"strip_s16x2_R16x1_G32", 4050}, {"strip_s16x2_R8x2_G32", 4130},
+        {"strip_f16x2_R50x1_G1", 7250}, {"strip_f16x2_R25x2_G1", 7480}, {"strip_f16x2_R25x1_G2", 6090},
+        {"strip_f16x2_R38x1_G4", 5120}, {"strip_f16x2_R19x2_G4", 5100}, {"strip_f16x2_R25x3_G1", 7170},
+        {"strip_hyb16_R50x1_G1", 6825}, {"strip_hyb16_R25x2_G1", 7305}, {"strip_hyb16_R32x2_G1", 7930},
+        {"strip_hyb16_R25x1_G2", 6270}, {"strip_hyb16_R38x1_G4", 6060}, {"strip_hyb16_R38x2_G1", 7640},
+        {"strip_hyb16_R25x3_G1", 7770}, {"strip_hyb16_R30x1_G1", 7225}, {"strip_hyb16_R19x4_G1", 7480},
     };
     for (auto &t : tab) if (std::strcmp(t.name, v->name) == 0) return t.gcups;
     return 5000.0;
@@ -310,7 +314,7 @@ int choose_variant(const sw_handle *h, const GpuCtx &g, uint32_t maxq, bool allo
     double best_cost = 0;
     for (int i = 0; i < nv; ++i) {
         const SwStripVariant *v = sw_strip_variant(i);
-        if (v->arith == 1 && !allow_f16) continue;
+        if (v->arith != 0 && !allow_f16) continue;
         if (h->force_arith >= 0 && v->arith != h->force_arith) continue;
         const int P = v->R * v->G;
         const double rows = (double)((maxq + P - 1) / P) * P;
@@ -359,13 +363,13 @@ int score_gpu(sw_handle *h, GpuCtx &g)
     // value range: exact s16 needs match * min(m, n) to stay clear of 32767
     const uint64_t smax = (uint64_t)sc.match * std::min<uint64_t>(h->q_max_len, g.max_len);
     const bool fits16 = sc.limit ? true : (smax + (uint64_t)sc.match < 32000ull);
-    const bool fitsf16 = !sc.limit && smax <= 2048ull;
+    const bool fitsf16 = !sc.limit && smax + (uint64_t)sc.match <= 2047ull;
     int vidx = -1;
     if (!h->force32 && fits16) {
-        if (h->force_arith == 1 && !fitsf16) return SW_EINVAL;
+        if (h->force_arith >= 1 && !fitsf16) return SW_EINVAL;
         vidx = choose_variant(h, g, h->q_max_len, fitsf16);
         if (vidx < 0 && (h->force_R || h->force_G)) return SW_EINVAL;
-        if (vidx >= 0 && sw_strip_variant(vidx)->arith == 1 && !fitsf16) return SW_EINVAL;
+        if (vidx >= 0 && sw_strip_variant(vidx)->arith != 0 && !fitsf16) return SW_EINVAL;
     }
 
     // query chunks: a handful of launches so that D2H of finished rows overlaps compute
@@ -373,20 +377,21 @@ int score_gpu(sw_handle *h, GpuCtx &g)
     SW_CUDA(h, g.d_counters.reserve(kMaxCounters * sizeof(unsigned)));
     SW_CUDA(h, cudaMemsetAsync(g.d_counters.p, 0, kMaxCounters * sizeof(unsigned), g.st_compute));
 
-    int grid = 0, chunk_rows = 0;
+    int grid = 0, chunk_passes = 1;
     if (vidx >= 0) {
         const SwStripVariant *v = sw_strip_variant(vidx);
         const int P = v->R * v->G;
-        const int need_rows = (int)((h->q_max_len + P - 1) / P) * P;
-        const int budget_rows = std::max(P, (768 / P) * P);
-        chunk_rows = std::min(need_rows, budget_rows);
+        const int need_passes = (int)((h->q_max_len + P - 1) / P);
+        const size_t pass_bytes = sw_strip_smem_bytes(vidx, 1);
+        const int budget_passes = std::max<int>(1, (int)((48 * 1024) / pass_bytes));
+        chunk_passes = std::max(1, std::min(need_passes, budget_passes));
         int bps = 0;
-        SW_CUDA(h, sw_strip_occupancy(vidx, (size_t)chunk_rows * 64, &bps));
+        SW_CUDA(h, sw_strip_occupancy(vidx, sw_strip_smem_bytes(vidx, chunk_passes), &bps));
         if (bps < 1) return SW_ECUDA;
         const int ppb = v->block_threads / v->G;
         const uint32_t npb = (g.npairs + ppb - 1) / ppb;
         grid = (int)std::min<uint64_t>(npb, (uint64_t)g.num_sms * bps);
-        if (need_rows > P) {
+        if (need_passes > 1) {
             const size_t bytes = (size_t)grid * g.max_len * ppb * sizeof(uint2);
             SW_CUDA(h, g.d_bnd.reserve(bytes));
         }
@@ -406,7 +411,7 @@ int score_gpu(sw_handle *h, GpuCtx &g)
         if (vidx >= 0) {
             SW_CUDA(h, sw_launch_strip(vidx, g.st_compute, db, dq, qc.q0, qc.q1, sc, g.d_out.as<int32_t>(), n,
                                        g.d_bnd.as<uint2>(), g.max_len, g.d_counters.as<unsigned>() + (c % kMaxCounters),
-                                       grid, chunk_rows));
+                                       grid, chunk_passes));
         } else {
             SW_CUDA(h, sw_launch_generic32(g.st_compute, db, dq, qc.q0, qc.q1, sc, g.d_out.as<int32_t>(), n,
                                            g.d_scratch32.as<int32_t>(), g.num_sms * 2 * 128));
@@ -764,7 +769,7 @@ int sw_set_kernel_name(sw_handle_t *h, const char *name)
 
 int sw_set_arith(sw_handle_t *h, int arith)
 {
-    if (!h || arith < -1 || arith > 1) return SW_EINVAL;
+    if (!h || arith < -1 || arith > 2) return SW_EINVAL;
     h->force_arith = arith;
     return SW_OK;
 }

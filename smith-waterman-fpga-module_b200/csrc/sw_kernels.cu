@@ -29,6 +29,13 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
+#ifndef SW_MPASS_BOTTOM_UP
+#define SW_MPASS_BOTTOM_UP 0
+#endif
+#ifndef SW_STEP_UNROLL
+#define SW_STEP_UNROLL 4      /* columns per trip of the step loop; nsteps is rounded up to a multiple */
+#endif
+
 namespace {
 
 constexpr int kPadScoreS16 = -8192;   // profile value of padding rows: M becomes 0, nothing can grow
@@ -42,6 +49,7 @@ struct ArithS16 {
     static __device__ __forceinline__ uint32_t pack(int lo, int hi) {
         return (uint32_t)(lo & 0xFFFF) | ((uint32_t)(hi & 0xFFFF) << 16);
     }
+    static __device__ __forceinline__ uint32_t pack_score(int lo, int hi) { return pack(lo, hi); }
     static __device__ __forceinline__ int extract(uint32_t v, int h) {
         return (int)(int16_t)(h ? (v >> 16) : (v & 0xFFFF));
     }
@@ -66,6 +74,7 @@ struct ArithF16 {
         __half2 h = __halves2half2(__int2half_rn(lo), __int2half_rn(hi));
         return *reinterpret_cast<uint32_t *>(&h);
     }
+    static __device__ __forceinline__ uint32_t pack_score(int lo, int hi) { return pack(lo, hi); }
     static __device__ __forceinline__ int extract(uint32_t v, int h) {
         __half2 x = *reinterpret_cast<__half2 *>(&v);
         return __half2int_rn(h ? __high2half(x) : __low2half(x));
@@ -92,6 +101,38 @@ struct ArithF16 {
     static __device__ __forceinline__ uint32_t wrap_clamp(uint32_t m, uint32_t) { return m; }
 };
 
+// Hybrid: every value is a plain packed s16 integer, but M = max(H_diag + s, 0) is computed by
+// HFMA2.RELU on the FMA-side pipe.  This is exact because an fp16 whose bit pattern is the
+// integer v (0 <= v < 2048) has the value v * 2^-24 (subnormals and the first normal binade are
+// linear in their bit pattern), fp16 add/fma of such numbers is exact while the result stays
+// below 2048, and relu() returns +0 for every negative sum.  Only the substitution score (the
+// one operand that can be negative) is stored sign-magnitude, i.e. as the fp16 -|s| * 2^-24.
+// M and H are never negative, so the integer DPX instructions (ALU pipe) read them unchanged.
+// Per cell pair: 3.5 ALU-pipe + 2 FMA-pipe instructions.  Valid while the best possible score
+// is <= 2047 -- the same range the reference's 12-bit datapath has.
+struct ArithHyb {
+    static constexpr int kPad = -2047;
+    static __device__ __forceinline__ uint32_t pack(int lo, int hi) { return ArithS16::pack(lo, hi); }
+    static __device__ __forceinline__ uint32_t pack_score(int lo, int hi) {
+        const uint32_t l = lo >= 0 ? (uint32_t)lo : (0x8000u | (uint32_t)(-lo));
+        const uint32_t h = hi >= 0 ? (uint32_t)hi : (0x8000u | (uint32_t)(-hi));
+        return l | (h << 16);
+    }
+    static __device__ __forceinline__ int extract(uint32_t v, int h) { return ArithS16::extract(v, h); }
+    static __device__ __forceinline__ uint32_t add_relu(uint32_t a, uint32_t b, uint32_t) {
+        uint32_t d;
+        const uint32_t one = 0x3C003C00u;
+        asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+        return d;
+    }
+    static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return __vadd2(a, b); }
+    static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
+    static __device__ __forceinline__ uint32_t addmax(uint32_t a, uint32_t b, uint32_t c) {
+        return __viaddmax_s16x2(a, b, c);
+    }
+    static __device__ __forceinline__ uint32_t wrap_clamp(uint32_t m, uint32_t) { return m; }
+};
+
 struct StripArgs {
     const uint32_t *tp;
     const uint64_t *tile_woff;
@@ -108,63 +149,44 @@ struct StripArgs {
     uint2 *bnd;
     uint32_t bnd_cols;
     unsigned *counter;
-    int chunk_rows;            // profile rows resident in shared memory (multiple of R*G)
+    int chunk_passes;          // passes whose query profile is resident in shared memory at once
     int match, mismatch, goe, ge, limit;
     uint32_t zero;             // always 0, but opaque to the compiler
 };
 
-// One column of one register sub-strip.  H[r] / Gl[r] hold H and G of the previous column on
-// entry and of this column on exit.  hd_top = H(row0-1, c-1), g_top = G(row0-1, c).
-template <int RS, class AR, bool W12>
-__device__ __forceinline__ void column_step(uint32_t (&H)[RS], uint32_t (&Gl)[RS], uint32_t &best,
-                                            uint32_t hd_top, uint32_t g_top, const uint32_t *prow,
-                                            uint32_t goe2, uint32_t ge2, uint32_t zero, uint32_t lim2)
-{
-    // M pass, bottom-up and in place: H[r] <- M(r, c) = relu(H(r-1, c-1) + s(r, c))
-#pragma unroll
-    for (int r = RS - 1; r >= 1; --r) {
-        uint32_t m = AR::add_relu(H[r - 1], prow[r * 16], zero);
-        if (W12) m = AR::wrap_clamp(m, lim2);
-        H[r] = m;
-    }
-    {
-        uint32_t m = AR::add_relu(hd_top, prow[0], zero);
-        if (W12) m = AR::wrap_clamp(m, lim2);
-        H[0] = m;
-    }
-    // gap pass, top-down: the only serial chain of the column (I -> I+ge -> G)
-    uint32_t gu = g_top;
-#pragma unroll
-    for (int r = 0; r < RS; ++r) {
-        const uint32_t i_ = AR::max2(Gl[r], gu);          // I = max(G_left, G_up)
-        const uint32_t j_ = AR::add(i_, ge2);             // I + ge            (FMA-side pipe)
-        gu = AR::addmax(H[r], goe2, j_);                  // G = max(M + goe, I + ge)
-        Gl[r] = gu;
-        H[r] = AR::max2(H[r], i_);                        // H = max(M, I)
-        best = AR::max2(best, H[r]);                      // ptxas pairs these into VIMNMX3
-    }
-}
+constexpr int kPadCode = 16;        // 17th column code: "no column" (before the start / past the end)
+constexpr int kCodesPerRow = 32;    // profile entries per row pair (codes 0..16 used): 256 bytes
 
-// S sub-strips of one lane, each on its own column (sub-strip s is one column behind s-1):
-// S independent dependency chains in one basic block, so that a warp always has an
-// instruction whose operands are ready (the PE array's pipelining, inside one thread).
+// One column step of the S sub-strips of a lane, each sub-strip on its own column (sub-strip s
+// is one column behind s-1): S independent dependency chains in one basic block, so a warp
+// always has an instruction whose operands are ready (the PE array's pipelining, inside one
+// thread).  H[s][r] / Gl[s][r] hold H and G of the previous column on entry and of this column
+// on exit; hd_top = H(row0-1, c-1), g_top = G(row0-1, c); prow[s] points at the profile entry
+// of (first row pair of the sub-strip, this column's code), one uint2 = two consecutive rows.
 template <int RS, int S, class AR, bool W12>
 __device__ __forceinline__ void column_step_multi(uint32_t (&H)[S][RS], uint32_t (&Gl)[S][RS], uint32_t &best,
                                                   const uint32_t (&hd_top)[S], const uint32_t (&g_top)[S],
-                                                  const uint32_t *const (&prow)[S], uint32_t goe2,
+                                                  const uint2 *const (&prow)[S], uint32_t goe2,
                                                   uint32_t ge2, uint32_t zero, uint32_t lim2)
 {
+    constexpr int RP = (RS + 1) / 2;
+    // substitution scores of this column: one LDS.64 per row pair
+    uint2 sv[S][RP];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int k = 0; k < RP; ++k) sv[s][k] = prow[s][k * kCodesPerRow];
+#if SW_MPASS_BOTTOM_UP
+    // M pass, bottom-up and in place: H[r] <- M(r, c) = relu(H(r-1, c-1) + s(r, c))
 #pragma unroll
     for (int s = 0; s < S; ++s) {
 #pragma unroll
-        for (int r = RS - 1; r >= 1; --r) {
-            uint32_t m = AR::add_relu(H[s][r - 1], prow[s][r * 16], zero);
+        for (int r = RS - 1; r >= 0; --r) {
+            const uint32_t sc = (r & 1) ? sv[s][r >> 1].y : sv[s][r >> 1].x;
+            uint32_t m = AR::add_relu(r ? H[s][r - 1] : hd_top[s], sc, zero);
             if (W12) m = AR::wrap_clamp(m, lim2);
             H[s][r] = m;
         }
-        uint32_t m = AR::add_relu(hd_top[s], prow[s][0], zero);
-        if (W12) m = AR::wrap_clamp(m, lim2);
-        H[s][0] = m;
     }
     uint32_t gu[S];
 #pragma unroll
@@ -181,17 +203,56 @@ __device__ __forceinline__ void column_step_multi(uint32_t (&H)[S][RS], uint32_t
             best = AR::max2(best, H[s][r]);
         }
     }
+#else
+    // Single top-down sweep.  M of row r+1 is formed one row ahead, from the still-old H[r]
+    // (= H(r, c-1), its diagonal), so that H[r] can then be overwritten in place.
+    uint32_t gu[S], m_cur[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        gu[s] = g_top[s];
+        uint32_t m = AR::add_relu(hd_top[s], sv[s][0].x, zero);     // M(r,c) = relu(H(r-1,c-1) + s)
+        if (W12) m = AR::wrap_clamp(m, lim2);
+        m_cur[s] = m;
+    }
+#pragma unroll
+    for (int r = 0; r < RS; ++r) {
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            uint32_t m_next = zero;
+            if (r + 1 < RS) {
+                const uint32_t sc = ((r + 1) & 1) ? sv[s][(r + 1) >> 1].y : sv[s][(r + 1) >> 1].x;
+                m_next = AR::add_relu(H[s][r], sc, zero);
+                if (W12) m_next = AR::wrap_clamp(m_next, lim2);
+            }
+            // the serial chain of a column is I -> I+ge -> G; the S chains interleave
+            const uint32_t i_ = AR::max2(Gl[s][r], gu[s]);      // I = max(G_left, G_up)
+            const uint32_t j_ = AR::add(i_, ge2);               // I + ge          (FMA-side pipe)
+            gu[s] = AR::addmax(m_cur[s], goe2, j_);             // G = max(M + goe, I + ge)
+            Gl[s][r] = gu[s];
+            H[s][r] = AR::max2(m_cur[s], i_);                   // H = max(M, I)
+            best = AR::max2(best, H[s][r]);                     // ptxas pairs these into 3-input max
+            m_cur[s] = m_next;
+        }
+    }
+#endif
 }
 
 // RS rows per sub-strip, S sub-strips per lane, G lanes per pair: R = RS*S rows per lane,
 // P = R*G rows per pass.  Virtual PE v = lane_in_group*S + s works on column t - v at step t.
+// A virtual PE that has no column at step t (pipeline fill / drain, shorter pair in the warp)
+// works on the PAD column code whose profile entries are very negative: M becomes 0, H keeps
+// decaying values <= the best already recorded, and G only drifts among non-positive values,
+// which never reach H (M >= 0).  That keeps the loop body free of per-lane branches.
 template <int RS, int S, int G, class AR, bool W12, int BT, int MINB>
 __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
 {
-    extern __shared__ uint32_t s_prof[];
+    extern __shared__ uint2 s_prof[];
     __shared__ unsigned s_work;
     constexpr int R = RS * S;
     constexpr int P = R * G;
+    constexpr int RP = (RS + 1) / 2;
+    constexpr int VPE = G * S;                       // virtual PEs per pair
+    constexpr int PASS_ENTRIES = VPE * RP * kCodesPerRow;
     constexpr int PPB = BT / G;
     constexpr unsigned FULL = 0xFFFFFFFFu;
 
@@ -222,7 +283,8 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
             subj_lo = a.pair_subj[2 * pair];
             subj_hi = a.pair_subj[2 * pair + 1];
         }
-        const int nsteps = __reduce_max_sync(FULL, ncols) + (G * S - 1);
+        // rounded up: the step loop is unrolled (extra steps are PAD columns)
+        const int nsteps = (__reduce_max_sync(FULL, ncols) + (VPE - 1) + SW_STEP_UNROLL - 1) / SW_STEP_UNROLL * SW_STEP_UNROLL;
 
         for (int q = a.q0; q < a.q1; ++q) {
             const int m = (int)a.qlen[q];
@@ -231,25 +293,36 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
             uint32_t best = zero;
 
             for (int pass = 0; pass < npass; ++pass) {
-                const int row_in_chunk = (pass * P) % a.chunk_rows;
-                if (row_in_chunk == 0) {
-                    // (re)build the query profile chunk: prof[row][code], code = t_lo | t_hi << 2
+                const int pass_in_chunk = pass % a.chunk_passes;
+                if (pass_in_chunk == 0) {
+                    // (re)build the profile chunk: entry (vpe, row pair, code) = packed scores of
+                    // rows 2k, 2k+1 of that virtual PE against column code = t_lo | t_hi << 2
                     __syncthreads();
-                    const int row0 = pass * P;
-                    for (int idx = threadIdx.x; idx < a.chunk_rows * 16; idx += BT) {
-                        const int i = row0 + (idx >> 4);
-                        const int code = idx & 15;
-                        int lo = AR::kPad, hi = AR::kPad;
-                        if (i < m) {
-                            const int qi = (qp[i >> 2] >> ((i & 3) * 2)) & 3;
-                            lo = (qi == (code & 3)) ? a.match : a.mismatch;   // v1.0.v:119
-                            hi = (qi == (code >> 2)) ? a.match : a.mismatch;
+                    const int npc = min(a.chunk_passes, npass - pass);
+                    for (int idx = threadIdx.x; idx < npc * PASS_ENTRIES; idx += BT) {
+                        const int code = idx & (kCodesPerRow - 1);
+                        if (code > kPadCode) continue;
+                        const int rp = (idx / kCodesPerRow) % RP;
+                        const int vpe = (idx / (kCodesPerRow * RP)) % VPE;
+                        const int pc = idx / PASS_ENTRIES;
+                        uint32_t e[2];
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const int rr = 2 * rp + k;
+                            const int i = (pass + pc) * P + vpe * RS + rr;
+                            int lo = AR::kPad, hi = AR::kPad;
+                            if (rr < RS && i < m && code < kPadCode) {
+                                const int qi = (qp[i >> 2] >> ((i & 3) * 2)) & 3;
+                                lo = (qi == (code & 3)) ? a.match : a.mismatch;   // v1.0.v:119
+                                hi = (qi == (code >> 2)) ? a.match : a.mismatch;
+                            }
+                            e[k] = AR::pack_score(lo, hi);
                         }
-                        s_prof[idx] = AR::pack(lo, hi);
+                        s_prof[idx] = make_uint2(e[0], e[1]);
                     }
                     __syncthreads();
                 }
-                const uint32_t *prof_lane = s_prof + (row_in_chunk + gl * R) * 16;
+                const uint2 *prof_lane = s_prof + (pass_in_chunk * VPE + gl * S) * RP * kCodesPerRow;
                 const bool has_top = pass > 0;
                 const bool has_bottom = pass + 1 < npass;
 
@@ -270,11 +343,13 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                 // s = S-1 the next lane): bottom H, bottom G and the column code it just used
                 uint32_t pub_h[S], pub_g[S], pub_t[S], hd_top[S];
 #pragma unroll
-                for (int s = 0; s < S; ++s) { pub_h[s] = zero; pub_g[s] = gb2; pub_t[s] = 0; hd_top[s] = zero; }
+                for (int s = 0; s < S; ++s) { pub_h[s] = zero; pub_g[s] = gb2; pub_t[s] = kPadCode; hd_top[s] = zero; }
 
 #pragma unroll 1
-                for (int t = 0; t < nsteps; ++t) {
-                    const int c0 = t - gl * S;                 // column of sub-strip 0
+                for (int t2 = 0; t2 < nsteps; t2 += SW_STEP_UNROLL) {
+#pragma unroll
+                  for (int u = 0; u < SW_STEP_UNROLL; ++u) {
+                    const int t = t2 + u;
                     uint32_t in_h[S], in_g[S], in_t[S];
                     if (G > 1) {
                         in_h[0] = __shfl_up_sync(FULL, pub_h[S - 1], 1, G);
@@ -282,48 +357,38 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                         in_t[0] = __shfl_up_sync(FULL, pub_t[S - 1], 1, G);
                     }
                     if (G == 1 || gl == 0) {
+                        // head of the systolic group: column t comes from the code stream, the row
+                        // above from the previous pass (or the zero boundary)
+                        const bool on = t < ncols;
                         in_h[0] = bcur.x;
                         in_g[0] = bcur.y;
-                        in_t[0] = (wcur >> ((c0 & 7) * 4)) & 15u;
+                        in_t[0] = on ? ((wcur >> ((t & 7) * 4)) & 15u) : (uint32_t)kPadCode;
+                        if (on) {
+                            if ((t & 7) == 7) {
+                                wcur = wnext;
+                                const int k = (t >> 3) + 2;
+                                if (k * 8 < ncols) wnext = __ldg(tpp + k * 32);
+                            }
+                            if (has_top && t + 1 < ncols) bcur = __ldcg(bnd + (size_t)(t + 1) * PPB);
+                        }
                     }
 #pragma unroll
                     for (int s = 1; s < S; ++s) { in_h[s] = pub_h[s - 1]; in_g[s] = pub_g[s - 1]; in_t[s] = pub_t[s - 1]; }
 
-                    const bool first_on = c0 >= 0 && c0 < ncols;
-                    const bool last_on = (c0 - (S - 1)) >= 0 && (c0 - (S - 1)) < ncols;
-                    if (first_on && (G == 1 || gl == 0)) {
-                        if ((c0 & 7) == 7) {
-                            wcur = wnext;
-                            const int k = (c0 >> 3) + 2;
-                            if (k * 8 < ncols) wnext = __ldg(tpp + k * 32);
-                        }
-                        if (has_top && c0 + 1 < ncols) bcur = __ldcg(bnd + (size_t)(c0 + 1) * PPB);
+                    const uint2 *prow[S];
+#pragma unroll
+                    for (int s = 0; s < S; ++s) prow[s] = prof_lane + s * RP * kCodesPerRow + in_t[s];
+                    column_step_multi<RS, S, AR, W12>(H, Gl, best, hd_top, in_g, prow, goe2, ge2, zero, lim2);
+#pragma unroll
+                    for (int s = 0; s < S; ++s) {
+                        hd_top[s] = in_h[s];
+                        pub_h[s] = H[s][RS - 1]; pub_g[s] = Gl[s][RS - 1]; pub_t[s] = in_t[s];
                     }
-                    if (S > 1 && first_on && last_on) {
-                        // steady state: all sub-strips active, one basic block
-                        const uint32_t *prow[S];
-#pragma unroll
-                        for (int s = 0; s < S; ++s) prow[s] = prof_lane + s * RS * 16 + in_t[s];
-                        column_step_multi<RS, S, AR, W12>(H, Gl, best, hd_top, in_g, prow, goe2, ge2, zero, lim2);
-#pragma unroll
-                        for (int s = 0; s < S; ++s) {
-                            hd_top[s] = in_h[s];
-                            pub_h[s] = H[s][RS - 1]; pub_g[s] = Gl[s][RS - 1]; pub_t[s] = in_t[s];
-                        }
-                    } else {
-#pragma unroll
-                        for (int s = 0; s < S; ++s) {
-                            const int c = c0 - s;
-                            if (c >= 0 && c < ncols) {
-                                column_step<RS, AR, W12>(H[s], Gl[s], best, hd_top[s], in_g[s],
-                                                         prof_lane + s * RS * 16 + in_t[s], goe2, ge2, zero, lim2);
-                                hd_top[s] = in_h[s];
-                                pub_h[s] = H[s][RS - 1]; pub_g[s] = Gl[s][RS - 1]; pub_t[s] = in_t[s];
-                            }
-                        }
+                    if (has_bottom && gl == G - 1) {
+                        const int cl = t - (VPE - 1);          // column the last virtual PE just finished
+                        if (cl >= 0 && cl < ncols) __stcg(bnd + (size_t)cl * PPB, make_uint2(pub_h[S - 1], pub_g[S - 1]));
                     }
-                    if (has_bottom && gl == G - 1 && last_on)
-                        __stcg(bnd + (size_t)(c0 - (S - 1)) * PPB, make_uint2(pub_h[S - 1], pub_g[S - 1]));
+                  }
                 }
                 if (has_bottom) __syncwarp();   // bottom row written by lane G-1, read by lane 0
             }
@@ -492,6 +557,10 @@ struct VariantEntry {
     { {RS * S, G, 1, kBT, S, MINB, "strip_f16x2_R" #RS "x" #S "_G" #G},                         \
       sw_strip_kernel<RS, S, G, ArithF16, false, kBT, MINB>, nullptr }
 
+#define SW_VARIANT_HYB(RS, S, G, MINB)                                                          \
+    { {RS * S, G, 2, kBT, S, MINB, "strip_hyb16_R" #RS "x" #S "_G" #G},                         \
+      sw_strip_kernel<RS, S, G, ArithHyb, false, kBT, MINB>, nullptr }
+
 const VariantEntry g_variants[] = {
     SW_VARIANT_S16(32, 1, 1, 4),
     SW_VARIANT_S16(50, 1, 1, 3),
@@ -501,16 +570,28 @@ const VariantEntry g_variants[] = {
     SW_VARIANT_S16(32, 2, 1, 2),
     SW_VARIANT_S16(75, 1, 2, 2),
     SW_VARIANT_S16(25, 3, 2, 2),
+    SW_VARIANT_S16(25, 3, 1, 2),
+    SW_VARIANT_S16(38, 2, 1, 2),
     SW_VARIANT_S16(38, 1, 4, 3),
     SW_VARIANT_S16(19, 2, 4, 3),
     SW_VARIANT_S16(32, 1, 4, 4),
-    SW_VARIANT_S16(32, 1, 32, 4),
-    SW_VARIANT_S16(16, 2, 32, 4),
+    SW_VARIANT_S16(16, 1, 32, 3),
+    SW_VARIANT_S16(8, 2, 32, 3),
     SW_VARIANT_F16(50, 1, 1, 3),
     SW_VARIANT_F16(25, 2, 1, 3),
     SW_VARIANT_F16(25, 1, 2, 5),
     SW_VARIANT_F16(38, 1, 4, 3),
     SW_VARIANT_F16(19, 2, 4, 3),
+    SW_VARIANT_F16(25, 3, 1, 2),
+    SW_VARIANT_HYB(50, 1, 1, 3),
+    SW_VARIANT_HYB(25, 2, 1, 3),
+    SW_VARIANT_HYB(32, 2, 1, 2),
+    SW_VARIANT_HYB(25, 1, 2, 5),
+    SW_VARIANT_HYB(38, 1, 4, 3),
+    SW_VARIANT_HYB(38, 2, 1, 2),
+    SW_VARIANT_HYB(25, 3, 1, 2),
+    SW_VARIANT_HYB(30, 1, 1, 4),
+    SW_VARIANT_HYB(19, 4, 1, 2),
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 
@@ -521,6 +602,14 @@ int sw_strip_variant_count(void) { return kNumVariants; }
 const SwStripVariant *sw_strip_variant(int idx)
 {
     return (idx >= 0 && idx < kNumVariants) ? &g_variants[idx].info : nullptr;
+}
+
+size_t sw_strip_smem_bytes(int idx, int chunk_passes)
+{
+    if (idx < 0 || idx >= kNumVariants) return 0;
+    const SwStripVariant &v = g_variants[idx].info;
+    const int rs = v.R / v.S;
+    return (size_t)chunk_passes * v.G * v.S * ((rs + 1) / 2) * kCodesPerRow * sizeof(uint2);
 }
 
 cudaError_t sw_strip_occupancy(int idx, size_t smem_bytes, int *blocks_per_sm)
@@ -535,7 +624,7 @@ cudaError_t sw_strip_occupancy(int idx, size_t smem_bytes, int *blocks_per_sm)
 
 cudaError_t sw_launch_strip(int idx, cudaStream_t st, const SwDevDb &db, const SwDevQueries &q,
                             int q0, int q1, const SwScoring &sc, int32_t *out, size_t out_stride,
-                            uint2 *bnd, uint32_t bnd_cols, unsigned *counter, int grid, int chunk_rows)
+                            uint2 *bnd, uint32_t bnd_cols, unsigned *counter, int grid, int chunk_passes)
 {
     if (idx < 0 || idx >= kNumVariants) return cudaErrorInvalidValue;
     const VariantEntry &v = g_variants[idx];
@@ -547,10 +636,10 @@ cudaError_t sw_launch_strip(int idx, cudaStream_t st, const SwDevDb &db, const S
     a.npairs = db.npairs; a.npb = (db.npairs + ppb - 1) / ppb;
     a.qpacked = q.packed; a.qoff = q.off; a.qlen = q.len; a.q0 = q0; a.q1 = q1;
     a.out = out; a.out_stride = out_stride; a.bnd = bnd; a.bnd_cols = bnd_cols; a.counter = counter;
-    a.chunk_rows = chunk_rows;
+    a.chunk_passes = chunk_passes;
     a.match = sc.match; a.mismatch = sc.mismatch; a.goe = sc.goe; a.ge = sc.ge; a.limit = sc.limit;
     a.zero = 0;
-    const size_t smem = (size_t)chunk_rows * 16 * sizeof(uint32_t);
+    const size_t smem = sw_strip_smem_bytes(idx, chunk_passes);
     cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     fn<<<grid, v.info.block_threads, smem, st>>>(a);

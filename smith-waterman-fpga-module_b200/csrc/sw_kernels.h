@@ -48,7 +48,8 @@ struct SwScoring {
 /* One strip-kernel variant = (rows per lane R, lanes per pair G, arithmetic). */
 struct SwStripVariant {
     int R, G;
-    int arith;        /* 0 = packed s16 (DPX), 1 = packed f16 (exact while score <= 2048) */
+    int arith;        /* 0 = packed s16 (DPX), 1 = packed f16, 2 = s16 with M on the fp16 FMA pipe;
+                         1 and 2 are exact while the largest possible score is <= 2047 */
     int block_threads;
     int S;            /* independent sub-strips per lane (R = RS * S) */
     int min_blocks;   /* resident blocks per SM the kernel was compiled for */
@@ -58,17 +59,20 @@ struct SwStripVariant {
 int sw_strip_variant_count(void);
 const SwStripVariant *sw_strip_variant(int idx);
 
+/* Dynamic shared memory of variant idx when the query profile of chunk_passes passes is resident. */
+size_t sw_strip_smem_bytes(int idx, int chunk_passes);
+
 /* Resident blocks per SM of variant idx with smem_bytes of dynamic shared memory. */
 cudaError_t sw_strip_occupancy(int idx, size_t smem_bytes, int *blocks_per_sm);
 
 /* Scores queries [q0,q1) against all pairs of db.  out[(q)*out_stride + subj].
  * bnd: scratch for pass boundaries, grid * bnd_cols * (block_threads/G) uint2.
- * counter: zeroed device word (work queue).  chunk_rows: profile rows held in
- * shared memory at once (multiple of R*G). */
+ * counter: zeroed device word (work queue).  chunk_passes: passes (of R*G rows) whose
+ * query profile is held in shared memory at once. */
 cudaError_t sw_launch_strip(int idx, cudaStream_t st, const SwDevDb &db, const SwDevQueries &q,
                             int q0, int q1, const SwScoring &sc, int32_t *out, size_t out_stride,
                             uint2 *bnd, uint32_t bnd_cols, unsigned *counter, int grid,
-                            int chunk_rows);
+                            int chunk_passes);
 
 /* 32-bit fallback: any length, any score range.  scratch: 2 * (q.max_len) * threads int32. */
 cudaError_t sw_launch_generic32(cudaStream_t st, const SwDevDb &db, const SwDevQueries &q,

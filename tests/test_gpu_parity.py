@@ -42,11 +42,15 @@ def _oracle_matrix(oracle_mod, pkg, queries, subjects, **params):
 STRIP_VARIANTS = [
     "strip_s16x2_R32x1_G1", "strip_s16x2_R50x1_G1", "strip_s16x2_R25x2_G1", "strip_s16x2_R25x1_G2",
     "strip_s16x2_R64x1_G1", "strip_s16x2_R32x2_G1", "strip_s16x2_R75x1_G2", "strip_s16x2_R25x3_G2",
-    "strip_s16x2_R38x1_G4", "strip_s16x2_R19x2_G4", "strip_s16x2_R32x1_G4", "strip_s16x2_R32x1_G32",
-    "strip_s16x2_R16x2_G32", "strip_f16x2_R50x1_G1", "strip_f16x2_R25x2_G1", "strip_f16x2_R25x1_G2",
-    "strip_f16x2_R38x1_G4", "strip_f16x2_R19x2_G4",
+    "strip_s16x2_R25x3_G1", "strip_s16x2_R38x2_G1", "strip_s16x2_R38x1_G4", "strip_s16x2_R19x2_G4",
+    "strip_s16x2_R32x1_G4", "strip_s16x2_R16x1_G32", "strip_s16x2_R8x2_G32", "strip_f16x2_R50x1_G1",
+    "strip_f16x2_R25x2_G1", "strip_f16x2_R25x1_G2", "strip_f16x2_R38x1_G4", "strip_f16x2_R19x2_G4",
+    "strip_f16x2_R25x3_G1", "strip_hyb16_R50x1_G1", "strip_hyb16_R25x2_G1", "strip_hyb16_R32x2_G1",
+    "strip_hyb16_R25x1_G2", "strip_hyb16_R38x1_G4", "strip_hyb16_R38x2_G1", "strip_hyb16_R25x3_G1",
+    "strip_hyb16_R30x1_G1", "strip_hyb16_R19x4_G1",
 ]
 S16_VARIANTS = [v for v in STRIP_VARIANTS if "s16x2" in v]
+SMALL_SCORE_VARIANTS = [v for v in STRIP_VARIANTS if "s16x2" not in v]   # exact while score <= 2047
 VARIANTS = ["auto", "generic32"] + STRIP_VARIANTS
 
 
@@ -154,7 +158,7 @@ def test_score_width_12_wrap_then_clamp(oracle_mod, pkg):
     noise = [_mutate(rng, s, 0.02, 0.01) for s in seqs]
     for width in (0, 12):
         o = oracle_mod.Oracle(score_width=width)
-        for choice in ["auto", "strip_s16x2_R50x1_G1", "strip_s16x2_R25x2_G1", "strip_s16x2_R16x2_G32", "generic32"]:
+        for choice in ["auto", "strip_s16x2_R50x1_G1", "strip_s16x2_R25x2_G1", "strip_s16x2_R8x2_G32", "generic32"]:
             with pkg.Engine(score_width=width) as e:
                 _choose(e, choice)
                 got = e.score(seqs, seqs + noise)
