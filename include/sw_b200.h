@@ -112,6 +112,12 @@ int sw_score_db(sw_handle_t *h);
 int sw_wait(sw_handle_t *h, int timeout_ms);
 int sw_fetch_db(sw_handle_t *h, int32_t *scores, size_t cap);
 
+/* The shard plan sw_load_db uses: contiguous input ranges [starts[g], starts[g+1]) balanced by
+ * residue count (the work of a subject is proportional to its length).  Pure host code;
+ * starts must hold n_shards + 1 entries.  Replaces the bank's broadcast-query /
+ * distribute-targets structure (ScoreBank_v2.v:78-139) at the GPU level. */
+int sw_plan_shards(const uint32_t *len, size_t ns, int n_shards, uint64_t *starts);
+
 /* Per-query best hit over the resident db, reduced on the GPU: the `max` /
  * `vld_max` outputs ScoreBank_v2 declares but never drives (ScoreBank_v2.v:42-43).
  * best_score[iq], best_index[iq] (input index of the first subject reaching it). */

@@ -83,6 +83,7 @@ def load_library():
     L.sw_kernel_variant_name.argtypes = [i32]
     L.sw_kernel_variant_name.restype = C.c_char_p
     L.sw_set_kernel_name.argtypes = [vp, C.c_char_p]
+    L.sw_plan_shards.argtypes = [vp, sz, i32, vp]
     L.sw_device_count.restype = i32
     L.sw_version.restype = C.c_char_p
     L.sw_pack_2bit.argtypes = [C.c_char_p, sz, vp]
@@ -230,6 +231,16 @@ class Engine:
 def kernel_variants():
     L = load_library()
     return [L.sw_kernel_variant_name(i).decode() for i in range(L.sw_kernel_variant_count())]
+
+
+def plan_shards(lengths, n_shards):
+    """Contiguous shard boundaries [n_shards + 1] as sw_load_db computes them (pure host)."""
+    ln = np.ascontiguousarray(lengths, dtype=np.uint32)
+    starts = np.zeros(n_shards + 1, dtype=np.uint64)
+    rc = load_library().sw_plan_shards(_ptr(ln), len(ln), n_shards, _ptr(starts))
+    if rc != SW_OK:
+        raise SwError(rc, "sw_plan_shards")
+    return starts
 
 
 def device_count():

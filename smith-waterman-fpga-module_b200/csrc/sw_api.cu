@@ -593,6 +593,23 @@ int sw_set_queries(sw_handle_t *h, const uint8_t *packed, const uint32_t *len, c
     return SW_OK;
 }
 
+int sw_plan_shards(const uint32_t *len, size_t ns, int n_shards, uint64_t *starts)
+{
+    if (n_shards <= 0 || !starts || (ns > 0 && !len)) return SW_EINVAL;
+    uint64_t total = 0;
+    for (size_t s = 0; s < ns; ++s) total += len[s];
+    size_t s = 0;
+    uint64_t acc = 0;
+    for (int gi = 0; gi < n_shards; ++gi) {
+        starts[gi] = s;
+        const uint64_t target = (total * (uint64_t)(gi + 1)) / (uint64_t)n_shards;
+        if (gi + 1 == n_shards) s = ns;
+        else while (s < ns && acc + len[s] / 2 < target) { acc += len[s]; ++s; }
+    }
+    starts[n_shards] = ns;
+    return SW_OK;
+}
+
 int sw_load_db(sw_handle_t *h, const uint8_t *packed, const uint32_t *len, const uint64_t *off,
                const uint64_t *ids, size_t ns)
 {
@@ -604,18 +621,9 @@ int sw_load_db(sw_handle_t *h, const uint8_t *packed, const uint32_t *len, const
     if (ids) h->ids.assign(ids, ids + ns); else h->ids.clear();
     // contiguous input ranges balanced by residue count (cells per query row)
     const size_t ng = h->gpus.size();
-    uint64_t total = 0;
-    for (size_t s = 0; s < ns; ++s) total += len[s];
-    size_t s = 0;
-    uint64_t acc = 0;
-    for (size_t gi = 0; gi < ng; ++gi) {
-        GpuCtx &g = h->gpus[gi];
-        g.s0 = s;
-        const uint64_t target = (gi + 1 == ng) ? total : (total * (gi + 1)) / ng;
-        if (gi + 1 == ng) s = ns;
-        else while (s < ns && acc + len[s] / 2 < target) { acc += len[s]; ++s; }
-        g.s1 = s;
-    }
+    std::vector<uint64_t> starts(ng + 1);
+    sw_plan_shards(len, ns, (int)ng, starts.data());
+    for (size_t gi = 0; gi < ng; ++gi) { h->gpus[gi].s0 = starts[gi]; h->gpus[gi].s1 = starts[gi + 1]; }
     for (auto &g : h->gpus) {
         int rc = load_shard(h, g, packed, len, off);
         if (rc != SW_OK) return rc;
