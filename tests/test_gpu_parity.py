@@ -294,3 +294,51 @@ def test_multi_gpu_handle_if_available(oracle_mod, pkg):
     with pkg.Engine(gpu_ids=list(range(n))) as e:
         got = e.score(queries, subjects)
     np.testing.assert_array_equal(got, want)
+
+
+def test_config4_long_query_sample_vs_oracle(oracle_mod, pkg):
+    """BASELINE config 4 shape at reduced count: a 10 kb query against 1 kb subjects (scores up to
+    5000 => packed 16-bit exact), automatic variant choice and the warp-wide systolic variants."""
+    rng = random.Random(4)
+    q = _rand(rng, 10000)
+    subjects = []
+    for k in range(240):
+        if k % 3 == 0:
+            a = rng.randint(0, 9000)
+            subjects.append((_mutate(rng, q[a:a + 1000], 0.04, 0.02) + _rand(rng, 1000))[:1000])
+        else:
+            subjects.append(_rand(rng, 1000))
+    want = _oracle_matrix(oracle_mod, pkg, [q], subjects)
+    assert want.max() > 3000
+    for choice in ["auto", "strip_s16x2_R16x1_G32", "strip_s16x2_R8x2_G32", "strip_s16x2_R25x3_G1"]:
+        with pkg.Engine() as e:
+            _choose(e, choice)
+            got = e.score([q], subjects)
+            assert "s16x2" in e.last_kernel_name
+        np.testing.assert_array_equal(got, want, err_msg=choice)
+
+
+def test_config5_mixed_length_sweep_vs_oracle(oracle_mod, pkg):
+    """BASELINE config 5: lengths log-uniform 32..4096, length-bucketed batching, plus the hand
+    cases (all-mismatch, single base, gap-only-profitable)."""
+    rng = random.Random(55)
+    nrng = np.random.default_rng(55)
+    lens = np.exp(nrng.uniform(np.log(32), np.log(4096), size=700)).astype(int)
+    queries = [_rand(rng, 32), _rand(rng, 150), _rand(rng, 1000), _rand(rng, 4096)]
+    subjects = []
+    for L in lens:
+        if rng.random() < 0.4:
+            src = rng.choice(queries)
+            a = rng.randint(0, max(0, len(src) - 1))
+            s = _mutate(rng, src[a:a + int(L)], 0.06, 0.04)
+            s = (s + _rand(rng, int(L)))[:int(L)]
+        else:
+            s = _rand(rng, int(L))
+        subjects.append(s)
+    subjects += ["A" * 500, "T" * 500, "G", "ACGT" * 200 + "TTTT" + "ACGT" * 200]
+    queries.append("ACGT" * 200 + "ACGT" * 200)          # the subject above needs a 4-base gap
+    want = _oracle_matrix(oracle_mod, pkg, queries, subjects)
+    with pkg.Engine() as e:
+        got = e.score(queries, subjects)
+    np.testing.assert_array_equal(got, want)
+    assert 7960 <= want[4, -1] < 8000                       # 1600 matches minus one gap of ~4 residues
