@@ -102,6 +102,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads():
+    """All cores this process may use (torchrun sets OMP_NUM_THREADS=1; the CPU arm must not inherit that)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def make_inputs(pkg, n_subjects, n_queries, rank):
     db = pkg.random_packed_db(n_subjects, TLEN, seed=SEED + 1000 * rank)
     q = pkg.random_packed_db(n_queries, QLEN, seed=SEED - 1)
@@ -123,10 +131,11 @@ def run_reference(args, rank, world):
     cells = ns * TLEN * args.queries * QLEN
     used = 1
     for _ in range(max(args.warmup, 0)):
-        _, used = o.score_batch_packed(q[0], q[1], q[2], db[0][: (ns // 8) * 38 + 16], db[1][: ns // 8], db[2][: ns // 8])
+        _, used = o.score_batch_packed(q[0], q[1], q[2], db[0][: (ns // 8) * 38 + 16], db[1][: ns // 8], db[2][: ns // 8],
+                                       nthreads=host_threads())
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        _, used = o.score_batch_packed(q[0], q[1], q[2], db[0], db[1], db[2])
+        _, used = o.score_batch_packed(q[0], q[1], q[2], db[0], db[1], db[2], nthreads=host_threads())
     dt = time.perf_counter() - t0
     gcups = cells * args.steps / dt / 1e9
     sample = f"first {ns} of the synthetic 150-nt subjects x {args.queries} queries per step ({cells:.3g} cells)"
@@ -264,7 +273,8 @@ def main():
         ns = min(args.cpu_subjects, args.subjects)
         nb = (TLEN + 3) // 4
         t0 = time.perf_counter()
-        ref, used = o.score_batch_packed(q[0], q[1], q[2], db[0][: ns * nb + 16], db[1][:ns], db[2][:ns])
+        ref, used = o.score_batch_packed(q[0], q[1], q[2], db[0][: ns * nb + 16], db[1][:ns], db[2][:ns],
+                                         nthreads=host_threads())
         dt = time.perf_counter() - t0
         assert np.array_equal(ref, chk[:, :ns]), "GPU scores differ from the CPU oracle on the sample"
         cpu = {"value": ns * TLEN * args.queries * QLEN / dt / 1e9, "unit": "GCUPS", "cores": used, "kind": "port",
