@@ -40,14 +40,17 @@ def mixed_db(n, lo, hi, seed):
 which = sys.argv[1:] or ["2", "4", "4w", "5"]
 if "2" in which:    # query100 x data500 shape: 128-nt query, 499 x 128-nt subjects (latency bound)
     run("2: 1 x 128 nt query vs 499 x 128 nt", pkg.random_packed_db(1, 128, 1), pkg.random_packed_db(499, 128, 2), reps=5)
+KERNELS = os.environ.get("SW_KERNELS", "").split()
 if "4" in which:    # 10 kb query vs 1 kb subjects; 200k subjects = 2e12 cells per query
-    run("4: 1 x 10 kb query vs 200k x 1 kb (automatic variant)", pkg.random_packed_db(1, 10000, 3),
-        pkg.random_packed_db(200000, 1000, 4))
+    for k in KERNELS or [None]:
+        run("4: 1 x 10 kb query vs 200k x 1 kb (%s)" % (k or "automatic variant"), pkg.random_packed_db(1, 10000, 3),
+            pkg.random_packed_db(200000, 1000, 4), kernel=k)
 if "4w" in which:   # same shape, few pairs: the warp-wide systolic (intra-task) variant
     run("4w: 1 x 10 kb query vs 2000 x 1 kb (automatic variant)", pkg.random_packed_db(1, 10000, 3),
         pkg.random_packed_db(2000, 1000, 4))
     run("4w: same, forced G=32 wavefront", pkg.random_packed_db(1, 10000, 3), pkg.random_packed_db(2000, 1000, 4),
         kernel="strip_s16x2_R16x1_G32")
 if "5" in which:    # lengths log-uniform 32..4096
-    run("5: 8 x (32..4096) queries vs 300k subjects log-uniform 32..4096", mixed_db(8, 32, 4096, 5),
-        mixed_db(300000, 32, 4096, 6))
+    for k in KERNELS or [None]:
+        run("5: 8 x (32..4096) queries vs 300k subjects log-uniform 32..4096 (%s)" % (k or "automatic variant"),
+            mixed_db(8, 32, 4096, 5), mixed_db(300000, 32, 4096, 6), kernel=k)

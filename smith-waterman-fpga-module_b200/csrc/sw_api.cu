@@ -280,16 +280,16 @@ SwDevDb dev_db(const GpuCtx &g)
 double variant_speed(const SwStripVariant *v)
 {
     struct { const char *name; double gcups; } tab[] = {
-        {"strip_s16x2_R32x1_G1", 6210}, {"strip_s16x2_R50x1_G1", 6360}, {"strip_s16x2_R25x2_G1", 6580},
-        {"strip_s16x2_R25x1_G2", 5690}, {"strip_s16x2_R64x1_G1", 5770}, {"strip_s16x2_R32x2_G1", 6870},
-        {"strip_s16x2_R75x1_G2", 5570}, {"strip_s16x2_R25x3_G2", 6100}, {"strip_s16x2_R25x3_G1", 6740},
-        {"strip_s16x2_R38x2_G1", 6580}, {"strip_s16x2_R38x1_G4", 5170}, {"strip_s16x2_R19x2_G4", 5000},
+        {"strip_s16x2_R32x1_G1", 6500}, {"strip_s16x2_R50x1_G1", 6750}, {"strip_s16x2_R25x2_G1", 7350},
+        {"strip_s16x2_R25x1_G2", 5690}, {"strip_s16x2_R64x1_G1", 6800}, {"strip_s16x2_R32x2_G1", 6800},
+        {"strip_s16x2_R75x1_G2", 5570}, {"strip_s16x2_R25x3_G2", 6100}, {"strip_s16x2_R25x3_G1", 7430},
+        {"strip_s16x2_R38x2_G1", 7250}, {"strip_s16x2_R38x1_G4", 5170}, {"strip_s16x2_R19x2_G4", 5000},
         {"strip_s16x2_R32x1_G4", 5110}, {"strip_s16x2_R16x1_G32", 4050}, {"strip_s16x2_R8x2_G32", 4130},
         {"strip_f16x2_R50x1_G1", 7250}, {"strip_f16x2_R25x2_G1", 7480}, {"strip_f16x2_R25x1_G2", 6090},
         {"strip_f16x2_R38x1_G4", 5120}, {"strip_f16x2_R19x2_G4", 5100}, {"strip_f16x2_R25x3_G1", 7170},
         {"strip_hyb16_R50x1_G1", 6825}, {"strip_hyb16_R25x2_G1", 7305}, {"strip_hyb16_R32x2_G1", 7930},
         {"strip_hyb16_R25x1_G2", 6270}, {"strip_hyb16_R38x1_G4", 6060}, {"strip_hyb16_R38x2_G1", 7640},
-        {"strip_hyb16_R25x3_G1", 7770}, {"strip_hyb16_R30x1_G1", 7225}, {"strip_hyb16_R19x4_G1", 7480},
+        {"strip_hyb16_R25x3_G1", 7750}, {"strip_hyb16_R30x1_G1", 7225}, {"strip_hyb16_R19x4_G1", 7480},
     };
     for (auto &t : tab) if (std::strcmp(t.name, v->name) == 0) return t.gcups;
     return 5000.0;

@@ -46,6 +46,10 @@ constexpr int kPadScoreF16 = -2048;
 // ------------------------------------------------------------------------------------------
 struct ArithS16 {
     static constexpr int kPad = kPadScoreS16;
+    static constexpr bool kClampForm = true;     // see column_step_multi: M is never materialised
+    static __device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) {
+        return __viaddmax_s16x2_relu(a, b, c);   // max(a + b, c, 0)
+    }
     static __device__ __forceinline__ uint32_t pack(int lo, int hi) {
         return (uint32_t)(lo & 0xFFFF) | ((uint32_t)(hi & 0xFFFF) << 16);
     }
@@ -70,6 +74,8 @@ struct ArithS16 {
 
 struct ArithF16 {
     static constexpr int kPad = kPadScoreF16;
+    static constexpr bool kClampForm = false;
+    static __device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) { return addmax(a, b, c); }
     static __device__ __forceinline__ uint32_t pack(int lo, int hi) {
         __half2 h = __halves2half2(__int2half_rn(lo), __int2half_rn(hi));
         return *reinterpret_cast<uint32_t *>(&h);
@@ -112,6 +118,10 @@ struct ArithF16 {
 // is <= 2047 -- the same range the reference's 12-bit datapath has.
 struct ArithHyb {
     static constexpr int kPad = -2047;
+    static constexpr bool kClampForm = false;
+    static __device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) {
+        return __viaddmax_s16x2_relu(a, b, c);
+    }
     static __device__ __forceinline__ uint32_t pack(int lo, int hi) { return ArithS16::pack(lo, hi); }
     static __device__ __forceinline__ uint32_t pack_score(int lo, int hi) {
         const uint32_t l = lo >= 0 ? (uint32_t)lo : (0x8000u | (uint32_t)(-lo));
@@ -176,6 +186,42 @@ __device__ __forceinline__ void column_step_multi(uint32_t (&H)[S][RS], uint32_t
     for (int s = 0; s < S; ++s)
 #pragma unroll
         for (int k = 0; k < RP; ++k) sv[s][k] = prow[s][k * kCodesPerRow];
+    if (AR::kClampForm && !W12) {
+        // Clamped form (exact): every gap value is clamped at 0 -- non-positive
+        // gap values can never reach H because M >= 0 -- and then
+        //     t = H(r-1,c-1) + s                      (FMA-side pipe, may be negative)
+        //     I = max(G_left, G_up)      >= 0
+        //     G = max(t + goe, I + ge, 0)             one VIADDMNMX.RELU
+        //     H = max(t, I)              = max(max(t,0), I) because I >= 0
+        // so M = max(t, 0) is never materialised: 3.5 ALU-pipe + 2 FMA-pipe instructions per
+        // cell pair over the full 16-bit range.  t of row r+1 is formed one row ahead from the
+        // still-old H[r], so H[r] can be overwritten in place.
+        uint32_t gu[S], t_cur[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            gu[s] = g_top[s];
+            t_cur[s] = AR::add(hd_top[s], sv[s][0].x);
+        }
+#pragma unroll
+        for (int r = 0; r < RS; ++r) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                uint32_t t_next = zero;
+                if (r + 1 < RS) {
+                    const uint32_t sc = ((r + 1) & 1) ? sv[s][(r + 1) >> 1].y : sv[s][(r + 1) >> 1].x;
+                    t_next = AR::add(H[s][r], sc);
+                }
+                const uint32_t i_ = AR::max2(Gl[s][r], gu[s]);
+                const uint32_t j_ = AR::add(i_, ge2);
+                gu[s] = AR::addmax_relu(t_cur[s], goe2, j_);
+                Gl[s][r] = gu[s];
+                H[s][r] = AR::max2(t_cur[s], i_);
+                best = AR::max2(best, H[s][r]);
+                t_cur[s] = t_next;
+            }
+        }
+        return;
+    }
 #if SW_MPASS_BOTTOM_UP
     // M pass, bottom-up and in place: H[r] <- M(r, c) = relu(H(r-1, c-1) + s(r, c))
 #pragma unroll
@@ -243,7 +289,7 @@ __device__ __forceinline__ void column_step_multi(uint32_t (&H)[S][RS], uint32_t
 // works on the PAD column code whose profile entries are very negative: M becomes 0, H keeps
 // decaying values <= the best already recorded, and G only drifts among non-positive values,
 // which never reach H (M >= 0).  That keeps the loop body free of per-lane branches.
-template <int RS, int S, int G, class AR, bool W12, int BT, int MINB>
+template <int RS, int S, int G, class AR, bool W12, int BT, int MINB, int U = SW_STEP_UNROLL>
 __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
 {
     extern __shared__ uint2 s_prof[];
@@ -261,7 +307,8 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
     const int pslot = threadIdx.x / G;
     const uint32_t zero = a.zero;
     const uint32_t goe2 = AR::pack(a.goe, a.goe), ge2 = AR::pack(a.ge, a.ge);
-    const int gbv = a.goe > a.ge ? a.goe : a.ge;
+    // boundary gap value G(0,j) = G(i,0): max(goe, ge) <= 0, or its clamp 0 in the clamped form
+    const int gbv = (AR::kClampForm && !W12) ? 0 : (a.goe > a.ge ? a.goe : a.ge);
     const uint32_t gb2 = AR::pack(gbv, gbv);
     const uint32_t lim2 = AR::pack(a.limit, a.limit);
     uint2 *bnd = a.bnd + (size_t)blockIdx.x * a.bnd_cols * PPB + pslot;
@@ -284,7 +331,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
             subj_hi = a.pair_subj[2 * pair + 1];
         }
         // rounded up: the step loop is unrolled (extra steps are PAD columns)
-        const int nsteps = (__reduce_max_sync(FULL, ncols) + (VPE - 1) + SW_STEP_UNROLL - 1) / SW_STEP_UNROLL * SW_STEP_UNROLL;
+        const int nsteps = (__reduce_max_sync(FULL, ncols) + (VPE - 1) + U - 1) / U * U;
 
         for (int q = a.q0; q < a.q1; ++q) {
             const int m = (int)a.qlen[q];
@@ -346,9 +393,9 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                 for (int s = 0; s < S; ++s) { pub_h[s] = zero; pub_g[s] = gb2; pub_t[s] = kPadCode; hd_top[s] = zero; }
 
 #pragma unroll 1
-                for (int t2 = 0; t2 < nsteps; t2 += SW_STEP_UNROLL) {
+                for (int t2 = 0; t2 < nsteps; t2 += U) {
 #pragma unroll
-                  for (int u = 0; u < SW_STEP_UNROLL; ++u) {
+                  for (int u = 0; u < U; ++u) {
                     const int t = t2 + u;
                     uint32_t in_h[S], in_g[S], in_t[S];
                     if (G > 1) {
@@ -560,6 +607,11 @@ struct VariantEntry {
 #define SW_VARIANT_HYB(RS, S, G, MINB)                                                          \
     { {RS * S, G, 2, kBT, S, MINB, "strip_hyb16_R" #RS "x" #S "_G" #G},                         \
       sw_strip_kernel<RS, S, G, ArithHyb, false, kBT, MINB>, nullptr }
+
+// experimental: explicit block size and step unroll, tagged in the name
+#define SW_VARIANT_HYB_X(RS, S, G, MINB, BT_, U_)                                               \
+    { {RS * S, G, 2, BT_, S, MINB, "strip_hyb16_R" #RS "x" #S "_G" #G "_b" #BT_ "u" #U_},       \
+      sw_strip_kernel<RS, S, G, ArithHyb, false, BT_, MINB, U_>, nullptr }
 
 const VariantEntry g_variants[] = {
     SW_VARIANT_S16(32, 1, 1, 4),
