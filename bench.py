@@ -293,7 +293,19 @@ def main():
         # instructions of the recurrence run on the FMA-side pipe and overlap
         alu_per_pair = {"f16x2": 3.5, "s16x2+f16x2": 3.5, "s16x2": 4.5, "int32": 12.0}[arith]
         tight_gcups = SM_COUNT * pk["sm_max_mhz"] * 1e6 * R_INT * 2.0 / alu_per_pair / 1e9
-        algo_bytes = args.subjects * ((TLEN + 7) // 8 * 4 / 2 + 8) * 8 + args.subjects * args.queries * 4
+        # per launch: the pair's code stream (19 words) + pair_len + pair_subj, read once; per step 8 launches
+        # plus one int32 score per (query, subject) written once
+        n_launch = max(1, launches // max(1, args.steps))
+        algo_bytes = (args.subjects / 2) * (((TLEN + 7) // 8) * 4 + 4 + 8) * n_launch + args.subjects * args.queries * 4
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+                tr = json.load(f)
+            if tr["kernel"] == kname and tr["subjects_per_gpu"] == args.subjects and tr["queries"] == args.queries:
+                traffic = {"dram_bytes_per_launch": tr["dram_bytes_read_per_launch"] + tr["dram_bytes_write_per_launch"],
+                           "algorithmic_bytes_per_launch": int(algo_bytes / n_launch), "source": tr["source"]}
+        except Exception:
+            pass
         line = {
             "metric": "GCUPS (score-only SW)", "value": gcups, "unit": "GCUPS", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
@@ -307,7 +319,7 @@ def main():
                          "frac": per_gpu / roof_gcups,
                          "peak_def": f"148 SM x {pk['sm_max_mhz']:.0f} MHz x R_int {R_INT:.0f} thread-instr/clk/SM "
                                      f"(measured, profiles/r01_pipe_pairs_1024thr.json) x 2 cells / 6 instr (SURVEY 8d)",
-                         "traffic": None,
+                         "traffic": traffic,
                          "tight": {"peak": tight_gcups, "frac": per_gpu / tight_gcups,
                                    "def": f"ALU-pipe bound of this kernel: {alu_per_pair} ALU-pipe instr per 2 cells, "
                                           f"adds co-issue on the FMA-side pipe (profiles/r01_pipe_pairs_1024thr.json)"},
