@@ -373,7 +373,9 @@ int score_gpu(sw_handle *h, GpuCtx &g)
     }
 
     // query chunks: a handful of launches so that D2H of finished rows overlaps compute
-    const int nchunks = std::max(1, std::min(nq, 8));
+    // (each launch has its own tail: aim for >= ~50 ms of work per launch, at ~6 TCUPS)
+    const double est_ms = (double)g.sum_len * (double)h->q_sum_len / 6.0e9;
+    const int nchunks = std::max(1, std::min(std::min(nq, 8), (int)(est_ms / 50.0)));
     SW_CUDA(h, g.d_counters.reserve(kMaxCounters * sizeof(unsigned)));
     SW_CUDA(h, cudaMemsetAsync(g.d_counters.p, 0, kMaxCounters * sizeof(unsigned), g.st_compute));
 

@@ -317,8 +317,10 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
         __syncthreads();
         if (threadIdx.x == 0) s_work = atomicAdd(a.counter, 1u);
         __syncthreads();
-        const unsigned pb = s_work;
-        if (pb >= a.npb) break;
+        if (s_work >= a.npb) break;
+        // pairs are sorted by ascending length: hand out the longest blocks first so that the
+        // tail of the launch is made of short work items
+        const unsigned pb = a.npb - 1u - s_work;
 
         const unsigned pair = pb * PPB + pslot;
         const bool valid = pair < a.npairs;
@@ -612,6 +614,11 @@ struct VariantEntry {
 #define SW_VARIANT_HYB_X(RS, S, G, MINB, BT_, U_)                                               \
     { {RS * S, G, 2, BT_, S, MINB, "strip_hyb16_R" #RS "x" #S "_G" #G "_b" #BT_ "u" #U_},       \
       sw_strip_kernel<RS, S, G, ArithHyb, false, BT_, MINB, U_>, nullptr }
+
+// smaller blocks = smaller work items (32 / 64 pairs): better packing when subjects are long
+#define SW_VARIANT_S16_B(RS, S, G, MINB, BT_)                                                   \
+    { {RS * S, G, 0, BT_, S, MINB, "strip_s16x2_R" #RS "x" #S "_G" #G "_b" #BT_},               \
+      sw_strip_kernel<RS, S, G, ArithS16, false, BT_, MINB>, sw_strip_kernel<RS, S, G, ArithS16, true, BT_, MINB> }
 
 const VariantEntry g_variants[] = {
     SW_VARIANT_S16(32, 1, 1, 4),
