@@ -75,14 +75,24 @@ void sw_destroy(sw_handle_t *h);
 int sw_set_queries(sw_handle_t *h, const uint8_t *packed, const uint32_t *len,
                    const uint64_t *off, int nq);
 
+/* Both strands: when enabled (before sw_set_queries), every query is also scored as its reverse
+ * complement; the score matrix then has 2*nq rows, row nq + i = reverse complement of query i.
+ * The reference ran ssearch36 with -3 to switch this off (data/ssearch36_command:2) while
+ * data/res shows [r] hits; default is forward only.  sw_query_rows = rows per subject. */
+int sw_set_strands(sw_handle_t *h, int both);
+int sw_query_rows(const sw_handle_t *h);
+
 /* Replaces: the stream of type-10 records with feeder / PrioEncoder arbitration
  * (ScoreBank_v2.v:142-169, SM_Feeder2.v:104-205, PrioEncoder.v:18-21) and the
  * DMA read of the sequence array (afu.v:383-398).  Subjects are length-bucketed,
  * sharded over the handle's GPUs, copied H2D and scored against every query.
  * Asynchronous with respect to the GPUs: returns once the work is enqueued; the
  * caller's buffers may be reused as soon as it returns.  ids may be NULL
- * (then id = input index); they are returned by sw_fetch_ids.  SW_EAGAIN while a
- * previous batch has not been fetched. */
+ * (then id = input index); they are returned by sw_fetch_ids.
+ * Streaming: TWO batches may be in flight (double buffering like the feeder's two target
+ * slots): submit batch k+1 before fetching batch k and its sort / H2D / kernels overlap the
+ * D2H of batch k.  SW_EAGAIN when both buffers are busy (the bank's `full` wire);
+ * sw_fetch returns batches in submission order. */
 int sw_score_batch(sw_handle_t *h, const uint8_t *packed, const uint32_t *len,
                    const uint64_t *off, const uint64_t *ids, size_t ns);
 
@@ -93,6 +103,7 @@ int sw_score_batch(sw_handle_t *h, const uint8_t *packed, const uint32_t *len,
  * query iq against subject is, in INPUT order (deterministic, unlike the RTL's
  * completion order).  cap = number of int32 the buffer holds. */
 int sw_fetch(sw_handle_t *h, int32_t *scores, size_t cap, int timeout_ms);
+int sw_batches_in_flight(const sw_handle_t *h);      /* 0, 1 or 2 */
 
 /* Replaces: the 48-bit ID that travels with every target record and comes back next to
  * its score (ScoreBank_v2.v:26-28,40; fifo.v:36-64).  ids[is] = the id given to

@@ -84,6 +84,9 @@ def load_library():
     L.sw_kernel_variant_name.restype = C.c_char_p
     L.sw_set_kernel_name.argtypes = [vp, C.c_char_p]
     L.sw_plan_shards.argtypes = [vp, sz, i32, vp]
+    L.sw_set_strands.argtypes = [vp, i32]
+    L.sw_query_rows.argtypes = [vp]
+    L.sw_batches_in_flight.argtypes = [vp]
     L.sw_device_count.restype = i32
     L.sw_version.restype = C.c_char_p
     L.sw_pack_2bit.argtypes = [C.c_char_p, sz, vp]
@@ -113,8 +116,9 @@ class Engine:
         if rc != SW_OK:
             self.h = C.c_void_p()
             raise SwError(rc, self.lib.sw_strerror(rc).decode())
-        self.nq = 0
-        self.ns = 0
+        self.nq = 0          # rows of the score matrix (queries x strands)
+        self.ns = 0          # subjects of the resident database / last submitted batch
+        self._batch_ns = []  # subjects of the batches in flight, oldest first
 
     # -- plumbing ---------------------------------------------------------------------
     def _check(self, rc):
@@ -150,22 +154,35 @@ class Engine:
         return pack_sequences(seqs)
 
     # -- operator surface ---------------------------------------------------------------
+    def set_strands(self, both):
+        """both=True: also score the reverse complement of every query (rows nq..2nq-1)."""
+        self._check(self.lib.sw_set_strands(self.h, int(bool(both))))
+
     def set_queries(self, queries):
         packed, ln, off = self._as_packed(queries)
         self._check(self.lib.sw_set_queries(self.h, _ptr(packed), _ptr(ln), _ptr(off), len(ln)))
-        self.nq = len(ln)
+        self.nq = int(self.lib.sw_query_rows(self.h))
 
     def score_batch(self, subjects, ids=None):
         packed, ln, off = self._as_packed(subjects)
         ids_a = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint64)
         self._check(self.lib.sw_score_batch(self.h, _ptr(packed), _ptr(ln), _ptr(off), _ptr(ids_a), len(ln)))
         self.ns = len(ln)
+        self._batch_ns.append(len(ln))
 
     def fetch(self, timeout_ms=-1, out=None):
+        """Scores of the OLDEST batch in flight (two may be in flight)."""
+        ns = self._batch_ns[0] if self._batch_ns else self.ns
         if out is None:
-            out = np.empty((self.nq, self.ns), dtype=np.int32)
+            out = np.empty((self.nq, ns), dtype=np.int32)
         self._check(self.lib.sw_fetch(self.h, _ptr(out), out.size, timeout_ms))
+        if self._batch_ns:
+            self._batch_ns.pop(0)
         return out
+
+    @property
+    def batches_in_flight(self):
+        return int(self.lib.sw_batches_in_flight(self.h))
 
     def fetch_ids(self):
         ids = np.empty(self.ns, dtype=np.uint64)

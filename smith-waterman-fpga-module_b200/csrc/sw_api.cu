@@ -54,23 +54,39 @@ struct DevBuf {
 
 struct QueryChunk { int q0, q1; cudaEvent_t done; };
 
+// Everything that belongs to one database batch on one GPU.  Two slots per GPU: while the
+// kernels of batch k run, batch k+1 can be sorted, uploaded and enqueued, and batch k-1 copied
+// back (the feeder's double buffering, SM_Feeder2.v:104-205, at batch granularity).
+struct Slot {
+    size_t s0 = 0, s1 = 0;            // global subject range [s0, s1) of this GPU's shard
+    DevBuf d_raw, d_off, d_len, d_pair_subj, d_pair_len, d_tile_woff, d_tp, d_out;
+    uint32_t npairs = 0, max_len = 0;
+    uint64_t sum_len = 0;
+    PinnedBuf h_stage_a, h_stage_b, h_stage_c, h_stage_d;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_upload = nullptr;
+    std::vector<QueryChunk> chunks;
+    bool scored = false;
+};
+
 struct GpuCtx {
     int dev = 0;
     int num_sms = 0;
     cudaStream_t st_compute = nullptr, st_copy = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_upload = nullptr;
     // queries
     DevBuf d_qpacked, d_qoff, d_qlen;
-    // database shard
-    size_t s0 = 0, s1 = 0;            // global subject range [s0, s1)
-    DevBuf d_raw, d_off, d_len, d_pair_subj, d_pair_len, d_tile_woff, d_tp;
-    uint32_t npairs = 0, max_len = 0;
-    uint64_t sum_len = 0;
-    PinnedBuf h_stage_a, h_stage_b, h_stage_c, h_stage_d;
-    // scoring
-    DevBuf d_out, d_bnd, d_counters, d_scratch32, d_best_score, d_best_index;
-    std::vector<QueryChunk> chunks;
-    bool scored = false;
+    Slot slot[2];
+    // scratch shared by both slots (kernels of one GPU run in stream order)
+    DevBuf d_bnd, d_counters, d_scratch32, d_best_score, d_best_index;
+};
+
+// Host-side description of one batch (all GPUs).
+struct Batch {
+    size_t ns = 0;
+    int nq = 0;                       // query rows the scores of this batch have
+    bool loaded = false, scored = false;
+    std::vector<uint64_t> ids;
+    bool have_ids = false;
+    uint64_t cells = 0;
 };
 
 }  // namespace
@@ -83,12 +99,13 @@ struct sw_handle {
     std::vector<uint32_t> q_off, q_len;
     uint32_t q_max_len = 0;
     uint64_t q_sum_len = 0;
-    // database
-    size_t ns = 0;
-    bool db_loaded = false;
-    bool batch_in_flight = false;
-    std::vector<uint64_t> ids;
-    bool have_ids = false;
+    bool both_strands = false;
+    int nq_user = 0;                  // queries given by the caller (rows = nq_user * strands)
+    // database batches: slot 0 doubles as the resident database of sw_load_db
+    Batch batch[2];
+    int fifo[2] = {0, 0};             // slots in flight, oldest first
+    int n_inflight = 0;
+    int last_slot = 0;                // slot of the most recent load / fetch (ids, cells)
     // bookkeeping
     int last_cuda = 0;
     uint64_t launches = 0;
@@ -129,16 +146,19 @@ int validate_params(const sw_params_t *p)
 void free_gpu(GpuCtx &g)
 {
     cudaSetDevice(g.dev);
-    for (auto &c : g.chunks) if (c.done) cudaEventDestroy(c.done);
-    g.chunks.clear();
-    DevBuf *bufs[] = {&g.d_qpacked, &g.d_qoff, &g.d_qlen, &g.d_raw, &g.d_off, &g.d_len, &g.d_pair_subj,
-                      &g.d_pair_len, &g.d_tile_woff, &g.d_tp, &g.d_out, &g.d_bnd, &g.d_counters,
-                      &g.d_scratch32, &g.d_best_score, &g.d_best_index};
-    for (DevBuf *b : bufs) b->release();
-    g.h_stage_a.release(); g.h_stage_b.release(); g.h_stage_c.release(); g.h_stage_d.release();
-    if (g.ev_start) cudaEventDestroy(g.ev_start);
-    if (g.ev_stop) cudaEventDestroy(g.ev_stop);
-    if (g.ev_upload) cudaEventDestroy(g.ev_upload);
+    for (Slot &b : g.slot) {
+        for (auto &c : b.chunks) if (c.done) cudaEventDestroy(c.done);
+        b.chunks.clear();
+        DevBuf *bufs[] = {&b.d_raw, &b.d_off, &b.d_len, &b.d_pair_subj, &b.d_pair_len, &b.d_tile_woff, &b.d_tp, &b.d_out};
+        for (DevBuf *d : bufs) d->release();
+        b.h_stage_a.release(); b.h_stage_b.release(); b.h_stage_c.release(); b.h_stage_d.release();
+        if (b.ev_start) cudaEventDestroy(b.ev_start);
+        if (b.ev_stop) cudaEventDestroy(b.ev_stop);
+        if (b.ev_upload) cudaEventDestroy(b.ev_upload);
+    }
+    DevBuf *bufs[] = {&g.d_qpacked, &g.d_qoff, &g.d_qlen, &g.d_bnd, &g.d_counters, &g.d_scratch32,
+                      &g.d_best_score, &g.d_best_index};
+    for (DevBuf *d : bufs) d->release();
     if (g.st_compute) cudaStreamDestroy(g.st_compute);
     if (g.st_copy) cudaStreamDestroy(g.st_copy);
 }
@@ -159,9 +179,9 @@ int upload_queries(sw_handle *h, GpuCtx &g)
 }
 
 // Length-sorts the shard's subjects, pairs equal lengths, lays out 32-pair tiles, uploads.
-int load_shard(sw_handle *h, GpuCtx &g, const uint8_t *packed, const uint32_t *len, const uint64_t *off)
+int load_shard(sw_handle *h, GpuCtx &gc, Slot &g, const uint8_t *packed, const uint32_t *len, const uint64_t *off)
 {
-    SW_CUDA(h, cudaSetDevice(g.dev));
+    SW_CUDA(h, cudaSetDevice(gc.dev));
     const size_t n = g.s1 - g.s0;
     g.npairs = 0; g.max_len = 0; g.sum_len = 0; g.scored = false;
     if (n == 0) return SW_OK;
@@ -245,7 +265,7 @@ int load_shard(sw_handle *h, GpuCtx &g, const uint8_t *packed, const uint32_t *l
     SW_CUDA(h, g.d_pair_len.reserve(ntiles * 32 * sizeof(uint32_t)));
     SW_CUDA(h, g.d_tile_woff.reserve((ntiles + 1) * sizeof(uint64_t)));
     SW_CUDA(h, g.d_tp.reserve((w + 32) * sizeof(uint32_t)));
-    cudaStream_t cs = g.st_copy;
+    cudaStream_t cs = gc.st_copy;
     SW_CUDA(h, cudaMemcpyAsync(g.d_raw.p, packed + bmin, raw_bytes, cudaMemcpyHostToDevice, cs));
     SW_CUDA(h, cudaMemcpyAsync(g.d_len.p, ln, n * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
     SW_CUDA(h, cudaMemcpyAsync(g.d_off.p, loc_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, cs));
@@ -253,19 +273,19 @@ int load_shard(sw_handle *h, GpuCtx &g, const uint8_t *packed, const uint32_t *l
     SW_CUDA(h, cudaMemcpyAsync(g.d_pair_len.p, pair_len, ntiles * 32 * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
     SW_CUDA(h, cudaMemcpyAsync(g.d_tile_woff.p, tile_woff, (ntiles + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, cs));
     SW_CUDA(h, cudaEventRecord(g.ev_upload, cs));
-    SW_CUDA(h, cudaStreamWaitEvent(g.st_compute, g.ev_upload, 0));
+    SW_CUDA(h, cudaStreamWaitEvent(gc.st_compute, g.ev_upload, 0));
 
     SwDevDb db;
     db.raw = g.d_raw.as<uint8_t>(); db.off = g.d_off.as<uint64_t>(); db.len = g.d_len.as<uint32_t>();
     db.ns = (uint32_t)n; db.pair_subj = g.d_pair_subj.as<uint32_t>(); db.pair_len = g.d_pair_len.as<uint32_t>();
     db.tile_woff = g.d_tile_woff.as<uint64_t>(); db.tp = g.d_tp.as<uint32_t>();
     db.npairs = g.npairs; db.max_len = g.max_len;
-    SW_CUDA(h, sw_launch_build_tp(g.st_compute, db));
+    SW_CUDA(h, sw_launch_build_tp(gc.st_compute, db));
     h->launches++;
     return SW_OK;
 }
 
-SwDevDb dev_db(const GpuCtx &g)
+SwDevDb dev_db(const Slot &g)
 {
     SwDevDb db;
     db.raw = g.d_raw.as<uint8_t>(); db.off = g.d_off.as<uint64_t>(); db.len = g.d_len.as<uint32_t>();
@@ -297,7 +317,7 @@ double variant_speed(const SwStripVariant *v)
 
 // Picks the strip variant: least estimated time = padded rows x (columns + pipeline fill)
 // / measured speed / fraction of the GPU the pairs can keep busy.
-int choose_variant(const sw_handle *h, const GpuCtx &g, uint32_t maxq, bool allow_f16)
+int choose_variant(const sw_handle *h, const GpuCtx &gc, const Slot &g, uint32_t maxq, bool allow_f16)
 {
     const int nv = sw_strip_variant_count();
     if (h->force_variant >= 0) return h->force_variant;
@@ -319,7 +339,7 @@ int choose_variant(const sw_handle *h, const GpuCtx &g, uint32_t maxq, bool allo
         const int P = v->R * v->G;
         const double rows = (double)((maxq + P - 1) / P) * P;
         const double lanes = (double)g.npairs * v->G;
-        const double fill = (double)g.num_sms * v->min_blocks * v->block_threads;
+        const double fill = (double)gc.num_sms * v->min_blocks * v->block_threads;
         const double util = std::min(1.0, lanes / fill);
         const double cols = (double)std::max<uint32_t>(g.max_len, 1);
         const double cost = rows * (cols + v->G * v->S - 1) / cols / variant_speed(v) / util;
@@ -328,9 +348,9 @@ int choose_variant(const sw_handle *h, const GpuCtx &g, uint32_t maxq, bool allo
     return best;
 }
 
-int score_gpu(sw_handle *h, GpuCtx &g)
+int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
 {
-    SW_CUDA(h, cudaSetDevice(g.dev));
+    SW_CUDA(h, cudaSetDevice(gc.dev));
     const int nq = (int)h->q_len.size();
     const size_t n = g.s1 - g.s0;
     for (auto &c : g.chunks) if (c.done) cudaEventDestroy(c.done);
@@ -339,13 +359,13 @@ int score_gpu(sw_handle *h, GpuCtx &g)
     if (n == 0 || nq == 0) return SW_OK;
 
     SW_CUDA(h, g.d_out.reserve((size_t)nq * n * sizeof(int32_t)));
-    SW_CUDA(h, cudaMemsetAsync(g.d_out.p, 0, (size_t)nq * n * sizeof(int32_t), g.st_compute));
-    SW_CUDA(h, cudaEventRecord(g.ev_start, g.st_compute));
+    SW_CUDA(h, cudaMemsetAsync(g.d_out.p, 0, (size_t)nq * n * sizeof(int32_t), gc.st_compute));
+    SW_CUDA(h, cudaEventRecord(g.ev_start, gc.st_compute));
     if (g.npairs == 0) {
-        SW_CUDA(h, cudaEventRecord(g.ev_stop, g.st_compute));
+        SW_CUDA(h, cudaEventRecord(g.ev_stop, gc.st_compute));
         QueryChunk c{0, nq, nullptr};
         SW_CUDA(h, cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
-        SW_CUDA(h, cudaEventRecord(c.done, g.st_compute));
+        SW_CUDA(h, cudaEventRecord(c.done, gc.st_compute));
         g.chunks.push_back(c);
         return SW_OK;
     }
@@ -357,7 +377,7 @@ int score_gpu(sw_handle *h, GpuCtx &g)
 
     SwDevDb db = dev_db(g);
     SwDevQueries dq;
-    dq.packed = g.d_qpacked.as<uint8_t>(); dq.off = g.d_qoff.as<uint32_t>(); dq.len = g.d_qlen.as<uint32_t>();
+    dq.packed = gc.d_qpacked.as<uint8_t>(); dq.off = gc.d_qoff.as<uint32_t>(); dq.len = gc.d_qlen.as<uint32_t>();
     dq.nq = nq; dq.max_len = h->q_max_len;
 
     // value range: exact s16 needs match * min(m, n) to stay clear of 32767
@@ -367,7 +387,7 @@ int score_gpu(sw_handle *h, GpuCtx &g)
     int vidx = -1;
     if (!h->force32 && fits16) {
         if (h->force_arith >= 1 && !fitsf16) return SW_EINVAL;
-        vidx = choose_variant(h, g, h->q_max_len, fitsf16);
+        vidx = choose_variant(h, gc, g, h->q_max_len, fitsf16);
         if (vidx < 0 && (h->force_R || h->force_G)) return SW_EINVAL;
         if (vidx >= 0 && sw_strip_variant(vidx)->arith != 0 && !fitsf16) return SW_EINVAL;
     }
@@ -376,8 +396,8 @@ int score_gpu(sw_handle *h, GpuCtx &g)
     // (each launch has its own tail: aim for >= ~50 ms of work per launch, at ~6 TCUPS)
     const double est_ms = (double)g.sum_len * (double)h->q_sum_len / 6.0e9;
     const int nchunks = std::max(1, std::min(std::min(nq, 8), (int)(est_ms / 50.0)));
-    SW_CUDA(h, g.d_counters.reserve(kMaxCounters * sizeof(unsigned)));
-    SW_CUDA(h, cudaMemsetAsync(g.d_counters.p, 0, kMaxCounters * sizeof(unsigned), g.st_compute));
+    SW_CUDA(h, gc.d_counters.reserve(kMaxCounters * sizeof(unsigned)));
+    SW_CUDA(h, cudaMemsetAsync(gc.d_counters.p, 0, kMaxCounters * sizeof(unsigned), gc.st_compute));
 
     int grid = 0, chunk_passes = 1;
     if (vidx >= 0) {
@@ -392,15 +412,15 @@ int score_gpu(sw_handle *h, GpuCtx &g)
         if (bps < 1) return SW_ECUDA;
         const int ppb = v->block_threads / v->G;
         const uint32_t npb = (g.npairs + ppb - 1) / ppb;
-        grid = (int)std::min<uint64_t>(npb, (uint64_t)g.num_sms * bps);
+        grid = (int)std::min<uint64_t>(npb, (uint64_t)gc.num_sms * bps);
         if (need_passes > 1) {
             const size_t bytes = (size_t)grid * g.max_len * ppb * sizeof(uint2);
-            SW_CUDA(h, g.d_bnd.reserve(bytes));
+            SW_CUDA(h, gc.d_bnd.reserve(bytes));
         }
         h->last_kernel = v->name;
     } else {
-        const int threads_total = g.num_sms * 2 * 128;
-        SW_CUDA(h, g.d_scratch32.reserve((size_t)2 * std::max<uint32_t>(h->q_max_len, 1) * threads_total * sizeof(int32_t)));
+        const int threads_total = gc.num_sms * 2 * 128;
+        SW_CUDA(h, gc.d_scratch32.reserve((size_t)2 * std::max<uint32_t>(h->q_max_len, 1) * threads_total * sizeof(int32_t)));
         h->last_kernel = "generic32";
     }
 
@@ -411,19 +431,19 @@ int score_gpu(sw_handle *h, GpuCtx &g)
         qc.done = nullptr;
         if (qc.q1 <= qc.q0) continue;
         if (vidx >= 0) {
-            SW_CUDA(h, sw_launch_strip(vidx, g.st_compute, db, dq, qc.q0, qc.q1, sc, g.d_out.as<int32_t>(), n,
-                                       g.d_bnd.as<uint2>(), g.max_len, g.d_counters.as<unsigned>() + (c % kMaxCounters),
+            SW_CUDA(h, sw_launch_strip(vidx, gc.st_compute, db, dq, qc.q0, qc.q1, sc, g.d_out.as<int32_t>(), n,
+                                       gc.d_bnd.as<uint2>(), g.max_len, gc.d_counters.as<unsigned>() + (c % kMaxCounters),
                                        grid, chunk_passes));
         } else {
-            SW_CUDA(h, sw_launch_generic32(g.st_compute, db, dq, qc.q0, qc.q1, sc, g.d_out.as<int32_t>(), n,
-                                           g.d_scratch32.as<int32_t>(), g.num_sms * 2 * 128));
+            SW_CUDA(h, sw_launch_generic32(gc.st_compute, db, dq, qc.q0, qc.q1, sc, g.d_out.as<int32_t>(), n,
+                                           gc.d_scratch32.as<int32_t>(), gc.num_sms * 2 * 128));
         }
         h->launches++;
         SW_CUDA(h, cudaEventCreateWithFlags(&qc.done, cudaEventDisableTiming));
-        SW_CUDA(h, cudaEventRecord(qc.done, g.st_compute));
+        SW_CUDA(h, cudaEventRecord(qc.done, gc.st_compute));
         g.chunks.push_back(qc);
     }
-    SW_CUDA(h, cudaEventRecord(g.ev_stop, g.st_compute));
+    SW_CUDA(h, cudaEventRecord(g.ev_stop, gc.st_compute));
     return SW_OK;
 }
 
@@ -440,41 +460,87 @@ int wait_event(sw_handle *h, cudaEvent_t ev, const std::chrono::steady_clock::ti
     }
 }
 
-int copy_out(sw_handle *h, int32_t *scores, size_t cap, int timeout_ms)
+int copy_out(sw_handle *h, int si, int32_t *scores, size_t cap, int timeout_ms)
 {
-    const size_t nq = h->q_len.size();
-    if (cap < nq * h->ns) return SW_ECAPACITY;
+    const Batch &bt = h->batch[si];
+    const size_t nq = (size_t)bt.nq;
+    if (cap < nq * bt.ns) return SW_ECAPACITY;
     const bool forever = timeout_ms < 0;
     const auto t_end = std::chrono::steady_clock::now() + std::chrono::milliseconds(forever ? 0 : timeout_ms);
     size_t maxchunks = 0;
-    for (auto &g : h->gpus) maxchunks = std::max(maxchunks, g.chunks.size());
+    for (auto &g : h->gpus) maxchunks = std::max(maxchunks, g.slot[si].chunks.size());
     for (size_t c = 0; c < maxchunks; ++c) {
         for (auto &g : h->gpus) {
-            if (c >= g.chunks.size()) continue;
-            const size_t n = g.s1 - g.s0;
+            Slot &b = g.slot[si];
+            if (c >= b.chunks.size()) continue;
+            const size_t n = b.s1 - b.s0;
             if (n == 0) continue;
             SW_CUDA(h, cudaSetDevice(g.dev));
-            const QueryChunk &qc = g.chunks[c];
+            const QueryChunk &qc = b.chunks[c];
             int rc = wait_event(h, qc.done, t_end, forever);
             if (rc != SW_OK) return rc;
-            SW_CUDA(h, cudaMemcpy2DAsync(scores + (size_t)qc.q0 * h->ns + g.s0, h->ns * sizeof(int32_t),
-                                         g.d_out.as<int32_t>() + (size_t)qc.q0 * n, n * sizeof(int32_t),
+            SW_CUDA(h, cudaMemcpy2DAsync(scores + (size_t)qc.q0 * bt.ns + b.s0, bt.ns * sizeof(int32_t),
+                                         b.d_out.as<int32_t>() + (size_t)qc.q0 * n, n * sizeof(int32_t),
                                          n * sizeof(int32_t), (size_t)(qc.q1 - qc.q0), cudaMemcpyDeviceToHost,
                                          g.st_copy));
         }
     }
     double ms_max = 0.0;
     for (auto &g : h->gpus) {
+        Slot &b = g.slot[si];
         SW_CUDA(h, cudaSetDevice(g.dev));
         SW_CUDA(h, cudaStreamSynchronize(g.st_copy));
-        if (g.scored && (g.s1 > g.s0) && nq) {
-            SW_CUDA(h, cudaEventSynchronize(g.ev_stop));
+        if (b.scored && (b.s1 > b.s0) && nq) {
+            SW_CUDA(h, cudaEventSynchronize(b.ev_stop));
             float ms = 0.f;
-            SW_CUDA(h, cudaEventElapsedTime(&ms, g.ev_start, g.ev_stop));
+            SW_CUDA(h, cudaEventElapsedTime(&ms, b.ev_start, b.ev_stop));
             ms_max = std::max(ms_max, (double)ms);
         }
     }
     h->last_ms = ms_max;
+    h->last_cells = bt.cells;
+    h->last_slot = si;
+    return SW_OK;
+}
+
+int load_batch(sw_handle *h, int si, const uint8_t *packed, const uint32_t *len, const uint64_t *off,
+               const uint64_t *ids, size_t ns)
+{
+    Batch &bt = h->batch[si];
+    bt.ns = ns; bt.loaded = false; bt.scored = false; bt.cells = 0;
+    bt.have_ids = ids != nullptr;
+    if (ids) bt.ids.assign(ids, ids + ns); else bt.ids.clear();
+    const size_t ng = h->gpus.size();
+    std::vector<uint64_t> starts(ng + 1);
+    sw_plan_shards(len, ns, (int)ng, starts.data());
+    for (size_t gi = 0; gi < ng; ++gi) { h->gpus[gi].slot[si].s0 = starts[gi]; h->gpus[gi].slot[si].s1 = starts[gi + 1]; }
+    for (auto &g : h->gpus) {
+        int rc = load_shard(h, g, g.slot[si], packed, len, off);
+        if (rc != SW_OK) return rc;
+    }
+    // caller's buffers must be reusable on return
+    for (auto &g : h->gpus) {
+        SW_CUDA(h, cudaSetDevice(g.dev));
+        SW_CUDA(h, cudaStreamSynchronize(g.st_copy));
+    }
+    bt.loaded = true;
+    h->last_slot = si;
+    return SW_OK;
+}
+
+int score_batch_slot(sw_handle *h, int si)
+{
+    Batch &bt = h->batch[si];
+    uint64_t db_len = 0;
+    for (auto &g : h->gpus) db_len += g.slot[si].sum_len;
+    bt.cells = db_len * h->q_sum_len;
+    bt.nq = (int)h->q_len.size();
+    h->last_cells = bt.cells;
+    for (auto &g : h->gpus) {
+        int rc = score_gpu(h, g, g.slot[si]);
+        if (rc != SW_OK) return rc;
+    }
+    bt.scored = true;
     return SW_OK;
 }
 
@@ -546,9 +612,11 @@ int sw_init(sw_handle_t **out, const sw_params_t *p, const int *gpu_ids, int n_g
         }
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g.st_compute, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g.st_copy, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaEventCreate(&g.ev_start);
-        if (e == cudaSuccess) e = cudaEventCreate(&g.ev_stop);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g.ev_upload, cudaEventDisableTiming);
+        for (Slot &b : g.slot) {
+            if (e == cudaSuccess) e = cudaEventCreate(&b.ev_start);
+            if (e == cudaSuccess) e = cudaEventCreate(&b.ev_stop);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev_upload, cudaEventDisableTiming);
+        }
         if (e != cudaSuccess) {
             for (auto &gg : h->gpus) free_gpu(gg);
             delete h;
@@ -571,27 +639,53 @@ void sw_destroy(sw_handle_t *h)
     delete h;
 }
 
+int sw_set_strands(sw_handle_t *h, int both)
+{
+    if (!h) return SW_EINVAL;
+    if (h->n_inflight) return SW_EAGAIN;
+    h->both_strands = both != 0;
+    return SW_OK;
+}
+
 int sw_set_queries(sw_handle_t *h, const uint8_t *packed, const uint32_t *len, const uint64_t *off, int nq)
 {
     if (!h || nq < 0 || (nq > 0 && (!packed || !len || !off))) return SW_EINVAL;
-    if (h->batch_in_flight) return SW_EAGAIN;
+    if (h->n_inflight) return SW_EAGAIN;
     h->q_packed.clear(); h->q_off.clear(); h->q_len.clear();
     h->q_max_len = 0; h->q_sum_len = 0;
-    for (int i = 0; i < nq; ++i) {
-        const size_t bytes = ((size_t)len[i] + 3) / 4;
-        if (h->q_packed.size() + bytes > 0xFFFFFFF0ull) return SW_EINVAL;
-        h->q_off.push_back((uint32_t)h->q_packed.size());
-        h->q_len.push_back(len[i]);
-        h->q_packed.insert(h->q_packed.end(), packed + off[i], packed + off[i] + bytes);
-        h->q_max_len = std::max(h->q_max_len, len[i]);
-        h->q_sum_len += len[i];
+    h->nq_user = nq;
+    const int strands = h->both_strands ? 2 : 1;
+    for (int st = 0; st < strands; ++st) {
+        for (int i = 0; i < nq; ++i) {
+            const size_t bytes = ((size_t)len[i] + 3) / 4;
+            if (h->q_packed.size() + bytes > 0xFFFFFFF0ull) return SW_EINVAL;
+            h->q_off.push_back((uint32_t)h->q_packed.size());
+            h->q_len.push_back(len[i]);
+            const uint8_t *src = packed + off[i];
+            if (st == 0) {
+                h->q_packed.insert(h->q_packed.end(), src, src + bytes);
+                if (len[i] & 3) h->q_packed.back() &= (uint8_t)((1u << (2 * (len[i] & 3))) - 1u);
+            } else {
+                // reverse complement: A(10) <-> T(00), C(01) <-> G(11)  =  code ^ 2, order reversed
+                const size_t base = h->q_packed.size();
+                h->q_packed.resize(base + bytes, 0);
+                for (uint32_t k = 0; k < len[i]; ++k) {
+                    const uint32_t j = len[i] - 1 - k;
+                    const uint8_t c = (uint8_t)(((src[j >> 2] >> ((j & 3) * 2)) & 3) ^ 2);
+                    h->q_packed[base + (k >> 2)] |= (uint8_t)(c << ((k & 3) * 2));
+                }
+            }
+            h->q_max_len = std::max(h->q_max_len, len[i]);
+            h->q_sum_len += len[i];
+        }
     }
     h->q_packed.resize(h->q_packed.size() + 16, 0);
     for (auto &g : h->gpus) {
         int rc = upload_queries(h, g);
         if (rc != SW_OK) return rc;
-        g.scored = false;
+        for (Slot &b : g.slot) b.scored = false;
     }
+    for (Batch &bt : h->batch) bt.scored = false;
     return SW_OK;
 }
 
@@ -616,41 +710,16 @@ int sw_load_db(sw_handle_t *h, const uint8_t *packed, const uint32_t *len, const
                const uint64_t *ids, size_t ns)
 {
     if (!h || (ns > 0 && (!packed || !len || !off))) return SW_EINVAL;
-    if (h->batch_in_flight) return SW_EAGAIN;
-    h->ns = ns;
-    h->db_loaded = false;
-    h->have_ids = ids != nullptr;
-    if (ids) h->ids.assign(ids, ids + ns); else h->ids.clear();
-    // contiguous input ranges balanced by residue count (cells per query row)
-    const size_t ng = h->gpus.size();
-    std::vector<uint64_t> starts(ng + 1);
-    sw_plan_shards(len, ns, (int)ng, starts.data());
-    for (size_t gi = 0; gi < ng; ++gi) { h->gpus[gi].s0 = starts[gi]; h->gpus[gi].s1 = starts[gi + 1]; }
-    for (auto &g : h->gpus) {
-        int rc = load_shard(h, g, packed, len, off);
-        if (rc != SW_OK) return rc;
-    }
-    // caller's buffers must be reusable on return
-    for (auto &g : h->gpus) {
-        SW_CUDA(h, cudaSetDevice(g.dev));
-        SW_CUDA(h, cudaStreamSynchronize(g.st_copy));
-    }
-    h->db_loaded = true;
-    return SW_OK;
+    if (h->n_inflight) return SW_EAGAIN;
+    return load_batch(h, 0, packed, len, off, ids, ns);
 }
 
 int sw_score_db(sw_handle_t *h)
 {
     if (!h) return SW_EINVAL;
-    if (!h->db_loaded) return SW_ESTATE;
-    uint64_t db_len = 0;
-    for (auto &g : h->gpus) db_len += g.sum_len;
-    h->last_cells = db_len * h->q_sum_len;
-    for (auto &g : h->gpus) {
-        int rc = score_gpu(h, g);
-        if (rc != SW_OK) return rc;
-    }
-    return SW_OK;
+    if (h->n_inflight) return SW_EAGAIN;
+    if (!h->batch[0].loaded) return SW_ESTATE;
+    return score_batch_slot(h, 0);
 }
 
 int sw_wait(sw_handle_t *h, int timeout_ms)
@@ -660,88 +729,101 @@ int sw_wait(sw_handle_t *h, int timeout_ms)
     const auto t_end = std::chrono::steady_clock::now() + std::chrono::milliseconds(forever ? 0 : timeout_ms);
     double ms_max = 0.0;
     for (auto &g : h->gpus) {
-        if (!g.scored || g.chunks.empty()) continue;
+        Slot &b = g.slot[0];
+        if (!b.scored || b.chunks.empty()) continue;
         SW_CUDA(h, cudaSetDevice(g.dev));
-        int rc = wait_event(h, g.chunks.back().done, t_end, forever);
+        int rc = wait_event(h, b.chunks.back().done, t_end, forever);
         if (rc != SW_OK) return rc;
-        SW_CUDA(h, cudaEventSynchronize(g.ev_stop));
+        SW_CUDA(h, cudaEventSynchronize(b.ev_stop));
         float ms = 0.f;
-        SW_CUDA(h, cudaEventElapsedTime(&ms, g.ev_start, g.ev_stop));
+        SW_CUDA(h, cudaEventElapsedTime(&ms, b.ev_start, b.ev_stop));
         ms_max = std::max(ms_max, (double)ms);
     }
     h->last_ms = ms_max;
+    h->last_cells = h->batch[0].cells;
     return SW_OK;
 }
 
 int sw_fetch_db(sw_handle_t *h, int32_t *scores, size_t cap)
 {
     if (!h || !scores) return SW_EINVAL;
-    if (!h->db_loaded) return SW_ESTATE;
-    for (auto &g : h->gpus) if (!g.scored) return SW_ESTATE;
-    return copy_out(h, scores, cap, -1);
+    if (h->n_inflight) return SW_EAGAIN;
+    if (!h->batch[0].loaded || !h->batch[0].scored) return SW_ESTATE;
+    return copy_out(h, 0, scores, cap, -1);
 }
 
 int sw_score_batch(sw_handle_t *h, const uint8_t *packed, const uint32_t *len, const uint64_t *off,
                    const uint64_t *ids, size_t ns)
 {
-    if (!h) return SW_EINVAL;
-    if (h->batch_in_flight) return SW_EAGAIN;
-    int rc = sw_load_db(h, packed, len, off, ids, ns);
+    if (!h || (ns > 0 && (!packed || !len || !off))) return SW_EINVAL;
+    if (h->n_inflight >= 2) return SW_EAGAIN;          // both buffers busy: the bank's `full`
+    // take the slot that is not in flight; this replaces whatever sw_load_db left there
+    const int si = (h->n_inflight == 1) ? (1 - h->fifo[0]) : 0;
+    int rc = load_batch(h, si, packed, len, off, ids, ns);
     if (rc != SW_OK) return rc;
-    rc = sw_score_db(h);
+    rc = score_batch_slot(h, si);
     if (rc != SW_OK) return rc;
-    h->batch_in_flight = true;
+    h->fifo[h->n_inflight++] = si;
     return SW_OK;
 }
 
 int sw_fetch(sw_handle_t *h, int32_t *scores, size_t cap, int timeout_ms)
 {
     if (!h || (!scores && cap)) return SW_EINVAL;
-    if (!h->batch_in_flight) return SW_ESTATE;
-    int rc = copy_out(h, scores, cap, timeout_ms);
-    if (rc == SW_ETIMEOUT) return rc;          // batch stays in flight; fetch again later
-    h->batch_in_flight = false;
+    if (h->n_inflight == 0) return SW_ESTATE;
+    const int si = h->fifo[0];
+    int rc = copy_out(h, si, scores, cap, timeout_ms);
+    if (rc == SW_ETIMEOUT || rc == SW_ECAPACITY) return rc;   // batch stays in flight; fetch again
+    h->fifo[0] = h->fifo[1];
+    h->n_inflight--;
     return rc;
 }
+
+int sw_batches_in_flight(const sw_handle_t *h) { return h ? h->n_inflight : 0; }
 
 int sw_fetch_ids(sw_handle_t *h, uint64_t *ids, size_t cap)
 {
     if (!h || !ids) return SW_EINVAL;
-    if (cap < h->ns) return SW_ECAPACITY;
-    for (size_t s = 0; s < h->ns; ++s) ids[s] = h->have_ids ? h->ids[s] : (uint64_t)s;
+    const Batch &bt = h->batch[h->last_slot];
+    if (cap < bt.ns) return SW_ECAPACITY;
+    for (size_t s = 0; s < bt.ns; ++s) ids[s] = bt.have_ids ? bt.ids[s] : (uint64_t)s;
     return SW_OK;
 }
 
 int sw_fetch_best(sw_handle_t *h, int32_t *best_score, uint64_t *best_index, int nq_cap)
 {
     if (!h || !best_score || !best_index) return SW_EINVAL;
-    const int nq = (int)h->q_len.size();
+    if (h->n_inflight) return SW_EAGAIN;
+    const Batch &bt = h->batch[0];
+    const int nq = bt.nq;
+    if (!bt.loaded || !bt.scored) return SW_ESTATE;
     if (nq_cap < nq) return SW_ECAPACITY;
-    if (!h->db_loaded) return SW_ESTATE;
-    for (auto &g : h->gpus) if (!g.scored) return SW_ESTATE;
     for (int q = 0; q < nq; ++q) { best_score[q] = 0; best_index[q] = 0; }
     std::vector<int32_t> hs(nq);
     std::vector<uint32_t> hi(nq);
     bool first = true;
     for (auto &g : h->gpus) {
-        const size_t n = g.s1 - g.s0;
+        Slot &b = g.slot[0];
+        const size_t n = b.s1 - b.s0;
         if (n == 0 || nq == 0) continue;
         SW_CUDA(h, cudaSetDevice(g.dev));
         SW_CUDA(h, g.d_best_score.reserve(nq * sizeof(int32_t)));
         SW_CUDA(h, g.d_best_index.reserve(nq * sizeof(uint32_t)));
-        SW_CUDA(h, sw_launch_best(g.st_compute, g.d_out.as<int32_t>(), n, (uint32_t)n, nq,
+        SW_CUDA(h, sw_launch_best(g.st_compute, b.d_out.as<int32_t>(), n, (uint32_t)n, nq,
                                   g.d_best_score.as<int32_t>(), g.d_best_index.as<uint32_t>()));
         h->launches++;
         SW_CUDA(h, cudaMemcpyAsync(hs.data(), g.d_best_score.p, nq * sizeof(int32_t), cudaMemcpyDeviceToHost, g.st_compute));
         SW_CUDA(h, cudaMemcpyAsync(hi.data(), g.d_best_index.p, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost, g.st_compute));
         SW_CUDA(h, cudaStreamSynchronize(g.st_compute));
         for (int q = 0; q < nq; ++q) {
-            if (first || hs[q] > best_score[q]) { best_score[q] = hs[q]; best_index[q] = g.s0 + hi[q]; }
+            if (first || hs[q] > best_score[q]) { best_score[q] = hs[q]; best_index[q] = b.s0 + hi[q]; }
         }
         first = false;
     }
     return SW_OK;
 }
+
+int sw_query_rows(const sw_handle_t *h) { return h ? (int)h->q_len.size() : 0; }
 
 int sw_last_cuda_error(const sw_handle_t *h) { return h ? h->last_cuda : 0; }
 const char *sw_last_cuda_error_string(const sw_handle_t *h)

@@ -270,11 +270,16 @@ def test_state_errors_and_timeout(pkg):
         assert ei.value.code == pkg.SW_ESTATE
         e.set_queries(["ACGT" * 30])
         e.score_batch(["ACGT" * 30] * 10)
+        e.score_batch(["ACGT" * 30] * 3)               # second buffer
+        assert e.batches_in_flight == 2
         with pytest.raises(pkg.SwError) as ei:
             e.score_batch(["ACGT"])
-        assert ei.value.code == pkg.SW_EAGAIN          # the bank's `full`
+        assert ei.value.code == pkg.SW_EAGAIN          # both buffers busy: the bank's `full`
+        e._batch_ns.pop()                              # (the refused batch was never queued)
         out = e.fetch(timeout_ms=10000)
         assert out[0].tolist() == [600] * 10
+        assert e.fetch(timeout_ms=10000)[0].tolist() == [600] * 3
+        assert e.batches_in_flight == 0
     with pytest.raises(pkg.SwError) as ei:
         pkg.Engine(gap_extend=3)
     assert ei.value.code == pkg.SW_EINVAL
@@ -342,3 +347,40 @@ def test_config5_mixed_length_sweep_vs_oracle(oracle_mod, pkg):
         got = e.score(queries, subjects)
     np.testing.assert_array_equal(got, want)
     assert 7960 <= want[4, -1] < 8000                       # 1600 matches minus one gap of ~4 residues
+
+
+def test_streaming_double_buffered_batches(oracle_mod, pkg):
+    """Streaming database mode: batches are submitted ahead of the fetch of the
+    previous one; results come back in submission order and equal the one-shot result."""
+    rng = random.Random(31)
+    queries = [_rand(rng, 150) for _ in range(3)]
+    batches = [[_rand(rng, rng.randint(1, 220)) for _ in range(n)] for n in (700, 1, 350, 0, 512)]
+    want = [_oracle_matrix(oracle_mod, pkg, queries, b) if b else np.zeros((3, 0), np.int32) for b in batches]
+    with pkg.Engine() as e:
+        e.set_queries(queries)
+        got = []
+        e.score_batch(batches[0], ids=np.arange(700, dtype=np.uint64) + 7)
+        for k in range(1, len(batches)):
+            e.score_batch(batches[k])                  # batch k is enqueued ...
+            assert e.batches_in_flight == 2
+            got.append(e.fetch())                      # ... before batch k-1 is fetched
+        got.append(e.fetch())
+        assert e.batches_in_flight == 0
+    for g, w in zip(got, want):
+        np.testing.assert_array_equal(g, w)
+
+
+def test_both_strands(oracle_mod, pkg):
+    rng = random.Random(32)
+    comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+    queries = [_rand(rng, n) for n in (31, 150, 77)]
+    rc = ["".join(comp[c] for c in reversed(q)) for q in queries]
+    subjects = [_rand(rng, rng.randint(20, 200)) for _ in range(200)]
+    subjects += [rc[1][10:120], queries[2][5:70], rc[0]]
+    want = _oracle_matrix(oracle_mod, pkg, queries + rc, subjects)
+    with pkg.Engine() as e:
+        e.set_strands(True)
+        got = e.score(queries, subjects)
+        assert got.shape == (6, len(subjects))
+    np.testing.assert_array_equal(got, want)
+    assert got[4, 200] == 5 * 110 and got[3, 202] == 5 * 31
