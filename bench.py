@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--rows", type=int, default=0, help="force rows-per-lane of the strip kernel")
     ap.add_argument("--lanes", type=int, default=0, help="force lanes-per-pair of the strip kernel")
-    ap.add_argument("--arith", type=int, default=-1, help="-1 auto, 0 s16x2, 1 f16x2")
+    ap.add_argument("--arith", type=int, default=-1, help="-1 auto, 0 s16x2")
     ap.add_argument("--kernel", default="", help="force a strip-kernel variant by name")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -291,11 +291,10 @@ def main():
         per_gpu = gcups / world
         # algorithmic HBM bytes per step and GPU: column-code stream once per query chunk (8 launches)
         # + one int32 score per pair written once
-        arith = ("f16x2" if "f16x2" in kname else "s16x2+f16x2" if "hyb16" in kname else
-                 "s16x2" if "s16x2" in kname else "int32")
+        arith = "s16x2" if "s16x2" in kname else "int32"
         # ALU-pipe instructions per cell pair of the chosen kernel (DESIGN.md "roofline"): the other
         # instructions of the recurrence run on the FMA-side pipe and overlap
-        alu_per_pair = {"f16x2": 3.5, "s16x2+f16x2": 3.5, "s16x2": 4.5, "int32": 12.0}[arith]
+        alu_per_pair = {"s16x2": 3.5, "int32": 12.0}[arith]
         tight_gcups = SM_COUNT * pk["sm_max_mhz"] * 1e6 * R_INT * 2.0 / alu_per_pair / 1e9
         # per launch: the pair's code stream (19 words) + pair_len + pair_subj, read once; per step 8 launches
         # plus one int32 score per (query, subject) written once

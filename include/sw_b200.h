@@ -152,8 +152,8 @@ const char *sw_last_kernel_name(const sw_handle_t *h);
  * rows_per_lane in {0=auto, ...}, lanes_per_pair in {0=auto,1,2,4,8,16,32},
  * force32 != 0 forces the 32-bit fallback kernel. */
 int sw_set_kernel_choice(sw_handle_t *h, int rows_per_lane, int lanes_per_pair, int force32);
-/* arith: -1 = automatic, 0 = packed signed 16-bit (DPX), 1 = packed fp16 (exact while the
- * largest possible score is <= 2048; rejected with SW_EINVAL otherwise). */
+/* arith: -1 = automatic, 0 = packed signed 16-bit (DPX).  Other arithmetic policies were
+ * measured and dropped; anything else is SW_EINVAL. */
 int sw_set_arith(sw_handle_t *h, int arith);
 /* The strip-kernel variants compiled into the library, and forcing one by name
  * (NULL or "" = back to automatic).  Names look like "strip_s16x2_R25x2_G1":

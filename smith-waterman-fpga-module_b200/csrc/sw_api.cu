@@ -300,16 +300,13 @@ SwDevDb dev_db(const Slot &g)
 double variant_speed(const SwStripVariant *v)
 {
     struct { const char *name; double gcups; } tab[] = {
-        {"strip_s16x2_R32x1_G1", 6500}, {"strip_s16x2_R50x1_G1", 6750}, {"strip_s16x2_R25x2_G1", 7350},
-        {"strip_s16x2_R25x1_G2", 5690}, {"strip_s16x2_R64x1_G1", 6800}, {"strip_s16x2_R32x2_G1", 6800},
-        {"strip_s16x2_R75x1_G2", 5570}, {"strip_s16x2_R25x3_G2", 6100}, {"strip_s16x2_R25x3_G1", 7430},
-        {"strip_s16x2_R38x2_G1", 7250}, {"strip_s16x2_R38x1_G4", 5170}, {"strip_s16x2_R19x2_G4", 5000},
-        {"strip_s16x2_R32x1_G4", 5110}, {"strip_s16x2_R16x1_G32", 4050}, {"strip_s16x2_R8x2_G32", 4130},
-        {"strip_f16x2_R50x1_G1", 7250}, {"strip_f16x2_R25x2_G1", 7480}, {"strip_f16x2_R25x1_G2", 6090},
-        {"strip_f16x2_R38x1_G4", 5120}, {"strip_f16x2_R19x2_G4", 5100}, {"strip_f16x2_R25x3_G1", 7170},
-        {"strip_hyb16_R50x1_G1", 6825}, {"strip_hyb16_R25x2_G1", 7305}, {"strip_hyb16_R32x2_G1", 7930},
-        {"strip_hyb16_R25x1_G2", 6270}, {"strip_hyb16_R38x1_G4", 6060}, {"strip_hyb16_R38x2_G1", 7640},
-        {"strip_hyb16_R25x3_G1", 7750}, {"strip_hyb16_R30x1_G1", 7225}, {"strip_hyb16_R19x4_G1", 7480},
+        {"strip_s16x2_R32x1_G1", 8090}, {"strip_s16x2_R50x1_G1", 7800}, {"strip_s16x2_R25x2_G1", 8260},
+        {"strip_s16x2_R19x2_G1", 7790}, {"strip_s16x2_R15x3_G1", 7685}, {"strip_s16x2_R30x2_G1", 7890},
+        {"strip_s16x2_R64x1_G1", 7770}, {"strip_s16x2_R32x2_G1", 8360}, {"strip_s16x2_R25x3_G1", 8090},
+        {"strip_s16x2_R38x2_G1", 8340}, {"strip_s16x2_R25x4_G1", 7320}, {"strip_s16x2_R25x1_G2", 6890},
+        {"strip_s16x2_R75x1_G2", 7425}, {"strip_s16x2_R25x3_G2", 7295}, {"strip_s16x2_R38x1_G4", 7205},
+        {"strip_s16x2_R19x2_G4", 7130}, {"strip_s16x2_R32x1_G4", 7070}, {"strip_s16x2_R16x1_G32", 6005},
+        {"strip_s16x2_R8x2_G32", 6410},
     };
     for (auto &t : tab) if (std::strcmp(t.name, v->name) == 0) return t.gcups;
     return 5000.0;
@@ -317,15 +314,14 @@ double variant_speed(const SwStripVariant *v)
 
 // Picks the strip variant: least estimated time = padded rows x (columns + pipeline fill)
 // / measured speed / fraction of the GPU the pairs can keep busy.
-int choose_variant(const sw_handle *h, const GpuCtx &gc, const Slot &g, uint32_t maxq, bool allow_f16)
+int choose_variant(const sw_handle *h, const GpuCtx &gc, const Slot &g, uint32_t maxq)
 {
     const int nv = sw_strip_variant_count();
     if (h->force_variant >= 0) return h->force_variant;
     if (h->force_R || h->force_G) {
-        const int want_arith = h->force_arith >= 0 ? h->force_arith : 0;
         for (int i = 0; i < nv; ++i) {
             const SwStripVariant *v = sw_strip_variant(i);
-            if (v->arith == want_arith && (!h->force_R || v->R == h->force_R) && (!h->force_G || v->G == h->force_G))
+            if ((!h->force_R || v->R == h->force_R) && (!h->force_G || v->G == h->force_G))
                 return i;
         }
         return -1;
@@ -334,8 +330,6 @@ int choose_variant(const sw_handle *h, const GpuCtx &gc, const Slot &g, uint32_t
     double best_cost = 0;
     for (int i = 0; i < nv; ++i) {
         const SwStripVariant *v = sw_strip_variant(i);
-        if (v->arith != 0 && !allow_f16) continue;
-        if (h->force_arith >= 0 && v->arith != h->force_arith) continue;
         const int P = v->R * v->G;
         const double rows = (double)((maxq + P - 1) / P) * P;
         const double lanes = (double)g.npairs * v->G;
@@ -383,13 +377,10 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
     // value range: exact s16 needs match * min(m, n) to stay clear of 32767
     const uint64_t smax = (uint64_t)sc.match * std::min<uint64_t>(h->q_max_len, g.max_len);
     const bool fits16 = sc.limit ? true : (smax + (uint64_t)sc.match < 32000ull);
-    const bool fitsf16 = !sc.limit && smax + (uint64_t)sc.match <= 2047ull;
     int vidx = -1;
     if (!h->force32 && fits16) {
-        if (h->force_arith >= 1 && !fitsf16) return SW_EINVAL;
-        vidx = choose_variant(h, gc, g, h->q_max_len, fitsf16);
+        vidx = choose_variant(h, gc, g, h->q_max_len);
         if (vidx < 0 && (h->force_R || h->force_G)) return SW_EINVAL;
-        if (vidx >= 0 && sw_strip_variant(vidx)->arith != 0 && !fitsf16) return SW_EINVAL;
     }
 
     // query chunks: a handful of launches so that D2H of finished rows overlaps compute
@@ -861,7 +852,7 @@ int sw_set_kernel_name(sw_handle_t *h, const char *name)
 
 int sw_set_arith(sw_handle_t *h, int arith)
 {
-    if (!h || arith < -1 || arith > 2) return SW_EINVAL;
+    if (!h || arith < -1 || arith > 0) return SW_EINVAL;     /* only packed s16 is compiled in */
     h->force_arith = arith;
     return SW_OK;
 }

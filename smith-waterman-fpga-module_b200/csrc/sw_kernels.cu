@@ -14,8 +14,8 @@
  *   - two subjects of equal length share every 32-bit register (low / high 16-bit lane) --
  *     the PE's toggle-0 / toggle-1 sequences;
  *   - a lane keeps R consecutive query rows of H and G in registers and walks the subject
- *     columns; per cell pair the arithmetic is 4.5 ALU-pipe + 1 FMA-pipe instructions
- *     (VIADDMNMX.S16x2.RELU, VIMNMX.S16x2 x2, VIADDMNMX.S16x2, 1/2 VIMNMX3.S16x2; VIADD.16x2);
+ *     columns; per cell pair the arithmetic is 3.5 ALU-pipe + 1 FMA-pipe instructions
+ *     (VIMNMX.S16x2, VIADDMNMX.S16x2.RELU, VIADDMNMX.S16x2, 1/2 VIMNMX3.S16x2; VIADD.16x2);
  *   - G lanes of a warp form a systolic group over R*G rows: lane l is one column behind
  *     lane l-1 and receives (H, G, column code) with __shfl_up_sync, exactly like
  *     M_in / I_in / data_in travel from PE to PE;
@@ -29,9 +29,6 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 
-#ifndef SW_MPASS_BOTTOM_UP
-#define SW_MPASS_BOTTOM_UP 0
-#endif
 #ifndef SW_STEP_UNROLL
 #define SW_STEP_UNROLL 4      /* columns per trip of the step loop; nsteps is rounded up to a multiple */
 #endif
@@ -39,7 +36,6 @@
 namespace {
 
 constexpr int kPadScoreS16 = -8192;   // profile value of padding rows: M becomes 0, nothing can grow
-constexpr int kPadScoreF16 = -2048;
 
 // ------------------------------------------------------------------------------------------
 // Arithmetic policies.  Both pack two independent lanes into one 32-bit register.
@@ -72,77 +68,6 @@ struct ArithS16 {
     }
 };
 
-struct ArithF16 {
-    static constexpr int kPad = kPadScoreF16;
-    static constexpr bool kClampForm = false;
-    static __device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) { return addmax(a, b, c); }
-    static __device__ __forceinline__ uint32_t pack(int lo, int hi) {
-        __half2 h = __halves2half2(__int2half_rn(lo), __int2half_rn(hi));
-        return *reinterpret_cast<uint32_t *>(&h);
-    }
-    static __device__ __forceinline__ uint32_t pack_score(int lo, int hi) { return pack(lo, hi); }
-    static __device__ __forceinline__ int extract(uint32_t v, int h) {
-        __half2 x = *reinterpret_cast<__half2 *>(&v);
-        return __half2int_rn(h ? __high2half(x) : __low2half(x));
-    }
-    static __device__ __forceinline__ uint32_t add_relu(uint32_t a, uint32_t b, uint32_t) {
-        uint32_t d;
-        const uint32_t one = 0x3C003C00u;
-        asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
-        return d;
-    }
-    static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) {
-        uint32_t d;
-        asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-        return d;
-    }
-    static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
-        uint32_t d;
-        asm("max.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
-        return d;
-    }
-    static __device__ __forceinline__ uint32_t addmax(uint32_t a, uint32_t b, uint32_t c) {
-        return max2(add(a, b), c);
-    }
-    static __device__ __forceinline__ uint32_t wrap_clamp(uint32_t m, uint32_t) { return m; }
-};
-
-// Hybrid: every value is a plain packed s16 integer, but M = max(H_diag + s, 0) is computed by
-// HFMA2.RELU on the FMA-side pipe.  This is exact because an fp16 whose bit pattern is the
-// integer v (0 <= v < 2048) has the value v * 2^-24 (subnormals and the first normal binade are
-// linear in their bit pattern), fp16 add/fma of such numbers is exact while the result stays
-// below 2048, and relu() returns +0 for every negative sum.  Only the substitution score (the
-// one operand that can be negative) is stored sign-magnitude, i.e. as the fp16 -|s| * 2^-24.
-// M and H are never negative, so the integer DPX instructions (ALU pipe) read them unchanged.
-// Per cell pair: 3.5 ALU-pipe + 2 FMA-pipe instructions.  Valid while the best possible score
-// is <= 2047 -- the same range the reference's 12-bit datapath has.
-struct ArithHyb {
-    static constexpr int kPad = -2047;
-    static constexpr bool kClampForm = false;
-    static __device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) {
-        return __viaddmax_s16x2_relu(a, b, c);
-    }
-    static __device__ __forceinline__ uint32_t pack(int lo, int hi) { return ArithS16::pack(lo, hi); }
-    static __device__ __forceinline__ uint32_t pack_score(int lo, int hi) {
-        const uint32_t l = lo >= 0 ? (uint32_t)lo : (0x8000u | (uint32_t)(-lo));
-        const uint32_t h = hi >= 0 ? (uint32_t)hi : (0x8000u | (uint32_t)(-hi));
-        return l | (h << 16);
-    }
-    static __device__ __forceinline__ int extract(uint32_t v, int h) { return ArithS16::extract(v, h); }
-    static __device__ __forceinline__ uint32_t add_relu(uint32_t a, uint32_t b, uint32_t) {
-        uint32_t d;
-        const uint32_t one = 0x3C003C00u;
-        asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
-        return d;
-    }
-    static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return __vadd2(a, b); }
-    static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
-    static __device__ __forceinline__ uint32_t addmax(uint32_t a, uint32_t b, uint32_t c) {
-        return __viaddmax_s16x2(a, b, c);
-    }
-    static __device__ __forceinline__ uint32_t wrap_clamp(uint32_t m, uint32_t) { return m; }
-};
-
 struct StripArgs {
     const uint32_t *tp;
     const uint64_t *tile_woff;
@@ -173,7 +98,7 @@ constexpr int kCodesPerRow = 32;    // profile entries per row pair (codes 0..16
 // thread).  H[s][r] / Gl[s][r] hold H and G of the previous column on entry and of this column
 // on exit; hd_top = H(row0-1, c-1), g_top = G(row0-1, c); prow[s] points at the profile entry
 // of (first row pair of the sub-strip, this column's code), one uint2 = two consecutive rows.
-template <int RS, int S, class AR, bool W12>
+template <int RS, int S, int G, class AR, bool W12>
 __device__ __forceinline__ void column_step_multi(uint32_t (&H)[S][RS], uint32_t (&Gl)[S][RS], uint32_t &best,
                                                   const uint32_t (&hd_top)[S], const uint32_t (&g_top)[S],
                                                   const uint2 *const (&prow)[S], uint32_t goe2,
@@ -185,17 +110,18 @@ __device__ __forceinline__ void column_step_multi(uint32_t (&H)[S][RS], uint32_t
 #pragma unroll
     for (int s = 0; s < S; ++s)
 #pragma unroll
-        for (int k = 0; k < RP; ++k) sv[s][k] = prow[s][k * kCodesPerRow];
+        for (int k = 0; k < RP; ++k) sv[s][k] = prow[s][k * kCodesPerRow * G];
     if (AR::kClampForm && !W12) {
-        // Clamped form (exact): every gap value is clamped at 0 -- non-positive
-        // gap values can never reach H because M >= 0 -- and then
-        //     t = H(r-1,c-1) + s                      (FMA-side pipe, may be negative)
-        //     I = max(G_left, G_up)      >= 0
-        //     G = max(t + goe, I + ge, 0)             one VIADDMNMX.RELU
-        //     H = max(t, I)              = max(max(t,0), I) because I >= 0
-        // so M = max(t, 0) is never materialised: 3.5 ALU-pipe + 2 FMA-pipe instructions per
-        // cell pair over the full 16-bit range.  t of row r+1 is formed one row ahead from the
-        // still-old H[r], so H[r] can be overwritten in place.
+        // Clamped, goe-shifted form (exact).  Every gap value is clamped at 0
+        // (non-positive gap values can never reach H because M >= 0) and the register strip holds
+        // K = H + goe instead of H.  With tg = K(r-1,c-1) + s  (= H_diag + s + goe):
+        //     I = max(G_left, G_up)            >= 0                 VIMNMX
+        //     G = max(I + ge, tg, 0)                                VIADDMNMX.RELU
+        //     K = max(I + goe, tg)    (= max(I, H_diag + s) + goe)  VIADDMNMX
+        // M = max(H_diag + s, 0) is never materialised (I >= 0 does the clamping) and both adds
+        // of the gap path are fused: 3.5 ALU-pipe + 1 FMA-pipe instruction per cell pair.
+        // tg of row r+1 is formed one row ahead from the still-old H[r], so H[r] is overwritten
+        // in place.  The reported score is max K - goe.
         uint32_t gu[S], t_cur[S];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
@@ -212,44 +138,15 @@ __device__ __forceinline__ void column_step_multi(uint32_t (&H)[S][RS], uint32_t
                     t_next = AR::add(H[s][r], sc);
                 }
                 const uint32_t i_ = AR::max2(Gl[s][r], gu[s]);
-                const uint32_t j_ = AR::add(i_, ge2);
-                gu[s] = AR::addmax_relu(t_cur[s], goe2, j_);
+                gu[s] = AR::addmax_relu(i_, ge2, t_cur[s]);
                 Gl[s][r] = gu[s];
-                H[s][r] = AR::max2(t_cur[s], i_);
+                H[s][r] = AR::addmax(i_, goe2, t_cur[s]);
                 best = AR::max2(best, H[s][r]);
                 t_cur[s] = t_next;
             }
         }
         return;
     }
-#if SW_MPASS_BOTTOM_UP
-    // M pass, bottom-up and in place: H[r] <- M(r, c) = relu(H(r-1, c-1) + s(r, c))
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-#pragma unroll
-        for (int r = RS - 1; r >= 0; --r) {
-            const uint32_t sc = (r & 1) ? sv[s][r >> 1].y : sv[s][r >> 1].x;
-            uint32_t m = AR::add_relu(r ? H[s][r - 1] : hd_top[s], sc, zero);
-            if (W12) m = AR::wrap_clamp(m, lim2);
-            H[s][r] = m;
-        }
-    }
-    uint32_t gu[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) gu[s] = g_top[s];
-#pragma unroll
-    for (int r = 0; r < RS; ++r) {
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const uint32_t i_ = AR::max2(Gl[s][r], gu[s]);
-            const uint32_t j_ = AR::add(i_, ge2);
-            gu[s] = AR::addmax(H[s][r], goe2, j_);
-            Gl[s][r] = gu[s];
-            H[s][r] = AR::max2(H[s][r], i_);
-            best = AR::max2(best, H[s][r]);
-        }
-    }
-#else
     // Single top-down sweep.  M of row r+1 is formed one row ahead, from the still-old H[r]
     // (= H(r, c-1), its diagonal), so that H[r] can then be overwritten in place.
     uint32_t gu[S], m_cur[S];
@@ -280,7 +177,6 @@ __device__ __forceinline__ void column_step_multi(uint32_t (&H)[S][RS], uint32_t
             m_cur[s] = m_next;
         }
     }
-#endif
 }
 
 // RS rows per sub-strip, S sub-strips per lane, G lanes per pair: R = RS*S rows per lane,
@@ -311,6 +207,8 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
     const int gbv = (AR::kClampForm && !W12) ? 0 : (a.goe > a.ge ? a.goe : a.ge);
     const uint32_t gb2 = AR::pack(gbv, gbv);
     const uint32_t lim2 = AR::pack(a.limit, a.limit);
+    // value of "H = 0" in the strip's representation (K = H + goe in the clamped form)
+    const uint32_t h0 = (AR::kClampForm && !W12) ? goe2 : zero;
     uint2 *bnd = a.bnd + (size_t)blockIdx.x * a.bnd_cols * PPB + pslot;
 
     for (;;) {
@@ -339,7 +237,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
             const int m = (int)a.qlen[q];
             const uint8_t *qp = a.qpacked + a.qoff[q];
             const int npass = (m + P - 1) / P;
-            uint32_t best = zero;
+            uint32_t best = h0;
 
             for (int pass = 0; pass < npass; ++pass) {
                 const int pass_in_chunk = pass % a.chunk_passes;
@@ -349,11 +247,15 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                     __syncthreads();
                     const int npc = min(a.chunk_passes, npass - pass);
                     for (int idx = threadIdx.x; idx < npc * PASS_ENTRIES; idx += BT) {
-                        const int code = idx & (kCodesPerRow - 1);
+                        // layout: (((pass * S + s) * RP + rp) * 32 + code) * G + gl -- the G lanes of a
+                        // group sit in consecutive 8-byte slots, so a warp-wide group reads 32 banks
+                        const int lg = idx % G;
+                        const int code = (idx / G) & (kCodesPerRow - 1);
                         if (code > kPadCode) continue;
-                        const int rp = (idx / kCodesPerRow) % RP;
-                        const int vpe = (idx / (kCodesPerRow * RP)) % VPE;
+                        const int rp = (idx / (G * kCodesPerRow)) % RP;
+                        const int ss = (idx / (G * kCodesPerRow * RP)) % S;
                         const int pc = idx / PASS_ENTRIES;
+                        const int vpe = lg * S + ss;
                         uint32_t e[2];
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {
@@ -371,7 +273,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                     }
                     __syncthreads();
                 }
-                const uint2 *prof_lane = s_prof + (pass_in_chunk * VPE + gl * S) * RP * kCodesPerRow;
+                const uint2 *prof_lane = s_prof + (size_t)pass_in_chunk * PASS_ENTRIES + gl;
                 const bool has_top = pass > 0;
                 const bool has_bottom = pass + 1 < npass;
 
@@ -379,10 +281,10 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
 #pragma unroll
                 for (int s = 0; s < S; ++s)
 #pragma unroll
-                    for (int r = 0; r < RS; ++r) { H[s][r] = zero; Gl[s][r] = gb2; }
+                    for (int r = 0; r < RS; ++r) { H[s][r] = h0; Gl[s][r] = gb2; }
 
                 uint32_t wcur = 0, wnext = 0;
-                uint2 bcur = make_uint2(zero, gb2);          // (H, G) of the row above, column c
+                uint2 bcur = make_uint2(h0, gb2);            // (H, G) of the row above, column c
                 if (gl == 0 && ncols > 0) {
                     wcur = __ldg(tpp);
                     if (ncols > 8) wnext = __ldg(tpp + 32);
@@ -392,7 +294,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                 // s = S-1 the next lane): bottom H, bottom G and the column code it just used
                 uint32_t pub_h[S], pub_g[S], pub_t[S], hd_top[S];
 #pragma unroll
-                for (int s = 0; s < S; ++s) { pub_h[s] = zero; pub_g[s] = gb2; pub_t[s] = kPadCode; hd_top[s] = zero; }
+                for (int s = 0; s < S; ++s) { pub_h[s] = h0; pub_g[s] = gb2; pub_t[s] = kPadCode; hd_top[s] = h0; }
 
 #pragma unroll 1
                 for (int t2 = 0; t2 < nsteps; t2 += U) {
@@ -426,8 +328,8 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
 
                     const uint2 *prow[S];
 #pragma unroll
-                    for (int s = 0; s < S; ++s) prow[s] = prof_lane + s * RP * kCodesPerRow + in_t[s];
-                    column_step_multi<RS, S, AR, W12>(H, Gl, best, hd_top, in_g, prow, goe2, ge2, zero, lim2);
+                    for (int s = 0; s < S; ++s) prow[s] = prof_lane + (s * RP * kCodesPerRow + in_t[s]) * G;
+                    column_step_multi<RS, S, G, AR, W12>(H, Gl, best, hd_top, in_g, prow, goe2, ge2, zero, lim2);
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
                         hd_top[s] = in_h[s];
@@ -446,8 +348,9 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
             for (int o = G / 2; o >= 1; o >>= 1) best = AR::max2(best, __shfl_xor_sync(FULL, best, o));
             if (gl == 0 && valid) {
                 int32_t *orow = a.out + (size_t)q * a.out_stride;
-                orow[subj_lo] = AR::extract(best, 0);
-                if (subj_hi != SW_NO_SUBJECT) orow[subj_hi] = AR::extract(best, 1);
+                const int shift = (AR::kClampForm && !W12) ? a.goe : 0;
+                orow[subj_lo] = AR::extract(best, 0) - shift;
+                if (subj_hi != SW_NO_SUBJECT) orow[subj_hi] = AR::extract(best, 1) - shift;
             }
         }
     }
@@ -600,57 +503,30 @@ struct VariantEntry {
 };
 
 #define SW_VARIANT_S16(RS, S, G, MINB)                                                          \
-    { {RS * S, G, 0, kBT, S, MINB, "strip_s16x2_R" #RS "x" #S "_G" #G},                         \
+    { {RS * S, G, kBT, S, MINB, "strip_s16x2_R" #RS "x" #S "_G" #G},                            \
       sw_strip_kernel<RS, S, G, ArithS16, false, kBT, MINB>, sw_strip_kernel<RS, S, G, ArithS16, true, kBT, MINB> }
-#define SW_VARIANT_F16(RS, S, G, MINB)                                                          \
-    { {RS * S, G, 1, kBT, S, MINB, "strip_f16x2_R" #RS "x" #S "_G" #G},                         \
-      sw_strip_kernel<RS, S, G, ArithF16, false, kBT, MINB>, nullptr }
-
-#define SW_VARIANT_HYB(RS, S, G, MINB)                                                          \
-    { {RS * S, G, 2, kBT, S, MINB, "strip_hyb16_R" #RS "x" #S "_G" #G},                         \
-      sw_strip_kernel<RS, S, G, ArithHyb, false, kBT, MINB>, nullptr }
-
-// experimental: explicit block size and step unroll, tagged in the name
-#define SW_VARIANT_HYB_X(RS, S, G, MINB, BT_, U_)                                               \
-    { {RS * S, G, 2, BT_, S, MINB, "strip_hyb16_R" #RS "x" #S "_G" #G "_b" #BT_ "u" #U_},       \
-      sw_strip_kernel<RS, S, G, ArithHyb, false, BT_, MINB, U_>, nullptr }
-
-// smaller blocks = smaller work items (32 / 64 pairs): better packing when subjects are long
-#define SW_VARIANT_S16_B(RS, S, G, MINB, BT_)                                                   \
-    { {RS * S, G, 0, BT_, S, MINB, "strip_s16x2_R" #RS "x" #S "_G" #G "_b" #BT_},               \
-      sw_strip_kernel<RS, S, G, ArithS16, false, BT_, MINB>, sw_strip_kernel<RS, S, G, ArithS16, true, BT_, MINB> }
-
 const VariantEntry g_variants[] = {
+    // one lane per subject pair (inter-task): RS rows x S sub-strips per lane
     SW_VARIANT_S16(32, 1, 1, 4),
     SW_VARIANT_S16(50, 1, 1, 3),
     SW_VARIANT_S16(25, 2, 1, 3),
-    SW_VARIANT_S16(25, 1, 2, 5),
+    SW_VARIANT_S16(19, 2, 1, 4),
+    SW_VARIANT_S16(15, 3, 1, 4),
+    SW_VARIANT_S16(30, 2, 1, 3),
     SW_VARIANT_S16(64, 1, 1, 2),
     SW_VARIANT_S16(32, 2, 1, 2),
-    SW_VARIANT_S16(75, 1, 2, 2),
-    SW_VARIANT_S16(25, 3, 2, 2),
     SW_VARIANT_S16(25, 3, 1, 2),
     SW_VARIANT_S16(38, 2, 1, 2),
+    SW_VARIANT_S16(25, 4, 1, 2),
+    // G lanes per subject pair (systolic group, shuffles): small databases / few long pairs
+    SW_VARIANT_S16(25, 1, 2, 5),
+    SW_VARIANT_S16(75, 1, 2, 2),
+    SW_VARIANT_S16(25, 3, 2, 2),
     SW_VARIANT_S16(38, 1, 4, 3),
     SW_VARIANT_S16(19, 2, 4, 3),
     SW_VARIANT_S16(32, 1, 4, 4),
     SW_VARIANT_S16(16, 1, 32, 3),
     SW_VARIANT_S16(8, 2, 32, 3),
-    SW_VARIANT_F16(50, 1, 1, 3),
-    SW_VARIANT_F16(25, 2, 1, 3),
-    SW_VARIANT_F16(25, 1, 2, 5),
-    SW_VARIANT_F16(38, 1, 4, 3),
-    SW_VARIANT_F16(19, 2, 4, 3),
-    SW_VARIANT_F16(25, 3, 1, 2),
-    SW_VARIANT_HYB(50, 1, 1, 3),
-    SW_VARIANT_HYB(25, 2, 1, 3),
-    SW_VARIANT_HYB(32, 2, 1, 2),
-    SW_VARIANT_HYB(25, 1, 2, 5),
-    SW_VARIANT_HYB(38, 1, 4, 3),
-    SW_VARIANT_HYB(38, 2, 1, 2),
-    SW_VARIANT_HYB(25, 3, 1, 2),
-    SW_VARIANT_HYB(30, 1, 1, 4),
-    SW_VARIANT_HYB(19, 4, 1, 2),
 };
 constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
 

@@ -45,11 +45,9 @@ struct SwScoring {
     int limit;                /* 0 = exact; else 2^(W-1)-1: M above it restarts at 0 */
 };
 
-/* One strip-kernel variant = (rows per lane R, lanes per pair G, arithmetic). */
+/* One strip-kernel variant = (rows per lane R = RS*S, lanes per pair G). */
 struct SwStripVariant {
     int R, G;
-    int arith;        /* 0 = packed s16 (DPX), 1 = packed f16, 2 = s16 with M on the fp16 FMA pipe;
-                         1 and 2 are exact while the largest possible score is <= 2047 */
     int block_threads;
     int S;            /* independent sub-strips per lane (R = RS * S) */
     int min_blocks;   /* resident blocks per SM the kernel was compiled for */

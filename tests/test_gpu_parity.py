@@ -40,17 +40,13 @@ def _oracle_matrix(oracle_mod, pkg, queries, subjects, **params):
 # every strip-kernel variant the library instantiates (kept in sync by
 # tests/test_host_abi.py::test_variant_list_matches_library) + automatic choice + 32-bit fallback
 STRIP_VARIANTS = [
-    "strip_s16x2_R32x1_G1", "strip_s16x2_R50x1_G1", "strip_s16x2_R25x2_G1", "strip_s16x2_R25x1_G2",
-    "strip_s16x2_R64x1_G1", "strip_s16x2_R32x2_G1", "strip_s16x2_R75x1_G2", "strip_s16x2_R25x3_G2",
-    "strip_s16x2_R25x3_G1", "strip_s16x2_R38x2_G1", "strip_s16x2_R38x1_G4", "strip_s16x2_R19x2_G4",
-    "strip_s16x2_R32x1_G4", "strip_s16x2_R16x1_G32", "strip_s16x2_R8x2_G32", "strip_f16x2_R50x1_G1",
-    "strip_f16x2_R25x2_G1", "strip_f16x2_R25x1_G2", "strip_f16x2_R38x1_G4", "strip_f16x2_R19x2_G4",
-    "strip_f16x2_R25x3_G1", "strip_hyb16_R50x1_G1", "strip_hyb16_R25x2_G1", "strip_hyb16_R32x2_G1",
-    "strip_hyb16_R25x1_G2", "strip_hyb16_R38x1_G4", "strip_hyb16_R38x2_G1", "strip_hyb16_R25x3_G1",
-    "strip_hyb16_R30x1_G1", "strip_hyb16_R19x4_G1",
+    "strip_s16x2_R32x1_G1", "strip_s16x2_R50x1_G1", "strip_s16x2_R25x2_G1", "strip_s16x2_R19x2_G1",
+    "strip_s16x2_R15x3_G1", "strip_s16x2_R30x2_G1", "strip_s16x2_R64x1_G1", "strip_s16x2_R32x2_G1",
+    "strip_s16x2_R25x3_G1", "strip_s16x2_R38x2_G1", "strip_s16x2_R25x4_G1", "strip_s16x2_R25x1_G2",
+    "strip_s16x2_R75x1_G2", "strip_s16x2_R25x3_G2", "strip_s16x2_R38x1_G4", "strip_s16x2_R19x2_G4",
+    "strip_s16x2_R32x1_G4", "strip_s16x2_R16x1_G32", "strip_s16x2_R8x2_G32",
 ]
 S16_VARIANTS = [v for v in STRIP_VARIANTS if "s16x2" in v]
-SMALL_SCORE_VARIANTS = [v for v in STRIP_VARIANTS if "s16x2" not in v]   # exact while score <= 2047
 VARIANTS = ["auto", "generic32"] + STRIP_VARIANTS
 
 
@@ -143,7 +139,7 @@ def test_parameter_sets_vs_oracle(oracle_mod, pkg, params):
     subjects = [(_mutate(rng, rng.choice(queries), 0.15, 0.15) or "A") for _ in range(200)]
     keys = dict(zip(("match", "mismatch", "gap_open", "gap_extend"), params))
     want = _oracle_matrix(oracle_mod, pkg, queries, subjects, **keys)
-    for choice in ["auto", "strip_s16x2_R38x1_G4", "strip_s16x2_R25x2_G1", "generic32"]:
+    for choice in ["auto", "strip_s16x2_R38x1_G4", "strip_s16x2_R25x2_G1", "strip_s16x2_R25x3_G1", "generic32"]:
         with pkg.Engine(*params) as e:
             _choose(e, choice)
             got = e.score(queries, subjects)
