@@ -68,6 +68,26 @@ struct ArithS16 {
     }
 };
 
+// Pass-boundary scratch accesses: L2-only (never stale in L1) and tagged evict_last so that the
+// scratch lines, which are rewritten every pass, stay resident in L2 instead of being written
+// back to HBM between passes.
+__device__ __forceinline__ uint64_t l2_evict_last_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint2 bnd_load(const uint2 *p, uint64_t pol)
+{
+    uint2 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void bnd_store(uint2 *p, uint2 v, uint64_t pol)
+{
+    asm volatile("st.global.cg.L2::cache_hint.v2.u32 [%0], {%1, %2}, %3;" :: "l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
+}
+
 struct StripArgs {
     const uint32_t *tp;
     const uint64_t *tile_woff;
@@ -210,6 +230,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
     // value of "H = 0" in the strip's representation (K = H + goe in the clamped form)
     const uint32_t h0 = (AR::kClampForm && !W12) ? goe2 : zero;
     uint2 *bnd = a.bnd + (size_t)blockIdx.x * a.bnd_cols * PPB + pslot;
+    const uint64_t bnd_pol = l2_evict_last_policy();
 
     for (;;) {
         __syncthreads();
@@ -288,7 +309,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                 if (gl == 0 && ncols > 0) {
                     wcur = __ldg(tpp);
                     if (ncols > 8) wnext = __ldg(tpp + 32);
-                    if (has_top) bcur = __ldcg(bnd);
+                    if (has_top) bcur = bnd_load(bnd, bnd_pol);
                 }
                 // what each sub-strip hands to the next virtual PE (the next sub-strip, or for
                 // s = S-1 the next lane): bottom H, bottom G and the column code it just used
@@ -320,7 +341,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                                 const int k = (t >> 3) + 2;
                                 if (k * 8 < ncols) wnext = __ldg(tpp + k * 32);
                             }
-                            if (has_top && t + 1 < ncols) bcur = __ldcg(bnd + (size_t)(t + 1) * PPB);
+                            if (has_top && t + 1 < ncols) bcur = bnd_load(bnd + (size_t)(t + 1) * PPB, bnd_pol);
                         }
                     }
 #pragma unroll
@@ -337,7 +358,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                     }
                     if (has_bottom && gl == G - 1) {
                         const int cl = t - (VPE - 1);          // column the last virtual PE just finished
-                        if (cl >= 0 && cl < ncols) __stcg(bnd + (size_t)cl * PPB, make_uint2(pub_h[S - 1], pub_g[S - 1]));
+                        if (cl >= 0 && cl < ncols) bnd_store(bnd + (size_t)cl * PPB, make_uint2(pub_h[S - 1], pub_g[S - 1]), bnd_pol);
                     }
                   }
                 }
