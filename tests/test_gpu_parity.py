@@ -380,3 +380,38 @@ def test_both_strands(oracle_mod, pkg):
         assert got.shape == (6, len(subjects))
     np.testing.assert_array_equal(got, want)
     assert got[4, 200] == 5 * 110 and got[3, 202] == 5 * 31
+
+
+def test_cli_regenerates_golden_files(golden, tmp_path):
+    """File-level drop-in: the CLI, the counterpart of `main_test -q -l -t`, reads the
+    FASTA pair and writes both text layouts; scores equal data500.fa_query100.fa_out.txt / score500.txt."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = os.path.join(root, "bin", "sw_b200_cli")
+    assert os.path.exists(cli), "bin/sw_b200_cli missing: run __graft_entry__.build()"
+    qf, lf = tmp_path / "query100.fa", tmp_path / "data500.fa"
+    qf.write_text(">query\n" + golden["fasta"]["query100.fa"][0][1] + "\n")
+    lf.write_text("".join(f">{n}\n{s}\n" for n, s in golden["fasta"]["data500.fa"]))
+    out_txt, score_txt = tmp_path / "out.txt", tmp_path / "score.txt"
+    r = subprocess.run([cli, "-q", str(qf), "-l", str(lf), "-t", "30", "-o", str(out_txt), "-R", str(score_txt)],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    rtl = dict((n, s) for n, s, _t in [x for x in golden["rtl"] if x["file"] == "data500.fa_query100.fa_out.txt"][0]["rows"])
+    got = {}
+    for line in out_txt.read_text().splitlines():
+        m = re.match(r"@\s*(\d+)ns:\s+>(\S+) score:\s+(-?\d+)", line)
+        assert m, line
+        got[m.group(2)] = int(m.group(3))
+    assert got == rtl
+    ss = dict([x for x in golden["ssearch"] if x["file"] == "score500.txt"][0]["rows"])
+    rows = [l.split() for l in score_txt.read_text().splitlines() if not l.startswith(("#", ">"))]
+    assert {r_[0]: int(r_[5]) for r_ in rows} == ss
+    # the one-pair form prints like main_test.c:528
+    c = golden["capi"]
+    (tmp_path / "query").write_text(c["query"] + "\n")
+    (tmp_path / "library").write_text(c["library"] + "\n")
+    r = subprocess.run([cli, "-q", str(tmp_path / "query"), "-l", str(tmp_path / "library"), "-w", "12"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "result: 102, biased: 2150(0x0866)" in r.stdout, r.stdout
