@@ -191,6 +191,9 @@ def main():
         return 1
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner off it
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -263,7 +266,7 @@ def main():
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         assert np.array_equal(out, chk), "e2e scores differ from the resident-path scores"
         e2e = {"value": cells_step * world * args.e2e_steps / e2e_s / 1e9, "unit": "GCUPS",
-               "h2d_bytes_per_step": int(hp.nbytes + hl.nbytes + ho.nbytes), "d2h_bytes_per_step": int(out.nbytes),
+               "h2d_bytes_per_step": int(hp.nbytes + hl.nbytes + ho.nbytes) * world, "d2h_bytes_per_step": int(out.nbytes) * world,
                "ms_per_step": e2e_s / args.e2e_steps * 1e3, "steps": args.e2e_steps,
                "api": "sw_score_batch + sw_fetch (two batches in flight), pinned host buffers"}
         del out

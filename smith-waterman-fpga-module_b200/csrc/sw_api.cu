@@ -12,6 +12,7 @@
 #include "sw_kernels.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdlib>
 #include <cstring>
@@ -108,7 +109,7 @@ struct sw_handle {
     int last_slot = 0;                // slot of the most recent load / fetch (ids, cells)
     // bookkeeping
     int last_cuda = 0;
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};
     uint64_t last_cells = 0;
     double last_ms = 0.0;
     const char *last_kernel = "none";
@@ -505,9 +506,17 @@ int load_batch(sw_handle *h, int si, const uint8_t *packed, const uint32_t *len,
     std::vector<uint64_t> starts(ng + 1);
     sw_plan_shards(len, ns, (int)ng, starts.data());
     for (size_t gi = 0; gi < ng; ++gi) { h->gpus[gi].slot[si].s0 = starts[gi]; h->gpus[gi].slot[si].s1 = starts[gi + 1]; }
-    for (auto &g : h->gpus) {
-        int rc = load_shard(h, g, g.slot[si], packed, len, off);
+    // one host worker per GPU: the shards' length sort / pairing / uploads run concurrently
+    if (ng == 1) {
+        int rc = load_shard(h, h->gpus[0], h->gpus[0].slot[si], packed, len, off);
         if (rc != SW_OK) return rc;
+    } else {
+        std::vector<int> rcs(ng, SW_OK);
+        std::vector<std::thread> workers;
+        for (size_t gi = 0; gi < ng; ++gi)
+            workers.emplace_back([&, gi]() { rcs[gi] = load_shard(h, h->gpus[gi], h->gpus[gi].slot[si], packed, len, off); });
+        for (auto &w : workers) w.join();
+        for (int rc : rcs) if (rc != SW_OK) return rc;
     }
     // caller's buffers must be reusable on return
     for (auto &g : h->gpus) {
@@ -822,7 +831,7 @@ const char *sw_last_cuda_error_string(const sw_handle_t *h)
     return cudaGetErrorString((cudaError_t)(h ? h->last_cuda : 0));
 }
 double sw_last_kernel_ms(const sw_handle_t *h) { return h ? h->last_ms : 0.0; }
-uint64_t sw_kernel_launches(const sw_handle_t *h) { return h ? h->launches : 0; }
+uint64_t sw_kernel_launches(const sw_handle_t *h) { return h ? h->launches.load() : 0; }
 uint64_t sw_last_cells(const sw_handle_t *h) { return h ? h->last_cells : 0; }
 const char *sw_last_kernel_name(const sw_handle_t *h) { return h ? h->last_kernel : "none"; }
 

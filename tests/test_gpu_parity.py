@@ -415,3 +415,35 @@ def test_cli_regenerates_golden_files(golden, tmp_path):
     r = subprocess.run([cli, "-q", str(tmp_path / "query"), "-l", str(tmp_path / "library"), "-w", "12"],
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "result: 102, biased: 2150(0x0866)" in r.stdout, r.stdout
+
+
+def test_very_long_subjects_short_queries(oracle_mod, pkg):
+    """Long column loops (a 60 kb 'genome' as subject), few pairs: the warp-wide variants."""
+    rng = random.Random(60)
+    queries = [_rand(rng, 150), _rand(rng, 90)]
+    genome = _rand(rng, 60000)
+    genome = genome[:30000] + _mutate(rng, queries[0], 0.03, 0.02) + genome[30000:]
+    subjects = [genome, _rand(rng, 20000), _rand(rng, 20000), _rand(rng, 777)]
+    want = _oracle_matrix(oracle_mod, pkg, queries, subjects)
+    assert want[0, 0] > 500
+    for choice in ["auto", "strip_s16x2_R16x1_G32", "strip_s16x2_R25x2_G1", "strip_s16x2_R38x1_G4"]:
+        with pkg.Engine() as e:
+            _choose(e, choice)
+            got = e.score(queries, subjects)
+        np.testing.assert_array_equal(got, want, err_msg=choice)
+
+
+def test_fetch_timeout_then_success(pkg):
+    """The host's -t option (main_test.c:422-477): a fetch that times out leaves the batch in
+    flight; a later fetch returns it."""
+    db = pkg.random_packed_db(1500000, 150, seed=9)
+    q = pkg.random_packed_db(60, 150, seed=10)
+    with pkg.Engine() as e:
+        e.set_queries(q)
+        e.score_batch(db)
+        with pytest.raises(pkg.SwError) as ei:
+            e.fetch(timeout_ms=1)
+        assert ei.value.code == pkg.SW_ETIMEOUT and e.batches_in_flight == 1
+        out = e.fetch(timeout_ms=-1)
+        assert out.shape == (60, 1500000) and e.batches_in_flight == 0
+        assert 20 <= int(out.max()) <= 750 and int(out.min()) >= 0
