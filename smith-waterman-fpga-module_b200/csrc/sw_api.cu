@@ -387,7 +387,10 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
     // query chunks: a handful of launches so that D2H of finished rows overlaps compute
     // (each launch has its own tail: aim for >= ~50 ms of work per launch, at ~6 TCUPS)
     const double est_ms = (double)g.sum_len * (double)h->q_sum_len / 6.0e9;
-    const int nchunks = std::max(1, std::min(std::min(nq, 8), (int)(est_ms / 50.0)));
+    int nchunks = std::max(1, std::min(std::min(nq, 8), (int)(est_ms / 50.0)));
+    // the device work counter is 32-bit: (pair blocks) x (queries per launch) must stay below 2^31
+    while (nchunks < nq && (uint64_t)(g.npairs / 4 + 1) * (uint64_t)((nq + nchunks - 1) / nchunks) >= (1ull << 31)) nchunks *= 2;
+    nchunks = std::min(nchunks, nq);
     SW_CUDA(h, gc.d_counters.reserve(kMaxCounters * sizeof(unsigned)));
     SW_CUDA(h, cudaMemsetAsync(gc.d_counters.p, 0, kMaxCounters * sizeof(unsigned), gc.st_compute));
 

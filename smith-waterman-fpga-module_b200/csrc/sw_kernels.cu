@@ -236,10 +236,12 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
         __syncthreads();
         if (threadIdx.x == 0) s_work = atomicAdd(a.counter, 1u);
         __syncthreads();
-        if (s_work >= a.npb) break;
-        // pairs are sorted by ascending length: hand out the longest blocks first so that the
-        // tail of the launch is made of short work items
-        const unsigned pb = a.npb - 1u - s_work;
+        // work item = (block of pairs, query).  Pairs are sorted by ascending length: hand out the
+        // longest blocks first so that the tail of the launch is made of short items.
+        const unsigned nql = (unsigned)(a.q1 - a.q0);
+        if (s_work >= a.npb * nql) break;
+        const unsigned pb = a.npb - 1u - s_work / nql;
+        const int q = a.q0 + (int)(s_work % nql);
 
         const unsigned pair = pb * PPB + pslot;
         const bool valid = pair < a.npairs;
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
         // rounded up: the step loop is unrolled (extra steps are PAD columns)
         const int nsteps = (__reduce_max_sync(FULL, ncols) + (VPE - 1) + U - 1) / U * U;
 
-        for (int q = a.q0; q < a.q1; ++q) {
+        {
             const int m = (int)a.qlen[q];
             const uint8_t *qp = a.qpacked + a.qoff[q];
             const int npass = (m + P - 1) / P;
