@@ -158,6 +158,11 @@ int sw_set_arith(sw_handle_t *h, int arith);
 /* The strip-kernel variants compiled into the library, and forcing one by name
  * (NULL or "" = back to automatic).  Names look like "strip_s16x2_R25x2_G1":
  * 25 rows x 2 sub-strips per lane, 1 lane per subject pair. */
+/* The main variants also exist with the reference's default gap penalties (-12 / -4) compiled in
+ * as immediates (faster: fewer register operands); they are used automatically when the
+ * handle's penalties match.  enable = 0 forces the run-time-penalty kernels (process-wide;
+ * for A/B measurements and tests). */
+int sw_set_fixed_penalty_kernels(int enable);
 int sw_kernel_variant_count(void);
 const char *sw_kernel_variant_name(int idx);
 int sw_set_kernel_name(sw_handle_t *h, const char *name);

@@ -84,6 +84,7 @@ def load_library():
     L.sw_kernel_variant_name.restype = C.c_char_p
     L.sw_set_kernel_name.argtypes = [vp, C.c_char_p]
     L.sw_plan_shards.argtypes = [vp, sz, i32, vp]
+    L.sw_set_fixed_penalty_kernels.argtypes = [i32]
     L.sw_set_strands.argtypes = [vp, i32]
     L.sw_query_rows.argtypes = [vp]
     L.sw_batches_in_flight.argtypes = [vp]
@@ -258,6 +259,11 @@ def plan_shards(lengths, n_shards):
     if rc != SW_OK:
         raise SwError(rc, "sw_plan_shards")
     return starts
+
+
+def set_fixed_penalty_kernels(enable):
+    """False: never use the kernel instances with the default gap penalties compiled in."""
+    load_library().sw_set_fixed_penalty_kernels(int(bool(enable)))
 
 
 def device_count():

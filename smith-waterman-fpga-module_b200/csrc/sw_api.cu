@@ -301,12 +301,12 @@ SwDevDb dev_db(const Slot &g)
 double variant_speed(const SwStripVariant *v)
 {
     struct { const char *name; double gcups; } tab[] = {
-        {"strip_s16x2_R32x1_G1", 8090}, {"strip_s16x2_R50x1_G1", 7800}, {"strip_s16x2_R25x2_G1", 8260},
-        {"strip_s16x2_R19x2_G1", 7790}, {"strip_s16x2_R15x3_G1", 7685}, {"strip_s16x2_R30x2_G1", 7890},
-        {"strip_s16x2_R64x1_G1", 7770}, {"strip_s16x2_R32x2_G1", 8360}, {"strip_s16x2_R25x3_G1", 8090},
-        {"strip_s16x2_R38x2_G1", 8340}, {"strip_s16x2_R25x4_G1", 7320}, {"strip_s16x2_R25x1_G2", 6890},
-        {"strip_s16x2_R75x1_G2", 7425}, {"strip_s16x2_R25x3_G2", 7295}, {"strip_s16x2_R38x1_G4", 7205},
-        {"strip_s16x2_R19x2_G4", 7130}, {"strip_s16x2_R32x1_G4", 7070}, {"strip_s16x2_R16x1_G32", 6005},
+        {"strip_s16x2_R32x1_G1", 8540}, {"strip_s16x2_R50x1_G1", 8750}, {"strip_s16x2_R25x2_G1", 8680},
+        {"strip_s16x2_R19x2_G1", 8060}, {"strip_s16x2_R15x3_G1", 7780}, {"strip_s16x2_R30x2_G1", 7935},
+        {"strip_s16x2_R64x1_G1", 8400}, {"strip_s16x2_R32x2_G1", 8300}, {"strip_s16x2_R25x3_G1", 8500},
+        {"strip_s16x2_R38x2_G1", 8820}, {"strip_s16x2_R25x4_G1", 7600}, {"strip_s16x2_R25x1_G2", 7160},
+        {"strip_s16x2_R75x1_G2", 7005}, {"strip_s16x2_R25x3_G2", 7335}, {"strip_s16x2_R38x1_G4", 7245},
+        {"strip_s16x2_R19x2_G4", 7080}, {"strip_s16x2_R32x1_G4", 7050}, {"strip_s16x2_R16x1_G32", 6005},
         {"strip_s16x2_R8x2_G32", 6410},
     };
     for (auto &t : tab) if (std::strcmp(t.name, v->name) == 0) return t.gcups;
@@ -332,7 +332,9 @@ int choose_variant(const sw_handle *h, const GpuCtx &gc, const Slot &g, uint32_t
     for (int i = 0; i < nv; ++i) {
         const SwStripVariant *v = sw_strip_variant(i);
         const int P = v->R * v->G;
-        const double rows = (double)((maxq + P - 1) / P) * P;
+        double rows = 0;                      // padded rows over all queries
+        for (uint32_t ql : h->q_len) rows += (double)((ql + P - 1) / P) * P;
+        if (rows == 0) rows = (double)((maxq + P - 1) / P) * P;
         const double lanes = (double)g.npairs * v->G;
         const double fill = (double)gc.num_sms * v->min_blocks * v->block_threads;
         const double util = std::min(1.0, lanes / fill);
@@ -860,6 +862,12 @@ int sw_set_kernel_name(sw_handle_t *h, const char *name)
     for (int i = 0; i < sw_strip_variant_count(); ++i)
         if (std::strcmp(sw_strip_variant(i)->name, name) == 0) { h->force_variant = i; return SW_OK; }
     return SW_EINVAL;
+}
+
+int sw_set_fixed_penalty_kernels(int enable)
+{
+    sw_strip_disable_fixed(enable == 0);
+    return SW_OK;
 }
 
 int sw_set_arith(sw_handle_t *h, int arith)

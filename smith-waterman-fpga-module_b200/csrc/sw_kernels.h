@@ -55,6 +55,8 @@ struct SwStripVariant {
 };
 
 int sw_strip_variant_count(void);
+/* testing hook: true = never use the instances with compile-time gap penalties */
+void sw_strip_disable_fixed(bool off);
 const SwStripVariant *sw_strip_variant(int idx);
 
 /* Dynamic shared memory of variant idx when the query profile of chunk_passes passes is resident. */

@@ -447,3 +447,27 @@ def test_fetch_timeout_then_success(pkg):
         out = e.fetch(timeout_ms=-1)
         assert out.shape == (60, 1500000) and e.batches_in_flight == 0
         assert 20 <= int(out.max()) <= 750 and int(out.min()) >= 0
+
+
+@pytest.mark.parametrize("fixed", [True, False])
+def test_fixed_and_runtime_penalty_instances_agree(golden, oracle_mod, pkg, fixed):
+    """The main variants exist twice: gap penalties as immediates (default set) and as run-time
+    operands.  Both must give the golden / oracle scores for the default penalties."""
+    rng = random.Random(71)
+    queries = [_rand(rng, 150), _rand(rng, 64)]
+    subjects = [(_mutate(rng, rng.choice(queries), 0.1, 0.08) or "A") for _ in range(400)]
+    want = _oracle_matrix(oracle_mod, pkg, queries, subjects)
+    q = _fasta(golden, "query100.fa")[0][1]
+    db = _fasta(golden, "data500.fa")
+    ss = dict([x for x in golden["ssearch"] if x["file"] == "score500.txt"][0]["rows"])
+    pkg.set_fixed_penalty_kernels(fixed)
+    try:
+        for name in ["strip_s16x2_R25x2_G1", "strip_s16x2_R38x2_G1", "strip_s16x2_R50x1_G1", "strip_s16x2_R38x1_G4",
+                     "strip_s16x2_R16x1_G32"]:
+            with pkg.Engine() as e:
+                e.set_kernel_name(name)
+                np.testing.assert_array_equal(e.score(queries, subjects), want, err_msg=name)
+                sc = e.score([q], [s for _, s in db])
+                assert dict(zip([n for n, _ in db], sc[0].tolist())) == ss, name
+    finally:
+        pkg.set_fixed_penalty_kernels(True)
