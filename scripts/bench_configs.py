@@ -37,10 +37,31 @@ def mixed_db(n, lo, hi, seed):
     return packed, lens, off
 
 
+def latency(name, queries, db, reps=200):
+    """Wall-clock of sw_score_batch + sw_fetch through the ABI (host buffers), after warm-up."""
+    import time
+    with pkg.Engine() as e:
+        e.set_queries(queries)
+        out = np.empty((len(queries[1]), len(db[1])), dtype=np.int32)
+        for _ in range(20):
+            e.score_batch(db); e.fetch(out=out)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            e.score_batch(db); e.fetch(out=out)
+        dt = (time.perf_counter() - t0) / reps
+        print(json.dumps({"config": name, "kernel": e.last_kernel_name, "e2e_us_per_call": dt * 1e6,
+                          "kernel_us": e.last_kernel_ms * 1e3, "gcups_e2e": e.last_cells / dt / 1e9}), flush=True)
+
+
 which = sys.argv[1:] or ["2", "4", "4w", "5"]
 if "2" in which:    # query100 x data500 shape: 128-nt query, 499 x 128-nt subjects (latency bound)
     run("2: 1 x 128 nt query vs 499 x 128 nt", pkg.random_packed_db(1, 128, 1), pkg.random_packed_db(499, 128, 2), reps=5)
 KERNELS = os.environ.get("SW_KERNELS", "").split()
+if "2" in which or "lat" in which:
+    latency("2 (latency): sw_score_batch + sw_fetch, 1 x 128 nt query vs 499 x 128 nt",
+            pkg.random_packed_db(1, 128, 1), pkg.random_packed_db(499, 128, 2))
+    latency("1 pair (latency): 32 nt query vs one 128 nt subject (the CAPI sample's job)",
+            pkg.random_packed_db(1, 32, 1), pkg.random_packed_db(1, 128, 2))
 if "4" in which:    # 10 kb query vs 1 kb subjects; 200k subjects = 2e12 cells per query
     for k in KERNELS or [None]:
         run("4: 1 x 10 kb query vs 200k x 1 kb (%s)" % (k or "automatic variant"), pkg.random_packed_db(1, 10000, 3),

@@ -21,12 +21,15 @@
  *     M_in / I_in / data_in travel from PE to PE;
  *   - queries longer than R*G rows are processed in passes; the bottom row of a pass is kept
  *     in an L2-resident scratch line per column and read back by lane 0 in the next pass;
- *   - substitution scores come from a shared-memory query profile prof[row][16 column codes],
- *     so that all lanes of a warp that sit on the same row hit 16 distinct banks.
+ *   - substitution scores come from a shared-memory query profile
+ *     prof[sub-strip][row pair][column code][lane of the group] (one uint2 = two rows), laid out
+ *     so that the lanes of a warp hit distinct banks: one LDS.64 per two rows.
+ * The recurrence is evaluated in an algebraically equivalent "clamped, goe-shifted" form (see
+ * column_step_multi) that needs 3.5 ALU-pipe + 1 FMA-pipe instructions per two cells; the
+ * RTL-faithful 12-bit mode keeps the explicit M form.
  */
 #include "sw_kernels.h"
 
-#include <cuda_fp16.h>
 #include <stdint.h>
 
 #ifndef SW_STEP_UNROLL
@@ -38,11 +41,11 @@ namespace {
 constexpr int kPadScoreS16 = -8192;   // profile value of padding rows: M becomes 0, nothing can grow
 
 // ------------------------------------------------------------------------------------------
-// Arithmetic policies.  Both pack two independent lanes into one 32-bit register.
+// Packed signed 16-bit arithmetic: two independent subjects per 32-bit register, one DPX
+// instruction per operation.
 // ------------------------------------------------------------------------------------------
 struct ArithS16 {
     static constexpr int kPad = kPadScoreS16;
-    static constexpr bool kClampForm = true;     // see column_step_multi: M is never materialised
     static __device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) {
         return __viaddmax_s16x2_relu(a, b, c);   // max(a + b, c, 0)
     }
@@ -132,7 +135,7 @@ __device__ __forceinline__ void column_step_multi(uint32_t (&H)[S][RS], uint32_t
     for (int s = 0; s < S; ++s)
 #pragma unroll
         for (int k = 0; k < RP; ++k) sv[s][k] = prow[s][k * kCodesPerRow * G];
-    if constexpr (AR::kClampForm && !W12) {
+    if constexpr (!W12) {
         // Clamped, goe-shifted form (exact).  Every gap value is clamped at 0
         // (non-positive gap values can never reach H because M >= 0) and the register strip holds
         // K = H + goe instead of H.  With tg = K(r-1,c-1) + s  (= H_diag + s + goe):
@@ -168,8 +171,9 @@ __device__ __forceinline__ void column_step_multi(uint32_t (&H)[S][RS], uint32_t
         }
         return;
     }
-    // Single top-down sweep.  M of row r+1 is formed one row ahead, from the still-old H[r]
-    // (= H(r, c-1), its diagonal), so that H[r] can then be overwritten in place.
+    // W-bit faithful mode (score_width != 0): the explicit form of SW_ProcessingElement_v1.0.v with
+    // the M overflow ("MSB clear => ZERO", :287-288) applied to every M.  M of row r+1 is formed one
+    // row ahead, from the still-old H[r] (its diagonal), so that H[r] is overwritten in place.
     uint32_t gu[S], m_cur[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) {
@@ -203,9 +207,9 @@ __device__ __forceinline__ void column_step_multi(uint32_t (&H)[S][RS], uint32_t
 // RS rows per sub-strip, S sub-strips per lane, G lanes per pair: R = RS*S rows per lane,
 // P = R*G rows per pass.  Virtual PE v = lane_in_group*S + s works on column t - v at step t.
 // A virtual PE that has no column at step t (pipeline fill / drain, shorter pair in the warp)
-// works on the PAD column code whose profile entries are very negative: M becomes 0, H keeps
-// decaying values <= the best already recorded, and G only drifts among non-positive values,
-// which never reach H (M >= 0).  That keeps the loop body free of per-lane branches.
+// works on the PAD column code whose profile entries are very negative: H keeps decaying values
+// <= the best already recorded and G stays clamped / non-positive, which never reaches H
+// (DESIGN.md section 2).  That keeps the loop body free of per-lane branches.
 // CGOE / CGE != 0: gap penalties fixed at compile time.  ptxas then encodes them as immediates
 // (VIADDMNMX.S16x2 R, R, 0xfffcfffc, R): two register operands instead of three per fused
 // add-max, which removes register-bank conflicts on the ALU pipe (+6..13 % measured).  Used for
@@ -230,11 +234,11 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
     const uint32_t goe2 = CGOE ? ((uint32_t)(CGOE & 0xFFFF) * 0x10001u) : a.goe2;
     const uint32_t ge2 = CGOE ? ((uint32_t)(CGE & 0xFFFF) * 0x10001u) : a.ge2;
     // boundary gap value G(0,j) = G(i,0): max(goe, ge) <= 0, or its clamp 0 in the clamped form
-    const int gbv = (AR::kClampForm && !W12) ? 0 : (a.goe > a.ge ? a.goe : a.ge);
+    const int gbv = !W12 ? 0 : (a.goe > a.ge ? a.goe : a.ge);
     const uint32_t gb2 = AR::pack(gbv, gbv);
     const uint32_t lim2 = AR::pack(a.limit, a.limit);
     // value of "H = 0" in the strip's representation (K = H + goe in the clamped form)
-    const uint32_t h0 = (AR::kClampForm && !W12) ? goe2 : zero;
+    const uint32_t h0 = !W12 ? goe2 : zero;
     uint2 *bnd = a.bnd + (size_t)blockIdx.x * a.bnd_cols * PPB + pslot;
     const uint64_t bnd_pol = l2_evict_last_policy();
 
@@ -377,7 +381,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
             for (int o = G / 2; o >= 1; o >>= 1) best = AR::max2(best, __shfl_xor_sync(FULL, best, o));
             if (gl == 0 && valid) {
                 int32_t *orow = a.out + (size_t)q * a.out_stride;
-                const int shift = (AR::kClampForm && !W12) ? a.goe : 0;
+                const int shift = !W12 ? a.goe : 0;
                 orow[subj_lo] = AR::extract(best, 0) - shift;
                 if (subj_hi != SW_NO_SUBJECT) orow[subj_hi] = AR::extract(best, 1) - shift;
             }
