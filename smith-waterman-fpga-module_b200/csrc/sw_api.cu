@@ -377,11 +377,13 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
     dq.packed = gc.d_qpacked.as<uint8_t>(); dq.off = gc.d_qoff.as<uint32_t>(); dq.len = gc.d_qlen.as<uint32_t>();
     dq.nq = nq; dq.max_len = h->q_max_len;
 
-    // value range: exact s16 needs match * min(m, n) to stay clear of 32767
+    // Value range: the packed 16-bit kernel is always used; when match * min(m, n) could exceed
+    // the 16-bit range it flags the (rare) pairs whose running maximum got near 32767 and the
+    // 32-bit kernel recomputes exactly those.
     const uint64_t smax = (uint64_t)sc.match * std::min<uint64_t>(h->q_max_len, g.max_len);
-    const bool fits16 = sc.limit ? true : (smax + (uint64_t)sc.match < 32000ull);
+    const bool may_overflow = !sc.limit && (smax + (uint64_t)sc.match >= 32000ull);
     int vidx = -1;
-    if (!h->force32 && fits16) {
+    if (!h->force32) {
         vidx = choose_variant(h, gc, g, h->q_max_len);
         if (vidx < 0 && (h->force_R || h->force_G)) return SW_EINVAL;
     }
@@ -415,10 +417,11 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
             SW_CUDA(h, gc.d_bnd.reserve(bytes));
         }
         h->last_kernel = v->name;
-    } else {
+    }
+    if (vidx < 0 || may_overflow) {
         const int threads_total = gc.num_sms * 2 * 128;
-        SW_CUDA(h, gc.d_scratch32.reserve((size_t)2 * std::max<uint32_t>(h->q_max_len, 1) * threads_total * sizeof(int32_t)));
-        h->last_kernel = "generic32";
+        SW_CUDA(h, gc.d_scratch32.reserve((size_t)2 * std::max<uint32_t>(g.max_len, 1) * threads_total * sizeof(int32_t)));
+        if (vidx < 0) h->last_kernel = "generic32";
     }
 
     for (int c = 0; c < nchunks; ++c) {
@@ -431,9 +434,14 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
             SW_CUDA(h, sw_launch_strip(vidx, gc.st_compute, db, dq, qc.q0, qc.q1, sc, g.d_out.as<int32_t>(), n,
                                        gc.d_bnd.as<uint2>(), g.max_len, gc.d_counters.as<unsigned>() + (c % kMaxCounters),
                                        grid, chunk_passes));
+            if (may_overflow) {
+                SW_CUDA(h, sw_launch_generic32(gc.st_compute, db, dq, qc.q0, qc.q1, sc, g.d_out.as<int32_t>(), n,
+                                               gc.d_scratch32.as<int32_t>(), gc.num_sms * 2 * 128, true));
+                h->launches++;
+            }
         } else {
             SW_CUDA(h, sw_launch_generic32(gc.st_compute, db, dq, qc.q0, qc.q1, sc, g.d_out.as<int32_t>(), n,
-                                           gc.d_scratch32.as<int32_t>(), gc.num_sms * 2 * 128));
+                                           gc.d_scratch32.as<int32_t>(), gc.num_sms * 2 * 128, false));
         }
         h->launches++;
         SW_CUDA(h, cudaEventCreateWithFlags(&qc.done, cudaEventDisableTiming));

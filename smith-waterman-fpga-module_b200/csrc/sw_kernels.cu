@@ -110,6 +110,7 @@ struct StripArgs {
     int chunk_passes;          // passes whose query profile is resident in shared memory at once
     int match, mismatch, goe, ge, limit;
     uint32_t goe2, ge2;        // goe / ge packed in both 16-bit lanes (host side: uniform operands)
+    int ovf_limit;             // 32767 - match - 1: a larger final maximum means a possible wrap
     uint32_t zero;             // always 0, but opaque to the compiler
 };
 
@@ -381,9 +382,15 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
             for (int o = G / 2; o >= 1; o >>= 1) best = AR::max2(best, __shfl_xor_sync(FULL, best, o));
             if (gl == 0 && valid) {
                 int32_t *orow = a.out + (size_t)q * a.out_stride;
+                // While every value so far is <= 32767 - match the next cell cannot wrap, and the
+                // running maximum is monotone: a final best above that threshold is the only way a
+                // 16-bit overflow can have happened.  Such pairs get a sentinel and are recomputed
+                // by the 32-bit kernel (sw_launch_generic32 with fix_only).
                 const int shift = !W12 ? a.goe : 0;
-                orow[subj_lo] = AR::extract(best, 0) - shift;
-                if (subj_hi != SW_NO_SUBJECT) orow[subj_hi] = AR::extract(best, 1) - shift;
+                const int b0 = AR::extract(best, 0), b1 = AR::extract(best, 1);
+                orow[subj_lo] = (!W12 && b0 > a.ovf_limit) ? SW_OVERFLOW_SENTINEL : b0 - shift;
+                if (subj_hi != SW_NO_SUBJECT)
+                    orow[subj_hi] = (!W12 && b1 > a.ovf_limit) ? SW_OVERFLOW_SENTINEL : b1 - shift;
             }
         }
     }
@@ -440,48 +447,73 @@ __global__ void __launch_bounds__(256) build_tp_kernel(const uint8_t *raw, const
 }
 
 // ------------------------------------------------------------------------------------------
-// 32-bit fallback: one thread per (subject, query) job, H/G columns in global scratch laid
-// out [row][thread] so that a warp touches one 128-byte line per row.
+// 32-bit kernel: one thread per (subject, query) job, any length, any score range, W-bit mode.
+// The query is walked in strips of 16 rows held in registers (their 2-bit codes fit one word);
+// the bottom row (H, G) of a strip is parked per column in global scratch laid out
+// [column][thread], so a warp touches one 128-byte line per access and a cell costs 4/16 memory
+// operations.  Explicit form of SW_ProcessingElement_v1.0.v (M, I = max(G_left, G_up), ...).
 // ------------------------------------------------------------------------------------------
+constexpr int kGR = 16;
+
 __global__ void __launch_bounds__(128) generic32_kernel(const uint8_t *raw, const uint64_t *off,
                                                        const uint32_t *len, uint32_t ns,
                                                        const uint8_t *qpacked, const uint32_t *qoff,
                                                        const uint32_t *qlen, int q0, int q1,
                                                        int32_t *out, size_t out_stride, int32_t *scratch,
-                                                       uint32_t max_q, int match, int mismatch, int goe,
-                                                       int ge, int limit)
+                                                       uint32_t max_t, int match, int mismatch, int goe,
+                                                       int ge, int limit, int fix_only)
 {
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int32_t *Hc = scratch + tid;                          // Hc[i * nthreads]
-    int32_t *Gc = scratch + (size_t)max_q * nthreads + tid;
+    int32_t *Hb = scratch + tid;                          // Hb[j * nthreads]: H(strip bottom, j)
+    int32_t *Gb = scratch + (size_t)max_t * nthreads + tid;
     const int gb = goe > ge ? goe : ge;
     const size_t njobs = (size_t)ns * (size_t)(q1 - q0);
     for (size_t job = tid; job < njobs; job += nthreads) {
         const uint32_t s = (uint32_t)(job % ns);
         const int q = q0 + (int)(job / ns);
+        if (fix_only && out[(size_t)q * out_stride + s] != SW_OVERFLOW_SENTINEL) continue;
         const int m = (int)qlen[q], n = (int)len[s];
         const uint8_t *qp = qpacked + qoff[q];
         const uint8_t *tpk = raw + off[s];
-        for (int i = 0; i < m; ++i) { Hc[(size_t)i * nthreads] = 0; Gc[(size_t)i * nthreads] = gb; }
+        for (int j = 0; j < n; ++j) { Hb[(size_t)j * nthreads] = 0; Gb[(size_t)j * nthreads] = gb; }
         int best = 0;
-        for (int j = 0; j < n; ++j) {
-            const int tj = (tpk[j >> 2] >> ((j & 3) * 2)) & 3;
-            int hd = 0, gu = gb;
-            for (int i = 0; i < m; ++i) {
-                const int qi = (qp[i >> 2] >> ((i & 3) * 2)) & 3;
-                int mm = hd + (qi == tj ? match : mismatch);
-                mm = mm > 0 ? mm : 0;
-                if (limit && mm > limit) mm = 0;
-                const int gl_ = Gc[(size_t)i * nthreads];
-                const int ii = gl_ > gu ? gl_ : gu;
-                hd = Hc[(size_t)i * nthreads];
-                const int hn = mm > ii ? mm : ii;
-                const int a1 = mm + goe, a2 = ii + ge;
-                gu = a1 > a2 ? a1 : a2;
-                Gc[(size_t)i * nthreads] = gu;
-                Hc[(size_t)i * nthreads] = hn;
-                best = hn > best ? hn : best;
+        for (int r0 = 0; r0 < m; r0 += kGR) {
+            const int nr = (m - r0 < kGR) ? (m - r0) : kGR;
+            uint32_t qw = 0;                               // 2-bit codes of the strip's rows
+            for (int r = 0; r < nr; ++r) {
+                const int i = r0 + r;
+                qw |= (uint32_t)((qp[i >> 2] >> ((i & 3) * 2)) & 3) << (2 * r);
+            }
+            int H[kGR], Gv[kGR];
+#pragma unroll
+            for (int r = 0; r < kGR; ++r) { H[r] = 0; Gv[r] = gb; }
+            int hd_top = 0;                                // H(r0-1, j-1)
+            int nx_h = n ? Hb[0] : 0, nx_g = n ? Gb[0] : gb;
+            for (int j = 0; j < n; ++j) {
+                const int tj = (tpk[j >> 2] >> ((j & 3) * 2)) & 3;
+                const int top_h = nx_h, top_g = nx_g;      // H, G of row r0-1 in this column
+                if (j + 1 < n) { nx_h = Hb[(size_t)(j + 1) * nthreads]; nx_g = Gb[(size_t)(j + 1) * nthreads]; }
+                int diag = hd_top, gu = top_g;
+#pragma unroll
+                for (int r = 0; r < kGR; ++r) {
+                    if (r < nr) {
+                        const int sc = ((int)((qw >> (2 * r)) & 3) == tj) ? match : mismatch;
+                        int mm = diag + sc;                             // v1.0.v:287
+                        mm = mm > 0 ? mm : 0;                           // v1.0.v:288
+                        if (limit && mm > limit) mm = 0;                // W-bit wrap-then-clamp
+                        const int ii = Gv[r] > gu ? Gv[r] : gu;         // v1.0.v:126-129, 291
+                        diag = H[r];
+                        const int a1 = mm + goe, a2 = ii + ge;
+                        gu = a1 > a2 ? a1 : a2;
+                        Gv[r] = gu;
+                        H[r] = mm > ii ? mm : ii;
+                        best = H[r] > best ? H[r] : best;               // v1.0.v:411-420
+                    }
+                }
+                hd_top = top_h;
+                Hb[(size_t)j * nthreads] = H[kGR - 1];                  // used only below full strips
+                Gb[(size_t)j * nthreads] = Gv[kGR - 1];
             }
         }
         out[(size_t)q * out_stride + s] = best;
@@ -620,6 +652,7 @@ cudaError_t sw_launch_strip(int idx, cudaStream_t st, const SwDevDb &db, const S
     a.chunk_passes = chunk_passes;
     a.match = sc.match; a.mismatch = sc.mismatch; a.goe = sc.goe; a.ge = sc.ge; a.limit = sc.limit;
     a.goe2 = ((uint32_t)sc.goe & 0xFFFFu) * 0x10001u; a.ge2 = ((uint32_t)sc.ge & 0xFFFFu) * 0x10001u;
+    a.ovf_limit = 32767 - sc.match - 1;
     a.zero = 0;
     const size_t smem = sw_strip_smem_bytes(idx, chunk_passes);
     cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -630,14 +663,14 @@ cudaError_t sw_launch_strip(int idx, cudaStream_t st, const SwDevDb &db, const S
 
 cudaError_t sw_launch_generic32(cudaStream_t st, const SwDevDb &db, const SwDevQueries &q, int q0, int q1,
                                 const SwScoring &sc, int32_t *out, size_t out_stride, int32_t *scratch,
-                                int threads_total)
+                                int threads_total, bool fix_only)
 {
     const int bt = 128;
     const int grid = threads_total / bt;
     if (grid <= 0) return cudaErrorInvalidValue;
     generic32_kernel<<<grid, bt, 0, st>>>(db.raw, db.off, db.len, db.ns, q.packed, q.off, q.len, q0, q1, out,
-                                          out_stride, scratch, q.max_len, sc.match, sc.mismatch, sc.goe,
-                                          sc.ge, sc.limit);
+                                          out_stride, scratch, db.max_len, sc.match, sc.mismatch, sc.goe,
+                                          sc.ge, sc.limit, fix_only ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -9,6 +9,7 @@
 #include <stdint.h>
 
 #define SW_NO_SUBJECT 0xFFFFFFFFu
+#define SW_OVERFLOW_SENTINEL (-1)   /* strip kernel: 16-bit range possibly exceeded, recompute in 32 bit */
 
 /* Database shard resident in HBM.  Layout (DESIGN.md "data layout"):
  *   raw/off/len   : the caller's 2-bit packed records, as uploaded
@@ -74,10 +75,11 @@ cudaError_t sw_launch_strip(int idx, cudaStream_t st, const SwDevDb &db, const S
                             uint2 *bnd, uint32_t bnd_cols, unsigned *counter, int grid,
                             int chunk_passes);
 
-/* 32-bit fallback: any length, any score range.  scratch: 2 * (q.max_len) * threads int32. */
+/* 32-bit kernel: any length, any score range.  scratch: 2 * (db.max_len) * threads int32.
+ * fix_only: recompute only the entries the strip kernel marked SW_OVERFLOW_SENTINEL. */
 cudaError_t sw_launch_generic32(cudaStream_t st, const SwDevDb &db, const SwDevQueries &q,
                                 int q0, int q1, const SwScoring &sc, int32_t *out, size_t out_stride,
-                                int32_t *scratch, int threads_total);
+                                int32_t *scratch, int threads_total, bool fix_only);
 
 cudaError_t sw_launch_build_tp(cudaStream_t st, const SwDevDb &db);
 

@@ -185,15 +185,25 @@ def test_long_query_multi_pass_and_chunks(oracle_mod, pkg):
         np.testing.assert_array_equal(got, want, err_msg=str(choice))
 
 
-def test_scores_beyond_int16_use_32bit_path(oracle_mod, pkg):
+def test_scores_beyond_int16_are_recomputed_in_32bit(oracle_mod, pkg):
+    """Pairs whose score leaves the 16-bit range are flagged by the packed kernel and recomputed
+    by the 32-bit kernel; everything else in the batch stays on the fast path."""
     rng = random.Random(5)
-    s = _rand(rng, 7000)                      # identical pair scores 35000 > 32767
-    t = _mutate(rng, s, 0.01, 0.005)
-    with pkg.Engine() as e:
-        got = e.score([s], [s, t, "ACGT"])
-        assert e.last_kernel_name == "generic32"
+    s = _rand(rng, 6700)                      # identical pair scores 33500 > 32767
+    t = _mutate(rng, s, 0.004, 0.002)         # around the threshold
+    u = _mutate(rng, s, 0.10, 0.05)           # well inside 16 bit
+    others = [_rand(rng, rng.randint(100, 3000)) for _ in range(12)]
+    subjects = [s, t, u, "ACGT", s[:6560], s[100:6652] + "A"] + others
     o = oracle_mod.Oracle()
-    assert got[0].tolist() == [35000, o.score(s, t), o.score(s, "ACGT")]
+    want = [o.score(s, x) for x in subjects]
+    assert want[0] == 33500 and 32700 < want[4] == 32800 and max(want[6:]) < 2000
+    for choice in ["auto", "strip_s16x2_R38x2_G1", "strip_s16x2_R16x1_G32", "generic32"]:
+        sub = subjects[:5] if choice == "generic32" else subjects      # the scalar kernel is slow
+        with pkg.Engine() as e:
+            _choose(e, choice)
+            got = e.score([s], sub)
+            assert (e.last_kernel_name == "generic32") == (choice == "generic32")
+        assert got[0].tolist() == want[:len(sub)], choice
 
 
 def test_edge_cases(pkg):
