@@ -481,3 +481,22 @@ def test_fixed_and_runtime_penalty_instances_agree(golden, oracle_mod, pkg, fixe
                 assert dict(zip([n for n, _ in db], sc[0].tolist())) == ss, name
     finally:
         pkg.set_fixed_penalty_kernels(True)
+
+
+def test_every_shipped_fasta_file_vs_oracle(golden, oracle_mod, pkg):
+    """All 18 FASTA files of the reference's data/ directory (including the ones that ship
+    without an expected-output file: data.fa, data2.fa, data50/80/200/300/400.fa, score_test.fa,
+    datal.fa and the 23 unpinned records of data40.fa) against both shipped queries.
+    Expectations here are ORACLE-GENERATED (the pinned subsets are covered by the golden tests)."""
+    queries = [golden["fasta"]["query1.fa"][0][1], golden["fasta"]["query100.fa"][0][1]]
+    n_files = 0
+    with pkg.Engine() as e:
+        for fn, recs in sorted(golden["fasta"].items()):
+            subjects = [s for _n, s in recs]
+            if not subjects:
+                continue
+            want = _oracle_matrix(oracle_mod, pkg, queries, subjects)
+            got = e.score(queries, subjects)
+            np.testing.assert_array_equal(got, want, err_msg=fn)
+            n_files += 1
+    assert n_files == 18
