@@ -301,6 +301,7 @@ SwDevDb dev_db(const Slot &g)
 double variant_speed(const SwStripVariant *v)
 {
     struct { const char *name; double gcups; } tab[] = {
+        {"strip_s16x2_R30x1_G1", 8450}, {"strip_s16x2_R38x1_G1", 8560}, {"strip_s16x2_R75x1_G1", 8526},
         {"strip_s16x2_R32x1_G1", 8540}, {"strip_s16x2_R50x1_G1", 8750}, {"strip_s16x2_R25x2_G1", 8680},
         {"strip_s16x2_R19x2_G1", 8060}, {"strip_s16x2_R15x3_G1", 7780}, {"strip_s16x2_R30x2_G1", 7935},
         {"strip_s16x2_R64x1_G1", 8400}, {"strip_s16x2_R32x2_G1", 8300}, {"strip_s16x2_R25x3_G1", 8500},

@@ -580,6 +580,9 @@ constexpr int kFixedGoe = -16, kFixedGe = -4;
       sw_strip_kernel<RS, S, G, ArithS16, false, kBT, MINB>, sw_strip_kernel<RS, S, G, ArithS16, true, kBT, MINB>, \
       sw_strip_kernel<RS, S, G, ArithS16, false, kBT, MINB, kFixedGoe, kFixedGe> }
 const VariantEntry g_variants[] = {
+    SW_VARIANT_S16F(30, 1, 1, 4),
+    SW_VARIANT_S16F(38, 1, 1, 4),
+    SW_VARIANT_S16F(75, 1, 1, 2),
     // one lane per subject pair (inter-task): RS rows x S sub-strips per lane
     SW_VARIANT_S16F(32, 1, 1, 4),
     SW_VARIANT_S16F(50, 1, 1, 3),

@@ -40,11 +40,12 @@ def _oracle_matrix(oracle_mod, pkg, queries, subjects, **params):
 # every strip-kernel variant the library instantiates (kept in sync by
 # tests/test_host_abi.py::test_variant_list_matches_library) + automatic choice + 32-bit fallback
 STRIP_VARIANTS = [
-    "strip_s16x2_R32x1_G1", "strip_s16x2_R50x1_G1", "strip_s16x2_R25x2_G1", "strip_s16x2_R19x2_G1",
-    "strip_s16x2_R15x3_G1", "strip_s16x2_R30x2_G1", "strip_s16x2_R64x1_G1", "strip_s16x2_R32x2_G1",
-    "strip_s16x2_R25x3_G1", "strip_s16x2_R38x2_G1", "strip_s16x2_R25x4_G1", "strip_s16x2_R25x1_G2",
-    "strip_s16x2_R75x1_G2", "strip_s16x2_R25x3_G2", "strip_s16x2_R38x1_G4", "strip_s16x2_R19x2_G4",
-    "strip_s16x2_R32x1_G4", "strip_s16x2_R16x1_G32", "strip_s16x2_R8x2_G32",
+    "strip_s16x2_R30x1_G1", "strip_s16x2_R38x1_G1", "strip_s16x2_R75x1_G1", "strip_s16x2_R32x1_G1",
+    "strip_s16x2_R50x1_G1", "strip_s16x2_R25x2_G1", "strip_s16x2_R19x2_G1", "strip_s16x2_R15x3_G1",
+    "strip_s16x2_R30x2_G1", "strip_s16x2_R64x1_G1", "strip_s16x2_R32x2_G1", "strip_s16x2_R25x3_G1",
+    "strip_s16x2_R38x2_G1", "strip_s16x2_R25x4_G1", "strip_s16x2_R25x1_G2", "strip_s16x2_R75x1_G2",
+    "strip_s16x2_R25x3_G2", "strip_s16x2_R38x1_G4", "strip_s16x2_R19x2_G4", "strip_s16x2_R32x1_G4",
+    "strip_s16x2_R16x1_G32", "strip_s16x2_R8x2_G32",
 ]
 S16_VARIANTS = [v for v in STRIP_VARIANTS if "s16x2" in v]
 VARIANTS = ["auto", "generic32"] + STRIP_VARIANTS
