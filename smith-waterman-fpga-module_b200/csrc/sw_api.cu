@@ -206,7 +206,7 @@ int load_shard(sw_handle *h, GpuCtx &gc, Slot &g, const uint8_t *packed, const u
 
     // --- order by length (counting sort when the range is small, else comparison sort)
     SW_CUDA(h, g.h_stage_a.reserve((n + 64) * 2 * sizeof(uint32_t)));      // pair_subj
-    SW_CUDA(h, g.h_stage_b.reserve((n + 64) * sizeof(uint32_t)));          // pair_len
+    SW_CUDA(h, g.h_stage_b.reserve((n + 128) * sizeof(uint32_t)));         // pair_len (2 per pair)
     std::vector<uint32_t> order;
     order.reserve(n);
     if (maxlen <= (1u << 22)) {
@@ -220,26 +220,26 @@ int load_shard(sw_handle *h, GpuCtx &gc, Slot &g, const uint8_t *packed, const u
         for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ln[a] < ln[b]; });
     }
-    // --- pair equal lengths; an odd one out is paired with itself (high lane unused)
+    // --- pair neighbours in length order: the longer member drives the column loop (low lane),
+    //     the shorter one (high lane) sees PAD columns once it has ended
     uint32_t *pair_subj = (uint32_t *)g.h_stage_a.p;
     uint32_t *pair_len = (uint32_t *)g.h_stage_b.p;
     size_t np = 0, i = 0;
     while (i < n && ln[order[i]] == 0) ++i;           // empty subjects score 0 (output is pre-zeroed)
-    while (i < n) {
-        const uint32_t a = order[i];
-        if (i + 1 < n && ln[order[i + 1]] == ln[a]) {
-            pair_subj[2 * np] = a; pair_subj[2 * np + 1] = order[i + 1];
-            i += 2;
-        } else {
-            pair_subj[2 * np] = a; pair_subj[2 * np + 1] = SW_NO_SUBJECT;
-            i += 1;
-        }
-        pair_len[np] = ln[a];
-        ++np;
+    if ((n - i) & 1) {                                // odd count: the shortest one stays single
+        pair_subj[0] = order[i]; pair_subj[1] = SW_NO_SUBJECT;
+        pair_len[0] = ln[order[i]]; pair_len[1] = 0;
+        ++i; ++np;
+    }
+    for (; i + 1 < n; i += 2, ++np) {
+        const uint32_t shorter = order[i], longer = order[i + 1];
+        pair_subj[2 * np] = longer; pair_subj[2 * np + 1] = shorter;
+        pair_len[2 * np] = ln[longer]; pair_len[2 * np + 1] = ln[shorter];
     }
     const size_t ntiles = (np + 31) / 32;
     for (size_t p = np; p < ntiles * 32; ++p) {
-        pair_subj[2 * p] = SW_NO_SUBJECT; pair_subj[2 * p + 1] = SW_NO_SUBJECT; pair_len[p] = 0;
+        pair_subj[2 * p] = SW_NO_SUBJECT; pair_subj[2 * p + 1] = SW_NO_SUBJECT;
+        pair_len[2 * p] = 0; pair_len[2 * p + 1] = 0;
     }
     SW_CUDA(h, g.h_stage_c.reserve((ntiles + 1) * sizeof(uint64_t)));
     uint64_t *tile_woff = (uint64_t *)g.h_stage_c.p;
@@ -247,7 +247,7 @@ int load_shard(sw_handle *h, GpuCtx &gc, Slot &g, const uint8_t *packed, const u
     for (size_t t = 0; t < ntiles; ++t) {
         tile_woff[t] = w;
         const size_t last = std::min(np, (t + 1) * 32) - 1;     // lengths ascend: last valid pair is longest
-        w += 32ull * ((pair_len[last] + 7) / 8);
+        w += 32ull * ((pair_len[2 * last] + 3) / 4);        // one byte per column, 4 per word
     }
     tile_woff[ntiles] = w;
     g.npairs = (uint32_t)np;
@@ -263,7 +263,7 @@ int load_shard(sw_handle *h, GpuCtx &gc, Slot &g, const uint8_t *packed, const u
     SW_CUDA(h, g.d_off.reserve(n * sizeof(uint64_t)));
     SW_CUDA(h, g.d_len.reserve(n * sizeof(uint32_t)));
     SW_CUDA(h, g.d_pair_subj.reserve(ntiles * 32 * 2 * sizeof(uint32_t)));
-    SW_CUDA(h, g.d_pair_len.reserve(ntiles * 32 * sizeof(uint32_t)));
+    SW_CUDA(h, g.d_pair_len.reserve(ntiles * 32 * 2 * sizeof(uint32_t)));
     SW_CUDA(h, g.d_tile_woff.reserve((ntiles + 1) * sizeof(uint64_t)));
     SW_CUDA(h, g.d_tp.reserve((w + 32) * sizeof(uint32_t)));
     cudaStream_t cs = gc.st_copy;
@@ -271,7 +271,7 @@ int load_shard(sw_handle *h, GpuCtx &gc, Slot &g, const uint8_t *packed, const u
     SW_CUDA(h, cudaMemcpyAsync(g.d_len.p, ln, n * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
     SW_CUDA(h, cudaMemcpyAsync(g.d_off.p, loc_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, cs));
     SW_CUDA(h, cudaMemcpyAsync(g.d_pair_subj.p, pair_subj, ntiles * 32 * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
-    SW_CUDA(h, cudaMemcpyAsync(g.d_pair_len.p, pair_len, ntiles * 32 * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
+    SW_CUDA(h, cudaMemcpyAsync(g.d_pair_len.p, pair_len, ntiles * 32 * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
     SW_CUDA(h, cudaMemcpyAsync(g.d_tile_woff.p, tile_woff, (ntiles + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, cs));
     SW_CUDA(h, cudaEventRecord(g.ev_upload, cs));
     SW_CUDA(h, cudaStreamWaitEvent(gc.st_compute, g.ev_upload, 0));

@@ -114,8 +114,12 @@ struct StripArgs {
     uint32_t zero;             // always 0, but opaque to the compiler
 };
 
-constexpr int kPadCode = 16;        // 17th column code: "no column" (before the start / past the end)
-constexpr int kCodesPerRow = 32;    // profile entries per row pair (codes 0..16 used): 256 bytes
+// Column codes: 0..15 = t_lo | t_hi << 2 (both members have a base in this column);
+// 16..19 = 16 + t_lo (the shorter member, always the high lane, has ended: its lane sees PAD);
+// 20 = no column at all (pipeline fill / drain, past the end of the pair).
+constexpr int kHiEndedCode = 16;
+constexpr int kPadCode = 20;
+constexpr int kCodesPerRow = 32;    // profile entries per row pair (codes 0..20 used): 256 bytes
 
 // One column step of the S sub-strips of a lane, each sub-strip on its own column (sub-strip s
 // is one column behind s-1): S independent dependency chains in one basic block, so a warp
@@ -227,6 +231,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
     constexpr int PASS_ENTRIES = VPE * RP * kCodesPerRow;
     constexpr int PPB = BT / G;
     constexpr unsigned FULL = 0xFFFFFFFFu;
+    static_assert(U == 4, "the step loop consumes one 4-column code word per trip");
 
     const int lane = threadIdx.x & 31;
     const int gl = (G == 1) ? 0 : (lane & (G - 1));
@@ -256,7 +261,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
 
         const unsigned pair = pb * PPB + pslot;
         const bool valid = pair < a.npairs;
-        const int ncols = valid ? (int)a.pair_len[pair] : 0;
+        const int ncols = valid ? (int)a.pair_len[2 * pair] : 0;          // longer member (low lane)
         const uint32_t *tpp = a.tp;
         uint32_t subj_lo = SW_NO_SUBJECT, subj_hi = SW_NO_SUBJECT;
         if (valid) {
@@ -299,7 +304,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                             if (rr < RS && i < m && code < kPadCode) {
                                 const int qi = (qp[i >> 2] >> ((i & 3) * 2)) & 3;
                                 lo = (qi == (code & 3)) ? a.match : a.mismatch;   // v1.0.v:119
-                                hi = (qi == (code >> 2)) ? a.match : a.mismatch;
+                                if (code < kHiEndedCode) hi = (qi == (code >> 2)) ? a.match : a.mismatch;
                             }
                             e[k] = AR::pack_score(lo, hi);
                         }
@@ -321,7 +326,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                 uint2 bcur = make_uint2(h0, gb2);            // (H, G) of the row above, column c
                 if (gl == 0 && ncols > 0) {
                     wcur = __ldg(tpp);
-                    if (ncols > 8) wnext = __ldg(tpp + 32);
+                    if (ncols > 4) wnext = __ldg(tpp + 32);
                     if (has_top) bcur = bnd_load(bnd, bnd_pol);
                 }
                 // what each sub-strip hands to the next virtual PE (the next sub-strip, or for
@@ -347,12 +352,16 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                         const bool on = t < ncols;
                         in_h[0] = bcur.x;
                         in_g[0] = bcur.y;
-                        in_t[0] = on ? ((wcur >> ((t & 7) * 4)) & 15u) : (uint32_t)kPadCode;
+                        // U == 4 and t2 % 4 == 0: the four columns of this trip are the four bytes of wcur
+                        in_t[0] = on ? ((wcur >> (8 * u)) & 255u) : (uint32_t)kPadCode;
                         if (on) {
-                            if ((t & 7) == 7) {
+                            if (u == U - 1) {
                                 wcur = wnext;
-                                const int k = (t >> 3) + 2;
-                                if (k * 8 < ncols) wnext = __ldg(tpp + k * 32);
+                                const int k = (t >> 2) + 2;
+                                if (k * 4 < ncols) wnext = __ldg(tpp + k * 32);
+                                // the word after that goes to L1 now, so the load above stays
+                                // short even if ptxas sinks it towards its use to save a register
+                                if ((k + 1) * 4 < ncols) asm volatile("prefetch.global.L1 [%0];" :: "l"(tpp + (k + 1) * 32));
                             }
                             if (has_top && t + 1 < ncols) bcur = bnd_load(bnd + (size_t)(t + 1) * PPB, bnd_pol);
                         }
@@ -397,27 +406,14 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
 }
 
 // ------------------------------------------------------------------------------------------
-// Column-pair code stream builder: interleaves the 2-bit codes of the two members of a pair.
-// One thread per (pair, word); a word covers 8 columns.
+// Column code stream builder: one byte per column of a pair (codes 0..20, see kHiEndedCode /
+// kPadCode), four columns per 32-bit word, word k of the 32 pairs of a tile contiguous.
+// One warp per tile: lane = pair slot, loop over words -> coalesced 128-byte stores.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t spread2(uint32_t x)
+__device__ __forceinline__ uint32_t load8_bases(const uint8_t *rec, uint32_t len, uint32_t k)
 {
-    // 16 bits = eight 2-bit groups  ->  eight 4-bit groups with the payload in the low 2 bits
-    x &= 0xFFFFu;
-    x = (x | (x << 8)) & 0x00FF00FFu;
-    x = (x | (x << 4)) & 0x0F0F0F0Fu;
-    x = (x | (x << 2)) & 0x33333333u;
-    return x;
-}
-
-__device__ __forceinline__ uint32_t load16_bases(const uint8_t *rec, uint32_t len, uint32_t k)
-{
-    const uint32_t nbytes = (len + 3) >> 2;
-    const uint32_t b0 = 2 * k, b1 = 2 * k + 1;
-    uint32_t v = 0;
-    if (b0 < nbytes) v |= rec[b0];
-    if (b1 < nbytes) v |= (uint32_t)rec[b1] << 8;
-    return v;
+    // the 4 bases of columns 4k .. 4k+3 (one packed byte), 0 past the end of the record
+    return (k < ((len + 3) >> 2)) ? rec[k] : 0u;
 }
 
 __global__ void __launch_bounds__(256) build_tp_kernel(const uint8_t *raw, const uint64_t *off,
@@ -425,7 +421,6 @@ __global__ void __launch_bounds__(256) build_tp_kernel(const uint8_t *raw, const
                                                       const uint32_t *pair_len, const uint64_t *tile_woff,
                                                       uint32_t *tp, uint32_t ntiles)
 {
-    // one warp per tile: lane = pair slot, loop over words -> coalesced 128-byte stores
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     if (warp >= ntiles) return;
@@ -433,14 +428,19 @@ __global__ void __launch_bounds__(256) build_tp_kernel(const uint8_t *raw, const
     const uint32_t kmax = (uint32_t)((w1 - w0) >> 5);
     const uint32_t pair = warp * 32 + lane;
     const uint32_t slo = pair_subj[2 * pair], shi = pair_subj[2 * pair + 1];
-    const uint32_t n = pair_len[pair];
+    const uint32_t nlo = pair_len[2 * pair], nhi = pair_len[2 * pair + 1];
     const uint8_t *rlo = (slo != SW_NO_SUBJECT) ? raw + off[slo] : nullptr;
-    const uint8_t *rhi = (shi != SW_NO_SUBJECT) ? raw + off[shi] : rlo;
+    const uint8_t *rhi = (shi != SW_NO_SUBJECT) ? raw + off[shi] : nullptr;
     for (uint32_t k = 0; k < kmax; ++k) {
+        const uint32_t a = rlo ? load8_bases(rlo, nlo, k) : 0u;
+        const uint32_t b = rhi ? load8_bases(rhi, nhi, k) : 0u;
         uint32_t w = 0;
-        if (rlo != nullptr && k * 8 < n) {
-            const uint32_t a = load16_bases(rlo, n, k), b = load16_bases(rhi, n, k);
-            w = spread2(a) | (spread2(b) << 2);
+#pragma unroll
+        for (uint32_t c = 0; c < 4; ++c) {
+            const uint32_t col = 4 * k + c;
+            const uint32_t tlo = (a >> (2 * c)) & 3u, thi = (b >> (2 * c)) & 3u;
+            const uint32_t code = col < nhi ? (tlo | (thi << 2)) : col < nlo ? (kHiEndedCode + tlo) : (uint32_t)kPadCode;
+            w |= code << (8 * c);
         }
         tp[w0 + (uint64_t)k * 32 + lane] = w;
     }

@@ -16,9 +16,10 @@
  *   pair_subj     : [2*npairs] shard-local subject index of the low / high 16-bit
  *                   lane of pair p (SW_NO_SUBJECT = lane unused)
  *   pair_len      : [npairs] columns of the pair (both members have this length)
- *   tp            : column-pair codes, 4 bit per column = t_lo | t_hi << 2, eight
- *                   columns per 32-bit word, tiles of 32 pairs, word k of the 32
- *                   pairs of a tile contiguous: tp[tile_woff[tile] + k*32 + slot]
+ *   tp            : column codes, one byte per column (0..15 = t_lo | t_hi << 2; 16..19 = the
+ *                   shorter member has ended; 20 = no column), four columns per 32-bit
+ *                   word, tiles of 32 pairs, word k of the 32 pairs of a tile contiguous:
+ *                   tp[tile_woff[tile] + k*32 + slot]
  */
 struct SwDevDb {
     const uint8_t  *raw;
