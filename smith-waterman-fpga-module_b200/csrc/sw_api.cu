@@ -301,14 +301,14 @@ SwDevDb dev_db(const Slot &g)
 double variant_speed(const SwStripVariant *v)
 {
     struct { const char *name; double gcups; } tab[] = {
-        {"strip_s16x2_R30x1_G1", 8450}, {"strip_s16x2_R38x1_G1", 8560}, {"strip_s16x2_R75x1_G1", 8526},
-        {"strip_s16x2_R32x1_G1", 8540}, {"strip_s16x2_R50x1_G1", 8750}, {"strip_s16x2_R25x2_G1", 8680},
-        {"strip_s16x2_R19x2_G1", 8060}, {"strip_s16x2_R15x3_G1", 7780}, {"strip_s16x2_R30x2_G1", 7935},
-        {"strip_s16x2_R64x1_G1", 8400}, {"strip_s16x2_R32x2_G1", 8300}, {"strip_s16x2_R25x3_G1", 8500},
-        {"strip_s16x2_R38x2_G1", 8820}, {"strip_s16x2_R25x4_G1", 7600}, {"strip_s16x2_R25x1_G2", 7160},
-        {"strip_s16x2_R75x1_G2", 7005}, {"strip_s16x2_R25x3_G2", 7335}, {"strip_s16x2_R38x1_G4", 7245},
-        {"strip_s16x2_R19x2_G4", 7080}, {"strip_s16x2_R32x1_G4", 7050}, {"strip_s16x2_R16x1_G32", 6005},
-        {"strip_s16x2_R8x2_G32", 6410},
+        {"strip_s16x2_R30x1_G1", 8220}, {"strip_s16x2_R38x1_G1", 8310}, {"strip_s16x2_R75x1_G1", 8040},
+        {"strip_s16x2_R32x1_G1", 8230}, {"strip_s16x2_R50x1_G1", 8180}, {"strip_s16x2_R25x2_G1", 8700},
+        {"strip_s16x2_R19x2_G1", 7810}, {"strip_s16x2_R15x3_G1", 7590}, {"strip_s16x2_R30x2_G1", 8040},
+        {"strip_s16x2_R64x1_G1", 7910}, {"strip_s16x2_R32x2_G1", 8000}, {"strip_s16x2_R25x3_G1", 8620},
+        {"strip_s16x2_R38x2_G1", 8600}, {"strip_s16x2_R25x4_G1", 7200}, {"strip_s16x2_R25x1_G2", 7345},
+        {"strip_s16x2_R75x1_G2", 7380}, {"strip_s16x2_R25x3_G2", 7480}, {"strip_s16x2_R38x1_G4", 7325},
+        {"strip_s16x2_R19x2_G4", 7220}, {"strip_s16x2_R32x1_G4", 7180}, {"strip_s16x2_R16x1_G32", 5980},
+        {"strip_s16x2_R8x2_G32", 6320},
     };
     for (auto &t : tab) if (std::strcmp(t.name, v->name) == 0) return t.gcups;
     return 5000.0;

@@ -71,9 +71,12 @@ struct ArithS16 {
     }
 };
 
-// Pass-boundary scratch accesses: L2-only (never stale in L1) and tagged evict_last so that the
-// scratch lines, which are rewritten every pass, stay resident in L2 instead of being written
-// back to HBM between passes.
+// Pass-boundary scratch accesses, tagged evict_last so that the scratch lines, which are rewritten
+// every pass, stay resident in L2 instead of being written back to HBM between passes.  A slot is
+// written and read by the same warp only (lane G-1 / lane 0), so L1 is coherent for it: loads are
+// cached in L1 and an explicit L1 prefetch runs a few steps ahead -- the load itself then costs an
+// L1 hit wherever ptxas schedules it inside the step (placed late, an L2-latency load showed up
+// as long-scoreboard stalls: ALU pipe 89 % -> 84 %).
 __device__ __forceinline__ uint64_t l2_evict_last_policy()
 {
     uint64_t pol;
@@ -83,8 +86,12 @@ __device__ __forceinline__ uint64_t l2_evict_last_policy()
 __device__ __forceinline__ uint2 bnd_load(const uint2 *p, uint64_t pol)
 {
     uint2 v;
-    asm volatile("ld.global.cg.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+    asm volatile("ld.global.ca.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
     return v;
+}
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
 }
 __device__ __forceinline__ void bnd_store(uint2 *p, uint2 v, uint64_t pol)
 {
@@ -327,7 +334,10 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                 if (gl == 0 && ncols > 0) {
                     wcur = __ldg(tpp);
                     if (ncols > 4) wnext = __ldg(tpp + 32);
-                    if (has_top) bcur = bnd_load(bnd, bnd_pol);
+                    if (has_top) {
+                        bcur = bnd_load(bnd, bnd_pol);
+                        for (int c = 1; c < 4 && c < ncols; ++c) prefetch_l1(bnd + (size_t)c * PPB);
+                    }
                 }
                 // what each sub-strip hands to the next virtual PE (the next sub-strip, or for
                 // s = S-1 the next lane): bottom H, bottom G and the column code it just used
@@ -361,9 +371,12 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                                 if (k * 4 < ncols) wnext = __ldg(tpp + k * 32);
                                 // the word after that goes to L1 now, so the load above stays
                                 // short even if ptxas sinks it towards its use to save a register
-                                if ((k + 1) * 4 < ncols) asm volatile("prefetch.global.L1 [%0];" :: "l"(tpp + (k + 1) * 32));
+                                if ((k + 1) * 4 < ncols) prefetch_l1(tpp + (k + 1) * 32);
                             }
-                            if (has_top && t + 1 < ncols) bcur = bnd_load(bnd + (size_t)(t + 1) * PPB, bnd_pol);
+                            if (has_top) {
+                                if (t + 1 < ncols) bcur = bnd_load(bnd + (size_t)(t + 1) * PPB, bnd_pol);
+                                if (t + 4 < ncols) prefetch_l1(bnd + (size_t)(t + 4) * PPB);
+                            }
                         }
                     }
 #pragma unroll
