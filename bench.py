@@ -299,10 +299,10 @@ def main():
         # instructions of the recurrence run on the FMA-side pipe and overlap
         alu_per_pair = {"s16x2": 3.5, "int32": 12.0}[arith]
         tight_gcups = SM_COUNT * pk["sm_max_mhz"] * 1e6 * R_INT * 2.0 / alu_per_pair / 1e9
-        # per launch: the pair's code stream (19 words) + pair_len + pair_subj, read once; per step 8 launches
+        # per launch: the pair's code stream (one byte per column) + pair_len + pair_subj, read once; 8 launches per step
         # plus one int32 score per (query, subject) written once
         n_launch = max(1, launches // max(1, args.steps))
-        algo_bytes = (args.subjects / 2) * (((TLEN + 7) // 8) * 4 + 4 + 8) * n_launch + args.subjects * args.queries * 4
+        algo_bytes = (args.subjects / 2) * (((TLEN + 3) // 4) * 4 + 8 + 8) * n_launch + args.subjects * args.queries * 4
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:

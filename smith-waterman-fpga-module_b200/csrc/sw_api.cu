@@ -340,7 +340,15 @@ int choose_variant(const sw_handle *h, const GpuCtx &gc, const Slot &g, uint32_t
         const double fill = (double)gc.num_sms * v->min_blocks * v->block_threads;
         const double util = std::min(1.0, lanes / fill);
         const double cols = (double)std::max<uint32_t>(g.max_len, 1);
-        const double cost = rows * (cols + v->G * v->S - 1) / cols / variant_speed(v) / util;
+        // time of the whole job at the variant's measured speed ...
+        const double job = rows * (cols + v->G * v->S - 1) / cols * (double)g.sum_len / variant_speed(v) / util;
+        // ... plus half the time of the longest work item (block of pairs x longest query) running
+        // at its share of an SM: with few, long items the tail of the launch is what matters, and
+        // variants with fewer resident blocks per SM finish a single item sooner
+        const int ppb = v->block_threads / v->G;
+        const double qrows = (double)((maxq + P - 1) / P) * P;
+        const double item = qrows * cols * 2.0 * ppb * ((double)gc.num_sms * v->min_blocks) / variant_speed(v);
+        const double cost = job + 0.5 * item;
         if (best < 0 || cost < best_cost) { best = i; best_cost = cost; }
     }
     return best;
