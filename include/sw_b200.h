@@ -41,7 +41,7 @@ extern "C" {
 #define SW_ETIMEOUT   -6   /* sw_fetch timed out (the host's -t option)         */
 #define SW_ECAPACITY  -7   /* caller's score buffer too small                   */
 #define SW_EIO        -8   /* file could not be read / written                  */
-#define SW_EAGAIN     -9   /* a batch is already in flight (the bank's `full`)  */
+#define SW_EAGAIN     -9   /* both batch buffers in flight (the bank's `full`)   */
 
 /* The `penalties` bus + SCORE_WIDTH parameter.
  * Replaces: ScoreBank_v2.v:34,161 (ld_penalties, penalties[4*W]),

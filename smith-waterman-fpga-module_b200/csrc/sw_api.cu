@@ -492,7 +492,11 @@ int copy_out(sw_handle *h, int si, int32_t *scores, size_t cap, int timeout_ms)
             SW_CUDA(h, cudaSetDevice(g.dev));
             const QueryChunk &qc = b.chunks[c];
             int rc = wait_event(h, qc.done, t_end, forever);
-            if (rc != SW_OK) return rc;
+            if (rc != SW_OK) {
+                // copies already enqueued must not outlive this call: the caller owns `scores`
+                for (auto &gg : h->gpus) { cudaSetDevice(gg.dev); cudaStreamSynchronize(gg.st_copy); }
+                return rc;
+            }
             SW_CUDA(h, cudaMemcpy2DAsync(scores + (size_t)qc.q0 * bt.ns + b.s0, bt.ns * sizeof(int32_t),
                                          b.d_out.as<int32_t>() + (size_t)qc.q0 * n, n * sizeof(int32_t),
                                          n * sizeof(int32_t), (size_t)(qc.q1 - qc.q0), cudaMemcpyDeviceToHost,
@@ -598,7 +602,7 @@ const char *sw_strerror(int code)
         case SW_ETIMEOUT: return "timed out";
         case SW_ECAPACITY: return "output buffer too small";
         case SW_EIO: return "I/O error";
-        case SW_EAGAIN: return "a batch is already in flight";
+        case SW_EAGAIN: return "busy: both batch buffers are in flight (fetch one first)";
         default: return "unknown error";
     }
 }

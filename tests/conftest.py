@@ -31,5 +31,10 @@ def oracle_mod():
 
 @pytest.fixture(scope="session")
 def pkg():
-    """The product package (hyphenated directory name => importlib)."""
-    return importlib.import_module(PKG_NAME)
+    """The product package (hyphenated directory name => importlib).  On a fresh checkout the
+    native library is built first (nvcc cross-compiles sm_100a without a GPU)."""
+    mod = importlib.import_module(PKG_NAME)
+    if not os.path.exists(mod.LIB_PATH) or not os.path.exists(os.path.join(ROOT, "bin", "sw_b200_cli")):
+        import __graft_entry__
+        __graft_entry__.build()
+    return mod
