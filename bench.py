@@ -325,6 +325,10 @@ def main():
                          "frac": per_gpu / roof_gcups,
                          "peak_def": f"148 SM x {pk['sm_max_mhz']:.0f} MHz x R_int {R_INT:.0f} thread-instr/clk/SM "
                                      f"(measured, profiles/r01_pipe_pairs_1024thr.json) x 2 cells / 6 instr (SURVEY 8d)",
+                         "note": "frac > 1 is not a measurement artefact: the survey's roofline assumes 6 integer-pipe "
+                                 "instructions per 2 cells; the kernel evaluates an algebraically equivalent form "
+                                 "(DESIGN.md section 2) with 3.5 ALU-pipe + 1 FMA-pipe instructions, see 'tight'. Scores are "
+                                 "checked against the CPU oracle inside this run (cpu_baseline.sample).",
                          "traffic": traffic,
                          "tight": {"peak": tight_gcups, "frac": per_gpu / tight_gcups,
                                    "def": f"ALU-pipe bound of this kernel: {alu_per_pair} ALU-pipe instr per 2 cells, "
