@@ -113,6 +113,9 @@ def host_threads():
 def make_inputs(pkg, n_subjects, n_queries, rank):
     db = pkg.random_packed_db(n_subjects, TLEN, seed=SEED + 1000 * rank)
     q = pkg.random_packed_db(n_queries, QLEN, seed=SEED - 1)
+    # 1 % of the subjects are homologs of a query (5 % substitutions, 2 % indels) so that the gap
+    # path carries real alignments; the kernel has no data-dependent exit
+    pkg.plant_homologs(db, q, 0.01, seed=SEED + 7 + rank)
     return q, db
 
 
@@ -319,6 +322,7 @@ def main():
             "data": "synthetic",
             "config": {"workload": workload_name(args), "queries": args.queries, "query_len": QLEN,
                        "subject_len": TLEN, "subjects_per_gpu": args.subjects, "penalties": "5/-4/-12/-4",
+                       "planted_homologs": "1 % of subjects = a query with 5 % substitutions + 2 % indels",
                        "kernel": kname, "l2": "inputs (code stream + 4 GB score matrix per GPU) larger than L2",
                        "wall_ms_per_step": wall_s / args.steps * 1e3, "checksum": checksum},
             "roofline": {"bound": "int_pipe", "achieved": per_gpu, "peak": roof_gcups, "unit": "GCUPS",

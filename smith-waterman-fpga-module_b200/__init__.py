@@ -17,7 +17,7 @@ import os
 
 import numpy as np
 
-from .seqio import pack_sequences, random_packed_db  # noqa: F401
+from .seqio import pack_sequences, plant_homologs, random_packed_db  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SW_B200_LIB", os.path.join(_HERE, "libsw_b200.so"))   # override: A/B builds

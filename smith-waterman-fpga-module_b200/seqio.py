@@ -49,6 +49,48 @@ def random_packed_db(n, length, seed):
     return flat, ln, off
 
 
+def unpack_codes(packed2d, length):
+    """[n, nbytes] packed rows -> [n, length] 2-bit codes."""
+    idx = np.arange(length)
+    return (packed2d[:, idx >> 2] >> ((idx & 3) * 2).astype(np.uint8)) & 3
+
+
+def plant_homologs(db, queries, frac, seed, psub=0.05, pindel=0.02):
+    """Replaces a fraction of the fixed-length subjects of `db` by mutated copies of the queries
+    (substitutions + indels), in place on the packed form, so that the
+    gap path of the recurrence carries real alignments.  Every round(1/frac)-th subject is planted."""
+    packed, ln, off = db
+    qpacked, qln, qoff = queries
+    n, length = len(ln), int(ln[0])
+    nb = (length + 3) // 4
+    qlen = int(qln[0])
+    assert np.all(ln == length) and np.all(qln == qlen) and qlen >= length
+    rng = np.random.default_rng(seed)
+    step = max(1, int(round(1.0 / frac)))
+    rows = np.arange(0, n, step)
+    qcodes = unpack_codes(qpacked[: len(qln) * ((qlen + 3) // 4)].reshape(len(qln), -1), qlen)
+    src = qcodes[rng.integers(0, len(qln), size=len(rows))][:, :length].copy()        # [k, length]
+    sub = rng.random(src.shape) < psub
+    src[sub] = (src[sub] + rng.integers(1, 4, size=int(sub.sum()))) & 3
+    # indels: delete one base and shift left (deletion) or shift right and insert (insertion)
+    nind = rng.binomial(length, pindel, size=len(rows))
+    for r in np.nonzero(nind)[0]:
+        for _ in range(int(nind[r])):
+            p = int(rng.integers(0, length))
+            if rng.random() < 0.5:
+                src[r, p:-1] = src[r, p + 1:]
+                src[r, -1] = rng.integers(0, 4)
+            else:
+                src[r, p + 1:] = src[r, p:-1]
+                src[r, p] = rng.integers(0, 4)
+    pad = (-length) % 4
+    c = np.concatenate([src, np.zeros((len(rows), pad), src.dtype)], axis=1).reshape(len(rows), -1, 4).astype(np.uint8)
+    rows_packed = c[:, :, 0] | (c[:, :, 1] << 2) | (c[:, :, 2] << 4) | (c[:, :, 3] << 6)
+    view = packed[: n * nb].reshape(n, nb)
+    view[rows] = rows_packed
+    return len(rows)
+
+
 def unpack_to_str(packed, length, off=0):
     idx = np.arange(length)
     codes = (packed[off + (idx >> 2)] >> ((idx & 3) * 2)) & 3

@@ -501,3 +501,38 @@ def test_every_shipped_fasta_file_vs_oracle(golden, oracle_mod, pkg):
             np.testing.assert_array_equal(got, want, err_msg=fn)
             n_files += 1
     assert n_files == 18
+
+
+def test_randomised_stress_vs_oracle(oracle_mod, pkg):
+    """Seeded property test: random penalties inside the supported domain, random score width,
+    random kernel variant, ragged lengths (including 0 and 1), a few planted homologs."""
+    rng = random.Random(20160912)
+    variants = ["auto", "generic32"] + STRIP_VARIANTS
+    for it in range(40):
+        match = rng.randint(1, 9)
+        mismatch = -rng.randint(0, 9)
+        gap_extend = -rng.randint(0, 6)
+        gap_open = -rng.randint(0, 14)
+        if gap_open + gap_extend > 0:
+            gap_open = -gap_extend
+        width = rng.choice([0, 0, 0, 9, 10, 12, 15])
+        if width and (match >= (1 << (width - 1)) or gap_open + 2 * gap_extend < -(1 << (width - 1))):
+            width = 0
+        nq = rng.randint(1, 4)
+        queries = [_rand(rng, rng.choice([1, 2, 31, 50, 75, 76, 77, 150, 300, rng.randint(1, 400)])) for _ in range(nq)]
+        subjects = []
+        for _ in range(rng.randint(1, 120)):
+            if rng.random() < 0.3:
+                src = rng.choice(queries)
+                s = _mutate(rng, src, 0.1, 0.1)
+                s = _rand(rng, rng.randint(0, 20)) + s + _rand(rng, rng.randint(0, 20))
+            else:
+                s = _rand(rng, rng.choice([0, 1, 3, rng.randint(1, 350)]))
+            subjects.append(s)
+        params = dict(match=match, mismatch=mismatch, gap_open=gap_open, gap_extend=gap_extend, score_width=width)
+        want = _oracle_matrix(oracle_mod, pkg, queries, subjects, **params)
+        choice = rng.choice(variants)
+        with pkg.Engine(**params) as e:
+            _choose(e, choice)
+            got = e.score(queries, subjects)
+        np.testing.assert_array_equal(got, want, err_msg=f"iteration {it}: {params} {choice} {e.last_kernel_name}")
