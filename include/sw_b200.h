@@ -163,6 +163,11 @@ int sw_set_arith(sw_handle_t *h, int arith);
  * handle's penalties match.  enable = 0 forces the run-time-penalty kernels (process-wide;
  * for A/B measurements and tests). */
 int sw_set_fixed_penalty_kernels(int enable);
+/* Large jobs (>= ~0.4 s of estimated work): the three variants the cost model ranks best are timed
+ * on a ~20 ms sample of the actual workload and the fastest one runs; the decision is cached per
+ * workload shape.  enable = 0 uses the model's first choice only.  Default: on
+ * (environment SW_B200_AUTOTUNE=0 turns it off at sw_init). */
+int sw_set_autotune(sw_handle_t *h, int enable);
 int sw_kernel_variant_count(void);
 const char *sw_kernel_variant_name(int idx);
 int sw_set_kernel_name(sw_handle_t *h, const char *name);

@@ -85,6 +85,7 @@ def load_library():
     L.sw_set_kernel_name.argtypes = [vp, C.c_char_p]
     L.sw_plan_shards.argtypes = [vp, sz, i32, vp]
     L.sw_set_fixed_penalty_kernels.argtypes = [i32]
+    L.sw_set_autotune.argtypes = [vp, i32]
     L.sw_set_strands.argtypes = [vp, i32]
     L.sw_query_rows.argtypes = [vp]
     L.sw_batches_in_flight.argtypes = [vp]
@@ -225,6 +226,9 @@ class Engine:
     def set_kernel_choice(self, rows_per_lane=0, lanes_per_pair=0, force32=False, arith=-1):
         self._check(self.lib.sw_set_kernel_choice(self.h, rows_per_lane, lanes_per_pair, int(force32)))
         self._check(self.lib.sw_set_arith(self.h, arith))
+
+    def set_autotune(self, enable):
+        self._check(self.lib.sw_set_autotune(self.h, int(bool(enable))))
 
     def set_kernel_name(self, name):
         self._check(self.lib.sw_set_kernel_name(self.h, name.encode() if name else None))

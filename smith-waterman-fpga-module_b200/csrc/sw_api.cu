@@ -115,6 +115,9 @@ struct sw_handle {
     const char *last_kernel = "none";
     int force_R = 0, force_G = 0, force32 = 0, force_arith = -1;
     int force_variant = -1;
+    bool autotune = true;             // time the model's top candidates on a sample of large jobs
+    uint64_t tune_key = 0;            // workload signature of the cached decision
+    int tune_choice = -1;
 };
 
 namespace {
@@ -316,7 +319,7 @@ double variant_speed(const SwStripVariant *v)
 
 // Picks the strip variant: least estimated time = padded rows x (columns + pipeline fill)
 // / measured speed / fraction of the GPU the pairs can keep busy.
-int choose_variant(const sw_handle *h, const GpuCtx &gc, const Slot &g, uint32_t maxq)
+int choose_variant(const sw_handle *h, const GpuCtx &gc, const Slot &g, uint32_t maxq, std::vector<int> *ranked = nullptr)
 {
     const int nv = sw_strip_variant_count();
     if (h->force_variant >= 0) return h->force_variant;
@@ -330,6 +333,7 @@ int choose_variant(const sw_handle *h, const GpuCtx &gc, const Slot &g, uint32_t
     }
     int best = -1;
     double best_cost = 0;
+    std::vector<std::pair<double, int>> costs;
     for (int i = 0; i < nv; ++i) {
         const SwStripVariant *v = sw_strip_variant(i);
         const int P = v->R * v->G;
@@ -350,7 +354,83 @@ int choose_variant(const sw_handle *h, const GpuCtx &gc, const Slot &g, uint32_t
         const double item = qrows * cols * 2.0 * ppb * ((double)gc.num_sms * v->min_blocks) / variant_speed(v);
         const double cost = job + 0.5 * item;
         if (best < 0 || cost < best_cost) { best = i; best_cost = cost; }
+        costs.emplace_back(cost, i);
     }
+    if (ranked) {
+        std::sort(costs.begin(), costs.end());
+        for (auto &c : costs) ranked->push_back(c.second);
+    }
+    return best;
+}
+
+// Launch geometry of a strip variant for this shard and query set (also grows the boundary scratch).
+int strip_setup(sw_handle *h, GpuCtx &gc, const Slot &g, int vidx, int *grid, int *chunk_passes)
+{
+    const SwStripVariant *v = sw_strip_variant(vidx);
+    const int P = v->R * v->G;
+    const int need_passes = (int)((h->q_max_len + P - 1) / P);
+    const size_t pass_bytes = sw_strip_smem_bytes(vidx, 1);
+    const int budget_passes = std::max<int>(1, (int)((48 * 1024) / pass_bytes));
+    *chunk_passes = std::max(1, std::min(need_passes, budget_passes));
+    int bps = 0;
+    SW_CUDA(h, sw_strip_occupancy(vidx, sw_strip_smem_bytes(vidx, *chunk_passes), &bps));
+    if (bps < 1) return SW_ECUDA;
+    const int ppb = v->block_threads / v->G;
+    const uint32_t npb = (g.npairs + ppb - 1) / ppb;
+    *grid = (int)std::min<uint64_t>(npb, (uint64_t)gc.num_sms * bps);
+    if (need_passes > 1) SW_CUDA(h, gc.d_bnd.reserve((size_t)*grid * g.max_len * ppb * sizeof(uint2)));
+    return SW_OK;
+}
+
+// Times the model's best candidates on a window of the pair list (middle of the length order)
+// and a few queries, and returns the fastest.  Every variant produces identical scores, so the
+// sample launches may write into the real output buffer.
+int autotune_variant(sw_handle *h, GpuCtx &gc, Slot &g, const SwDevDb &db, const SwDevQueries &dq,
+                     const SwScoring &sc, const std::vector<int> &ranked, int nq)
+{
+    const int ncand = std::min<int>(3, (int)ranked.size());
+    const int nqs = std::min(nq, 8);
+    uint64_t qrows = 0;
+    for (int q = 0; q < nqs; ++q) qrows += h->q_len[q];
+    const double mean_len = (double)g.sum_len / (double)std::max<size_t>(g.s1 - g.s0, 1);
+    const double cells_per_pair = 2.0 * mean_len * (double)std::max<uint64_t>(qrows, 1);
+    uint64_t pairs_s = (uint64_t)(1.5e11 / cells_per_pair);                      // ~20 ms of work
+    pairs_s = std::max<uint64_t>(pairs_s, (uint64_t)gc.num_sms * 4 * 128 * 4);   // >= 4 waves of blocks
+    pairs_s = std::min<uint64_t>(pairs_s, g.npairs) & ~31ull;
+    if (pairs_s < 1024) return ranked[0];
+    const uint64_t p0 = ((g.npairs - pairs_s) / 2) & ~31ull;
+    SwDevDb win = db;
+    win.pair_subj = db.pair_subj + 2 * p0;
+    win.pair_len = db.pair_len + 2 * p0;
+    win.tile_woff = db.tile_woff + p0 / 32;
+    win.npairs = (uint32_t)pairs_s;
+    cudaEvent_t e0, e1;
+    SW_CUDA(h, cudaEventCreate(&e0));
+    SW_CUDA(h, cudaEventCreate(&e1));
+    int best = ranked[0];
+    float best_ms = 0.f;
+    for (int c = 0; c < ncand; ++c) {
+        const int vidx = ranked[c];
+        int grid = 0, chunk_passes = 1;
+        Slot tmp_geom;                       // geometry of the window (npairs / max_len only)
+        tmp_geom.npairs = win.npairs; tmp_geom.max_len = g.max_len;
+        int rc = strip_setup(h, gc, tmp_geom, vidx, &grid, &chunk_passes);
+        if (rc != SW_OK) { cudaEventDestroy(e0); cudaEventDestroy(e1); return ranked[0]; }
+        float ms = 0.f;
+        for (int rep = 0; rep < 2; ++rep) {  // first run warms caches and the instruction cache
+            SW_CUDA(h, cudaMemsetAsync(gc.d_counters.p, 0, sizeof(unsigned), gc.st_compute));
+            SW_CUDA(h, cudaEventRecord(e0, gc.st_compute));
+            SW_CUDA(h, sw_launch_strip(vidx, gc.st_compute, win, dq, 0, nqs, sc, g.d_out.as<int32_t>(), g.s1 - g.s0,
+                                       gc.d_bnd.as<uint2>(), g.max_len, gc.d_counters.as<unsigned>(), grid, chunk_passes));
+            h->launches++;
+            SW_CUDA(h, cudaEventRecord(e1, gc.st_compute));
+            SW_CUDA(h, cudaEventSynchronize(e1));
+            SW_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+        }
+        if (c == 0 || ms < best_ms) { best = vidx; best_ms = ms; }
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
     return best;
 }
 
@@ -391,9 +471,11 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
     // 32-bit kernel recomputes exactly those.
     const uint64_t smax = (uint64_t)sc.match * std::min<uint64_t>(h->q_max_len, g.max_len);
     const bool may_overflow = !sc.limit && (smax + (uint64_t)sc.match >= 32000ull);
+    SW_CUDA(h, gc.d_counters.reserve(kMaxCounters * sizeof(unsigned)));
     int vidx = -1;
+    std::vector<int> ranked;
     if (!h->force32) {
-        vidx = choose_variant(h, gc, g, h->q_max_len);
+        vidx = choose_variant(h, gc, g, h->q_max_len, &ranked);
         if (vidx < 0 && (h->force_R || h->force_G)) return SW_EINVAL;
     }
 
@@ -404,28 +486,29 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
     // the device work counter is 32-bit: (pair blocks) x (queries per launch) must stay below 2^31
     while (nchunks < nq && (uint64_t)(g.npairs / 4 + 1) * (uint64_t)((nq + nchunks - 1) / nchunks) >= (1ull << 31)) nchunks *= 2;
     nchunks = std::min(nchunks, nq);
-    SW_CUDA(h, gc.d_counters.reserve(kMaxCounters * sizeof(unsigned)));
-    SW_CUDA(h, cudaMemsetAsync(gc.d_counters.p, 0, kMaxCounters * sizeof(unsigned), gc.st_compute));
 
+    // large jobs: let the GPU pick among the model's top candidates (decision cached per workload shape)
+    if (vidx >= 0 && h->autotune && h->force_variant < 0 && !h->force_R && !h->force_G && est_ms >= 400.0 && ranked.size() > 1) {
+        uint64_t key = 1469598103934665603ull;
+        auto log2b = [](uint64_t x) { uint64_t b = 0; while (x >>= 1) ++b; return b; };
+        const uint64_t parts[] = {h->q_max_len, h->q_sum_len, (uint64_t)nq, g.max_len, log2b(g.npairs), log2b(g.sum_len),
+                                  (uint64_t)(uint16_t)h->params.match, (uint64_t)(uint16_t)h->params.mismatch,
+                                  (uint64_t)(uint16_t)h->params.gap_open, (uint64_t)(uint16_t)h->params.gap_extend,
+                                  (uint64_t)h->params.score_width};
+        for (uint64_t x : parts) { key ^= x; key *= 1099511628211ull; }
+        if (h->tune_key != key || h->tune_choice < 0) {
+            h->tune_choice = autotune_variant(h, gc, g, db, dq, sc, ranked, nq);
+            h->tune_key = key;
+        }
+        vidx = h->tune_choice;
+    }
+
+    SW_CUDA(h, cudaMemsetAsync(gc.d_counters.p, 0, kMaxCounters * sizeof(unsigned), gc.st_compute));
     int grid = 0, chunk_passes = 1;
     if (vidx >= 0) {
-        const SwStripVariant *v = sw_strip_variant(vidx);
-        const int P = v->R * v->G;
-        const int need_passes = (int)((h->q_max_len + P - 1) / P);
-        const size_t pass_bytes = sw_strip_smem_bytes(vidx, 1);
-        const int budget_passes = std::max<int>(1, (int)((48 * 1024) / pass_bytes));
-        chunk_passes = std::max(1, std::min(need_passes, budget_passes));
-        int bps = 0;
-        SW_CUDA(h, sw_strip_occupancy(vidx, sw_strip_smem_bytes(vidx, chunk_passes), &bps));
-        if (bps < 1) return SW_ECUDA;
-        const int ppb = v->block_threads / v->G;
-        const uint32_t npb = (g.npairs + ppb - 1) / ppb;
-        grid = (int)std::min<uint64_t>(npb, (uint64_t)gc.num_sms * bps);
-        if (need_passes > 1) {
-            const size_t bytes = (size_t)grid * g.max_len * ppb * sizeof(uint2);
-            SW_CUDA(h, gc.d_bnd.reserve(bytes));
-        }
-        h->last_kernel = v->name;
+        int rc = strip_setup(h, gc, g, vidx, &grid, &chunk_passes);
+        if (rc != SW_OK) return rc;
+        h->last_kernel = sw_strip_variant(vidx)->name;
     }
     if (vidx < 0 || may_overflow) {
         const int threads_total = gc.num_sms * 2 * 128;
@@ -625,6 +708,7 @@ int sw_init(sw_handle_t **out, const sw_params_t *p, const int *gpu_ids, int n_g
     sw_handle *h = new (std::nothrow) sw_handle();
     if (!h) return SW_ENOMEM;
     h->params = prm;
+    if (const char *e = std::getenv("SW_B200_AUTOTUNE")) h->autotune = (e[0] != '0');
     h->gpus.resize(ids.size());
     for (size_t i = 0; i < ids.size(); ++i) {
         GpuCtx &g = h->gpus[i];
@@ -888,6 +972,14 @@ int sw_set_kernel_name(sw_handle_t *h, const char *name)
 int sw_set_fixed_penalty_kernels(int enable)
 {
     sw_strip_disable_fixed(enable == 0);
+    return SW_OK;
+}
+
+int sw_set_autotune(sw_handle_t *h, int enable)
+{
+    if (!h) return SW_EINVAL;
+    h->autotune = enable != 0;
+    h->tune_choice = -1;
     return SW_OK;
 }
 
