@@ -151,7 +151,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": used, "kind": "port", "sample": sample},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(args):
@@ -159,7 +159,28 @@ def workload_name(args):
             f"queries, inter-task kernel")
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """stdout must carry exactly ONE JSON line, but libraries print there too (NCCL's version banner
+    at communicator creation).  Point fd 1 at stderr for the whole run and keep the real stdout for
+    the final line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -190,7 +211,7 @@ def main():
     import torch.distributed as dist
 
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: this bench has no CPU fallback"}))
+        emit({"error": "no CUDA device: this bench has no CPU fallback"})
         return 1
     torch.cuda.set_device(local_rank)
     if world > 1:
@@ -343,7 +364,7 @@ def main():
                                  "frac": algo_bytes / (dev_s / args.steps) / 1e9 / pk["hbm_gbs"]}},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
