@@ -182,7 +182,7 @@ int upload_queries(sw_handle *h, GpuCtx &g)
     return SW_OK;
 }
 
-// Length-sorts the shard's subjects, pairs equal lengths, lays out 32-pair tiles, uploads.
+// Length-sorts the shard's subjects, pairs neighbours in length order, lays out 32-pair tiles, uploads.
 int load_shard(sw_handle *h, GpuCtx &gc, Slot &g, const uint8_t *packed, const uint32_t *len, const uint64_t *off)
 {
     SW_CUDA(h, cudaSetDevice(gc.dev));

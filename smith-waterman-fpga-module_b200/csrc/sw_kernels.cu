@@ -11,8 +11,8 @@
  *
  * How it is mapped to the GPU (replaces the systolic array of ScoringModule_v1.1.v and the
  * two-way time sharing of each PE, SW_ProcessingElement_v1.0.v:25-27):
- *   - two subjects of equal length share every 32-bit register (low / high 16-bit lane) --
- *     the PE's toggle-0 / toggle-1 sequences;
+ *   - two subjects of similar length share every 32-bit register (low / high 16-bit lane) --
+ *     the PE's toggle-0 / toggle-1 sequences; the shorter one sees PAD scores once it has ended;
  *   - a lane keeps R consecutive query rows of H and G in registers and walks the subject
  *     columns; per cell pair the arithmetic is 3.5 ALU-pipe + 1 FMA-pipe instructions
  *     (VIMNMX.S16x2, VIADDMNMX.S16x2.RELU, VIADDMNMX.S16x2, 1/2 VIMNMX3.S16x2; VIADD.16x2);
