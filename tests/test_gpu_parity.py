@@ -282,7 +282,6 @@ def test_state_errors_and_timeout(pkg):
         with pytest.raises(pkg.SwError) as ei:
             e.score_batch(["ACGT"])
         assert ei.value.code == pkg.SW_EAGAIN          # both buffers busy: the bank's `full`
-        e._batch_ns.pop()                              # (the refused batch was never queued)
         out = e.fetch(timeout_ms=10000)
         assert out[0].tolist() == [600] * 10
         assert e.fetch(timeout_ms=10000)[0].tolist() == [600] * 3
