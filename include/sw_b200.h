@@ -158,9 +158,9 @@ int sw_set_arith(sw_handle_t *h, int arith);
 /* The strip-kernel variants compiled into the library, and forcing one by name
  * (NULL or "" = back to automatic).  Names look like "strip_s16x2_R25x2_G1":
  * 25 rows x 2 sub-strips per lane, 1 lane per subject pair. */
-/* The main variants also exist with the reference's default gap penalties (-12 / -4) compiled in
- * as immediates (faster: fewer register operands); they are used automatically when the
- * handle's penalties match.  enable = 0 forces the run-time-penalty kernels (process-wide;
+/* The main variants also exist with the reference's gap penalty sets (-12 / -4, and -8 / -4 of its
+ * swalign vectors) compiled in as immediates (about 6 % faster: fewer register operands); they are
+ * used automatically when the handle's penalties match.  enable = 0 forces the run-time-penalty kernels (process-wide;
  * for A/B measurements and tests). */
 int sw_set_fixed_penalty_kernels(int enable);
 /* Large jobs (>= ~0.4 s of estimated work): the three variants the cost model ranks best are timed

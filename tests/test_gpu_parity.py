@@ -470,8 +470,17 @@ def test_fixed_and_runtime_penalty_instances_agree(golden, oracle_mod, pkg, fixe
     q = _fasta(golden, "query100.fa")[0][1]
     db = _fasta(golden, "data500.fa")
     ss = dict([x for x in golden["ssearch"] if x["file"] == "score500.txt"][0]["rows"])
+    # second compiled-in set (gap_open -8): the swalign golden vectors
+    sw = golden["swalign"]
+    sq = _fasta(golden, sw["query"])[0][1]
+    sdb = dict(_fasta(golden, sw["db"]))
     pkg.set_fixed_penalty_kernels(fixed)
     try:
+        for name in ["strip_s16x2_R25x2_G1", "strip_s16x2_R38x2_G1", "strip_s16x2_R50x1_G1"]:
+            with pkg.Engine(**sw["params"]) as e:
+                e.set_kernel_name(name)
+                got = e.score([sq], [sdb[n] for n, _ in sw["rows"]])
+            assert got[0].tolist() == [x for _, x in sw["rows"]], name
         for name in ["strip_s16x2_R25x2_G1", "strip_s16x2_R38x2_G1", "strip_s16x2_R50x1_G1", "strip_s16x2_R38x1_G4",
                      "strip_s16x2_R16x1_G32"]:
             with pkg.Engine() as e:
