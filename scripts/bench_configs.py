@@ -66,6 +66,9 @@ if "4" in which:    # 10 kb query vs 1 kb subjects; 200k subjects = 2e12 cells p
     for k in KERNELS or [None]:
         run("4: 1 x 10 kb query vs 200k x 1 kb (%s)" % (k or "automatic variant"), pkg.random_packed_db(1, 10000, 3),
             pkg.random_packed_db(200000, 1000, 4), kernel=k)
+if "4full" in which:   # BASELINE config 4 at its stated size: 1 M x 1 kb subjects, one 10 kb query = 1e13 cells
+    run("4 (full size): 1 x 10 kb query vs 1M x 1 kb (automatic variant)", pkg.random_packed_db(1, 10000, 3),
+        pkg.random_packed_db(1000000, 1000, 4), reps=2)
 if "4w" in which:   # same shape, few pairs: the warp-wide systolic (intra-task) variant
     run("4w: 1 x 10 kb query vs 2000 x 1 kb (automatic variant)", pkg.random_packed_db(1, 10000, 3),
         pkg.random_packed_db(2000, 1000, 4))
