@@ -378,7 +378,17 @@ int strip_setup(sw_handle *h, GpuCtx &gc, const Slot &g, int vidx, int *grid, in
     const int ppb = v->block_threads / v->G;
     const uint32_t npb = (g.npairs + ppb - 1) / ppb;
     *grid = (int)std::min<uint64_t>(npb, (uint64_t)gc.num_sms * bps);
-    if (need_passes > 1) SW_CUDA(h, gc.d_bnd.reserve((size_t)*grid * g.max_len * ppb * sizeof(uint2)));
+    if (need_passes > 1) {
+        // pass-boundary scratch: one (H, G) per column of the longest subject, per pair slot, per
+        // resident block.  A very long subject would make that huge, so the grid shrinks to keep
+        // the scratch within a budget (correct, slower; splitting the launch by length group is
+        // the better answer and is left for later).
+        const size_t per_block = (size_t)g.max_len * ppb * sizeof(uint2);
+        const size_t budget = (size_t)16 << 30;
+        if (per_block > budget) return SW_ENOMEM;
+        *grid = (int)std::min<size_t>((size_t)*grid, std::max<size_t>(1, budget / per_block));
+        SW_CUDA(h, gc.d_bnd.reserve((size_t)*grid * per_block));
+    }
     return SW_OK;
 }
 
