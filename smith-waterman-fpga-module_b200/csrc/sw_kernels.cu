@@ -255,16 +255,25 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
     uint2 *bnd = a.bnd + (size_t)blockIdx.x * a.bnd_cols * PPB + pslot;
     const uint64_t bnd_pol = l2_evict_last_policy();
 
+    int prof_q = -1, prof_pass = -1;     // which (query, first pass) the shared-memory profile holds
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_work = atomicAdd(a.counter, 1u);
         __syncthreads();
-        // work item = (block of pairs, query).  Pairs are sorted by ascending length: hand out the
-        // longest blocks first so that the tail of the launch is made of short items.
+        // work item = (block of pairs, query).  Pairs are sorted by ascending length: the longest
+        // blocks go first so that the tail is made of short items.
         const unsigned nql = (unsigned)(a.q1 - a.q0);
         if (s_work >= a.npb * nql) break;
-        const unsigned pb = a.npb - 1u - s_work / nql;
-        const int q = a.q0 + (int)(s_work % nql);
+        // Order: super-blocks of B pair blocks, longest first; inside a super-block query-major.
+        // With B >> grid (large databases) consecutive items of a thread block share the query and
+        // the profile in shared memory is reused; with B small the order degenerates to
+        // longest-first over everything, which is what short launches need for their tail.
+        const unsigned B = max(1u, a.npb >> 3);
+        const unsigned sb = s_work / (nql * B);
+        const unsigned rem = s_work - sb * nql * B;
+        const unsigned bcur = min(B, a.npb - sb * B);
+        const unsigned pb = a.npb - 1u - (sb * B + rem % bcur);
+        const int q = a.q0 + (int)(rem / bcur);
 
         const unsigned pair = pb * PPB + pslot;
         const bool valid = pair < a.npairs;
@@ -287,7 +296,9 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
 
             for (int pass = 0; pass < npass; ++pass) {
                 const int pass_in_chunk = pass % a.chunk_passes;
-                if (pass_in_chunk == 0) {
+                if (pass_in_chunk == 0 && (prof_q != q || prof_pass != pass)) {
+                    prof_q = q;
+                    prof_pass = pass;
                     // (re)build the profile chunk: entry (vpe, row pair, code) = packed scores of
                     // rows 2k, 2k+1 of that virtual PE against column code = t_lo | t_hi << 2
                     __syncthreads();
