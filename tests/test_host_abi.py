@@ -176,3 +176,20 @@ def test_random_packed_db_layout(pkg):
     assert (packed[37::38][:10] & 0xF0).sum() == 0           # unused tail bits are zero
     p2, _, _ = pkg.random_packed_db(10, 150, seed=1)
     assert np.array_equal(packed, p2)
+
+
+def test_cli_fails_loudly_without_inputs_or_gpu(pkg, golden, tmp_path):
+    """The CLI (counterpart of main_test -q -l -t): missing inputs print the reference's message;
+    without a GPU it stops at sw_init instead of falling back to anything."""
+    cli = os.path.join(ROOT, "bin", "sw_b200_cli")
+    assert os.path.exists(cli)
+    r = subprocess.run([cli], capture_output=True, text=True)
+    assert r.returncode != 0 and "Input files missing" in r.stdout          # main_test.c:281-285
+    r = subprocess.run([cli, "-q", str(tmp_path / "nope.fa"), "-l", str(tmp_path / "nope2.fa")],
+                       capture_output=True, text=True)
+    assert r.returncode != 0 and "Query file error!" in r.stdout            # main_test.c:246-250
+    if pkg.device_count() == 0:
+        q = tmp_path / "q.fa"
+        q.write_text(">query\nACGTACGT\n")
+        r = subprocess.run([cli, "-q", str(q), "-l", str(q)], capture_output=True, text=True)
+        assert r.returncode != 0 and "no usable CUDA device" in r.stdout
