@@ -10,14 +10,16 @@
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
     fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 1; } } while (0)
 
-enum { VIADDMNMX, VIMNMX, VIMNMX3, VIADD16, IMAD, HFMA2R, HADD2, VHMNMX, LOP3, IADD3, SHF, PRMT, FFMA, FMNMX, NOPS };
+enum { VIADDMNMX, VIMNMX, VIMNMX3, VIADD16, IMAD, HFMA2R, HADD2, VHMNMX, LOP3, IADD3, SHF, PRMT, FFMA, FMNMX, VIADDMNMX_IMM, NOPS };
 static const char *names[] = {"VIADDMNMX.S16x2", "VIMNMX.S16x2", "VIMNMX3.S16x2", "VIADD.16x2", "IMAD", "HFMA2.RELU",
-                              "HADD2", "VHMNMX(f16x2 max)", "LOP3", "IADD3", "SHF", "PRMT", "FFMA", "FMNMX"};
+                              "HADD2", "VHMNMX(f16x2 max)", "LOP3", "IADD3", "SHF", "PRMT", "FFMA", "FMNMX",
+                              "VIADDMNMX.S16x2 (immediate addend)"};
 
 template <int OP>
 __device__ __forceinline__ void step(unsigned &v, unsigned &w, unsigned k1, unsigned k2, unsigned one)
 {
     if (OP == VIADDMNMX) v = __viaddmax_s16x2(v, k1, w);
+    if (OP == VIADDMNMX_IMM) v = __viaddmax_s16x2(v, 0xfffcfffcu, w);
     if (OP == VIMNMX)  { unsigned t = __vmaxs2(v, w); w = v; v = t; }             // 1 VIMNMX (+ renaming)
     if (OP == VIMNMX3)   v = __vimax3_s16x2(v, k1, w);
     if (OP == VIADD16)   v = __vadd2(v, k1);
@@ -114,6 +116,8 @@ int main(int argc, char **argv)
     PAIR(IMAD, HFMA2R) PAIR(IMAD, FFMA) PAIR(IMAD, LOP3) PAIR(IMAD, IADD3)
     PAIR(HFMA2R, VHMNMX) PAIR(HFMA2R, FFMA) PAIR(HFMA2R, HADD2) PAIR(HADD2, VHMNMX)
     PAIR(FFMA, FMNMX) PAIR(FFMA, LOP3) PAIR(LOP3, IADD3)
+    // register-operand pressure: 3 register sources vs 2 + immediate, alone and next to the FMA-side add
+    SOLO(VIADDMNMX_IMM) PAIR(VIADDMNMX_IMM, VIADD16) PAIR(VIADDMNMX_IMM, VIMNMX3) PAIR(VIADDMNMX_IMM, IMAD)
     printf("]}\n");
     return rc;
 }
