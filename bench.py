@@ -32,10 +32,33 @@ sys.path.insert(0, ROOT)
 QLEN = 150
 TLEN = 150
 SEED = 20160912
-# measured with microbench/pipe_pairs.cu on this pool's B200 (profiles/r01_pipe_pairs_1024thr.json):
-# every packed-16-bit DPX / VIMNMX instruction issues at 64 thread-instructions / clock / SM
-R_INT = 64.0
 SM_COUNT = 148
+PIPE_PROFILE = "profiles/r01_pipe_pairs_1024thr.json"
+SASS_PROFILE = "profiles/r02_sass_hotloop.json"
+
+
+def measured_r_int():
+    """Issue rate of the packed 16-bit DPX / min-max instructions (thread-instr / clk / SM), as
+    MEASURED by microbench/pipe_pairs.cu on this pool's B200 and committed under profiles/."""
+    with open(os.path.join(ROOT, PIPE_PROFILE)) as f:
+        rows = json.load(f)["results"]
+    alone = [r["thread_instr_per_clk_per_sm"] for r in rows
+             if r["nb"] == 0 and r["a"] in ("VIADDMNMX.S16x2", "VIMNMX.S16x2", "VIMNMX3.S16x2")]
+    return min(alone)
+
+
+def alu_instr_per_cell_pair(kname):
+    """ALU-pipe instructions per two cells in the hot loop of the bench kernel, counted from its SASS
+    (scripts/sass_hotloop.py -> profiles/r02_sass_hotloop.json); 3.5 by construction."""
+    try:
+        with open(os.path.join(ROOT, SASS_PROFILE)) as f:
+            d = json.load(f)
+        k = d["kernels"].get(kname)
+        if k:
+            return float(k["alu_pipe_per_cell_pair"]), float(k["issue_slots_per_cell_pair"]), SASS_PROFILE
+    except Exception:
+        pass
+    return 3.5, None, "DESIGN.md section 2 (no SASS histogram for this kernel)"
 
 
 def peaks():
@@ -119,6 +142,14 @@ def make_inputs(pkg, n_subjects, n_queries, rank):
     return q, db
 
 
+def base_config(args):
+    """Identical for both arms (the driver compares the two `config` objects)."""
+    return {"workload": workload_name(args), "queries": args.queries, "query_len": QLEN, "subject_len": TLEN,
+            "subjects_per_gpu": args.subjects, "penalties": "5/-4/-12/-4",
+            "planted_homologs": "1 % of subjects = a query with 5 % substitutions + 2 % indels",
+            "l2": "inputs (code stream + score matrix per GPU) larger than L2"}
+
+
 def run_reference(args, rank, world):
     """CPU arm: the oracle port of the PE recurrence (the reference ships no CPU scorer and its
     RTL cannot be simulated here), all host threads, bounded sample per step."""
@@ -131,6 +162,7 @@ def run_reference(args, rank, world):
     ns = args.ref_subjects
     q = pkg_seq.random_packed_db(args.queries, QLEN, seed=SEED - 1)
     db = pkg_seq.random_packed_db(ns, TLEN, seed=SEED)
+    pkg_seq.plant_homologs(db, q, 0.01, seed=SEED + 7)
     cells = ns * TLEN * args.queries * QLEN
     used = 1
     for _ in range(max(args.warmup, 0)):
@@ -141,14 +173,15 @@ def run_reference(args, rank, world):
         _, used = o.score_batch_packed(q[0], q[1], q[2], db[0], db[1], db[2], nthreads=host_threads())
     dt = time.perf_counter() - t0
     gcups = cells * args.steps / dt / 1e9
-    sample = f"first {ns} of the synthetic 150-nt subjects x {args.queries} queries per step ({cells:.3g} cells)"
+    sample = (f"each step scores the first {ns} of the {args.subjects} synthetic 150-nt subjects x {args.queries} "
+              f"queries ({cells:.3g} cells); GCUPS is a rate, so the bounded sample does not change the metric")
     line = {"impl": "reference", "metric": "GCUPS (score-only SW)", "value": gcups, "unit": "GCUPS",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
-            "data": "synthetic",
-            "config": {"workload": workload_name(args), "queries": args.queries, "query_len": QLEN,
-                       "subject_len": TLEN, "penalties": "5/-4/-12/-4"},
-            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": used, "kind": "port", "sample": sample},
+            "data": "synthetic", "config": base_config(args),
+            "cpu_baseline": {"value": gcups, "unit": "GCUPS", "cores": used, "kind": "port", "sample": sample,
+                             "note": "scalar, un-vectorised int32 C port of the PE recurrence (the reference has no CPU "
+                                     "scorer): context for the GPU number, not a tuned CPU competitor"},
             "e2e": {"value": gcups, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -179,6 +212,62 @@ def emit(line):
     out.flush()
 
 
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def e2e_loop(eng, hdb, out, steps):
+    """Streaming use of the ABI: step k+1 is submitted (sort, H2D, kernels enqueued) before the scores
+    of step k are fetched -- two batches in flight, every byte still crosses PCIe each step."""
+    t0 = time.perf_counter()
+    eng.score_batch(hdb)
+    for k in range(steps):
+        if k + 1 < steps:
+            eng.score_batch(hdb)
+        eng.fetch(out=out)
+    return time.perf_counter() - t0
+
+
+def single_handle_phase(pkg, torch, args, world, q, hdb, out, chk, e2e_1gpu_s):
+    """north_star partition: ONE handle, ONE database sharded over all N GPUs of the box,
+    host-side gather into the caller's [nq][ns] matrix (ScoreBank_v2.v:78-139,162 at the GPU level).
+    Strong scaling of the literal config 3: the same 10 M x 150 database, 1 GPU vs N GPUs, end to end
+    with host buffers.  Runs on rank 0 while the other ranks idle on a CPU (gloo) barrier."""
+    steps = max(2, args.e2e_steps)
+    res = {"n_gpus": world, "subjects_total": int(len(hdb[1])), "steps": steps,
+           "api": "sw_init(gpu_ids=0..N-1) + sw_score_batch + sw_fetch, pinned host buffers, two batches in flight"}
+    # 1 GPU, alone on the box (the per-rank e2e above ran with N ranks sharing the host)
+    if world > 1:
+        with pkg.Engine(gpu_ids=[0]) as e1:
+            e1.set_queries(q)
+            e1.score_batch(hdb); e1.fetch(out=out)
+            t1 = e2e_loop(e1, hdb, out, steps) / steps
+            cells = e1.last_cells
+            res["kernel_1gpu"] = e1.last_kernel_name
+    else:
+        t1 = e2e_1gpu_s
+        cells = None
+    with pkg.Engine(gpu_ids=list(range(world))) as en:
+        en.set_queries(q)
+        en.score_batch(hdb); en.fetch(out=out)            # warm-up (autotune, allocations)
+        tn = e2e_loop(en, hdb, out, steps) / steps
+        cells = en.last_cells
+        res["kernel_ms_max_over_gpus"] = en.last_kernel_ms
+        res["kernel"] = en.last_kernel_name
+        st = en.stats() if hasattr(en, "stats") else None
+        if st:
+            res["host_ms"] = st
+    equal = bool(np.array_equal(out, chk))
+    assert equal, "single-handle N-GPU score matrix differs from the 1-GPU result"
+    res.update({"value": cells / tn / 1e9, "unit": "GCUPS", "ms_per_step": tn * 1e3,
+                "value_1gpu": cells / t1 / 1e9, "ms_per_step_1gpu": t1 * 1e3,
+                "strong_eff": (t1 / tn) / world, "matrix_equal_to_1gpu": equal,
+                "d2h_bytes_per_step": int(out.nbytes), "h2d_bytes_per_step": int(sum(a.nbytes for a in hdb))})
+    # what bounds it: device time vs host-visible step time
+    res["device_bound_frac"] = res["kernel_ms_max_over_gpus"] / (tn * 1e3)
+    return res
+
+
 def main():
     capture_stdout()
     ap = argparse.ArgumentParser()
@@ -197,6 +286,8 @@ def main():
     ap.add_argument("--kernel", default="", help="force a strip-kernel variant by name")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-single-handle", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs{} / latency{} blocks")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -214,11 +305,13 @@ def main():
         emit({"error": "no CUDA device: this bench has no CPU fallback"})
         return 1
     torch.cuda.set_device(local_rank)
+    cpu_group = None
     if world > 1:
         # stdout carries exactly one JSON line: keep NCCL's version banner off it
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        cpu_group = dist.new_group(backend="gloo")     # host-side barrier: waiting ranks keep their GPU idle
 
     def barrier():
         torch.cuda.synchronize()
@@ -266,34 +359,30 @@ def main():
     dev_s = max_over_ranks(sum(kernel_ms) / 1e3)
     wall_s = max_over_ranks(wall)
     gcups = cells_step * world * args.steps / dev_s / 1e9
+    log(f"resident arm: {gcups:.1f} GCUPS, kernel {kname}")
     # spot check: the timed output is the real thing (compare a slice with an independent launch)
     chk = eng.fetch_db()
     checksum = int(chk[:, :: max(1, args.subjects // 4096)].astype(np.int64).sum())
 
     # ---- end-to-end arm: host buffers in, host scores out, every step -----------------------
     e2e = None
+    hdb = out = None
+    e2e_s_local = None
     if not args.no_e2e:
         pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
-        hp, hl, ho = pin(db[0]), pin(db[1]), pin(db[2])
+        hdb = (pin(db[0]), pin(db[1]), pin(db[2]))
         out = torch.empty((args.queries, args.subjects), dtype=torch.int32, pin_memory=True).numpy()
-        eng.score_batch((hp, hl, ho)); eng.fetch(out=out)          # warm-up
+        eng.score_batch(hdb); eng.fetch(out=out)          # warm-up
         barrier()
-        t0 = time.perf_counter()
-        # streaming use of the ABI: step k+1 is submitted (sort, H2D, kernels enqueued) before the
-        # scores of step k are fetched -- two batches in flight, every byte still crosses PCIe each step
-        eng.score_batch((hp, hl, ho))
-        for k in range(args.e2e_steps):
-            if k + 1 < args.e2e_steps:
-                eng.score_batch((hp, hl, ho))
-            eng.fetch(out=out)
+        e2e_s_local = e2e_loop(eng, hdb, out, args.e2e_steps)
         barrier()
-        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e_s = max_over_ranks(e2e_s_local)
         assert np.array_equal(out, chk), "e2e scores differ from the resident-path scores"
         e2e = {"value": cells_step * world * args.e2e_steps / e2e_s / 1e9, "unit": "GCUPS",
-               "h2d_bytes_per_step": int(hp.nbytes + hl.nbytes + ho.nbytes) * world, "d2h_bytes_per_step": int(out.nbytes) * world,
+               "h2d_bytes_per_step": int(sum(a.nbytes for a in hdb)) * world, "d2h_bytes_per_step": int(out.nbytes) * world,
                "ms_per_step": e2e_s / args.e2e_steps * 1e3, "steps": args.e2e_steps,
                "api": "sw_score_batch + sw_fetch (two batches in flight), pinned host buffers"}
-        del out
+        log(f"e2e arm: {e2e['value']:.1f} GCUPS")
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle port on a bounded sample ---------------
     cpu = None
@@ -312,60 +401,93 @@ def main():
                "sample": f"first {ns} subjects x {args.queries} queries ({ns * TLEN * args.queries * QLEN:.3g} cells), "
                          f"scalar int32 C oracle, OpenMP; scores equal to the GPU's"}
 
+    # ---- configs 2 / 4 / 5 and the latency regime (rank 0, N=1): driver-visible evidence -----
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_configs:
+        try:
+            from scripts import bench_configs as bc
+            eng.close()
+            extra = bc.bench_blocks(pkg, log)
+        except Exception as ex:           # the headline line must still be printed
+            extra = {"configs_error": repr(ex)}
+
+    # ---- single handle over all GPUs (strong scaling of the literal config 3) ----------------
+    single = None
+    if not args.no_e2e and not args.no_single_handle and world > 1:
+        eng.close()
+        torch.cuda.empty_cache()
+        barrier()
+        if rank == 0:
+            try:
+                single = single_handle_phase(pkg, torch, args, world, q, hdb, out, chk, e2e_s_local / args.e2e_steps)
+                log(f"single handle over {world} GPUs: {single['value']:.1f} GCUPS, strong_eff {single['strong_eff']:.3f}")
+            except Exception as ex:
+                single = {"error": repr(ex)}
+        dist.barrier(group=cpu_group)
+    elif not args.no_e2e and world == 1 and e2e is not None:
+        single = {"n_gpus": 1, "value": e2e["value"], "unit": "GCUPS", "ms_per_step": e2e["ms_per_step"],
+                  "strong_eff": 1.0, "note": "N = 1: the e2e arm is the single-handle path"}
+
     if rank == 0:
         pk = peaks()
-        roof_gcups = SM_COUNT * pk["sm_max_mhz"] * 1e6 * R_INT * 2.0 / 6.0 / 1e9
+        r_int = measured_r_int()
         per_gpu = gcups / world
-        # algorithmic HBM bytes per step and GPU: column-code stream once per query chunk (8 launches)
-        # + one int32 score per pair written once
         arith = "s16x2" if "s16x2" in kname else "int32"
-        # ALU-pipe instructions per cell pair of the chosen kernel (DESIGN.md "roofline"): the other
-        # instructions of the recurrence run on the FMA-side pipe and overlap
-        alu_per_pair = {"s16x2": 3.5, "int32": 12.0}[arith]
-        tight_gcups = SM_COUNT * pk["sm_max_mhz"] * 1e6 * R_INT * 2.0 / alu_per_pair / 1e9
-        # per launch: the pair's code stream (one byte per column) + pair_len + pair_subj, read once; 8 launches per step
+        # ALU-pipe instructions per cell pair of the chosen kernel, counted in its SASS; the adds of the
+        # recurrence run on the FMA-side pipe and co-issue (profiles/r01_pipe_pairs_1024thr.json)
+        if arith == "s16x2":
+            alu_per_pair, issue_per_pair, alu_src = alu_instr_per_cell_pair(kname)
+        else:
+            alu_per_pair, issue_per_pair, alu_src = 12.0, None, "32-bit fallback"
+        pipe_gcups = SM_COUNT * pk["sm_max_mhz"] * 1e6 * r_int * 2.0 / alu_per_pair / 1e9
+        survey_gcups = SM_COUNT * pk["sm_max_mhz"] * 1e6 * r_int * 2.0 / 6.0 / 1e9
+        # per launch: the pair's code stream (one byte per column) + pair_len + pair_subj, read once;
         # plus one int32 score per (query, subject) written once
         n_launch = max(1, launches // max(1, args.steps))
         algo_bytes = (args.subjects / 2) * (((TLEN + 3) // 4) * 4 + 8 + 8) * n_launch + args.subjects * args.queries * 4
         traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-                tr = json.load(f)
-            if tr["kernel"] == kname and tr["subjects_per_gpu"] == args.subjects and tr["queries"] == args.queries:
-                traffic = {"dram_bytes_per_launch": tr["dram_bytes_read_per_launch"] + tr["dram_bytes_write_per_launch"],
-                           "algorithmic_bytes_per_launch": int(algo_bytes / n_launch), "source": tr["source"]}
-        except Exception:
-            pass
+        for tf in ("r02_traffic.json", "r01_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", tf)) as f:
+                    tr = json.load(f)
+                if tr["kernel"] == kname and tr["subjects_per_gpu"] == args.subjects and tr["queries"] == args.queries:
+                    dram = tr["dram_bytes_read_per_launch"] + tr["dram_bytes_write_per_launch"]
+                    traffic = {"dram_bytes_per_launch": dram, "algorithmic_bytes_per_launch": int(algo_bytes / n_launch),
+                               "ratio": dram / (algo_bytes / n_launch), "source": tr["source"]}
+                    break
+            except Exception:
+                pass
+        cfg = base_config(args)
         line = {
             "metric": "GCUPS (score-only SW)", "value": gcups, "unit": "GCUPS", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_s / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": arith,
-            "data": "synthetic",
-            "config": {"workload": workload_name(args), "queries": args.queries, "query_len": QLEN,
-                       "subject_len": TLEN, "subjects_per_gpu": args.subjects, "penalties": "5/-4/-12/-4",
-                       "planted_homologs": "1 % of subjects = a query with 5 % substitutions + 2 % indels",
-                       "kernel": kname, "l2": "inputs (code stream + 4 GB score matrix per GPU) larger than L2",
-                       "wall_ms_per_step": wall_s / args.steps * 1e3, "checksum": checksum},
-            "roofline": {"bound": "int_pipe", "achieved": per_gpu, "peak": roof_gcups, "unit": "GCUPS",
-                         "frac": per_gpu / roof_gcups,
-                         "peak_def": f"148 SM x {pk['sm_max_mhz']:.0f} MHz x R_int {R_INT:.0f} thread-instr/clk/SM "
-                                     f"(measured, profiles/r01_pipe_pairs_1024thr.json) x 2 cells / 6 instr (SURVEY 8d)",
-                         "note": "frac > 1 is not a measurement artefact: the survey's roofline assumes 6 integer-pipe "
-                                 "instructions per 2 cells; the kernel evaluates an algebraically equivalent form "
-                                 "(DESIGN.md section 2) with 3.5 ALU-pipe + 1 FMA-pipe instructions, see 'tight'. Scores are "
-                                 "checked against the CPU oracle inside this run (cpu_baseline.sample).",
+            "data": "synthetic", "config": cfg,
+            "detail": {"kernel": kname, "wall_ms_per_step": wall_s / args.steps * 1e3, "checksum": checksum},
+            "roofline": {"bound": "int_pipe", "achieved": per_gpu, "peak": pipe_gcups, "unit": "GCUPS",
+                         "frac": per_gpu / pipe_gcups,
+                         "peak_def": f"ALU-pipe bound of this kernel: 148 SM x {pk['sm_max_mhz']:.0f} MHz x R_int {r_int:.2f} "
+                                     f"thread-instr/clk/SM (measured, {PIPE_PROFILE}) x 2 cells / {alu_per_pair} ALU-pipe instr "
+                                     f"per cell pair ({alu_src}); the recurrence's adds co-issue on the FMA-side pipe",
+                         "issue_slots_per_cell_pair": issue_per_pair,
+                         "survey_frac": per_gpu / survey_gcups, "survey_peak": survey_gcups,
+                         "survey_def": "SURVEY 8(d): same peak with 6 integer-pipe instr per 2 cells; > 1 because the kernel "
+                                       "evaluates an algebraically equivalent 3.5-instruction form (DESIGN.md section 2), "
+                                       "checked against the CPU oracle inside this run",
                          "traffic": traffic,
-                         "tight": {"peak": tight_gcups, "frac": per_gpu / tight_gcups,
-                                   "def": f"ALU-pipe bound of this kernel: {alu_per_pair} ALU-pipe instr per 2 cells, "
-                                          f"adds co-issue on the FMA-side pipe (profiles/r01_pipe_pairs_1024thr.json)"},
                          "hbm": {"algorithmic_bytes_per_step": int(algo_bytes),
                                  "achieved_gbs": algo_bytes / (dev_s / args.steps) / 1e9,
                                  "peak_gbs": pk["hbm_gbs"], "peak_source": pk["source"],
                                  "frac": algo_bytes / (dev_s / args.steps) / 1e9 / pk["hbm_gbs"]}},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "single_handle": single,
+            "gpu_launches": int(launches), "clocks": clocks,
         }
+        line.update(extra)
         emit(line)
-    eng.close()
+    try:
+        eng.close()
+    except Exception:
+        pass
     if world > 1:
         dist.destroy_process_group()
     return 0

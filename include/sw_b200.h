@@ -42,6 +42,8 @@ extern "C" {
 #define SW_ECAPACITY  -7   /* caller's score buffer too small                   */
 #define SW_EIO        -8   /* file could not be read / written                  */
 #define SW_EAGAIN     -9   /* both batch buffers in flight (the bank's `full`)   */
+#define SW_ERANGE     -10  /* more scores beyond 16 bits than the side list holds: use int32 output */
+#define SW_EDEVICE    -11  /* a device-side check failed (bounds-check build / wavefront watchdog)   */
 
 /* The `penalties` bus + SCORE_WIDTH parameter.
  * Replaces: ScoreBank_v2.v:34,161 (ld_penalties, penalties[4*W]),
@@ -60,6 +62,18 @@ typedef struct sw_handle sw_handle_t;
 
 /* Fills *p with the reference defaults (5/-4/-12/-4, exact width). */
 void sw_default_params(sw_params_t *p);
+
+/* Exactness domain.  sw_init accepts every parameter set with match > 0, gap_extend <= 0 and
+ * gap_open + gap_extend <= 0 and scores it with the general recurrence (I(i,1) takes M(i-1,1)
+ * into account).  The RTL itself is only schedule-INdependent when match + gap_open <= 0: for the
+ * first target base of a stream the PE may ignore the upper neighbour's M -- always in PE v0.3
+ * (SW_ProcessingElement_v0.3.v:145-158), and in v1.0 whenever neither time-share slot is
+ * mid-sequence (SW_ProcessingElement_v1.0.v:120 vs :131-141).  Both forms coincide iff
+ * match + gap_open <= 0 (default: 5 - 12 < 0).
+ * Returns 1 = bit-exact against the RTL for every input, 0 = accepted, but the RTL's own result
+ * depends on its feeder schedule there (this engine returns the general-form score),
+ * SW_EINVAL = the set is rejected by sw_init.  p == NULL asks about the defaults. */
+int sw_params_in_exact_domain(const sw_params_t *p);
 
 /* Replaces: cxl_afu_open_dev + cxl_afu_attach (main_test.c:342,370) and the
  * ld_penalties cycle (ScoreBank_v1_tb.sv:175-181).  gpu_ids == NULL with
@@ -131,8 +145,39 @@ int sw_plan_shards(const uint32_t *len, size_t ns, int n_shards, uint64_t *start
 
 /* Per-query best hit over the resident db, reduced on the GPU: the `max` /
  * `vld_max` outputs ScoreBank_v2 declares but never drives (ScoreBank_v2.v:42-43).
- * best_score[iq], best_index[iq] (input index of the first subject reaching it). */
+ * best_score[iq], best_index[iq] (input index of the first subject reaching it).
+ * Matrix output modes only; in top-k mode use sw_fetch_db_topk. */
 int sw_fetch_best(sw_handle_t *h, int32_t *best_score, uint64_t *best_index, int nq_cap);
+
+/* ---- output path ------------------------------------------------------------
+ * The bank returns a 12-bit score per (ID) slot (ScoreBank_v2.v:39-41); the result buffer the
+ * reference planned (CAPI_template/ResBuffer.v:11-22) has ports only.  Three shapes here:
+ *   SW_OUTPUT_I32   int32 matrix [rows][ns]                     (default; sw_fetch / sw_fetch_db)
+ *   SW_OUTPUT_I16   int16 matrix [rows][ns]: half the HBM and half the D2H bytes.  A score above
+ *                   32767 is stored as -1 in the matrix and returned exactly by sw_fetch_overflow
+ *                   (flat index iq * ns + is, int32 score); SW_ERANGE if there are more than 2^20.
+ *   top-k           sw_set_topk(h, k), 1 <= k <= 32 (0 = back to matrices): NO score matrix is
+ *                   allocated or shipped; the strip kernel's epilogue keeps the k best
+ *                   (score, subject) per query -- the `max` / `vld_max` outputs of
+ *                   ScoreBank_v2.v:42-43, generalised to k -- merged across blocks, launches and
+ *                   the handle's GPUs.  Order: score descending, ties by ascending input index.
+ *                   With fewer than k subjects the tail has index UINT64_MAX and score -1.
+ * Modes are set while no batch is in flight and apply to the following sw_score_batch /
+ * sw_score_db calls.  Streaming (two batches in flight) works in every mode; each batch has its
+ * own top-k (merge across batches with a k-way merge on (score, index) if needed). */
+#define SW_OUTPUT_I32 0
+#define SW_OUTPUT_I16 1
+int sw_set_output(sw_handle_t *h, int mode);
+int sw_set_topk(sw_handle_t *h, int k);
+int sw_fetch_i16(sw_handle_t *h, int16_t *scores, size_t cap, int timeout_ms);
+int sw_fetch_db_i16(sw_handle_t *h, int16_t *scores, size_t cap);
+/* Scores above 32767 of the batch / database fetched last in SW_OUTPUT_I16 mode.  *count = how many
+ * there are; at most cap are written. */
+int sw_fetch_overflow(sw_handle_t *h, uint64_t *flat_index, int32_t *score, size_t cap, size_t *count);
+/* scores[iq * k + j], index[iq * k + j] (input index within the batch), j-th best hit of query iq;
+ * cap = entries both arrays hold (>= rows * k). */
+int sw_fetch_topk(sw_handle_t *h, int32_t *scores, uint64_t *index, size_t cap, int timeout_ms);
+int sw_fetch_db_topk(sw_handle_t *h, int32_t *scores, uint64_t *index, size_t cap);
 
 /* ---- introspection --------------------------------------------------------- */
 const char *sw_strerror(int code);
@@ -141,6 +186,23 @@ const char *sw_last_cuda_error_string(const sw_handle_t *h);
 /* Device time (CUDA events on the launching stream) of the scoring kernels of the
  * last sw_score_db / sw_score_batch, max over the handle's GPUs, milliseconds. */
 double sw_last_kernel_ms(const sw_handle_t *h);
+/* Host-visible phase times of the last sw_score_batch / sw_load_db (load_ms: length sort, pairing,
+ * H2D issue and completion; enqueue_ms: kernel launches) and of the last sw_fetch / sw_fetch_db
+ * (fetch_wait_ms: waiting for kernels while issuing the D2H copies of finished query chunks;
+ * fetch_drain_ms: waiting for the last copies).  kernel_ms_max / _min: device time (CUDA events) of
+ * the slowest / fastest GPU of the handle -- their ratio is the shard imbalance.  The reference's
+ * counterpart is the `_DEBUGGING_` cycle counter of afu.v:497-532. */
+typedef struct sw_stats {
+    double load_ms, enqueue_ms, fetch_wait_ms, fetch_drain_ms, kernel_ms_max, kernel_ms_min;
+} sw_stats_t;
+int sw_get_stats(const sw_handle_t *h, sw_stats_t *out);
+/* Device-side error word, OR-ed over the handle's GPUs (0 = clean): set by the index checks of the
+ * bounds-check build (libsw_b200_check.so, make CHECK=1 -- this pool has no compute-sanitizer) and
+ * by the wavefront kernel's spin-wait watchdog.  Also reports canary damage around device buffers
+ * (bit 31).  Fetch calls return SW_EDEVICE when it is non-zero. */
+unsigned sw_device_error_bits(sw_handle_t *h);
+/* 1 if this library was built with -DSW_BOUNDS_CHECK */
+int sw_is_check_build(void);
 /* Number of kernels this library launched since sw_init (all GPUs). */
 uint64_t sw_kernel_launches(const sw_handle_t *h);
 /* Cell updates (sum of qlen*tlen over all pairs) of the last scoring call. */
@@ -168,6 +230,22 @@ int sw_set_fixed_penalty_kernels(int enable);
  * workload shape.  enable = 0 uses the model's first choice only.  Default: on
  * (environment SW_B200_AUTOTUNE=0 turns it off at sw_init). */
 int sw_set_autotune(sw_handle_t *h, int enable);
+/* Run-time specialisation of the gap penalties (the reference loads them at run time: ld_penalties,
+ * ScoreBank_v2.v:34,161).  For a penalty set that is not compiled in, the one kernel variant a job
+ * uses is compiled with the penalties as immediates (NVRTC, loaded lazily with dlopen; cubins are
+ * cached in $SW_B200_JIT_CACHE, default ~/.cache/sw_b200) -- same speed as the default set instead
+ * of ~7 % less.  mode 0 = never, 1 = jobs of >= ~2 s of estimated work (default), 2 = always
+ * (environment SW_B200_JIT).  Without NVRTC the run-time-operand kernels are used; nothing fails. */
+int sw_set_jit(sw_handle_t *h, int mode);
+int sw_jit_is_available(void);
+/* Compiles (or takes from the cache) the specialised instance of one variant: 1 = ready, 0 = not
+ * available, msg says why (NVRTC missing, compile error, or no GPU to load the cubin on). */
+int sw_jit_compile_check(const char *variant_name, int gap_open, int gap_extend, char *msg, size_t msg_cap);
+/* Small batches (<= 8192 subjects, <= 1 MB of packed bases) submitted with sw_score_batch take a
+ * latency path: one staging copy, one kernel, scores written to mapped host memory (the regime of
+ * the reference's own data sets: data/data500.fa is 499 x 128 nt).  enable = 0 forces the regular
+ * path (environment SW_B200_SMALL_PATH=0). */
+int sw_set_small_batch_path(sw_handle_t *h, int enable);
 int sw_kernel_variant_count(void);
 const char *sw_kernel_variant_name(int idx);
 int sw_set_kernel_name(sw_handle_t *h, const char *name);

@@ -1,18 +1,66 @@
 #!/usr/bin/env python3
-"""Kernel-time GCUPS of BASELINE configs 2, 4 and 5 (config 3 is bench.py).  Prints JSON lines."""
+"""BASELINE configs 2, 4 and 5 and the latency regime (config 3 is bench.py's headline).
+
+  python scripts/bench_configs.py [2] [lat] [4] [4full] [4w] [5] [pair]      JSON lines, one per case
+  bench.py imports bench_blocks() and adds its result to the bench line as `configs` / `latency`.
+
+Every case is checked against the CPU oracle on a bounded sample inside the run (the oracle is the
+checker here, never the thing measured), and reports its fraction of the ALU-pipe bound.
+"""
 import importlib
 import json
 import os
 import sys
+import time
 
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT)
-pkg = importlib.import_module("smith-waterman-fpga-module_b200")
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SM_COUNT, SM_MHZ, R_INT, ALU_PER_PAIR = 148, 1965.0, 64.0, 3.5
+PIPE_BOUND_GCUPS = SM_COUNT * SM_MHZ * 1e6 * R_INT * 2.0 / ALU_PER_PAIR / 1e9
+# the reference's own (simulated) numbers for its data sets, BASELINE.md section 2
+REF_BANK_US_DATA500 = 66.094 - 0.028      # data/data500.fa_query100.fa_out.txt:499, query loaded @28 ns
+REF_PAIR_US = 0.538                       # data/data1.fa_query1.fa_out.txt:1 (simulation time)
 
 
-def run(name, queries, db, reps=3, kernel=None):
+def _oracle():
+    from oracle import oracle as om
+    om.build_oracle()
+    return om.Oracle()
+
+
+def _subset(db, idx):
+    """Sub-database (packed, len, off) of the records idx."""
+    packed, ln, off = db
+    bufs, offs, o = [], [], 0
+    for i in idx:
+        nb = (int(ln[i]) + 3) // 4
+        bufs.append(packed[int(off[i]): int(off[i]) + nb])
+        offs.append(o)
+        o += nb
+    flat = np.concatenate(bufs + [np.zeros(16, np.uint8)])
+    return flat, np.asarray(ln)[idx].astype(np.uint32), np.array(offs, dtype=np.uint64)
+
+
+def mixed_db(n, lo, hi, seed):
+    rng = np.random.default_rng(seed)
+    lens = np.exp(rng.uniform(np.log(lo), np.log(hi), size=n)).astype(np.uint32)
+    nbytes = (lens.astype(np.uint64) + 3) // 4
+    off = np.concatenate([[0], np.cumsum(nbytes)[:-1]]).astype(np.uint64)
+    packed = rng.integers(0, 256, size=int(nbytes.sum()) + 16, dtype=np.uint8)
+    # unused tail bits of every record are zero, as sw_pack_2bit leaves them
+    tail = (lens % 4).astype(np.int64)
+    last = (off + nbytes - 1).astype(np.int64)
+    m = tail > 0
+    packed[last[m]] &= ((1 << (2 * tail[m])) - 1).astype(np.uint8)
+    return packed, lens, off
+
+
+def run(pkg, name, queries, db, reps=3, kernel=None, check=0, seed=0):
+    """Kernel-time GCUPS on the resident database; `check` subjects are compared with the oracle."""
     with pkg.Engine() as e:
         if kernel:
             e.set_kernel_name(kernel)
@@ -24,57 +72,113 @@ def run(name, queries, db, reps=3, kernel=None):
             e.wait()
             ms.append(e.last_kernel_ms)
         best = min(ms[1:])
-        print(json.dumps({"config": name, "kernel": e.last_kernel_name, "cells": e.last_cells,
-                          "kernel_ms": best, "gcups": e.last_cells / best / 1e6}), flush=True)
+        res = {"config": name, "kernel": e.last_kernel_name, "cells": e.last_cells, "kernel_ms": best,
+               "gcups": e.last_cells / best / 1e6, "pipe_frac": e.last_cells / best / 1e6 / PIPE_BOUND_GCUPS}
+        if check:
+            got = e.fetch_db()
+            ns = len(db[1])
+            idx = np.unique(np.random.default_rng(seed).integers(0, ns, size=min(check, ns)))
+            sub = _subset(db, idx)
+            want, _ = _oracle().score_batch_packed(queries[0], queries[1], queries[2], sub[0], sub[1], sub[2])
+            assert np.array_equal(got[:, idx], want), f"{name}: GPU scores differ from the oracle"
+            res["oracle_checked_pairs"] = int(len(idx) * len(queries[1]))
+            res["max_score"] = int(got.max())
+    return res
 
 
-def mixed_db(n, lo, hi, seed):
-    rng = np.random.default_rng(seed)
-    lens = np.exp(rng.uniform(np.log(lo), np.log(hi), size=n)).astype(np.uint32)
-    nbytes = (lens.astype(np.uint64) + 3) // 4
-    off = np.concatenate([[0], np.cumsum(nbytes)[:-1]]).astype(np.uint64)
-    packed = rng.integers(0, 256, size=int(nbytes.sum()) + 16, dtype=np.uint8)
-    return packed, lens, off
-
-
-def latency(name, queries, db, reps=200):
-    """Wall-clock of sw_score_batch + sw_fetch through the ABI (host buffers), after warm-up."""
-    import time
+def latency(pkg, name, queries, db, reps=300, check=True):
+    """Wall clock of sw_score_batch + sw_fetch through the ABI (host buffers), after warm-up."""
     with pkg.Engine() as e:
         e.set_queries(queries)
         out = np.empty((len(queries[1]), len(db[1])), dtype=np.int32)
-        for _ in range(20):
+        for _ in range(30):
             e.score_batch(db); e.fetch(out=out)
-        t0 = time.perf_counter()
+        ts, kms = [], []
         for _ in range(reps):
+            t0 = time.perf_counter()
             e.score_batch(db); e.fetch(out=out)
-        dt = (time.perf_counter() - t0) / reps
-        print(json.dumps({"config": name, "kernel": e.last_kernel_name, "e2e_us_per_call": dt * 1e6,
-                          "kernel_us": e.last_kernel_ms * 1e3, "gcups_e2e": e.last_cells / dt / 1e9}), flush=True)
+            ts.append(time.perf_counter() - t0)
+            kms.append(e.last_kernel_ms)
+        ts.sort()
+        med = ts[len(ts) // 2]
+        res = {"config": name, "kernel": e.last_kernel_name, "e2e_us_median": med * 1e6, "e2e_us_min": ts[0] * 1e6,
+               "e2e_us_p90": ts[int(len(ts) * 0.9)] * 1e6, "device_us_median": sorted(kms)[len(kms) // 2] * 1e3,
+               "gcups_e2e": e.last_cells / med / 1e9, "cells": e.last_cells, "calls": reps}
+        if check:
+            want, _ = _oracle().score_batch_packed(queries[0], queries[1], queries[2], db[0], db[1], db[2])
+            assert np.array_equal(out, want), f"{name}: GPU scores differ from the oracle"
+            res["oracle_checked_pairs"] = int(want.size)
+    return res
 
 
-which = sys.argv[1:] or ["2", "4", "4w", "5"]
-if "2" in which:    # query100 x data500 shape: 128-nt query, 499 x 128-nt subjects (latency bound)
-    run("2: 1 x 128 nt query vs 499 x 128 nt", pkg.random_packed_db(1, 128, 1), pkg.random_packed_db(499, 128, 2), reps=5)
-KERNELS = os.environ.get("SW_KERNELS", "").split()
-if "2" in which or "lat" in which:
-    latency("2 (latency): sw_score_batch + sw_fetch, 1 x 128 nt query vs 499 x 128 nt",
-            pkg.random_packed_db(1, 128, 1), pkg.random_packed_db(499, 128, 2))
-    latency("1 pair (latency): 32 nt query vs one 128 nt subject (the CAPI sample's job)",
-            pkg.random_packed_db(1, 32, 1), pkg.random_packed_db(1, 128, 2))
-if "4" in which:    # 10 kb query vs 1 kb subjects; 200k subjects = 2e12 cells per query
-    for k in KERNELS or [None]:
-        run("4: 1 x 10 kb query vs 200k x 1 kb (%s)" % (k or "automatic variant"), pkg.random_packed_db(1, 10000, 3),
-            pkg.random_packed_db(200000, 1000, 4), kernel=k)
-if "4full" in which:   # BASELINE config 4 at its stated size: 1 M x 1 kb subjects, one 10 kb query = 1e13 cells
-    run("4 (full size): 1 x 10 kb query vs 1M x 1 kb (automatic variant)", pkg.random_packed_db(1, 10000, 3),
-        pkg.random_packed_db(1000000, 1000, 4), reps=2)
-if "4w" in which:   # same shape, few pairs: the warp-wide systolic (intra-task) variant
-    run("4w: 1 x 10 kb query vs 2000 x 1 kb (automatic variant)", pkg.random_packed_db(1, 10000, 3),
-        pkg.random_packed_db(2000, 1000, 4))
-    run("4w: same, forced G=32 wavefront", pkg.random_packed_db(1, 10000, 3), pkg.random_packed_db(2000, 1000, 4),
-        kernel="strip_s16x2_R16x1_G32")
-if "5" in which:    # lengths log-uniform 32..4096
-    for k in KERNELS or [None]:
-        run("5: 8 x (32..4096) queries vs 300k subjects log-uniform 32..4096 (%s)" % (k or "automatic variant"),
-            mixed_db(8, 32, 4096, 5), mixed_db(300000, 32, 4096, 6), kernel=k)
+def case_latency(pkg):
+    a = latency(pkg, "2 (latency): 1 x 128 nt query vs 499 x 128 nt, sw_score_batch + sw_fetch",
+                pkg.random_packed_db(1, 128, 1), pkg.random_packed_db(499, 128, 2))
+    a["reference_simulated_us"] = REF_BANK_US_DATA500
+    b = latency(pkg, "1 pair (latency): 32 nt query vs one 128 nt subject (the CAPI sample's job)",
+                pkg.random_packed_db(1, 32, 1), pkg.random_packed_db(1, 128, 2))
+    b["reference_simulated_us"] = REF_PAIR_US
+    return {"config2_499x128": a, "single_pair_32x128": b}
+
+
+def case_4full(pkg):
+    return run(pkg, "4: 1 x 10 kb query vs 1M x 1 kb subjects (full size, 1e13 cells)", pkg.random_packed_db(1, 10000, 3),
+               pkg.random_packed_db(1000000, 1000, 4), reps=2, check=1000, seed=4)
+
+
+def case_4(pkg, kernel=None):
+    return run(pkg, "4 (200k): 1 x 10 kb query vs 200k x 1 kb (%s)" % (kernel or "automatic variant"),
+               pkg.random_packed_db(1, 10000, 3), pkg.random_packed_db(200000, 1000, 4), kernel=kernel, check=300, seed=5)
+
+
+def case_4w(pkg, kernel=None):
+    return run(pkg, "4w: 1 x 10 kb query vs 2000 x 1 kb (%s)" % (kernel or "automatic variant"),
+               pkg.random_packed_db(1, 10000, 3), pkg.random_packed_db(2000, 1000, 4), kernel=kernel, check=200, seed=6)
+
+
+def case_5(pkg, kernel=None):
+    return run(pkg, "5: 8 x (32..4096) queries vs 300k subjects log-uniform 32..4096 (%s)" % (kernel or "automatic variant"),
+               mixed_db(8, 32, 4096, 5), mixed_db(300000, 32, 4096, 6), kernel=kernel, check=300, seed=7)
+
+
+def case_pair(pkg, n=100000):
+    """One long pair: the multi-warp (band-pipelined) path."""
+    return run(pkg, f"single pair: {n} x {n} nt", pkg.random_packed_db(1, n, 8), pkg.random_packed_db(1, n, 9),
+               reps=2, check=0)
+
+
+def bench_blocks(pkg, log=lambda *a: None):
+    """What bench.py adds to its JSON line (rank 0, N = 1): ~60 s in total."""
+    out = {"configs": {}, "latency": None}
+    t0 = time.perf_counter()
+    for key, fn in (("latency", case_latency), ("config4_full", case_4full), ("config4_200k", case_4),
+                    ("config4_2000_subjects", case_4w), ("config5_mixed", case_5)):
+        try:
+            r = fn(pkg)
+        except Exception as ex:
+            r = {"error": repr(ex)}
+        if key == "latency":
+            out["latency"] = r
+        else:
+            out["configs"][key] = r
+        log(key, json.dumps(r)[:400])
+    out["configs"]["pipe_bound_gcups"] = PIPE_BOUND_GCUPS
+    out["configs"]["seconds"] = time.perf_counter() - t0
+    return out
+
+
+if __name__ == "__main__":
+    pkg = importlib.import_module("smith-waterman-fpga-module_b200")
+    which = [a for a in sys.argv[1:]] or ["lat", "4", "4w", "5"]
+    kernels = os.environ.get("SW_KERNELS", "").split() or [None]
+    for w in which:
+        if w in ("2", "lat"):
+            for v in case_latency(pkg).values():
+                print(json.dumps(v), flush=True)
+        elif w == "4full":
+            print(json.dumps(case_4full(pkg)), flush=True)
+        elif w == "pair":
+            print(json.dumps(case_pair(pkg)), flush=True)
+        elif w in ("4", "4w", "5"):
+            for k in kernels:
+                print(json.dumps({"4": case_4, "4w": case_4w, "5": case_5}[w](pkg, k)), flush=True)

@@ -24,11 +24,18 @@ LIB_PATH = os.environ.get("SW_B200_LIB", os.path.join(_HERE, "libsw_b200.so"))  
 
 SW_OK, SW_EINVAL, SW_ENOMEM, SW_ECUDA, SW_ENODEV = 0, -1, -2, -3, -4
 SW_ESTATE, SW_ETIMEOUT, SW_ECAPACITY, SW_EIO, SW_EAGAIN = -5, -6, -7, -8, -9
+SW_ERANGE, SW_EDEVICE = -10, -11
+SW_OUTPUT_I32, SW_OUTPUT_I16 = 0, 1
 
 
 class SwParams(C.Structure):
     _fields_ = [("match", C.c_int16), ("mismatch", C.c_int16), ("gap_open", C.c_int16),
                 ("gap_extend", C.c_int16), ("score_width", C.c_int32)]
+
+
+class SwStats(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("load_ms", "enqueue_ms", "fetch_wait_ms", "fetch_drain_ms",
+                                          "kernel_ms_max", "kernel_ms_min")]
 
 
 class SwError(RuntimeError):
@@ -89,6 +96,22 @@ def load_library():
     L.sw_set_strands.argtypes = [vp, i32]
     L.sw_query_rows.argtypes = [vp]
     L.sw_batches_in_flight.argtypes = [vp]
+    L.sw_set_output.argtypes = [vp, i32]
+    L.sw_set_topk.argtypes = [vp, i32]
+    L.sw_fetch_i16.argtypes = [vp, vp, sz, i32]
+    L.sw_fetch_db_i16.argtypes = [vp, vp, sz]
+    L.sw_fetch_overflow.argtypes = [vp, vp, vp, sz, C.POINTER(sz)]
+    L.sw_fetch_topk.argtypes = [vp, vp, vp, sz, i32]
+    L.sw_fetch_db_topk.argtypes = [vp, vp, vp, sz]
+    L.sw_device_error_bits.argtypes = [vp]
+    L.sw_device_error_bits.restype = C.c_uint
+    L.sw_is_check_build.restype = i32
+    L.sw_set_jit.argtypes = [vp, i32]
+    L.sw_jit_is_available.restype = i32
+    L.sw_jit_compile_check.argtypes = [C.c_char_p, i32, i32, C.c_char_p, sz]
+    L.sw_set_small_batch_path.argtypes = [vp, i32]
+    L.sw_get_stats.argtypes = [vp, C.POINTER(SwStats)]
+    L.sw_params_in_exact_domain.argtypes = [C.POINTER(SwParams)]
     L.sw_device_count.restype = i32
     L.sw_version.restype = C.c_char_p
     L.sw_pack_2bit.argtypes = [C.c_char_p, sz, vp]
@@ -121,6 +144,9 @@ class Engine:
         self.nq = 0          # rows of the score matrix (queries x strands)
         self.ns = 0          # subjects of the resident database / last submitted batch
         self._batch_ns = []  # subjects of the batches in flight, oldest first
+        self.out_mode = SW_OUTPUT_I32
+        self.topk = 0
+        self._ids_ns = 0     # subjects of the batch sw_fetch_ids refers to (last loaded / fetched)
 
     # -- plumbing ---------------------------------------------------------------------
     def _check(self, rc):
@@ -173,21 +199,71 @@ class Engine:
         self._batch_ns.append(len(ln))
 
     def fetch(self, timeout_ms=-1, out=None):
-        """Scores of the OLDEST batch in flight (two may be in flight)."""
+        """Scores of the OLDEST batch in flight (two may be in flight): int32 or, after
+        set_output(SW_OUTPUT_I16), int16 matrix [rows, ns]."""
         ns = self._batch_ns[0] if self._batch_ns else self.ns
+        i16 = self.out_mode == SW_OUTPUT_I16
         if out is None:
-            out = np.empty((self.nq, ns), dtype=np.int32)
-        self._check(self.lib.sw_fetch(self.h, _ptr(out), out.size, timeout_ms))
+            out = np.empty((self.nq, ns), dtype=np.int16 if i16 else np.int32)
+        fn = self.lib.sw_fetch_i16 if i16 else self.lib.sw_fetch
+        self._check(fn(self.h, _ptr(out), out.size, timeout_ms))
         if self._batch_ns:
-            self._batch_ns.pop(0)
+            self._ids_ns = self._batch_ns.pop(0)
         return out
+
+    def set_output(self, mode):
+        """SW_OUTPUT_I32 (default) or SW_OUTPUT_I16 (half the HBM / D2H bytes; scores above 32767
+        come back through fetch_overflow)."""
+        self._check(self.lib.sw_set_output(self.h, mode))
+        self.out_mode = mode
+
+    def set_topk(self, k):
+        """k > 0: fused per-query top-k, no score matrix (fetch_topk / fetch_db_topk); 0 = matrices."""
+        self._check(self.lib.sw_set_topk(self.h, k))
+        self.topk = k
+
+    def fetch_overflow(self):
+        """(flat index iq * ns + is, int32 score) of the scores above 32767 of the batch fetched last."""
+        cnt = C.c_size_t(0)
+        self._check(self.lib.sw_fetch_overflow(self.h, None, None, 0, C.byref(cnt)))
+        idx = np.empty(cnt.value, dtype=np.uint64)
+        sc = np.empty(cnt.value, dtype=np.int32)
+        if cnt.value:
+            self._check(self.lib.sw_fetch_overflow(self.h, _ptr(idx), _ptr(sc), cnt.value, C.byref(cnt)))
+        return idx, sc
+
+    def fetch_topk(self, timeout_ms=-1):
+        """(scores [rows, k], index [rows, k]) of the oldest batch in flight; index = input index in the batch."""
+        sc = np.empty((self.nq, self.topk), dtype=np.int32)
+        ix = np.empty((self.nq, self.topk), dtype=np.uint64)
+        self._check(self.lib.sw_fetch_topk(self.h, _ptr(sc), _ptr(ix), sc.size, timeout_ms))
+        if self._batch_ns:
+            self._ids_ns = self._batch_ns.pop(0)
+        return sc, ix
+
+    def fetch_db_topk(self):
+        sc = np.empty((self.nq, self.topk), dtype=np.int32)
+        ix = np.empty((self.nq, self.topk), dtype=np.uint64)
+        self._check(self.lib.sw_fetch_db_topk(self.h, _ptr(sc), _ptr(ix), sc.size))
+        return sc, ix
+
+    def set_jit(self, mode):
+        self._check(self.lib.sw_set_jit(self.h, mode))
+
+    def set_small_batch_path(self, enable):
+        self._check(self.lib.sw_set_small_batch_path(self.h, int(bool(enable))))
+
+    @property
+    def device_error_bits(self):
+        return int(self.lib.sw_device_error_bits(self.h))
 
     @property
     def batches_in_flight(self):
         return int(self.lib.sw_batches_in_flight(self.h))
 
     def fetch_ids(self):
-        ids = np.empty(self.ns, dtype=np.uint64)
+        """ids of the batch fetched last (or of the resident database after load_db)."""
+        ids = np.empty(self._ids_ns, dtype=np.uint64)
         self._check(self.lib.sw_fetch_ids(self.h, _ptr(ids), ids.size))
         return ids
 
@@ -203,6 +279,7 @@ class Engine:
         ids_a = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint64)
         self._check(self.lib.sw_load_db(self.h, _ptr(packed), _ptr(ln), _ptr(off), _ptr(ids_a), len(ln)))
         self.ns = len(ln)
+        self._ids_ns = len(ln)
 
     def score_db(self):
         self._check(self.lib.sw_score_db(self.h))
@@ -211,9 +288,11 @@ class Engine:
         self._check(self.lib.sw_wait(self.h, timeout_ms))
 
     def fetch_db(self, out=None):
+        i16 = self.out_mode == SW_OUTPUT_I16
         if out is None:
-            out = np.empty((self.nq, self.ns), dtype=np.int32)
-        self._check(self.lib.sw_fetch_db(self.h, _ptr(out), out.size))
+            out = np.empty((self.nq, self.ns), dtype=np.int16 if i16 else np.int32)
+        fn = self.lib.sw_fetch_db_i16 if i16 else self.lib.sw_fetch_db
+        self._check(fn(self.h, _ptr(out), out.size))
         return out
 
     def fetch_best(self):
@@ -232,6 +311,11 @@ class Engine:
 
     def set_kernel_name(self, name):
         self._check(self.lib.sw_set_kernel_name(self.h, name.encode() if name else None))
+
+    def stats(self):
+        st = SwStats()
+        self._check(self.lib.sw_get_stats(self.h, C.byref(st)))
+        return {n: float(getattr(st, n)) for n, _ in SwStats._fields_}
 
     @property
     def last_kernel_ms(self):
@@ -268,6 +352,24 @@ def plan_shards(lengths, n_shards):
 def set_fixed_penalty_kernels(enable):
     """False: never use the kernel instances with the default gap penalties compiled in."""
     load_library().sw_set_fixed_penalty_kernels(int(bool(enable)))
+
+
+def params_in_exact_domain(match=5, mismatch=-4, gap_open=-12, gap_extend=-4, score_width=0):
+    """1 = bit-exact vs the RTL for every input, 0 = accepted but the RTL is schedule-dependent
+    there, negative = rejected by sw_init."""
+    p = SwParams(match, mismatch, gap_open, gap_extend, score_width)
+    return int(load_library().sw_params_in_exact_domain(C.byref(p)))
+
+
+def jit_compile_check(variant, gap_open, gap_extend):
+    """(ok, message) of compiling / loading the run-time specialised instance of one variant."""
+    buf = C.create_string_buffer(1024)
+    rc = load_library().sw_jit_compile_check(variant.encode(), gap_open, gap_extend, buf, 1024)
+    return rc, buf.value.decode(errors="replace")
+
+
+def is_check_build():
+    return bool(load_library().sw_is_check_build())
 
 
 def device_count():

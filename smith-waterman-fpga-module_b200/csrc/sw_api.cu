@@ -7,53 +7,99 @@
  * arbitration becomes a length-bucketed work queue drained by persistent blocks), sharded
  * over the handle's GPUs as contiguous input ranges, and moved with cudaMemcpyAsync from
  * pinned staging on per-GPU streams.  No CPU scoring path exists in this library.
+ *
+ * Two submit paths:
+ *   regular  -- length sort + pairing on the host, code stream built on the GPU (build_tp_kernel),
+ *               a launch plan of strip-kernel launches (per query group / query chunk), results
+ *               in an HBM matrix (int32 / int16) or fused per-query top-k lists;
+ *   small    -- latency path for small batches: ONE pinned staging buffer, ONE H2D copy, ONE
+ *               kernel (a DIRECT strip instance that forms the column codes on the fly), scores
+ *               written straight into mapped pinned host memory.  No memsets, no event creation,
+ *               no heap allocation per call.
  */
 #include "../../include/sw_b200.h"
+#include "sw_jit.h"
 #include "sw_kernels.h"
 
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <new>
 #include <thread>
 #include <vector>
 
 namespace {
 
+#ifdef SW_BOUNDS_CHECK
+constexpr size_t kGuard = 256;           // canary bytes on both sides of every device buffer
+constexpr int kGuardByte = 0xA5;
+#else
+constexpr size_t kGuard = 0;
+#endif
+
 struct PinnedBuf {
     void *p = nullptr;
+    void *dptr = nullptr;                // device view (mapped allocations)
     size_t cap = 0;
-    cudaError_t reserve(size_t bytes) {
+    cudaError_t reserve(size_t bytes, bool mapped = false) {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFreeHost(p);
-        p = nullptr; cap = 0;
+        p = nullptr; dptr = nullptr; cap = 0;
         size_t want = bytes + bytes / 4 + 4096;
-        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocDefault);
-        if (e == cudaSuccess) cap = want;
+        cudaError_t e = cudaHostAlloc(&p, want, mapped ? (cudaHostAllocMapped | cudaHostAllocPortable) : cudaHostAllocDefault);
+        if (e != cudaSuccess) return e;
+        if (mapped) {
+            e = cudaHostGetDevicePointer(&dptr, p, 0);
+            if (e != cudaSuccess) { cudaFreeHost(p); p = nullptr; return e; }
+        }
+        cap = want;
         return e;
     }
-    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; dptr = nullptr; cap = 0; }
 };
 
 struct DevBuf {
-    void *p = nullptr;
+    void *p = nullptr;                   // usable region
+    void *base = nullptr;                // allocation (p - kGuard)
     size_t cap = 0;
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap && p) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
+        if (base) cudaFree(base);
+        p = base = nullptr; cap = 0;
         size_t want = bytes ? bytes : 16;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
+        want = (want + 255) & ~(size_t)255;
+        cudaError_t e = cudaMalloc(&base, want + 2 * kGuard);
+        if (e != cudaSuccess) { base = nullptr; return e; }
+        p = (char *)base + kGuard;
+        cap = want;
+#ifdef SW_BOUNDS_CHECK
+        e = cudaMemset(base, kGuardByte, kGuard);
+        if (e == cudaSuccess) e = cudaMemset((char *)p + cap, kGuardByte, kGuard);
+#endif
         return e;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (base) cudaFree(base); p = base = nullptr; cap = 0; }
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+    // true if both canaries are intact (always true in regular builds)
+    bool canaries_ok() const {
+#ifdef SW_BOUNDS_CHECK
+        if (!base) return true;
+        unsigned char g[2 * kGuard];
+        if (cudaMemcpy(g, base, kGuard, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+        if (cudaMemcpy(g + kGuard, (char *)p + cap, kGuard, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+        for (size_t i = 0; i < 2 * kGuard; ++i) if (g[i] != kGuardByte) return false;
+#endif
+        return true;
+    }
 };
 
 struct QueryChunk { int q0, q1; cudaEvent_t done; };
+
+constexpr unsigned kOvfCap = 1u << 20;   // entries of the 16-bit-overflow side list
 
 // Everything that belongs to one database batch on one GPU.  Two slots per GPU: while the
 // kernels of batch k run, batch k+1 can be sorted, uploaded and enqueued, and batch k-1 copied
@@ -61,12 +107,23 @@ struct QueryChunk { int q0, q1; cudaEvent_t done; };
 struct Slot {
     size_t s0 = 0, s1 = 0;            // global subject range [s0, s1) of this GPU's shard
     DevBuf d_raw, d_off, d_len, d_pair_subj, d_pair_len, d_tile_woff, d_tp, d_out;
+    DevBuf d_ovf_count, d_ovf_list, d_ovf_score, d_topk_out;
     uint32_t npairs = 0, max_len = 0;
-    uint64_t sum_len = 0;
-    PinnedBuf h_stage_a, h_stage_b, h_stage_c, h_stage_d;
+    uint64_t sum_len = 0, tp_words = 0;
+    PinnedBuf h_stage_a, h_stage_b, h_stage_c, h_stage_d, h_topk, h_ovf;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_upload = nullptr;
+    std::vector<cudaEvent_t> ev_pool;  // chunk-done events, created once
     std::vector<QueryChunk> chunks;
+    std::vector<uint32_t> order, hist; // host scratch of the length sort (capacity is kept)
+    std::vector<uint32_t> empties;     // first few zero-length subjects (they score 0; top-k fill)
     bool scored = false;
+    bool ovf_used = false;
+    int out_mode = SW_OUT_I32;         // of the last scoring
+    int topk_k = 0;
+    // small (latency) path: one staging buffer in, mapped scores out
+    bool is_small = false;
+    PinnedBuf h_small_in, h_small_out;
+    DevBuf d_small_in;
 };
 
 struct GpuCtx {
@@ -74,20 +131,29 @@ struct GpuCtx {
     int num_sms = 0;
     cudaStream_t st_compute = nullptr, st_copy = nullptr;
     // queries
-    DevBuf d_qpacked, d_qoff, d_qlen;
+    DevBuf d_qpacked, d_qoff, d_qlen, d_qidx;
     Slot slot[2];
     // scratch shared by both slots (kernels of one GPU run in stream order)
-    DevBuf d_bnd, d_counters, d_scratch32, d_best_score, d_best_index;
+    DevBuf d_bnd, d_counters, d_scratch32, d_best_score, d_best_index, d_topk_keys, d_err;
+    unsigned counter_next = 0;        // next unused work-queue counter
+    // autotune: timing events and the cached decision, per GPU (shards differ in shape)
+    cudaEvent_t ev_tune0 = nullptr, ev_tune1 = nullptr;
+    uint64_t tune_key = 0;            // workload signature of the cached decision
+    int tune_choice = -1;
+    std::map<std::pair<int, int>, int> occ_cache;   // (variant, chunk_passes) -> resident blocks / SM
 };
 
 // Host-side description of one batch (all GPUs).
 struct Batch {
     size_t ns = 0;
     int nq = 0;                       // query rows the scores of this batch have
-    bool loaded = false, scored = false;
+    bool loaded = false, scored = false, small = false;
+    int out_mode = SW_OUT_I32, topk_k = 0;
     std::vector<uint64_t> ids;
     bool have_ids = false;
     uint64_t cells = 0;
+    std::vector<uint64_t> ovf_index;  // I16 mode: entries above 32767 of the batch fetched last
+    std::vector<int32_t> ovf_score;
 };
 
 }  // namespace
@@ -106,18 +172,21 @@ struct sw_handle {
     Batch batch[2];
     int fifo[2] = {0, 0};             // slots in flight, oldest first
     int n_inflight = 0;
-    int last_slot = 0;                // slot of the most recent load / fetch (ids, cells)
+    int last_slot = 0;                // slot of the most recent load / fetch (ids, cells, overflow list)
+    int out_mode = SW_OUT_I32;        // SW_OUTPUT_I32 / SW_OUTPUT_I16 for the next scoring
+    int topk_k = 0;                   // > 0: fused top-k instead of a matrix
+    bool small_path = true;
+    int jit = 1;                      // run-time specialisation of gap penalties: 0 off, 1 large jobs, 2 always
     // bookkeeping
-    int last_cuda = 0;
+    std::atomic<int> last_cuda{0};    // written by the per-GPU worker threads as well
     std::atomic<uint64_t> launches{0};
     uint64_t last_cells = 0;
     double last_ms = 0.0;
-    const char *last_kernel = "none";
+    sw_stats_t stats{};               // host-visible phase times of the last submit / fetch
+    char last_kernel[96] = "none";
     int force_R = 0, force_G = 0, force32 = 0, force_arith = -1;
     int force_variant = -1;
     bool autotune = true;             // time the model's top candidates on a sample of large jobs
-    uint64_t tune_key = 0;            // workload signature of the cached decision
-    int tune_choice = -1;
 };
 
 namespace {
@@ -127,7 +196,7 @@ const int kMaxCounters = 4096;
 #define SW_CUDA(h, call)                                                        \
     do {                                                                        \
         cudaError_t e__ = (call);                                               \
-        if (e__ != cudaSuccess) { (h)->last_cuda = (int)e__; return SW_ECUDA; } \
+        if (e__ != cudaSuccess) { (h)->last_cuda.store((int)e__); return (e__ == cudaErrorMemoryAllocation) ? SW_ENOMEM : SW_ECUDA; } \
     } while (0)
 
 int validate_params(const sw_params_t *p)
@@ -147,22 +216,43 @@ int validate_params(const sw_params_t *p)
     return SW_OK;
 }
 
+SwScoring scoring_of(const sw_handle *h)
+{
+    SwScoring sc;
+    sc.match = h->params.match; sc.mismatch = h->params.mismatch;
+    sc.goe = (int)h->params.gap_open + (int)h->params.gap_extend; sc.ge = h->params.gap_extend;
+    sc.limit = h->params.score_width ? (1 << (h->params.score_width - 1)) - 1 : 0;
+    return sc;
+}
+
+std::vector<DevBuf *> all_devbufs(GpuCtx &g)
+{
+    std::vector<DevBuf *> v = {&g.d_qpacked, &g.d_qoff, &g.d_qlen, &g.d_qidx, &g.d_bnd, &g.d_counters, &g.d_scratch32,
+                               &g.d_best_score, &g.d_best_index, &g.d_topk_keys, &g.d_err};
+    for (Slot &b : g.slot) {
+        DevBuf *bufs[] = {&b.d_raw, &b.d_off, &b.d_len, &b.d_pair_subj, &b.d_pair_len, &b.d_tile_woff, &b.d_tp, &b.d_out,
+                          &b.d_ovf_count, &b.d_ovf_list, &b.d_ovf_score, &b.d_topk_out, &b.d_small_in};
+        v.insert(v.end(), std::begin(bufs), std::end(bufs));
+    }
+    return v;
+}
+
 void free_gpu(GpuCtx &g)
 {
     cudaSetDevice(g.dev);
+    for (DevBuf *d : all_devbufs(g)) d->release();
     for (Slot &b : g.slot) {
-        for (auto &c : b.chunks) if (c.done) cudaEventDestroy(c.done);
+        for (cudaEvent_t e : b.ev_pool) cudaEventDestroy(e);
+        b.ev_pool.clear();
         b.chunks.clear();
-        DevBuf *bufs[] = {&b.d_raw, &b.d_off, &b.d_len, &b.d_pair_subj, &b.d_pair_len, &b.d_tile_woff, &b.d_tp, &b.d_out};
-        for (DevBuf *d : bufs) d->release();
-        b.h_stage_a.release(); b.h_stage_b.release(); b.h_stage_c.release(); b.h_stage_d.release();
+        PinnedBuf *pins[] = {&b.h_stage_a, &b.h_stage_b, &b.h_stage_c, &b.h_stage_d, &b.h_topk, &b.h_ovf, &b.h_small_in, &b.h_small_out};
+        for (PinnedBuf *p : pins) p->release();
         if (b.ev_start) cudaEventDestroy(b.ev_start);
         if (b.ev_stop) cudaEventDestroy(b.ev_stop);
         if (b.ev_upload) cudaEventDestroy(b.ev_upload);
     }
-    DevBuf *bufs[] = {&g.d_qpacked, &g.d_qoff, &g.d_qlen, &g.d_bnd, &g.d_counters, &g.d_scratch32,
-                      &g.d_best_score, &g.d_best_index};
-    for (DevBuf *d : bufs) d->release();
+    if (g.ev_tune0) cudaEventDestroy(g.ev_tune0);
+    if (g.ev_tune1) cudaEventDestroy(g.ev_tune1);
     if (g.st_compute) cudaStreamDestroy(g.st_compute);
     if (g.st_copy) cudaStreamDestroy(g.st_copy);
 }
@@ -182,13 +272,58 @@ int upload_queries(sw_handle *h, GpuCtx &g)
     return SW_OK;
 }
 
+// Orders the subjects [0, n) by ascending length into g.order (counting sort when the range is
+// small, else comparison sort) and records the first few empty ones.
+void sort_by_length(Slot &g, const uint32_t *ln, size_t n, uint32_t maxlen)
+{
+    g.order.resize(n);
+    if (maxlen <= (1u << 22) && (size_t)maxlen <= 4 * n + 4096) {
+        g.hist.assign((size_t)maxlen + 2, 0);
+        for (size_t i = 0; i < n; ++i) g.hist[ln[i] + 1]++;
+        for (size_t l = 1; l < g.hist.size(); ++l) g.hist[l] += g.hist[l - 1];
+        for (size_t i = 0; i < n; ++i) g.order[g.hist[ln[i]]++] = (uint32_t)i;
+    } else {
+        for (size_t i = 0; i < n; ++i) g.order[i] = (uint32_t)i;
+        std::stable_sort(g.order.begin(), g.order.end(), [&](uint32_t a, uint32_t b) { return ln[a] < ln[b]; });
+    }
+    g.empties.clear();
+    for (size_t i = 0; i < n && ln[g.order[i]] == 0 && g.empties.size() < SW_MAX_TOPK; ++i) g.empties.push_back(g.order[i]);
+    std::sort(g.empties.begin(), g.empties.end());
+}
+
+// Pairs neighbours in length order: the longer member drives the column loop (low lane), the
+// shorter one (high lane) sees PAD columns once it has ended.  Returns the number of pairs;
+// pair_subj / pair_len are padded to a multiple of 32 pairs.
+size_t make_pairs(const Slot &g, const uint32_t *ln, size_t n, uint32_t *pair_subj, uint32_t *pair_len)
+{
+    size_t np = 0, i = 0;
+    while (i < n && ln[g.order[i]] == 0) ++i;           // empty subjects score 0 (output is pre-zeroed)
+    if ((n - i) & 1) {                                  // odd count: the shortest one stays single
+        pair_subj[0] = g.order[i]; pair_subj[1] = SW_NO_SUBJECT;
+        pair_len[0] = ln[g.order[i]]; pair_len[1] = 0;
+        ++i; ++np;
+    }
+    for (; i + 1 < n; i += 2, ++np) {
+        const uint32_t shorter = g.order[i], longer = g.order[i + 1];
+        pair_subj[2 * np] = longer; pair_subj[2 * np + 1] = shorter;
+        pair_len[2 * np] = ln[longer]; pair_len[2 * np + 1] = ln[shorter];
+    }
+    const size_t ntiles = (np + 31) / 32;
+    for (size_t p = np; p < ntiles * 32; ++p) {
+        pair_subj[2 * p] = SW_NO_SUBJECT; pair_subj[2 * p + 1] = SW_NO_SUBJECT;
+        pair_len[2 * p] = 0; pair_len[2 * p + 1] = 0;
+    }
+    return np;
+}
+
 // Length-sorts the shard's subjects, pairs neighbours in length order, lays out 32-pair tiles, uploads.
 int load_shard(sw_handle *h, GpuCtx &gc, Slot &g, const uint8_t *packed, const uint32_t *len, const uint64_t *off)
 {
     SW_CUDA(h, cudaSetDevice(gc.dev));
     const size_t n = g.s1 - g.s0;
-    g.npairs = 0; g.max_len = 0; g.sum_len = 0; g.scored = false;
-    if (n == 0) return SW_OK;
+    g.npairs = 0; g.max_len = 0; g.sum_len = 0; g.tp_words = 0; g.is_small = false;
+    g.empties.clear();
+    if (n == 0) { g.scored = false; return SW_OK; }
     if (n >= 0xFFFFFFF0ull) return SW_EINVAL;
     const uint32_t *ln = len + g.s0;
     const uint64_t *of = off + g.s0;
@@ -205,45 +340,15 @@ int load_shard(sw_handle *h, GpuCtx &gc, Slot &g, const uint8_t *packed, const u
         sum += ln[i];
     }
     g.max_len = maxlen; g.sum_len = sum;
-    if (maxlen == 0) return SW_OK;
+    sort_by_length(g, ln, n, maxlen);
+    if (maxlen == 0) { g.scored = false; return SW_OK; }
 
-    // --- order by length (counting sort when the range is small, else comparison sort)
     SW_CUDA(h, g.h_stage_a.reserve((n + 64) * 2 * sizeof(uint32_t)));      // pair_subj
     SW_CUDA(h, g.h_stage_b.reserve((n + 128) * sizeof(uint32_t)));         // pair_len (2 per pair)
-    std::vector<uint32_t> order;
-    order.reserve(n);
-    if (maxlen <= (1u << 22)) {
-        std::vector<uint32_t> start((size_t)maxlen + 2, 0);
-        for (size_t i = 0; i < n; ++i) start[ln[i] + 1]++;
-        for (size_t l = 1; l < start.size(); ++l) start[l] += start[l - 1];
-        order.resize(n);
-        for (size_t i = 0; i < n; ++i) order[start[ln[i]]++] = (uint32_t)i;
-    } else {
-        order.resize(n);
-        for (size_t i = 0; i < n; ++i) order[i] = (uint32_t)i;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return ln[a] < ln[b]; });
-    }
-    // --- pair neighbours in length order: the longer member drives the column loop (low lane),
-    //     the shorter one (high lane) sees PAD columns once it has ended
     uint32_t *pair_subj = (uint32_t *)g.h_stage_a.p;
     uint32_t *pair_len = (uint32_t *)g.h_stage_b.p;
-    size_t np = 0, i = 0;
-    while (i < n && ln[order[i]] == 0) ++i;           // empty subjects score 0 (output is pre-zeroed)
-    if ((n - i) & 1) {                                // odd count: the shortest one stays single
-        pair_subj[0] = order[i]; pair_subj[1] = SW_NO_SUBJECT;
-        pair_len[0] = ln[order[i]]; pair_len[1] = 0;
-        ++i; ++np;
-    }
-    for (; i + 1 < n; i += 2, ++np) {
-        const uint32_t shorter = order[i], longer = order[i + 1];
-        pair_subj[2 * np] = longer; pair_subj[2 * np + 1] = shorter;
-        pair_len[2 * np] = ln[longer]; pair_len[2 * np + 1] = ln[shorter];
-    }
+    const size_t np = make_pairs(g, ln, n, pair_subj, pair_len);
     const size_t ntiles = (np + 31) / 32;
-    for (size_t p = np; p < ntiles * 32; ++p) {
-        pair_subj[2 * p] = SW_NO_SUBJECT; pair_subj[2 * p + 1] = SW_NO_SUBJECT;
-        pair_len[2 * p] = 0; pair_len[2 * p + 1] = 0;
-    }
     SW_CUDA(h, g.h_stage_c.reserve((ntiles + 1) * sizeof(uint64_t)));
     uint64_t *tile_woff = (uint64_t *)g.h_stage_c.p;
     uint64_t w = 0;
@@ -254,6 +359,7 @@ int load_shard(sw_handle *h, GpuCtx &gc, Slot &g, const uint8_t *packed, const u
     }
     tile_woff[ntiles] = w;
     g.npairs = (uint32_t)np;
+    g.tp_words = w;
 
     // --- local byte offsets
     SW_CUDA(h, g.h_stage_d.reserve(n * sizeof(uint64_t)));
@@ -270,6 +376,11 @@ int load_shard(sw_handle *h, GpuCtx &gc, Slot &g, const uint8_t *packed, const u
     SW_CUDA(h, g.d_tile_woff.reserve((ntiles + 1) * sizeof(uint64_t)));
     SW_CUDA(h, g.d_tp.reserve((w + 32) * sizeof(uint32_t)));
     cudaStream_t cs = gc.st_copy;
+    // the slot's buffers may still be read by scoring kernels queued on the compute stream (sw_score_db
+    // is asynchronous): the uploads wait for the tail of that work.  Only this slot's event is waited
+    // for, so the other slot's kernels keep overlapping with these copies.
+    if (g.scored) SW_CUDA(h, cudaStreamWaitEvent(cs, g.ev_stop, 0));
+    g.scored = false;
     SW_CUDA(h, cudaMemcpyAsync(g.d_raw.p, packed + bmin, raw_bytes, cudaMemcpyHostToDevice, cs));
     SW_CUDA(h, cudaMemcpyAsync(g.d_len.p, ln, n * sizeof(uint32_t), cudaMemcpyHostToDevice, cs));
     SW_CUDA(h, cudaMemcpyAsync(g.d_off.p, loc_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, cs));
@@ -279,10 +390,10 @@ int load_shard(sw_handle *h, GpuCtx &gc, Slot &g, const uint8_t *packed, const u
     SW_CUDA(h, cudaEventRecord(g.ev_upload, cs));
     SW_CUDA(h, cudaStreamWaitEvent(gc.st_compute, g.ev_upload, 0));
 
-    SwDevDb db;
+    SwDevDb db{};
     db.raw = g.d_raw.as<uint8_t>(); db.off = g.d_off.as<uint64_t>(); db.len = g.d_len.as<uint32_t>();
     db.ns = (uint32_t)n; db.pair_subj = g.d_pair_subj.as<uint32_t>(); db.pair_len = g.d_pair_len.as<uint32_t>();
-    db.tile_woff = g.d_tile_woff.as<uint64_t>(); db.tp = g.d_tp.as<uint32_t>();
+    db.tile_woff = g.d_tile_woff.as<uint64_t>(); db.tp = g.d_tp.as<uint32_t>(); db.tp_words = g.tp_words;
     db.npairs = g.npairs; db.max_len = g.max_len;
     SW_CUDA(h, sw_launch_build_tp(gc.st_compute, db));
     h->launches++;
@@ -291,12 +402,20 @@ int load_shard(sw_handle *h, GpuCtx &gc, Slot &g, const uint8_t *packed, const u
 
 SwDevDb dev_db(const Slot &g)
 {
-    SwDevDb db;
+    SwDevDb db{};
     db.raw = g.d_raw.as<uint8_t>(); db.off = g.d_off.as<uint64_t>(); db.len = g.d_len.as<uint32_t>();
     db.ns = (uint32_t)(g.s1 - g.s0); db.pair_subj = g.d_pair_subj.as<uint32_t>();
     db.pair_len = g.d_pair_len.as<uint32_t>(); db.tile_woff = g.d_tile_woff.as<uint64_t>();
-    db.tp = g.d_tp.as<uint32_t>(); db.npairs = g.npairs; db.max_len = g.max_len;
+    db.tp = g.d_tp.as<uint32_t>(); db.tp_words = g.tp_words; db.npairs = g.npairs; db.max_len = g.max_len;
     return db;
+}
+
+SwDevQueries dev_queries(const sw_handle *h, const GpuCtx &gc)
+{
+    SwDevQueries dq{};
+    dq.packed = gc.d_qpacked.as<uint8_t>(); dq.off = gc.d_qoff.as<uint32_t>(); dq.len = gc.d_qlen.as<uint32_t>();
+    dq.nq = (int)h->q_len.size(); dq.max_len = h->q_max_len;
+    return dq;
 }
 
 // Measured steady-state speed of each variant in GCUPS over PADDED cells (150-nt reads,
@@ -312,14 +431,40 @@ double variant_speed(const SwStripVariant *v)
         {"strip_s16x2_R75x1_G2", 7380}, {"strip_s16x2_R25x3_G2", 7480}, {"strip_s16x2_R38x1_G4", 7325},
         {"strip_s16x2_R19x2_G4", 7220}, {"strip_s16x2_R32x1_G4", 7180}, {"strip_s16x2_R16x1_G32", 5980},
         {"strip_s16x2_R8x2_G32", 6320},
+        // small-R latency variants: estimates (shuffle-bound), they are chosen for latency, not throughput
+        {"strip_s16x2_R1x1_G32", 900}, {"strip_s16x2_R2x1_G32", 1700}, {"strip_s16x2_R4x1_G32", 3000},
+        {"strip_s16x2_R8x1_G32", 4500}, {"strip_s16x2_R8x1_G16", 4600}, {"strip_s16x2_R16x1_G8", 5900},
     };
     for (auto &t : tab) if (std::strcmp(t.name, v->name) == 0) return t.gcups;
     return 5000.0;
 }
 
-// Picks the strip variant: least estimated time = padded rows x (columns + pipeline fill)
-// / measured speed / fraction of the GPU the pairs can keep busy.
-int choose_variant(const sw_handle *h, const GpuCtx &gc, const Slot &g, uint32_t maxq, std::vector<int> *ranked = nullptr)
+// Estimated time (arbitrary units) of scoring queries of the given lengths against the shard with
+// variant v = padded rows x (columns + pipeline fill) / measured speed / fraction of the GPU the
+// pairs can keep busy, plus half the time of the longest work item running at its share of an SM:
+// with few, long items the tail of the launch is what matters.
+double variant_cost(const GpuCtx &gc, const Slot &g, const SwStripVariant *v, const uint32_t *qlens, size_t nql, uint32_t maxq)
+{
+    const int P = v->R * v->G;
+    double rows = 0;                      // padded rows over all queries
+    for (size_t i = 0; i < nql; ++i) rows += (double)((qlens[i] + P - 1) / P) * P;
+    if (rows == 0) rows = (double)((maxq + P - 1) / P) * P;
+    const double lanes = (double)g.npairs * v->G;
+    const double fill = (double)gc.num_sms * v->min_blocks * v->block_threads;
+    const double util = std::min(1.0, lanes / fill);
+    const double cols = (double)std::max<uint32_t>(g.max_len, 1);
+    const double job = rows * (cols + v->G * v->S - 1) / cols * (double)g.sum_len / variant_speed(v) / util;
+    const int ppb = v->block_threads / v->G;
+    const double qrows = (double)((maxq + P - 1) / P) * P;
+    const double item = qrows * cols * 2.0 * ppb * ((double)gc.num_sms * v->min_blocks) / variant_speed(v);
+    return job + 0.5 * item;
+}
+
+bool variant_forced(const sw_handle *h) { return h->force_variant >= 0 || h->force_R || h->force_G; }
+
+// Picks the strip variant for a set of queries (least estimated time); ranked = all candidates, best first.
+int choose_variant(const sw_handle *h, const GpuCtx &gc, const Slot &g, const uint32_t *qlens, size_t nql, uint32_t maxq,
+                   std::vector<int> *ranked = nullptr)
 {
     const int nv = sw_strip_variant_count();
     if (h->force_variant >= 0) return h->force_variant;
@@ -335,24 +480,7 @@ int choose_variant(const sw_handle *h, const GpuCtx &gc, const Slot &g, uint32_t
     double best_cost = 0;
     std::vector<std::pair<double, int>> costs;
     for (int i = 0; i < nv; ++i) {
-        const SwStripVariant *v = sw_strip_variant(i);
-        const int P = v->R * v->G;
-        double rows = 0;                      // padded rows over all queries
-        for (uint32_t ql : h->q_len) rows += (double)((ql + P - 1) / P) * P;
-        if (rows == 0) rows = (double)((maxq + P - 1) / P) * P;
-        const double lanes = (double)g.npairs * v->G;
-        const double fill = (double)gc.num_sms * v->min_blocks * v->block_threads;
-        const double util = std::min(1.0, lanes / fill);
-        const double cols = (double)std::max<uint32_t>(g.max_len, 1);
-        // time of the whole job at the variant's measured speed ...
-        const double job = rows * (cols + v->G * v->S - 1) / cols * (double)g.sum_len / variant_speed(v) / util;
-        // ... plus half the time of the longest work item (block of pairs x longest query) running
-        // at its share of an SM: with few, long items the tail of the launch is what matters, and
-        // variants with fewer resident blocks per SM finish a single item sooner
-        const int ppb = v->block_threads / v->G;
-        const double qrows = (double)((maxq + P - 1) / P) * P;
-        const double item = qrows * cols * 2.0 * ppb * ((double)gc.num_sms * v->min_blocks) / variant_speed(v);
-        const double cost = job + 0.5 * item;
+        const double cost = variant_cost(gc, g, sw_strip_variant(i), qlens, nql, maxq);
         if (best < 0 || cost < best_cost) { best = i; best_cost = cost; }
         costs.emplace_back(cost, i);
     }
@@ -363,41 +491,63 @@ int choose_variant(const sw_handle *h, const GpuCtx &gc, const Slot &g, uint32_t
     return best;
 }
 
-// Launch geometry of a strip variant for this shard and query set (also grows the boundary scratch).
-int strip_setup(sw_handle *h, GpuCtx &gc, const Slot &g, int vidx, int *grid, int *chunk_passes)
+int cached_occupancy(sw_handle *h, GpuCtx &gc, int vidx, int chunk_passes, int *bps)
+{
+    auto key = std::make_pair(vidx, chunk_passes);
+    auto it = gc.occ_cache.find(key);
+    if (it != gc.occ_cache.end()) { *bps = it->second; return SW_OK; }
+    SW_CUDA(h, sw_strip_occupancy(vidx, sw_strip_smem_bytes(vidx, chunk_passes), bps));
+    gc.occ_cache[key] = *bps;
+    return SW_OK;
+}
+
+// Launch geometry of a strip variant for `npairs` pairs with subjects up to max_len and queries up to
+// maxq rows; also grows the pass-boundary scratch.
+int strip_setup(sw_handle *h, GpuCtx &gc, uint32_t npairs, uint32_t max_len, uint32_t maxq, int vidx, int *grid,
+                int *chunk_passes, size_t *bnd_elems)
 {
     const SwStripVariant *v = sw_strip_variant(vidx);
     const int P = v->R * v->G;
-    const int need_passes = (int)((h->q_max_len + P - 1) / P);
+    const int need_passes = (int)((maxq + P - 1) / P);
     const size_t pass_bytes = sw_strip_smem_bytes(vidx, 1);
     const int budget_passes = std::max<int>(1, (int)((48 * 1024) / pass_bytes));
     *chunk_passes = std::max(1, std::min(need_passes, budget_passes));
     int bps = 0;
-    SW_CUDA(h, sw_strip_occupancy(vidx, sw_strip_smem_bytes(vidx, *chunk_passes), &bps));
+    int rc = cached_occupancy(h, gc, vidx, *chunk_passes, &bps);
+    if (rc != SW_OK) return rc;
     if (bps < 1) return SW_ECUDA;
     const int ppb = v->block_threads / v->G;
-    const uint32_t npb = (g.npairs + ppb - 1) / ppb;
-    *grid = (int)std::min<uint64_t>(npb, (uint64_t)gc.num_sms * bps);
+    const uint32_t npb = (npairs + ppb - 1) / ppb;
+    *grid = (int)std::min<uint64_t>(std::max<uint32_t>(npb, 1), (uint64_t)gc.num_sms * bps);
+    *bnd_elems = 0;
     if (need_passes > 1) {
         // pass-boundary scratch: one (H, G) per column of the longest subject, per pair slot, per
         // resident block.  A very long subject would make that huge, so the grid shrinks to keep
-        // the scratch within a budget (correct, slower; splitting the launch by length group is
-        // the better answer and is left for later).
-        const size_t per_block = (size_t)g.max_len * ppb * sizeof(uint2);
+        // the scratch within a budget.
+        const size_t per_block = (size_t)max_len * ppb * sizeof(uint2);
         const size_t budget = (size_t)16 << 30;
         if (per_block > budget) return SW_ENOMEM;
         *grid = (int)std::min<size_t>((size_t)*grid, std::max<size_t>(1, budget / per_block));
         SW_CUDA(h, gc.d_bnd.reserve((size_t)*grid * per_block));
+        *bnd_elems = (size_t)*grid * per_block / sizeof(uint2);
     }
     return SW_OK;
 }
 
-// Times the model's best candidates on a window of the pair list (middle of the length order)
-// and a few queries, and returns the fastest.  Every variant produces identical scores, so the
-// sample launches may write into the real output buffer.
-int autotune_variant(sw_handle *h, GpuCtx &gc, Slot &g, const SwDevDb &db, const SwDevQueries &dq,
-                     const SwScoring &sc, const std::vector<int> &ranked, int nq)
+unsigned *next_counter(GpuCtx &gc)
 {
+    unsigned *c = gc.d_counters.as<unsigned>() + (gc.counter_next % kMaxCounters);
+    gc.counter_next++;
+    return c;
+}
+
+// Times the model's best candidates on a window of the pair list (middle of the length order)
+// and a few queries; *choice = the fastest.  Every variant produces identical scores, so the
+// sample launches may write into the real output buffer.  Returns a status; the events live in
+// the GpuCtx, so no exit path leaks them.
+int autotune_variant(sw_handle *h, GpuCtx &gc, Slot &g, SwStripLaunch base, const std::vector<int> &ranked, int nq, int *choice)
+{
+    *choice = ranked[0];
     const int ncand = std::min<int>(3, (int)ranked.size());
     const int nqs = std::min(nq, 8);
     uint64_t qrows = 0;
@@ -407,146 +557,285 @@ int autotune_variant(sw_handle *h, GpuCtx &gc, Slot &g, const SwDevDb &db, const
     uint64_t pairs_s = (uint64_t)(1.5e11 / cells_per_pair);                      // ~20 ms of work
     pairs_s = std::max<uint64_t>(pairs_s, (uint64_t)gc.num_sms * 4 * 128 * 4);   // >= 4 waves of blocks
     pairs_s = std::min<uint64_t>(pairs_s, g.npairs) & ~31ull;
-    if (pairs_s < 1024) return ranked[0];
+    if (pairs_s < 1024) return SW_OK;
     const uint64_t p0 = ((g.npairs - pairs_s) / 2) & ~31ull;
-    SwDevDb win = db;
-    win.pair_subj = db.pair_subj + 2 * p0;
-    win.pair_len = db.pair_len + 2 * p0;
-    win.tile_woff = db.tile_woff + p0 / 32;
-    win.npairs = (uint32_t)pairs_s;
-    cudaEvent_t e0, e1;
-    SW_CUDA(h, cudaEventCreate(&e0));
-    SW_CUDA(h, cudaEventCreate(&e1));
-    int best = ranked[0];
+    base.db.pair_subj += 2 * p0;
+    base.db.pair_len += 2 * p0;
+    base.db.tile_woff += p0 / 32;
+    base.db.npairs = (uint32_t)pairs_s;
+    base.q0 = 0; base.nql = nqs; base.qidx = nullptr;
+    if (!gc.ev_tune0) SW_CUDA(h, cudaEventCreate(&gc.ev_tune0));
+    if (!gc.ev_tune1) SW_CUDA(h, cudaEventCreate(&gc.ev_tune1));
     float best_ms = 0.f;
     for (int c = 0; c < ncand; ++c) {
-        const int vidx = ranked[c];
-        int grid = 0, chunk_passes = 1;
-        Slot tmp_geom;                       // geometry of the window (npairs / max_len only)
-        tmp_geom.npairs = win.npairs; tmp_geom.max_len = g.max_len;
-        int rc = strip_setup(h, gc, tmp_geom, vidx, &grid, &chunk_passes);
-        if (rc != SW_OK) { cudaEventDestroy(e0); cudaEventDestroy(e1); return ranked[0]; }
+        base.vidx = ranked[c];
+        int rc = strip_setup(h, gc, base.db.npairs, g.max_len, h->q_max_len, base.vidx, &base.grid, &base.chunk_passes, &base.bnd_elems);
+        if (rc != SW_OK) return rc;
+        base.bnd = gc.d_bnd.as<uint2>();
         float ms = 0.f;
         for (int rep = 0; rep < 2; ++rep) {  // first run warms caches and the instruction cache
-            SW_CUDA(h, cudaMemsetAsync(gc.d_counters.p, 0, sizeof(unsigned), gc.st_compute));
-            SW_CUDA(h, cudaEventRecord(e0, gc.st_compute));
-            SW_CUDA(h, sw_launch_strip(vidx, gc.st_compute, win, dq, 0, nqs, sc, g.d_out.as<int32_t>(), g.s1 - g.s0,
-                                       gc.d_bnd.as<uint2>(), g.max_len, gc.d_counters.as<unsigned>(), grid, chunk_passes));
+            base.counter = next_counter(gc);
+            SW_CUDA(h, cudaMemsetAsync(base.counter, 0, sizeof(unsigned), gc.st_compute));
+            SW_CUDA(h, cudaEventRecord(gc.ev_tune0, gc.st_compute));
+            SW_CUDA(h, sw_launch_strip(gc.st_compute, base));
             h->launches++;
-            SW_CUDA(h, cudaEventRecord(e1, gc.st_compute));
-            SW_CUDA(h, cudaEventSynchronize(e1));
-            SW_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+            SW_CUDA(h, cudaEventRecord(gc.ev_tune1, gc.st_compute));
+            SW_CUDA(h, cudaEventSynchronize(gc.ev_tune1));
+            SW_CUDA(h, cudaEventElapsedTime(&ms, gc.ev_tune0, gc.ev_tune1));
         }
-        if (c == 0 || ms < best_ms) { best = vidx; best_ms = ms; }
+        if (c == 0 || ms < best_ms) { *choice = base.vidx; best_ms = ms; }
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    return best;
+    return SW_OK;
 }
+
+cudaEvent_t pool_event(sw_handle *h, Slot &g, size_t i, int *rc)
+{
+    *rc = SW_OK;
+    while (g.ev_pool.size() <= i) {
+        cudaEvent_t e = nullptr;
+        cudaError_t ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        if (ce != cudaSuccess) { h->last_cuda.store((int)ce); *rc = SW_ECUDA; return nullptr; }
+        g.ev_pool.push_back(e);
+    }
+    return g.ev_pool[i];
+}
+
+// One group of queries that run with the same variant (q empty = all queries, contiguous).
+struct QueryGroup { int vidx; std::vector<int> q; uint64_t rows; };
 
 int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
 {
     SW_CUDA(h, cudaSetDevice(gc.dev));
     const int nq = (int)h->q_len.size();
     const size_t n = g.s1 - g.s0;
-    for (auto &c : g.chunks) if (c.done) cudaEventDestroy(c.done);
     g.chunks.clear();
     g.scored = true;
+    g.ovf_used = false;
+    g.out_mode = h->topk_k > 0 ? SW_OUT_TOPK : h->out_mode;
+    g.topk_k = h->topk_k;
     if (n == 0 || nq == 0) return SW_OK;
+    const bool topk = g.out_mode == SW_OUT_TOPK;
+    const size_t esz = g.out_mode == SW_OUT_I16 ? sizeof(int16_t) : sizeof(int32_t);
 
-    SW_CUDA(h, g.d_out.reserve((size_t)nq * n * sizeof(int32_t)));
-    SW_CUDA(h, cudaMemsetAsync(g.d_out.p, 0, (size_t)nq * n * sizeof(int32_t), gc.st_compute));
+    if (!topk) {
+        SW_CUDA(h, g.d_out.reserve((size_t)nq * n * esz));
+        SW_CUDA(h, cudaMemsetAsync(g.d_out.p, 0, (size_t)nq * n * esz, gc.st_compute));
+    } else {
+        SW_CUDA(h, g.d_topk_out.reserve((size_t)nq * g.topk_k * sizeof(unsigned long long)));
+        SW_CUDA(h, cudaMemsetAsync(g.d_topk_out.p, 0, (size_t)nq * g.topk_k * sizeof(unsigned long long), gc.st_compute));
+    }
     SW_CUDA(h, cudaEventRecord(g.ev_start, gc.st_compute));
+    int rc = SW_OK;
     if (g.npairs == 0) {
         SW_CUDA(h, cudaEventRecord(g.ev_stop, gc.st_compute));
-        QueryChunk c{0, nq, nullptr};
-        SW_CUDA(h, cudaEventCreateWithFlags(&c.done, cudaEventDisableTiming));
+        QueryChunk c{0, nq, pool_event(h, g, 0, &rc)};
+        if (rc != SW_OK) return rc;
         SW_CUDA(h, cudaEventRecord(c.done, gc.st_compute));
         g.chunks.push_back(c);
         return SW_OK;
     }
 
-    SwScoring sc;
-    sc.match = h->params.match; sc.mismatch = h->params.mismatch;
-    sc.goe = (int)h->params.gap_open + (int)h->params.gap_extend; sc.ge = h->params.gap_extend;
-    sc.limit = h->params.score_width ? (1 << (h->params.score_width - 1)) - 1 : 0;
-
-    SwDevDb db = dev_db(g);
-    SwDevQueries dq;
-    dq.packed = gc.d_qpacked.as<uint8_t>(); dq.off = gc.d_qoff.as<uint32_t>(); dq.len = gc.d_qlen.as<uint32_t>();
-    dq.nq = nq; dq.max_len = h->q_max_len;
+    const SwScoring sc = scoring_of(h);
+    const SwDevDb db = dev_db(g);
+    const SwDevQueries dq = dev_queries(h, gc);
 
     // Value range: the packed 16-bit kernel is always used; when match * min(m, n) could exceed
-    // the 16-bit range it flags the (rare) pairs whose running maximum got near 32767 and the
-    // 32-bit kernel recomputes exactly those.
+    // the 16-bit range it flags the (rare) pairs whose running maximum got near 32767: they go to
+    // the overflow list and the 32-bit kernel recomputes exactly those.
     const uint64_t smax = (uint64_t)sc.match * std::min<uint64_t>(h->q_max_len, g.max_len);
     const bool may_overflow = !sc.limit && (smax + (uint64_t)sc.match >= 32000ull);
     SW_CUDA(h, gc.d_counters.reserve(kMaxCounters * sizeof(unsigned)));
-    int vidx = -1;
+
+    // ---- which variant for which query -------------------------------------------------------
+    std::vector<QueryGroup> groups;
     std::vector<int> ranked;
+    int vall = -1;
     if (!h->force32) {
-        vidx = choose_variant(h, gc, g, h->q_max_len, &ranked);
-        if (vidx < 0 && (h->force_R || h->force_G)) return SW_EINVAL;
+        vall = choose_variant(h, gc, g, h->q_len.data(), h->q_len.size(), h->q_max_len, &ranked);
+        if (vall < 0) return SW_EINVAL;
+        if (variant_forced(h) || nq == 1) {
+            groups.push_back({vall, {}, h->q_sum_len});
+        } else {
+            // per query: the variant whose pass height fits its length best.  Small groups are folded
+            // into the overall choice (every launch has its own tail).
+            std::map<int, QueryGroup> by_variant;
+            for (int q = 0; q < nq; ++q) {
+                const uint32_t ql = h->q_len[q];
+                const int v = choose_variant(h, gc, g, &ql, 1, ql);
+                QueryGroup &gr = by_variant[v];
+                gr.vidx = v; gr.q.push_back(q); gr.rows += ql;
+            }
+            QueryGroup rest{vall, {}, 0};
+            for (auto &kv : by_variant) {
+                QueryGroup &gr = kv.second;
+                const double est_ms = (double)g.sum_len * (double)gr.rows / 6.0e9;
+                if (gr.vidx == vall || est_ms < 5.0 || (double)gr.rows < 0.03 * (double)h->q_sum_len) {
+                    rest.q.insert(rest.q.end(), gr.q.begin(), gr.q.end());
+                    rest.rows += gr.rows;
+                } else {
+                    groups.push_back(gr);
+                }
+            }
+            if (!rest.q.empty()) { std::sort(rest.q.begin(), rest.q.end()); groups.push_back(rest); }
+            if (groups.size() == 1) groups[0].q.clear();      // all queries, contiguous
+        }
     }
+    const bool single_group = groups.size() == 1 && groups[0].q.empty();
 
-    // query chunks: a handful of launches so that D2H of finished rows overlaps compute
-    // (each launch has its own tail: aim for >= ~50 ms of work per launch, at ~6 TCUPS)
-    const double est_ms = (double)g.sum_len * (double)h->q_sum_len / 6.0e9;
-    int nchunks = std::max(1, std::min(std::min(nq, 8), (int)(est_ms / 50.0)));
-    // the device work counter is 32-bit: (pair blocks) x (queries per launch) must stay below 2^31
-    while (nchunks < nq && (uint64_t)(g.npairs / 4 + 1) * (uint64_t)((nq + nchunks - 1) / nchunks) >= (1ull << 31)) nchunks *= 2;
-    nchunks = std::min(nchunks, nq);
-
+    SwStripLaunch base;
+    base.db = db; base.q = dq; base.sc = sc;
+    base.out = topk ? nullptr : g.d_out.p; base.out_stride = n; base.out_elems = (size_t)nq * n; base.out_mode = g.out_mode;
+    base.bnd_cols = g.max_len;
+    base.dev_err = gc.d_err.as<unsigned>();
+    if (may_overflow) {
+        SW_CUDA(h, g.d_ovf_count.reserve(sizeof(unsigned)));
+        SW_CUDA(h, g.d_ovf_list.reserve((size_t)kOvfCap * sizeof(uint2)));
+        SW_CUDA(h, g.d_ovf_score.reserve((size_t)kOvfCap * sizeof(int32_t)));
+        SW_CUDA(h, cudaMemsetAsync(g.d_ovf_count.p, 0, sizeof(unsigned), gc.st_compute));
+        base.ovf_count = g.d_ovf_count.as<unsigned>(); base.ovf_list = g.d_ovf_list.as<uint2>(); base.ovf_cap = kOvfCap;
+        g.ovf_used = true;
+    }
     // large jobs: let the GPU pick among the model's top candidates (decision cached per workload shape)
-    if (vidx >= 0 && h->autotune && h->force_variant < 0 && !h->force_R && !h->force_G && est_ms >= 400.0 && ranked.size() > 1) {
+    const double est_ms_all = (double)g.sum_len * (double)h->q_sum_len / 6.0e9;
+    if (single_group && !topk && h->autotune && !variant_forced(h) && est_ms_all >= 400.0 && ranked.size() > 1) {
         uint64_t key = 1469598103934665603ull;
         auto log2b = [](uint64_t x) { uint64_t b = 0; while (x >>= 1) ++b; return b; };
         const uint64_t parts[] = {h->q_max_len, h->q_sum_len, (uint64_t)nq, g.max_len, log2b(g.npairs), log2b(g.sum_len),
                                   (uint64_t)(uint16_t)h->params.match, (uint64_t)(uint16_t)h->params.mismatch,
                                   (uint64_t)(uint16_t)h->params.gap_open, (uint64_t)(uint16_t)h->params.gap_extend,
-                                  (uint64_t)h->params.score_width};
+                                  (uint64_t)h->params.score_width, (uint64_t)g.out_mode};
         for (uint64_t x : parts) { key ^= x; key *= 1099511628211ull; }
-        if (h->tune_key != key || h->tune_choice < 0) {
-            h->tune_choice = autotune_variant(h, gc, g, db, dq, sc, ranked, nq);
-            h->tune_key = key;
+        if (gc.tune_key != key || gc.tune_choice < 0) {
+            int choice = vall;
+            rc = autotune_variant(h, gc, g, base, ranked, nq, &choice);
+            if (rc != SW_OK) return rc;
+            gc.tune_choice = choice;
+            gc.tune_key = key;
         }
-        vidx = h->tune_choice;
+        groups[0].vidx = gc.tune_choice;
     }
 
-    SW_CUDA(h, cudaMemsetAsync(gc.d_counters.p, 0, kMaxCounters * sizeof(unsigned), gc.st_compute));
-    int grid = 0, chunk_passes = 1;
-    if (vidx >= 0) {
-        int rc = strip_setup(h, gc, g, vidx, &grid, &chunk_passes);
-        if (rc != SW_OK) return rc;
-        h->last_kernel = sw_strip_variant(vidx)->name;
-    }
-    if (vidx < 0 || may_overflow) {
-        const int threads_total = gc.num_sms * 2 * 128;
-        SW_CUDA(h, gc.d_scratch32.reserve((size_t)2 * std::max<uint32_t>(g.max_len, 1) * threads_total * sizeof(int32_t)));
-        if (vidx < 0) h->last_kernel = "generic32";
-    }
-
-    for (int c = 0; c < nchunks; ++c) {
-        QueryChunk qc;
-        qc.q0 = (int)((long long)nq * c / nchunks);
-        qc.q1 = (int)((long long)nq * (c + 1) / nchunks);
-        qc.done = nullptr;
-        if (qc.q1 <= qc.q0) continue;
-        if (vidx >= 0) {
-            SW_CUDA(h, sw_launch_strip(vidx, gc.st_compute, db, dq, qc.q0, qc.q1, sc, g.d_out.as<int32_t>(), n,
-                                       gc.d_bnd.as<uint2>(), g.max_len, gc.d_counters.as<unsigned>() + (c % kMaxCounters),
-                                       grid, chunk_passes));
-            if (may_overflow) {
-                SW_CUDA(h, sw_launch_generic32(gc.st_compute, db, dq, qc.q0, qc.q1, sc, g.d_out.as<int32_t>(), n,
-                                               gc.d_scratch32.as<int32_t>(), gc.num_sms * 2 * 128, true));
-                h->launches++;
+    // ---- launch plan --------------------------------------------------------------------------
+    struct Planned { SwStripLaunch L; int q0, q1; };
+    std::vector<Planned> plan;
+    std::vector<int> qidx_host;
+    int max_grid = 0;
+    if (!groups.empty()) {
+        size_t total_idx = 0;
+        for (auto &gr : groups) total_idx += gr.q.size();
+        if (total_idx) SW_CUDA(h, gc.d_qidx.reserve(total_idx * sizeof(int)));
+        size_t idx_off = 0;
+        size_t big = 0;
+        for (size_t gi = 0; gi < groups.size(); ++gi) {
+            QueryGroup &gr = groups[gi];
+            const bool all = gr.q.empty();
+            const int gq = all ? nq : (int)gr.q.size();
+            uint32_t gmaxq = 0;
+            if (all) { gmaxq = h->q_max_len; gr.rows = h->q_sum_len; }
+            else for (int q : gr.q) gmaxq = std::max(gmaxq, h->q_len[q]);
+            if (gr.rows > groups[big].rows) big = gi;
+            SwStripLaunch L = base;
+            L.vidx = gr.vidx;
+            rc = strip_setup(h, gc, g.npairs, g.max_len, gmaxq, gr.vidx, &L.grid, &L.chunk_passes, &L.bnd_elems);
+            if (rc != SW_OK) return rc;
+            max_grid = std::max(max_grid, L.grid);
+            // run-time specialisation of the gap penalties for jobs that are worth a compile
+            const double est_ms = (double)g.sum_len * (double)gr.rows / 6.0e9;
+            if (h->jit && !sc.limit && (est_ms >= 2000.0 || h->jit >= 2) && std::strcmp(sw_strip_instance_kind(L), "runtime") == 0)
+                L.jit_kernel = sw_jit_strip_kernel(sw_strip_variant(gr.vidx), sc.goe, sc.ge, nullptr, 0);
+            // query chunks: a handful of launches so that D2H of finished rows overlaps compute
+            // (each launch has its own tail: aim for >= ~50 ms of work per launch, at ~6 TCUPS)
+            int nchunks = std::max(1, std::min(std::min(gq, 8), (int)(est_ms / 50.0)));
+            if (!single_group || topk || may_overflow) nchunks = 1;
+            // the device work counter is 32-bit: (pair blocks) x (queries per launch) must stay below 2^31
+            while (nchunks < gq && (uint64_t)(g.npairs / 4 + 1) * (uint64_t)((gq + nchunks - 1) / nchunks) >= (1ull << 31)) nchunks *= 2;
+            nchunks = std::min(nchunks, gq);
+            if (!all) qidx_host.insert(qidx_host.end(), gr.q.begin(), gr.q.end());
+            for (int c = 0; c < nchunks; ++c) {
+                const int a0 = (int)((long long)gq * c / nchunks), a1 = (int)((long long)gq * (c + 1) / nchunks);
+                if (a1 <= a0) continue;
+                Planned p{L, a0, a1};
+                p.L.nql = a1 - a0;
+                if (all) { p.L.q0 = a0; p.L.qidx = nullptr; }
+                else { p.L.q0 = 0; p.L.qidx = gc.d_qidx.as<int>() + idx_off + a0; }
+                plan.push_back(p);
             }
-        } else {
-            SW_CUDA(h, sw_launch_generic32(gc.st_compute, db, dq, qc.q0, qc.q1, sc, g.d_out.as<int32_t>(), n,
-                                           gc.d_scratch32.as<int32_t>(), gc.num_sms * 2 * 128, false));
+            if (!all) idx_off += gr.q.size();
         }
+        if (!qidx_host.empty()) {
+            SW_CUDA(h, cudaMemcpyAsync(gc.d_qidx.p, qidx_host.data(), qidx_host.size() * sizeof(int), cudaMemcpyHostToDevice, gc.st_compute));
+            SW_CUDA(h, cudaStreamSynchronize(gc.st_compute));      // qidx_host is a local
+        }
+        // label: the variant that does most of the work
+        bool jit_used = false;
+        for (auto &p : plan) if (p.L.vidx == groups[big].vidx && p.L.jit_kernel) jit_used = true;
+        if (&gc == &h->gpus[0])      // one writer: the per-GPU workers run concurrently
+            std::snprintf(h->last_kernel, sizeof h->last_kernel, "%s%s%s", sw_strip_variant(groups[big].vidx)->name,
+                          jit_used ? "+jit" : "", groups.size() > 1 ? "+groups" : "");
+    } else if (&gc == &h->gpus[0]) {
+        std::snprintf(h->last_kernel, sizeof h->last_kernel, "generic32");
+    }
+
+    if (topk) {
+        if (groups.empty()) return SW_EINVAL;                 // the 32-bit scorer has no top-k epilogue
+        const size_t bytes = (size_t)max_grid * nq * g.topk_k * sizeof(unsigned long long);
+        SW_CUDA(h, gc.d_topk_keys.reserve(bytes));
+        SW_CUDA(h, cudaMemsetAsync(gc.d_topk_keys.p, 0, bytes, gc.st_compute));
+    }
+
+    // 32-bit scratch (force32, or the overflow fix-up of the few listed pairs)
+    const uint32_t max_cols = std::max<uint32_t>(1, std::min<uint32_t>(h->q_max_len, g.max_len));
+    int threads32 = 0;
+    if (groups.empty() || may_overflow) {
+        const size_t budget = (size_t)1 << 30;
+        size_t t = budget / ((size_t)2 * max_cols * sizeof(int32_t));
+        t = std::min<size_t>(t, groups.empty() ? (size_t)gc.num_sms * 2 * 128 : 4096);
+        t = std::max<size_t>(128, t / 128 * 128);
+        threads32 = (int)t;
+        SW_CUDA(h, gc.d_scratch32.reserve((size_t)2 * max_cols * threads32 * sizeof(int32_t)));
+    }
+    SwScore32Launch s32;
+    s32.db = db; s32.q = dq; s32.sc = sc; s32.out = topk ? nullptr : g.d_out.p; s32.out_stride = n; s32.out_mode = g.out_mode;
+    s32.scratch = gc.d_scratch32.as<int32_t>(); s32.max_cols = max_cols; s32.threads_total = threads32;
+
+    size_t nev = 0;
+    if (!groups.empty()) {
+        const bool chunk_events = single_group && plan.size() > 1 && !may_overflow && !topk;
+        for (size_t i = 0; i < plan.size(); ++i) {
+            Planned &p = plan[i];
+            p.L.bnd = gc.d_bnd.as<uint2>();
+            p.L.counter = next_counter(gc);
+            SW_CUDA(h, cudaMemsetAsync(p.L.counter, 0, sizeof(unsigned), gc.st_compute));
+            if (topk) { p.L.topk_keys = gc.d_topk_keys.as<unsigned long long>(); p.L.topk_k = g.topk_k; p.L.topk_nq = nq; }
+            SW_CUDA(h, sw_launch_strip(gc.st_compute, p.L));
+            h->launches++;
+            if (chunk_events) {
+                QueryChunk qc{p.q0, p.q1, pool_event(h, g, nev++, &rc)};
+                if (rc != SW_OK) return rc;
+                SW_CUDA(h, cudaEventRecord(qc.done, gc.st_compute));
+                g.chunks.push_back(qc);
+            }
+        }
+        if (may_overflow) {
+            s32.mode = 2; s32.list_count = g.d_ovf_count.as<unsigned>(); s32.list = g.d_ovf_list.as<uint2>();
+            s32.list_cap = kOvfCap; s32.list_score = g.d_ovf_score.as<int32_t>();
+            SW_CUDA(h, sw_launch_score32(gc.st_compute, s32));
+            h->launches++;
+        }
+        if (topk) {
+            SW_CUDA(h, sw_launch_topk_merge(gc.st_compute, gc.d_topk_keys.as<unsigned long long>(), max_grid, nq, g.topk_k,
+                                            may_overflow ? g.d_ovf_count.as<unsigned>() : nullptr, g.d_ovf_list.as<uint2>(),
+                                            g.d_ovf_score.as<int32_t>(), kOvfCap, g.d_topk_out.as<unsigned long long>()));
+            h->launches++;
+        }
+    } else {
+        s32.mode = 0; s32.q0 = 0; s32.q1 = nq;
+        SW_CUDA(h, sw_launch_score32(gc.st_compute, s32));
         h->launches++;
-        SW_CUDA(h, cudaEventCreateWithFlags(&qc.done, cudaEventDisableTiming));
+    }
+    if (g.chunks.empty()) {
+        QueryChunk qc{0, nq, pool_event(h, g, nev++, &rc)};
+        if (rc != SW_OK) return rc;
         SW_CUDA(h, cudaEventRecord(qc.done, gc.st_compute));
         g.chunks.push_back(qc);
     }
@@ -554,49 +843,130 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
     return SW_OK;
 }
 
-// waits for an event with a deadline; deadline_ms < 0 = forever
+// waits for an event with a deadline; forever = no deadline
 int wait_event(sw_handle *h, cudaEvent_t ev, const std::chrono::steady_clock::time_point &t_end, bool forever)
 {
-    if (forever) { SW_CUDA(h, cudaEventSynchronize(ev)); return SW_OK; }
+    const auto t_begin = std::chrono::steady_clock::now();
     for (;;) {
         cudaError_t e = cudaEventQuery(ev);
         if (e == cudaSuccess) return SW_OK;
-        if (e != cudaErrorNotReady) { h->last_cuda = (int)e; return SW_ECUDA; }
-        if (std::chrono::steady_clock::now() >= t_end) return SW_ETIMEOUT;
-        std::this_thread::sleep_for(std::chrono::microseconds(50));
+        if (e != cudaErrorNotReady) { h->last_cuda.store((int)e); return SW_ECUDA; }
+        const auto now = std::chrono::steady_clock::now();
+        if (!forever && now >= t_end) return SW_ETIMEOUT;
+        // short waits (small batches) are polled; long ones block / yield the core
+        if (now - t_begin > std::chrono::microseconds(300)) {
+            if (forever) { SW_CUDA(h, cudaEventSynchronize(ev)); return SW_OK; }
+            std::this_thread::sleep_for(std::chrono::microseconds(50));
+        }
     }
 }
 
-int copy_out(sw_handle *h, int si, int32_t *scores, size_t cap, int timeout_ms)
+void finish_timing(sw_handle *h, int si, const std::chrono::steady_clock::time_point &t0,
+                   const std::chrono::steady_clock::time_point &t1, double ms_max, double ms_min)
 {
-    const Batch &bt = h->batch[si];
-    const size_t nq = (size_t)bt.nq;
-    if (cap < nq * bt.ns) return SW_ECAPACITY;
-    const bool forever = timeout_ms < 0;
-    const auto t_end = std::chrono::steady_clock::now() + std::chrono::milliseconds(forever ? 0 : timeout_ms);
-    size_t maxchunks = 0;
-    for (auto &g : h->gpus) maxchunks = std::max(maxchunks, g.slot[si].chunks.size());
-    for (size_t c = 0; c < maxchunks; ++c) {
-        for (auto &g : h->gpus) {
-            Slot &b = g.slot[si];
-            if (c >= b.chunks.size()) continue;
-            const size_t n = b.s1 - b.s0;
-            if (n == 0) continue;
-            SW_CUDA(h, cudaSetDevice(g.dev));
-            const QueryChunk &qc = b.chunks[c];
-            int rc = wait_event(h, qc.done, t_end, forever);
-            if (rc != SW_OK) {
-                // copies already enqueued must not outlive this call: the caller owns `scores`
-                for (auto &gg : h->gpus) { cudaSetDevice(gg.dev); cudaStreamSynchronize(gg.st_copy); }
-                return rc;
-            }
-            SW_CUDA(h, cudaMemcpy2DAsync(scores + (size_t)qc.q0 * bt.ns + b.s0, bt.ns * sizeof(int32_t),
-                                         b.d_out.as<int32_t>() + (size_t)qc.q0 * n, n * sizeof(int32_t),
-                                         n * sizeof(int32_t), (size_t)(qc.q1 - qc.q0), cudaMemcpyDeviceToHost,
-                                         g.st_copy));
+    const auto t2 = std::chrono::steady_clock::now();
+    h->stats.fetch_wait_ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+    h->stats.fetch_drain_ms = std::chrono::duration<double, std::milli>(t2 - t1).count();
+    h->stats.kernel_ms_max = ms_max;
+    h->stats.kernel_ms_min = ms_min > 1e299 ? 0.0 : ms_min;
+    h->last_ms = ms_max;
+    h->last_cells = h->batch[si].cells;
+    h->last_slot = si;
+}
+
+unsigned device_error_bits(sw_handle *h)
+{
+    unsigned bits = 0;
+    for (auto &g : h->gpus) {
+        if (cudaSetDevice(g.dev) != cudaSuccess) continue;
+#ifdef SW_BOUNDS_CHECK
+        cudaDeviceSynchronize();
+        for (DevBuf *d : all_devbufs(g)) if (!d->canaries_ok()) bits |= 0x80000000u;
+#endif
+        if (g.d_err.p) {
+            unsigned v = 0;
+            if (cudaMemcpy(&v, g.d_err.p, sizeof v, cudaMemcpyDeviceToHost) == cudaSuccess) bits |= v;
         }
     }
-    double ms_max = 0.0;
+    return bits;
+}
+
+// what a fetch delivers
+enum FetchKind { FETCH_I32, FETCH_I16, FETCH_TOPK };
+
+int fetch_slot(sw_handle *h, int si, FetchKind kind, void *scores, uint64_t *index, size_t cap, int timeout_ms)
+{
+    Batch &bt = h->batch[si];
+    const size_t nq = (size_t)bt.nq;
+    const bool forever = timeout_ms < 0;
+    const auto t_fetch0 = std::chrono::steady_clock::now();
+    const auto t_end = t_fetch0 + std::chrono::milliseconds(forever ? 0 : timeout_ms);
+    if (kind == FETCH_TOPK) {
+        if (bt.topk_k <= 0) return SW_ESTATE;
+        if (cap < nq * (size_t)bt.topk_k) return SW_ECAPACITY;
+    } else {
+        if (bt.topk_k > 0) return SW_ESTATE;
+        if ((kind == FETCH_I16) != (bt.out_mode == SW_OUT_I16)) return SW_ESTATE;
+        if (cap < nq * bt.ns) return SW_ECAPACITY;
+    }
+
+    // ---- small (latency) path: scores are already in mapped host memory ----------------------
+    if (bt.small) {
+        GpuCtx &g = h->gpus[0];
+        Slot &b = g.slot[si];
+        int rc = wait_event(h, b.ev_stop, t_end, forever);
+        if (rc != SW_OK) return rc;
+        std::memcpy(scores, b.h_small_out.p, nq * bt.ns * sizeof(int32_t));
+        float ms = 0.f;
+        SW_CUDA(h, cudaEventElapsedTime(&ms, b.ev_start, b.ev_stop));
+        finish_timing(h, si, t_fetch0, std::chrono::steady_clock::now(), ms, ms);
+#ifdef SW_BOUNDS_CHECK
+        if (device_error_bits(h)) return SW_EDEVICE;
+#endif
+        return SW_OK;
+    }
+
+    const size_t esz = kind == FETCH_I16 ? sizeof(int16_t) : sizeof(int32_t);
+    bool any_ovf = false;
+    for (auto &g : h->gpus) any_ovf |= g.slot[si].ovf_used && g.slot[si].scored && g.slot[si].s1 > g.slot[si].s0;
+    bt.ovf_index.clear(); bt.ovf_score.clear();
+
+    if (kind != FETCH_TOPK) {
+        size_t maxchunks = 0;
+        for (auto &g : h->gpus) maxchunks = std::max(maxchunks, g.slot[si].chunks.size());
+        for (size_t c = 0; c < maxchunks; ++c) {
+            for (auto &g : h->gpus) {
+                Slot &b = g.slot[si];
+                if (c >= b.chunks.size()) continue;
+                const size_t n = b.s1 - b.s0;
+                if (n == 0) continue;
+                SW_CUDA(h, cudaSetDevice(g.dev));
+                const QueryChunk &qc = b.chunks[c];
+                int rc = wait_event(h, qc.done, t_end, forever);
+                if (rc != SW_OK) {
+                    // copies already enqueued must not outlive this call: the caller owns `scores`
+                    for (auto &gg : h->gpus) { cudaSetDevice(gg.dev); cudaStreamSynchronize(gg.st_copy); }
+                    return rc;
+                }
+                SW_CUDA(h, cudaMemcpy2DAsync((char *)scores + ((size_t)qc.q0 * bt.ns + b.s0) * esz, bt.ns * esz,
+                                             (char *)b.d_out.p + (size_t)qc.q0 * n * esz, n * esz,
+                                             n * esz, (size_t)(qc.q1 - qc.q0), cudaMemcpyDeviceToHost, g.st_copy));
+            }
+        }
+    } else {
+        for (auto &g : h->gpus) {
+            Slot &b = g.slot[si];
+            if (b.s1 == b.s0 || nq == 0 || b.chunks.empty()) continue;
+            SW_CUDA(h, cudaSetDevice(g.dev));
+            int rc = wait_event(h, b.chunks.back().done, t_end, forever);
+            if (rc != SW_OK) return rc;
+            const size_t bytes = nq * (size_t)bt.topk_k * sizeof(unsigned long long);
+            SW_CUDA(h, b.h_topk.reserve(bytes));
+            SW_CUDA(h, cudaMemcpyAsync(b.h_topk.p, b.d_topk_out.p, bytes, cudaMemcpyDeviceToHost, g.st_copy));
+        }
+    }
+    const auto t_fetch1 = std::chrono::steady_clock::now();
+    double ms_max = 0.0, ms_min = 1e300;
     for (auto &g : h->gpus) {
         Slot &b = g.slot[si];
         SW_CUDA(h, cudaSetDevice(g.dev));
@@ -606,19 +976,87 @@ int copy_out(sw_handle *h, int si, int32_t *scores, size_t cap, int timeout_ms)
             float ms = 0.f;
             SW_CUDA(h, cudaEventElapsedTime(&ms, b.ev_start, b.ev_stop));
             ms_max = std::max(ms_max, (double)ms);
+            ms_min = std::min(ms_min, (double)ms);
         }
     }
-    h->last_ms = ms_max;
-    h->last_cells = bt.cells;
-    h->last_slot = si;
+
+    // ---- scores that left the 16-bit range (rare): list length check, side list for int16 -----
+    if (any_ovf) {
+        for (auto &g : h->gpus) {
+            Slot &b = g.slot[si];
+            if (!b.ovf_used || b.s1 == b.s0) continue;
+            SW_CUDA(h, cudaSetDevice(g.dev));
+            unsigned cnt = 0;
+            SW_CUDA(h, cudaMemcpy(&cnt, b.d_ovf_count.p, sizeof cnt, cudaMemcpyDeviceToHost));
+            if (cnt == 0) continue;
+            const size_t n = b.s1 - b.s0;
+            if (cnt > kOvfCap) {
+                if (kind != FETCH_I32) return SW_ERANGE;
+                // more flagged pairs than the list holds: rescan the matrix for sentinels (32-bit matrix only)
+                SwScore32Launch s32;
+                s32.db = dev_db(b); s32.q = dev_queries(h, g); s32.sc = scoring_of(h); s32.out = b.d_out.p; s32.out_stride = n;
+                s32.out_mode = SW_OUT_I32; s32.scratch = g.d_scratch32.as<int32_t>();
+                s32.max_cols = std::max<uint32_t>(1, std::min<uint32_t>(h->q_max_len, b.max_len));
+                s32.threads_total = (int)(g.d_scratch32.cap / ((size_t)2 * s32.max_cols * sizeof(int32_t)) / 128 * 128);
+                s32.mode = 1; s32.q0 = 0; s32.q1 = (int)nq;
+                SW_CUDA(h, sw_launch_score32(g.st_compute, s32));
+                h->launches++;
+                SW_CUDA(h, cudaStreamSynchronize(g.st_compute));
+                SW_CUDA(h, cudaMemcpy2D((char *)scores + b.s0 * esz, bt.ns * esz, b.d_out.p, n * esz, n * esz, nq, cudaMemcpyDeviceToHost));
+                continue;
+            }
+            if (kind == FETCH_I16) {
+                SW_CUDA(h, b.h_ovf.reserve((size_t)cnt * (sizeof(uint2) + sizeof(int32_t))));
+                uint2 *hl = (uint2 *)b.h_ovf.p;
+                int32_t *hs = (int32_t *)(hl + cnt);
+                SW_CUDA(h, cudaMemcpy(hl, b.d_ovf_list.p, (size_t)cnt * sizeof(uint2), cudaMemcpyDeviceToHost));
+                SW_CUDA(h, cudaMemcpy(hs, b.d_ovf_score.p, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost));
+                for (unsigned i = 0; i < cnt; ++i) {
+                    if (hs[i] <= 32767) continue;
+                    bt.ovf_index.push_back((uint64_t)hl[i].x * bt.ns + b.s0 + hl[i].y);
+                    bt.ovf_score.push_back(hs[i]);
+                }
+            }
+        }
+    }
+
+    // ---- top-k: merge the per-GPU lists on the host -------------------------------------------
+    if (kind == FETCH_TOPK) {
+        const int K = bt.topk_k;
+        int32_t *os = (int32_t *)scores;
+        std::vector<std::pair<int64_t, uint64_t>> cand;      // (-score, index): ascending sort = best first
+        for (size_t q = 0; q < nq; ++q) {
+            cand.clear();
+            for (auto &g : h->gpus) {
+                Slot &b = g.slot[si];
+                if (b.s1 == b.s0) continue;
+                if (!b.chunks.empty() && b.h_topk.p && b.npairs) {
+                    const unsigned long long *keys = (const unsigned long long *)b.h_topk.p + q * K;
+                    for (int j = 0; j < K; ++j) {
+                        if (keys[j] == 0) continue;
+                        cand.emplace_back(-(int64_t)(keys[j] >> 32), b.s0 + (uint64_t)(uint32_t)~(uint32_t)(keys[j] & 0xFFFFFFFFu));
+                    }
+                }
+                for (uint32_t e : b.empties) cand.emplace_back(0, b.s0 + e);     // zero-length subjects score 0
+            }
+            std::sort(cand.begin(), cand.end());
+            for (int j = 0; j < K; ++j) {
+                if ((size_t)j < cand.size()) { os[q * K + j] = (int32_t)(-cand[j].first); index[q * K + j] = cand[j].second; }
+                else { os[q * K + j] = -1; index[q * K + j] = ~0ull; }
+            }
+        }
+    }
+    finish_timing(h, si, t_fetch0, t_fetch1, ms_max, ms_min);
+    if (device_error_bits(h)) return SW_EDEVICE;
     return SW_OK;
 }
 
 int load_batch(sw_handle *h, int si, const uint8_t *packed, const uint32_t *len, const uint64_t *off,
                const uint64_t *ids, size_t ns)
 {
+    const auto t_load0 = std::chrono::steady_clock::now();
     Batch &bt = h->batch[si];
-    bt.ns = ns; bt.loaded = false; bt.scored = false; bt.cells = 0;
+    bt.ns = ns; bt.loaded = false; bt.scored = false; bt.cells = 0; bt.small = false;
     bt.have_ids = ids != nullptr;
     if (ids) bt.ids.assign(ids, ids + ns); else bt.ids.clear();
     const size_t ng = h->gpus.size();
@@ -626,22 +1064,26 @@ int load_batch(sw_handle *h, int si, const uint8_t *packed, const uint32_t *len,
     sw_plan_shards(len, ns, (int)ng, starts.data());
     for (size_t gi = 0; gi < ng; ++gi) { h->gpus[gi].slot[si].s0 = starts[gi]; h->gpus[gi].slot[si].s1 = starts[gi + 1]; }
     // one host worker per GPU: the shards' length sort / pairing / uploads run concurrently
+    int rc_load = SW_OK;
     if (ng == 1) {
-        int rc = load_shard(h, h->gpus[0], h->gpus[0].slot[si], packed, len, off);
-        if (rc != SW_OK) return rc;
+        rc_load = load_shard(h, h->gpus[0], h->gpus[0].slot[si], packed, len, off);
     } else {
         std::vector<int> rcs(ng, SW_OK);
         std::vector<std::thread> workers;
         for (size_t gi = 0; gi < ng; ++gi)
             workers.emplace_back([&, gi]() { rcs[gi] = load_shard(h, h->gpus[gi], h->gpus[gi].slot[si], packed, len, off); });
         for (auto &w : workers) w.join();
-        for (int rc : rcs) if (rc != SW_OK) return rc;
+        for (int rc : rcs) if (rc != SW_OK && rc_load == SW_OK) rc_load = rc;
     }
-    // caller's buffers must be reusable on return
+    // the caller's buffers must be reusable on return -- on success AND on failure (copies of
+    // the GPUs that did not fail may still be reading them)
     for (auto &g : h->gpus) {
-        SW_CUDA(h, cudaSetDevice(g.dev));
-        SW_CUDA(h, cudaStreamSynchronize(g.st_copy));
+        cudaError_t e = cudaSetDevice(g.dev);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(g.st_copy);
+        if (e != cudaSuccess && rc_load == SW_OK) { h->last_cuda.store((int)e); rc_load = SW_ECUDA; }
     }
+    if (rc_load != SW_OK) return rc_load;
+    h->stats.load_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_load0).count();
     bt.loaded = true;
     h->last_slot = si;
     return SW_OK;
@@ -649,18 +1091,178 @@ int load_batch(sw_handle *h, int si, const uint8_t *packed, const uint32_t *len,
 
 int score_batch_slot(sw_handle *h, int si)
 {
+    const auto t_enq0 = std::chrono::steady_clock::now();
     Batch &bt = h->batch[si];
     uint64_t db_len = 0;
     for (auto &g : h->gpus) db_len += g.slot[si].sum_len;
     bt.cells = db_len * h->q_sum_len;
     bt.nq = (int)h->q_len.size();
+    bt.out_mode = h->out_mode;
+    bt.topk_k = h->topk_k;
     h->last_cells = bt.cells;
-    for (auto &g : h->gpus) {
-        int rc = score_gpu(h, g, g.slot[si]);
-        if (rc != SW_OK) return rc;
+    const size_t ng = h->gpus.size();
+    std::vector<int> rcs(ng, SW_OK);
+    if (ng == 1) {
+        rcs[0] = score_gpu(h, h->gpus[0], h->gpus[0].slot[si]);
+    } else {
+        // one host worker per GPU: launch plans, allocations and (first call) autotune run concurrently
+        std::vector<std::thread> workers;
+        for (size_t gi = 0; gi < ng; ++gi)
+            workers.emplace_back([&, gi]() { rcs[gi] = score_gpu(h, h->gpus[gi], h->gpus[gi].slot[si]); });
+        for (auto &w : workers) w.join();
+    }
+    for (int rc : rcs) {
+        if (rc != SW_OK) {
+            // GPUs that already launched keep reading this slot: drain them before the slot can be
+            // reused (the failed batch is not recorded in the fifo)
+            for (auto &gg : h->gpus) { cudaSetDevice(gg.dev); cudaStreamSynchronize(gg.st_compute); gg.slot[si].scored = false; }
+            return rc;
+        }
     }
     bt.scored = true;
+    h->stats.enqueue_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_enq0).count();
     return SW_OK;
+}
+
+// ---- small (latency) path ------------------------------------------------------------------------
+// One staging buffer [pair_subj | pair_len | off | raw], one H2D copy, one DIRECT strip launch with a
+// static schedule, scores written into mapped pinned host memory.  *taken = false when the batch
+// does not qualify (the regular path then handles it).
+int small_variant(const sw_handle *h, uint32_t qmax, size_t npairs)
+{
+    if (h->force_variant >= 0) return sw_strip_variant(h->force_variant)->has_direct ? h->force_variant : -1;
+    if (h->force_R || h->force_G || h->force32) return -1;
+    const char *want;
+    if (qmax <= 32) want = "strip_s16x2_R1x1_G32";
+    else if (qmax <= 64) want = "strip_s16x2_R2x1_G32";
+    else if (qmax <= 128) want = npairs <= 1500 ? "strip_s16x2_R4x1_G32" : npairs <= 3000 ? "strip_s16x2_R8x1_G16" : "strip_s16x2_R16x1_G8";
+    else if (qmax <= 256) want = "strip_s16x2_R8x1_G32";
+    else want = "strip_s16x2_R16x1_G32";
+    for (int i = 0; i < sw_strip_variant_count(); ++i)
+        if (std::strcmp(sw_strip_variant(i)->name, want) == 0) return i;
+    return -1;
+}
+
+int small_submit(sw_handle *h, int si, const uint8_t *packed, const uint32_t *len, const uint64_t *off,
+                 const uint64_t *ids, size_t ns, bool *taken)
+{
+    *taken = false;
+    const int nq = (int)h->q_len.size();
+    if (!h->small_path || ns == 0 || nq == 0 || ns > 8192 || (size_t)nq * ns > (1u << 20)) return SW_OK;
+    if (h->topk_k > 0 || h->out_mode != SW_OUT_I32 || h->params.score_width != 0) return SW_OK;
+    uint64_t bmin = ~0ull, bmax = 0, sum = 0;
+    uint32_t maxlen = 0;
+    for (size_t i = 0; i < ns; ++i) {
+        if (len[i] == 0) continue;
+        bmin = std::min(bmin, off[i]);
+        bmax = std::max<uint64_t>(bmax, off[i] + ((len[i] + 3ull) >> 2));
+        maxlen = std::max(maxlen, len[i]);
+        sum += len[i];
+    }
+    if (maxlen == 0 || bmax - bmin > (1u << 20) || maxlen > 65535) return SW_OK;
+    const SwScoring sc = scoring_of(h);
+    if ((uint64_t)sc.match * std::min<uint64_t>(h->q_max_len, maxlen) + (uint64_t)sc.match >= 32000ull) return SW_OK;
+    GpuCtx &gc = h->gpus[0];
+    Slot &g = gc.slot[si];
+    const size_t np_max = (ns + 1) / 2;
+    const int vidx = small_variant(h, h->q_max_len, np_max);
+    if (vidx < 0) return SW_OK;
+    *taken = true;
+
+    SW_CUDA(h, cudaSetDevice(gc.dev));
+    Batch &bt = h->batch[si];
+    bt.ns = ns; bt.loaded = true; bt.scored = true; bt.small = true;
+    bt.have_ids = ids != nullptr;
+    if (ids) bt.ids.assign(ids, ids + ns); else bt.ids.clear();
+    bt.nq = nq; bt.out_mode = SW_OUT_I32; bt.topk_k = 0;
+    bt.cells = sum * h->q_sum_len;
+    h->last_cells = bt.cells;
+    for (auto &gg : h->gpus) { gg.slot[si].s0 = 0; gg.slot[si].s1 = 0; gg.slot[si].chunks.clear(); gg.slot[si].ovf_used = false; }
+    g.s0 = 0; g.s1 = ns; g.is_small = true; g.max_len = maxlen; g.sum_len = sum; g.out_mode = SW_OUT_I32; g.topk_k = 0;
+
+    // ---- staging layout
+    const size_t ntiles = (np_max + 31) / 32;
+    const size_t o_subj = 0;
+    const size_t o_len = o_subj + ntiles * 32 * 2 * sizeof(uint32_t);
+    const size_t o_off = o_len + ntiles * 32 * 2 * sizeof(uint32_t);
+    const size_t o_raw = o_off + ns * sizeof(uint64_t);
+    const size_t raw_bytes = (size_t)(bmax - bmin);
+    const size_t total = o_raw + raw_bytes + 16;
+    SW_CUDA(h, g.h_small_in.reserve(total));
+    SW_CUDA(h, g.d_small_in.reserve(total));
+    SW_CUDA(h, g.h_small_out.reserve((size_t)nq * ns * sizeof(int32_t), true));
+    // the staging buffer is reused: the previous copy out of it finished before its batch was fetched
+    char *st = (char *)g.h_small_in.p;
+    sort_by_length(g, len, ns, maxlen);
+    const size_t np = make_pairs(g, len, ns, (uint32_t *)(st + o_subj), (uint32_t *)(st + o_len));
+    g.npairs = (uint32_t)np;
+    uint64_t *loc_off = (uint64_t *)(st + o_off);
+    for (size_t k = 0; k < ns; ++k) loc_off[k] = len[k] ? off[k] - bmin : 0;
+    std::memcpy(st + o_raw, packed + bmin, raw_bytes);
+    std::memset(st + o_raw + raw_bytes, 0, 16);
+    // scores of empty subjects (never touched by the kernel)
+    int32_t *hout = (int32_t *)g.h_small_out.p;
+    if (np * 2 != ns)
+        for (size_t k = 0; k < ns; ++k) if (len[k] == 0) for (int q = 0; q < nq; ++q) hout[(size_t)q * ns + k] = 0;
+
+    // ---- one copy, one kernel
+    cudaStream_t cs = gc.st_compute;
+    SW_CUDA(h, cudaMemcpyAsync(g.d_small_in.p, st, total, cudaMemcpyHostToDevice, cs));
+    const SwStripVariant *v = sw_strip_variant(vidx);
+    SwStripLaunch L;
+    char *d = (char *)g.d_small_in.p;
+    L.vidx = vidx; L.direct = true;
+    L.db.raw = (const uint8_t *)(d + o_raw); L.db.off = (const uint64_t *)(d + o_off); L.db.len = nullptr;
+    L.db.ns = (uint32_t)ns; L.db.pair_subj = (const uint32_t *)(d + o_subj); L.db.pair_len = (const uint32_t *)(d + o_len);
+    L.db.tile_woff = nullptr; L.db.tp = nullptr; L.db.tp_words = 0; L.db.npairs = (uint32_t)np; L.db.max_len = maxlen;
+    L.q = dev_queries(h, gc); L.q0 = 0; L.nql = nq; L.qidx = nullptr; L.sc = sc;
+    L.out = g.h_small_out.dptr; L.out_stride = ns; L.out_elems = (size_t)nq * ns; L.out_mode = SW_OUT_I32;
+    L.bnd_cols = maxlen; L.counter = nullptr;
+    L.dev_err = gc.d_err.as<unsigned>();
+    const int P = v->R * v->G;
+    const int need_passes = (int)((h->q_max_len + P - 1) / P);
+    const size_t pass_bytes = sw_strip_smem_bytes(vidx, 1);
+    L.chunk_passes = std::max(1, std::min(need_passes, std::max<int>(1, (int)((48 * 1024) / pass_bytes))));
+    const int ppb = v->block_threads / v->G;
+    const size_t items = ((np + ppb - 1) / ppb) * (size_t)nq;
+    L.grid = (int)std::min<size_t>(std::max<size_t>(items, 1), (size_t)gc.num_sms * 4);
+    if (need_passes > 1) {
+        const size_t per_block = (size_t)maxlen * ppb * sizeof(uint2);
+        SW_CUDA(h, gc.d_bnd.reserve((size_t)L.grid * per_block));
+        L.bnd_elems = (size_t)L.grid * per_block / sizeof(uint2);
+    }
+    L.bnd = gc.d_bnd.as<uint2>();
+    SW_CUDA(h, cudaEventRecord(g.ev_start, cs));
+    SW_CUDA(h, sw_launch_strip(cs, L));
+    h->launches++;
+    SW_CUDA(h, cudaEventRecord(g.ev_stop, cs));
+    g.scored = true;
+    std::snprintf(h->last_kernel, sizeof h->last_kernel, "%s+direct", v->name);
+    h->last_slot = si;
+    return SW_OK;
+}
+
+int pop_fifo(sw_handle *h, int rc)
+{
+    if (rc == SW_ETIMEOUT || rc == SW_ECAPACITY || rc == SW_ESTATE) return rc;   // batch stays in flight; fetch again
+    h->fifo[0] = h->fifo[1];
+    h->n_inflight--;
+    return rc;
+}
+
+int fetch_db_common(sw_handle_t *h, FetchKind kind, void *scores, uint64_t *index, size_t cap)
+{
+    if (!h || !scores) return SW_EINVAL;
+    if (h->n_inflight) return SW_EAGAIN;
+    if (!h->batch[0].loaded || !h->batch[0].scored) return SW_ESTATE;
+    return fetch_slot(h, 0, kind, scores, index, cap, -1);
+}
+
+int fetch_common(sw_handle_t *h, FetchKind kind, void *scores, uint64_t *index, size_t cap, int timeout_ms)
+{
+    if (!h || (!scores && cap)) return SW_EINVAL;
+    if (h->n_inflight == 0) return SW_ESTATE;
+    return pop_fifo(h, fetch_slot(h, h->fifo[0], kind, scores, index, cap, timeout_ms));
 }
 
 }  // namespace
@@ -668,13 +1270,37 @@ int score_batch_slot(sw_handle *h, int si)
 // ================================================================================================
 extern "C" {
 
+int sw_params_in_exact_domain(const sw_params_t *p)
+{
+    sw_params_t d;
+    if (!p) { sw_default_params(&d); p = &d; }
+    if (validate_params(p) != SW_OK) return SW_EINVAL;
+    return ((int)p->match + (int)p->gap_open <= 0) ? 1 : 0;
+}
+
 void sw_default_params(sw_params_t *p)
 {
     if (!p) return;
     p->match = 5; p->mismatch = -4; p->gap_open = -12; p->gap_extend = -4; p->score_width = 0;
 }
 
-const char *sw_version(void) { return "sw_b200 0.1 (sm_100a)"; }
+const char *sw_version(void)
+{
+#ifdef SW_BOUNDS_CHECK
+    return "sw_b200 0.2 (sm_100a, bounds-check build)";
+#else
+    return "sw_b200 0.2 (sm_100a)";
+#endif
+}
+
+int sw_is_check_build(void)
+{
+#ifdef SW_BOUNDS_CHECK
+    return 1;
+#else
+    return 0;
+#endif
+}
 
 int sw_device_count(void)
 {
@@ -696,6 +1322,8 @@ const char *sw_strerror(int code)
         case SW_ECAPACITY: return "output buffer too small";
         case SW_EIO: return "I/O error";
         case SW_EAGAIN: return "busy: both batch buffers are in flight (fetch one first)";
+        case SW_ERANGE: return "too many scores beyond the 16-bit range for this output mode (use int32 output)";
+        case SW_EDEVICE: return "device-side check failed (see sw_device_error_bits)";
         default: return "unknown error";
     }
 }
@@ -719,6 +1347,8 @@ int sw_init(sw_handle_t **out, const sw_params_t *p, const int *gpu_ids, int n_g
     if (!h) return SW_ENOMEM;
     h->params = prm;
     if (const char *e = std::getenv("SW_B200_AUTOTUNE")) h->autotune = (e[0] != '0');
+    if (const char *e = std::getenv("SW_B200_JIT")) h->jit = std::atoi(e);
+    if (const char *e = std::getenv("SW_B200_SMALL_PATH")) h->small_path = (e[0] != '0');
     h->gpus.resize(ids.size());
     for (size_t i = 0; i < ids.size(); ++i) {
         GpuCtx &g = h->gpus[i];
@@ -737,6 +1367,8 @@ int sw_init(sw_handle_t **out, const sw_params_t *p, const int *gpu_ids, int n_g
             if (e == cudaSuccess) e = cudaEventCreate(&b.ev_stop);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev_upload, cudaEventDisableTiming);
         }
+        if (e == cudaSuccess) e = g.d_err.reserve(sizeof(unsigned));
+        if (e == cudaSuccess) e = cudaMemset(g.d_err.p, 0, sizeof(unsigned));
         if (e != cudaSuccess) {
             for (auto &gg : h->gpus) free_gpu(gg);
             delete h;
@@ -767,10 +1399,30 @@ int sw_set_strands(sw_handle_t *h, int both)
     return SW_OK;
 }
 
+int sw_set_output(sw_handle_t *h, int mode)
+{
+    if (!h || (mode != SW_OUTPUT_I32 && mode != SW_OUTPUT_I16)) return SW_EINVAL;
+    if (h->n_inflight) return SW_EAGAIN;
+    h->out_mode = mode == SW_OUTPUT_I16 ? SW_OUT_I16 : SW_OUT_I32;
+    for (Batch &bt : h->batch) bt.scored = false;
+    return SW_OK;
+}
+
+int sw_set_topk(sw_handle_t *h, int k)
+{
+    if (!h || k < 0 || k > SW_MAX_TOPK) return SW_EINVAL;
+    if (h->n_inflight) return SW_EAGAIN;
+    h->topk_k = k;
+    for (Batch &bt : h->batch) bt.scored = false;
+    return SW_OK;
+}
+
 int sw_set_queries(sw_handle_t *h, const uint8_t *packed, const uint32_t *len, const uint64_t *off, int nq)
 {
     if (!h || nq < 0 || (nq > 0 && (!packed || !len || !off))) return SW_EINVAL;
     if (h->n_inflight) return SW_EAGAIN;
+    // kernels of a previous sw_score_db may still read the query buffers
+    for (auto &g : h->gpus) { cudaSetDevice(g.dev); cudaStreamSynchronize(g.st_compute); }
     h->q_packed.clear(); h->q_off.clear(); h->q_len.clear();
     h->q_max_len = 0; h->q_sum_len = 0;
     h->nq_user = nq;
@@ -803,7 +1455,6 @@ int sw_set_queries(sw_handle_t *h, const uint8_t *packed, const uint32_t *len, c
     for (auto &g : h->gpus) {
         int rc = upload_queries(h, g);
         if (rc != SW_OK) return rc;
-        for (Slot &b : g.slot) b.scored = false;
     }
     for (Batch &bt : h->batch) bt.scored = false;
     return SW_OK;
@@ -838,7 +1489,7 @@ int sw_score_db(sw_handle_t *h)
 {
     if (!h) return SW_EINVAL;
     if (h->n_inflight) return SW_EAGAIN;
-    if (!h->batch[0].loaded) return SW_ESTATE;
+    if (!h->batch[0].loaded || h->batch[0].small) return SW_ESTATE;
     return score_batch_slot(h, 0);
 }
 
@@ -864,12 +1515,12 @@ int sw_wait(sw_handle_t *h, int timeout_ms)
     return SW_OK;
 }
 
-int sw_fetch_db(sw_handle_t *h, int32_t *scores, size_t cap)
+int sw_fetch_db(sw_handle_t *h, int32_t *scores, size_t cap) { return fetch_db_common(h, FETCH_I32, scores, nullptr, cap); }
+int sw_fetch_db_i16(sw_handle_t *h, int16_t *scores, size_t cap) { return fetch_db_common(h, FETCH_I16, scores, nullptr, cap); }
+int sw_fetch_db_topk(sw_handle_t *h, int32_t *scores, uint64_t *index, size_t cap)
 {
-    if (!h || !scores) return SW_EINVAL;
-    if (h->n_inflight) return SW_EAGAIN;
-    if (!h->batch[0].loaded || !h->batch[0].scored) return SW_ESTATE;
-    return copy_out(h, 0, scores, cap, -1);
+    if (!index) return SW_EINVAL;
+    return fetch_db_common(h, FETCH_TOPK, scores, index, cap);
 }
 
 int sw_score_batch(sw_handle_t *h, const uint8_t *packed, const uint32_t *len, const uint64_t *off,
@@ -879,24 +1530,42 @@ int sw_score_batch(sw_handle_t *h, const uint8_t *packed, const uint32_t *len, c
     if (h->n_inflight >= 2) return SW_EAGAIN;          // both buffers busy: the bank's `full`
     // take the slot that is not in flight; this replaces whatever sw_load_db left there
     const int si = (h->n_inflight == 1) ? (1 - h->fifo[0]) : 0;
-    int rc = load_batch(h, si, packed, len, off, ids, ns);
+    bool taken = false;
+    int rc = small_submit(h, si, packed, len, off, ids, ns, &taken);
     if (rc != SW_OK) return rc;
-    rc = score_batch_slot(h, si);
-    if (rc != SW_OK) return rc;
+    if (!taken) {
+        rc = load_batch(h, si, packed, len, off, ids, ns);
+        if (rc != SW_OK) return rc;
+        rc = score_batch_slot(h, si);
+        if (rc != SW_OK) return rc;
+    }
     h->fifo[h->n_inflight++] = si;
     return SW_OK;
 }
 
 int sw_fetch(sw_handle_t *h, int32_t *scores, size_t cap, int timeout_ms)
 {
-    if (!h || (!scores && cap)) return SW_EINVAL;
-    if (h->n_inflight == 0) return SW_ESTATE;
-    const int si = h->fifo[0];
-    int rc = copy_out(h, si, scores, cap, timeout_ms);
-    if (rc == SW_ETIMEOUT || rc == SW_ECAPACITY) return rc;   // batch stays in flight; fetch again
-    h->fifo[0] = h->fifo[1];
-    h->n_inflight--;
-    return rc;
+    return fetch_common(h, FETCH_I32, scores, nullptr, cap, timeout_ms);
+}
+int sw_fetch_i16(sw_handle_t *h, int16_t *scores, size_t cap, int timeout_ms)
+{
+    return fetch_common(h, FETCH_I16, scores, nullptr, cap, timeout_ms);
+}
+int sw_fetch_topk(sw_handle_t *h, int32_t *scores, uint64_t *index, size_t cap, int timeout_ms)
+{
+    if (!index && cap) return SW_EINVAL;
+    return fetch_common(h, FETCH_TOPK, scores, index, cap, timeout_ms);
+}
+
+int sw_fetch_overflow(sw_handle_t *h, uint64_t *flat_index, int32_t *score, size_t cap, size_t *count)
+{
+    if (!h || !count) return SW_EINVAL;
+    const Batch &bt = h->batch[h->last_slot];
+    *count = bt.ovf_index.size();
+    const size_t n = std::min(cap, bt.ovf_index.size());
+    if (n && (!flat_index || !score)) return SW_EINVAL;
+    for (size_t i = 0; i < n; ++i) { flat_index[i] = bt.ovf_index[i]; score[i] = bt.ovf_score[i]; }
+    return SW_OK;
 }
 
 int sw_batches_in_flight(const sw_handle_t *h) { return h ? h->n_inflight : 0; }
@@ -916,7 +1585,7 @@ int sw_fetch_best(sw_handle_t *h, int32_t *best_score, uint64_t *best_index, int
     if (h->n_inflight) return SW_EAGAIN;
     const Batch &bt = h->batch[0];
     const int nq = bt.nq;
-    if (!bt.loaded || !bt.scored) return SW_ESTATE;
+    if (!bt.loaded || !bt.scored || bt.small || bt.topk_k > 0 || bt.out_mode != SW_OUT_I32) return SW_ESTATE;
     if (nq_cap < nq) return SW_ECAPACITY;
     for (int q = 0; q < nq; ++q) { best_score[q] = 0; best_index[q] = 0; }
     std::vector<int32_t> hs(nq);
@@ -945,10 +1614,19 @@ int sw_fetch_best(sw_handle_t *h, int32_t *best_score, uint64_t *best_index, int
 
 int sw_query_rows(const sw_handle_t *h) { return h ? (int)h->q_len.size() : 0; }
 
-int sw_last_cuda_error(const sw_handle_t *h) { return h ? h->last_cuda : 0; }
+int sw_get_stats(const sw_handle_t *h, sw_stats_t *out)
+{
+    if (!h || !out) return SW_EINVAL;
+    *out = h->stats;
+    return SW_OK;
+}
+
+unsigned sw_device_error_bits(sw_handle_t *h) { return h ? device_error_bits(h) : 0u; }
+
+int sw_last_cuda_error(const sw_handle_t *h) { return h ? h->last_cuda.load() : 0; }
 const char *sw_last_cuda_error_string(const sw_handle_t *h)
 {
-    return cudaGetErrorString((cudaError_t)(h ? h->last_cuda : 0));
+    return cudaGetErrorString((cudaError_t)(h ? h->last_cuda.load() : 0));
 }
 double sw_last_kernel_ms(const sw_handle_t *h) { return h ? h->last_ms : 0.0; }
 uint64_t sw_kernel_launches(const sw_handle_t *h) { return h ? h->launches.load() : 0; }
@@ -989,7 +1667,33 @@ int sw_set_autotune(sw_handle_t *h, int enable)
 {
     if (!h) return SW_EINVAL;
     h->autotune = enable != 0;
-    h->tune_choice = -1;
+    for (auto &g : h->gpus) g.tune_choice = -1;
+    return SW_OK;
+}
+
+int sw_set_jit(sw_handle_t *h, int mode)
+{
+    if (!h || mode < 0 || mode > 2) return SW_EINVAL;
+    h->jit = mode;
+    return SW_OK;
+}
+
+int sw_jit_is_available(void) { return sw_jit_available(); }
+
+int sw_jit_compile_check(const char *variant_name, int gap_open, int gap_extend, char *msg, size_t msg_cap)
+{
+    if (!variant_name) return SW_EINVAL;
+    for (int i = 0; i < sw_strip_variant_count(); ++i) {
+        if (std::strcmp(sw_strip_variant(i)->name, variant_name) != 0) continue;
+        return sw_jit_strip_kernel(sw_strip_variant(i), gap_open + gap_extend, gap_extend, msg, msg_cap) ? 1 : 0;
+    }
+    return SW_EINVAL;
+}
+
+int sw_set_small_batch_path(sw_handle_t *h, int enable)
+{
+    if (!h) return SW_EINVAL;
+    h->small_path = enable != 0;
     return SW_OK;
 }
 

@@ -1,433 +1,14 @@
 /*
- * sw_kernels.cu -- hand-written sm_100a kernels of the score-only Smith-Waterman engine.
- *
- * What is computed (reference: ScoreBank/SW_ProcessingElement_v1.0.v:119-129, 287-291,
- * 411-420), per (query, subject) pair, i = query row, j = subject column:
- *     M(i,j) = max(0, s(i,j) + H(i-1,j-1))          H = max(M, I)
- *     I(i,j) = max(G(i-1,j), G(i,j-1))              G = max(M + go + ge, I + ge)
- *     score  = max over all cells of H
- * with H = 0 and G = max(go+ge, ge) on both boundaries.  G is "the gap value leaving a
- * cell"; substituting it back gives exactly the RTL's M_open / I_extend form.
- *
- * How it is mapped to the GPU (replaces the systolic array of ScoringModule_v1.1.v and the
- * two-way time sharing of each PE, SW_ProcessingElement_v1.0.v:25-27):
- *   - two subjects of similar length share every 32-bit register (low / high 16-bit lane) --
- *     the PE's toggle-0 / toggle-1 sequences; the shorter one sees PAD scores once it has ended;
- *   - a lane keeps R consecutive query rows of H and G in registers and walks the subject
- *     columns; per cell pair the arithmetic is 3.5 ALU-pipe + 1 FMA-pipe instructions
- *     (VIMNMX.S16x2, VIADDMNMX.S16x2.RELU, VIADDMNMX.S16x2, 1/2 VIMNMX3.S16x2; VIADD.16x2);
- *   - G lanes of a warp form a systolic group over R*G rows: lane l is one column behind
- *     lane l-1 and receives (H, G, column code) with __shfl_up_sync, exactly like
- *     M_in / I_in / data_in travel from PE to PE;
- *   - queries longer than R*G rows are processed in passes; the bottom row of a pass is kept
- *     in an L2-resident scratch line per column and read back by lane 0 in the next pass;
- *   - substitution scores come from a shared-memory query profile
- *     prof[sub-strip][row pair][column code][lane of the group] (one uint2 = two rows), laid out
- *     so that the lanes of a warp hit distinct banks: one LDS.64 per two rows.
- * The recurrence is evaluated in an algebraically equivalent "clamped, goe-shifted" form (see
- * column_step_multi) that needs 3.5 ALU-pipe + 1 FMA-pipe instructions per two cells; the
- * RTL-faithful 12-bit mode keeps the explicit M form.
+ * sw_kernels.cu -- the kernels around the strip kernel (sw_strip.cuh): code-stream builder, 32-bit
+ * scorer / overflow fix-up, best-hit and top-k merge; the variant table and the launchers.
  */
-#include "sw_kernels.h"
+#include "sw_variants.h"
 
 #include <stdint.h>
 
-#ifndef SW_STEP_UNROLL
-#define SW_STEP_UNROLL 4      /* columns per trip of the step loop; nsteps is rounded up to a multiple */
-#endif
+#include <vector>
 
-namespace {
-
-constexpr int kPadScoreS16 = -8192;   // profile value of padding rows: M becomes 0, nothing can grow
-
-// ------------------------------------------------------------------------------------------
-// Packed signed 16-bit arithmetic: two independent subjects per 32-bit register, one DPX
-// instruction per operation.
-// ------------------------------------------------------------------------------------------
-struct ArithS16 {
-    static constexpr int kPad = kPadScoreS16;
-    static __device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) {
-        return __viaddmax_s16x2_relu(a, b, c);   // max(a + b, c, 0)
-    }
-    static __device__ __forceinline__ uint32_t pack(int lo, int hi) {
-        return (uint32_t)(lo & 0xFFFF) | ((uint32_t)(hi & 0xFFFF) << 16);
-    }
-    static __device__ __forceinline__ uint32_t pack_score(int lo, int hi) { return pack(lo, hi); }
-    static __device__ __forceinline__ int extract(uint32_t v, int h) {
-        return (int)(int16_t)(h ? (v >> 16) : (v & 0xFFFF));
-    }
-    // max(a + b, 0): `zero` is an opaque register holding 0 (a literal makes ptxas emit a PRMT per use)
-    static __device__ __forceinline__ uint32_t add_relu(uint32_t a, uint32_t b, uint32_t zero) {
-        return __viaddmax_s16x2_relu(a, b, zero);
-    }
-    static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return __vadd2(a, b); }
-    static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return __vmaxs2(a, b); }
-    static __device__ __forceinline__ uint32_t addmax(uint32_t a, uint32_t b, uint32_t c) {
-        return __viaddmax_s16x2(a, b, c);   // max(a + b, c)
-    }
-    // values above `lim` restart at 0 (W-bit wrap-then-clamp, SW_ProcessingElement_v1.0.v:287-288)
-    static __device__ __forceinline__ uint32_t wrap_clamp(uint32_t m, uint32_t lim) {
-        return m & ~__vcmpgts2(m, lim);
-    }
-};
-
-// Pass-boundary scratch accesses, tagged evict_last so that the scratch lines, which are rewritten
-// every pass, stay resident in L2 instead of being written back to HBM between passes.  A slot is
-// written and read by the same warp only (lane G-1 / lane 0), so L1 is coherent for it: loads are
-// cached in L1 and an explicit L1 prefetch runs a few steps ahead -- the load itself then costs an
-// L1 hit wherever ptxas schedules it inside the step (placed late, an L2-latency load showed up
-// as long-scoreboard stalls: ALU pipe 89 % -> 84 %).
-__device__ __forceinline__ uint64_t l2_evict_last_policy()
-{
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ uint2 bnd_load(const uint2 *p, uint64_t pol)
-{
-    uint2 v;
-    asm volatile("ld.global.ca.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ void prefetch_l1(const void *p)
-{
-    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
-}
-__device__ __forceinline__ void bnd_store(uint2 *p, uint2 v, uint64_t pol)
-{
-    asm volatile("st.global.cg.L2::cache_hint.v2.u32 [%0], {%1, %2}, %3;" :: "l"(p), "r"(v.x), "r"(v.y), "l"(pol) : "memory");
-}
-
-struct StripArgs {
-    const uint32_t *tp;
-    const uint64_t *tile_woff;
-    const uint32_t *pair_len;
-    const uint32_t *pair_subj;
-    uint32_t npairs;
-    uint32_t npb;              // pair blocks = ceil(npairs / pairs-per-block)
-    const uint8_t *qpacked;
-    const uint32_t *qoff;
-    const uint32_t *qlen;
-    int q0, q1;
-    int32_t *out;
-    size_t out_stride;
-    uint2 *bnd;
-    uint32_t bnd_cols;
-    unsigned *counter;
-    int chunk_passes;          // passes whose query profile is resident in shared memory at once
-    int match, mismatch, goe, ge, limit;
-    uint32_t goe2, ge2;        // goe / ge packed in both 16-bit lanes (host side: uniform operands)
-    int ovf_limit;             // 32767 - match - 1: a larger final maximum means a possible wrap
-    uint32_t zero;             // always 0, but opaque to the compiler
-};
-
-// Column codes: 0..15 = t_lo | t_hi << 2 (both members have a base in this column);
-// 16..19 = 16 + t_lo (the shorter member, always the high lane, has ended: its lane sees PAD);
-// 20 = no column at all (pipeline fill / drain, past the end of the pair).
-constexpr int kHiEndedCode = 16;
-constexpr int kPadCode = 20;
-constexpr int kCodesPerRow = 32;    // profile entries per row pair (codes 0..20 used): 256 bytes
-
-// One column step of the S sub-strips of a lane, each sub-strip on its own column (sub-strip s
-// is one column behind s-1): S independent dependency chains in one basic block, so a warp
-// always has an instruction whose operands are ready (the PE array's pipelining, inside one
-// thread).  H[s][r] / Gl[s][r] hold H and G of the previous column on entry and of this column
-// on exit; hd_top = H(row0-1, c-1), g_top = G(row0-1, c); prow[s] points at the profile entry
-// of (first row pair of the sub-strip, this column's code), one uint2 = two consecutive rows.
-template <int RS, int S, int G, class AR, bool W12>
-__device__ __forceinline__ void column_step_multi(uint32_t (&H)[S][RS], uint32_t (&Gl)[S][RS], uint32_t &best,
-                                                  const uint32_t (&hd_top)[S], const uint32_t (&g_top)[S],
-                                                  const uint2 *const (&prow)[S], uint32_t goe2,
-                                                  uint32_t ge2, uint32_t zero, uint32_t lim2)
-{
-    constexpr int RP = (RS + 1) / 2;
-    // substitution scores of this column: one LDS.64 per row pair
-    uint2 sv[S][RP];
-#pragma unroll
-    for (int s = 0; s < S; ++s)
-#pragma unroll
-        for (int k = 0; k < RP; ++k) sv[s][k] = prow[s][k * kCodesPerRow * G];
-    if constexpr (!W12) {
-        // Clamped, goe-shifted form (exact).  Every gap value is clamped at 0
-        // (non-positive gap values can never reach H because M >= 0) and the register strip holds
-        // K = H + goe instead of H.  With tg = K(r-1,c-1) + s  (= H_diag + s + goe):
-        //     I = max(G_left, G_up)            >= 0                 VIMNMX
-        //     G = max(I + ge, tg, 0)                                VIADDMNMX.RELU
-        //     K = max(I + goe, tg)    (= max(I, H_diag + s) + goe)  VIADDMNMX
-        // M = max(H_diag + s, 0) is never materialised (I >= 0 does the clamping) and both adds
-        // of the gap path are fused: 3.5 ALU-pipe + 1 FMA-pipe instruction per cell pair.
-        // tg of row r+1 is formed one row ahead from the still-old H[r], so H[r] is overwritten
-        // in place.  The reported score is max K - goe.
-        uint32_t gu[S], t_cur[S];
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            gu[s] = g_top[s];
-            t_cur[s] = AR::add(hd_top[s], sv[s][0].x);
-        }
-#pragma unroll
-        for (int r = 0; r < RS; ++r) {
-#pragma unroll
-            for (int s = 0; s < S; ++s) {
-                uint32_t t_next = zero;
-                if (r + 1 < RS) {
-                    const uint32_t sc = ((r + 1) & 1) ? sv[s][(r + 1) >> 1].y : sv[s][(r + 1) >> 1].x;
-                    t_next = AR::add(H[s][r], sc);
-                }
-                const uint32_t i_ = AR::max2(Gl[s][r], gu[s]);
-                gu[s] = AR::addmax_relu(i_, ge2, t_cur[s]);
-                Gl[s][r] = gu[s];
-                H[s][r] = AR::addmax(i_, goe2, t_cur[s]);
-                best = AR::max2(best, H[s][r]);
-                t_cur[s] = t_next;
-            }
-        }
-        return;
-    }
-    // W-bit faithful mode (score_width != 0): the explicit form of SW_ProcessingElement_v1.0.v with
-    // the M overflow ("MSB clear => ZERO", :287-288) applied to every M.  M of row r+1 is formed one
-    // row ahead, from the still-old H[r] (its diagonal), so that H[r] is overwritten in place.
-    uint32_t gu[S], m_cur[S];
-#pragma unroll
-    for (int s = 0; s < S; ++s) {
-        gu[s] = g_top[s];
-        uint32_t m = AR::add_relu(hd_top[s], sv[s][0].x, zero);     // M(r,c) = relu(H(r-1,c-1) + s)
-        if (W12) m = AR::wrap_clamp(m, lim2);
-        m_cur[s] = m;
-    }
-#pragma unroll
-    for (int r = 0; r < RS; ++r) {
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            uint32_t m_next = zero;
-            if (r + 1 < RS) {
-                const uint32_t sc = ((r + 1) & 1) ? sv[s][(r + 1) >> 1].y : sv[s][(r + 1) >> 1].x;
-                m_next = AR::add_relu(H[s][r], sc, zero);
-                if (W12) m_next = AR::wrap_clamp(m_next, lim2);
-            }
-            // the serial chain of a column is I -> I+ge -> G; the S chains interleave
-            const uint32_t i_ = AR::max2(Gl[s][r], gu[s]);      // I = max(G_left, G_up)
-            const uint32_t j_ = AR::add(i_, ge2);               // I + ge          (FMA-side pipe)
-            gu[s] = AR::addmax(m_cur[s], goe2, j_);             // G = max(M + goe, I + ge)
-            Gl[s][r] = gu[s];
-            H[s][r] = AR::max2(m_cur[s], i_);                   // H = max(M, I)
-            best = AR::max2(best, H[s][r]);                     // ptxas pairs these into 3-input max
-            m_cur[s] = m_next;
-        }
-    }
-}
-
-// RS rows per sub-strip, S sub-strips per lane, G lanes per pair: R = RS*S rows per lane,
-// P = R*G rows per pass.  Virtual PE v = lane_in_group*S + s works on column t - v at step t.
-// A virtual PE that has no column at step t (pipeline fill / drain, shorter pair in the warp)
-// works on the PAD column code whose profile entries are very negative: H keeps decaying values
-// <= the best already recorded and G stays clamped / non-positive, which never reaches H
-// (DESIGN.md section 2).  That keeps the loop body free of per-lane branches.
-// CGOE / CGE != 0: gap penalties fixed at compile time.  ptxas then encodes them as immediates
-// (VIADDMNMX.S16x2 R, R, 0xfffcfffc, R): two register operands instead of three per fused
-// add-max, which removes register-bank conflicts on the ALU pipe (+6..13 % measured).  Used for
-// the reference's own penalty set (ScoreBank_v1_tb.sv:16-19); any other set takes the generic path.
-template <int RS, int S, int G, class AR, bool W12, int BT, int MINB, int CGOE = 0, int CGE = 0, int U = SW_STEP_UNROLL>
-__global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
-{
-    extern __shared__ uint2 s_prof[];
-    __shared__ unsigned s_work;
-    constexpr int R = RS * S;
-    constexpr int P = R * G;
-    constexpr int RP = (RS + 1) / 2;
-    constexpr int VPE = G * S;                       // virtual PEs per pair
-    constexpr int PASS_ENTRIES = VPE * RP * kCodesPerRow;
-    constexpr int PPB = BT / G;
-    constexpr unsigned FULL = 0xFFFFFFFFu;
-    static_assert(U == 4, "the step loop consumes one 4-column code word per trip");
-
-    const int lane = threadIdx.x & 31;
-    const int gl = (G == 1) ? 0 : (lane & (G - 1));
-    const int pslot = threadIdx.x / G;
-    const uint32_t zero = a.zero;
-    const uint32_t goe2 = CGOE ? ((uint32_t)(CGOE & 0xFFFF) * 0x10001u) : a.goe2;
-    const uint32_t ge2 = CGOE ? ((uint32_t)(CGE & 0xFFFF) * 0x10001u) : a.ge2;
-    // boundary gap value G(0,j) = G(i,0): max(goe, ge) <= 0, or its clamp 0 in the clamped form
-    const int gbv = !W12 ? 0 : (a.goe > a.ge ? a.goe : a.ge);
-    const uint32_t gb2 = AR::pack(gbv, gbv);
-    const uint32_t lim2 = AR::pack(a.limit, a.limit);
-    // value of "H = 0" in the strip's representation (K = H + goe in the clamped form)
-    const uint32_t h0 = !W12 ? goe2 : zero;
-    uint2 *bnd = a.bnd + (size_t)blockIdx.x * a.bnd_cols * PPB + pslot;
-    const uint64_t bnd_pol = l2_evict_last_policy();
-
-    int prof_q = -1, prof_pass = -1;     // which (query, first pass) the shared-memory profile holds
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_work = atomicAdd(a.counter, 1u);
-        __syncthreads();
-        // work item = (block of pairs, query).  Pairs are sorted by ascending length: the longest
-        // blocks go first so that the tail is made of short items.
-        const unsigned nql = (unsigned)(a.q1 - a.q0);
-        if (s_work >= a.npb * nql) break;
-        // Order: super-blocks of B pair blocks, longest first; inside a super-block query-major.
-        // With B >> grid (large databases) consecutive items of a thread block share the query and
-        // the profile in shared memory is reused; with B small the order degenerates to
-        // longest-first over everything, which is what short launches need for their tail.
-        const unsigned B = max(1u, a.npb >> 3);
-        const unsigned sb = s_work / (nql * B);
-        const unsigned rem = s_work - sb * nql * B;
-        const unsigned bcur = min(B, a.npb - sb * B);
-        const unsigned pb = a.npb - 1u - (sb * B + rem % bcur);
-        const int q = a.q0 + (int)(rem / bcur);
-
-        const unsigned pair = pb * PPB + pslot;
-        const bool valid = pair < a.npairs;
-        const int ncols = valid ? (int)a.pair_len[2 * pair] : 0;          // longer member (low lane)
-        const uint32_t *tpp = a.tp;
-        uint32_t subj_lo = SW_NO_SUBJECT, subj_hi = SW_NO_SUBJECT;
-        if (valid) {
-            tpp += a.tile_woff[pair >> 5] + (pair & 31);
-            subj_lo = a.pair_subj[2 * pair];
-            subj_hi = a.pair_subj[2 * pair + 1];
-        }
-        // rounded up: the step loop is unrolled (extra steps are PAD columns)
-        const int nsteps = (__reduce_max_sync(FULL, ncols) + (VPE - 1) + U - 1) / U * U;
-
-        {
-            const int m = (int)a.qlen[q];
-            const uint8_t *qp = a.qpacked + a.qoff[q];
-            const int npass = (m + P - 1) / P;
-            uint32_t best = h0;
-
-            for (int pass = 0; pass < npass; ++pass) {
-                const int pass_in_chunk = pass % a.chunk_passes;
-                if (pass_in_chunk == 0 && (prof_q != q || prof_pass != pass)) {
-                    prof_q = q;
-                    prof_pass = pass;
-                    // (re)build the profile chunk: entry (vpe, row pair, code) = packed scores of
-                    // rows 2k, 2k+1 of that virtual PE against column code = t_lo | t_hi << 2
-                    __syncthreads();
-                    const int npc = min(a.chunk_passes, npass - pass);
-                    for (int idx = threadIdx.x; idx < npc * PASS_ENTRIES; idx += BT) {
-                        // layout: (((pass * S + s) * RP + rp) * 32 + code) * G + gl -- the G lanes of a
-                        // group sit in consecutive 8-byte slots, so a warp-wide group reads 32 banks
-                        const int lg = idx % G;
-                        const int code = (idx / G) & (kCodesPerRow - 1);
-                        if (code > kPadCode) continue;
-                        const int rp = (idx / (G * kCodesPerRow)) % RP;
-                        const int ss = (idx / (G * kCodesPerRow * RP)) % S;
-                        const int pc = idx / PASS_ENTRIES;
-                        const int vpe = lg * S + ss;
-                        uint32_t e[2];
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const int rr = 2 * rp + k;
-                            const int i = (pass + pc) * P + vpe * RS + rr;
-                            int lo = AR::kPad, hi = AR::kPad;
-                            if (rr < RS && i < m && code < kPadCode) {
-                                const int qi = (qp[i >> 2] >> ((i & 3) * 2)) & 3;
-                                lo = (qi == (code & 3)) ? a.match : a.mismatch;   // v1.0.v:119
-                                if (code < kHiEndedCode) hi = (qi == (code >> 2)) ? a.match : a.mismatch;
-                            }
-                            e[k] = AR::pack_score(lo, hi);
-                        }
-                        s_prof[idx] = make_uint2(e[0], e[1]);
-                    }
-                    __syncthreads();
-                }
-                const uint2 *prof_lane = s_prof + (size_t)pass_in_chunk * PASS_ENTRIES + gl;
-                const bool has_top = pass > 0;
-                const bool has_bottom = pass + 1 < npass;
-
-                uint32_t H[S][RS], Gl[S][RS];
-#pragma unroll
-                for (int s = 0; s < S; ++s)
-#pragma unroll
-                    for (int r = 0; r < RS; ++r) { H[s][r] = h0; Gl[s][r] = gb2; }
-
-                uint32_t wcur = 0, wnext = 0;
-                uint2 bcur = make_uint2(h0, gb2);            // (H, G) of the row above, column c
-                if (gl == 0 && ncols > 0) {
-                    wcur = __ldg(tpp);
-                    if (ncols > 4) wnext = __ldg(tpp + 32);
-                    if (has_top) {
-                        bcur = bnd_load(bnd, bnd_pol);
-                        for (int c = 1; c < 4 && c < ncols; ++c) prefetch_l1(bnd + (size_t)c * PPB);
-                    }
-                }
-                // what each sub-strip hands to the next virtual PE (the next sub-strip, or for
-                // s = S-1 the next lane): bottom H, bottom G and the column code it just used
-                uint32_t pub_h[S], pub_g[S], pub_t[S], hd_top[S];
-#pragma unroll
-                for (int s = 0; s < S; ++s) { pub_h[s] = h0; pub_g[s] = gb2; pub_t[s] = kPadCode; hd_top[s] = h0; }
-
-#pragma unroll 1
-                for (int t2 = 0; t2 < nsteps; t2 += U) {
-#pragma unroll
-                  for (int u = 0; u < U; ++u) {
-                    const int t = t2 + u;
-                    uint32_t in_h[S], in_g[S], in_t[S];
-                    if (G > 1) {
-                        in_h[0] = __shfl_up_sync(FULL, pub_h[S - 1], 1, G);
-                        in_g[0] = __shfl_up_sync(FULL, pub_g[S - 1], 1, G);
-                        in_t[0] = __shfl_up_sync(FULL, pub_t[S - 1], 1, G);
-                    }
-                    if (G == 1 || gl == 0) {
-                        // head of the systolic group: column t comes from the code stream, the row
-                        // above from the previous pass (or the zero boundary)
-                        const bool on = t < ncols;
-                        in_h[0] = bcur.x;
-                        in_g[0] = bcur.y;
-                        // U == 4 and t2 % 4 == 0: the four columns of this trip are the four bytes of wcur
-                        in_t[0] = on ? ((wcur >> (8 * u)) & 255u) : (uint32_t)kPadCode;
-                        if (on) {
-                            if (u == U - 1) {
-                                wcur = wnext;
-                                const int k = (t >> 2) + 2;
-                                if (k * 4 < ncols) wnext = __ldg(tpp + k * 32);
-                                // the word after that goes to L1 now, so the load above stays
-                                // short even if ptxas sinks it towards its use to save a register
-                                if ((k + 1) * 4 < ncols) prefetch_l1(tpp + (k + 1) * 32);
-                            }
-                            if (has_top) {
-                                if (t + 1 < ncols) bcur = bnd_load(bnd + (size_t)(t + 1) * PPB, bnd_pol);
-                                if (t + 4 < ncols) prefetch_l1(bnd + (size_t)(t + 4) * PPB);
-                            }
-                        }
-                    }
-#pragma unroll
-                    for (int s = 1; s < S; ++s) { in_h[s] = pub_h[s - 1]; in_g[s] = pub_g[s - 1]; in_t[s] = pub_t[s - 1]; }
-
-                    const uint2 *prow[S];
-#pragma unroll
-                    for (int s = 0; s < S; ++s) prow[s] = prof_lane + (s * RP * kCodesPerRow + in_t[s]) * G;
-                    column_step_multi<RS, S, G, AR, W12>(H, Gl, best, hd_top, in_g, prow, goe2, ge2, zero, lim2);
-#pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        hd_top[s] = in_h[s];
-                        pub_h[s] = H[s][RS - 1]; pub_g[s] = Gl[s][RS - 1]; pub_t[s] = in_t[s];
-                    }
-                    if (has_bottom && gl == G - 1) {
-                        const int cl = t - (VPE - 1);          // column the last virtual PE just finished
-                        if (cl >= 0 && cl < ncols) bnd_store(bnd + (size_t)cl * PPB, make_uint2(pub_h[S - 1], pub_g[S - 1]), bnd_pol);
-                    }
-                  }
-                }
-                if (has_bottom) __syncwarp();   // bottom row written by lane G-1, read by lane 0
-            }
-
-#pragma unroll
-            for (int o = G / 2; o >= 1; o >>= 1) best = AR::max2(best, __shfl_xor_sync(FULL, best, o));
-            if (gl == 0 && valid) {
-                int32_t *orow = a.out + (size_t)q * a.out_stride;
-                // While every value so far is <= 32767 - match the next cell cannot wrap, and the
-                // running maximum is monotone: a final best above that threshold is the only way a
-                // 16-bit overflow can have happened.  Such pairs get a sentinel and are recomputed
-                // by the 32-bit kernel (sw_launch_generic32 with fix_only).
-                const int shift = !W12 ? a.goe : 0;
-                const int b0 = AR::extract(best, 0), b1 = AR::extract(best, 1);
-                orow[subj_lo] = (!W12 && b0 > a.ovf_limit) ? SW_OVERFLOW_SENTINEL : b0 - shift;
-                if (subj_hi != SW_NO_SUBJECT)
-                    orow[subj_hi] = (!W12 && b1 > a.ovf_limit) ? SW_OVERFLOW_SENTINEL : b1 - shift;
-            }
-        }
-    }
-}
+namespace swk {
 
 // ------------------------------------------------------------------------------------------
 // Column code stream builder: one byte per column of a pair (codes 0..20, see kHiEndedCode /
@@ -458,89 +39,112 @@ __global__ void __launch_bounds__(256) build_tp_kernel(const uint8_t *raw, const
     for (uint32_t k = 0; k < kmax; ++k) {
         const uint32_t a = rlo ? load8_bases(rlo, nlo, k) : 0u;
         const uint32_t b = rhi ? load8_bases(rhi, nhi, k) : 0u;
-        uint32_t w = 0;
-#pragma unroll
-        for (uint32_t c = 0; c < 4; ++c) {
-            const uint32_t col = 4 * k + c;
-            const uint32_t tlo = (a >> (2 * c)) & 3u, thi = (b >> (2 * c)) & 3u;
-            const uint32_t code = col < nhi ? (tlo | (thi << 2)) : col < nlo ? (kHiEndedCode + tlo) : (uint32_t)kPadCode;
-            w |= code << (8 * c);
-        }
-        tp[w0 + (uint64_t)k * 32 + lane] = w;
+        tp[w0 + (uint64_t)k * 32 + lane] = make_code_word(a, b, k, nlo, nhi);
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// 32-bit kernel: one thread per (subject, query) job, any length, any score range, W-bit mode.
-// The query is walked in strips of 16 rows held in registers (their 2-bit codes fit one word);
-// the bottom row (H, G) of a strip is parked per column in global scratch laid out
-// [column][thread], so a warp touches one 128-byte line per access and a cell costs 4/16 memory
-// operations.  Explicit form of SW_ProcessingElement_v1.0.v (M, I = max(G_left, G_up), ...).
+// 32-bit scorer: one thread per (query, subject) job, any length, any score range, W-bit mode.
+// The recurrence is symmetric in its two sequences, so the SHORTER one is walked as columns and
+// the longer one in strips of 16 rows held in registers (their 2-bit codes fit one word); the
+// bottom row (H, G) of a strip is parked per column in global scratch laid out [column][thread],
+// so a warp touches one 128-byte line per access and a cell costs 4/16 memory operations -- and
+// the scratch is bounded by min(longest query, longest subject) columns per thread.
+// Explicit form of SW_ProcessingElement_v1.0.v (M, I = max(G_left, G_up), ...).
+// mode 0: all jobs; mode 1: matrix entries flagged SW_OVERFLOW_SENTINEL; mode 2: overflow list.
 // ------------------------------------------------------------------------------------------
 constexpr int kGR = 16;
 
-__global__ void __launch_bounds__(128) generic32_kernel(const uint8_t *raw, const uint64_t *off,
-                                                       const uint32_t *len, uint32_t ns,
-                                                       const uint8_t *qpacked, const uint32_t *qoff,
-                                                       const uint32_t *qlen, int q0, int q1,
-                                                       int32_t *out, size_t out_stride, int32_t *scratch,
-                                                       uint32_t max_t, int match, int mismatch, int goe,
-                                                       int ge, int limit, int fix_only)
+struct Score32Args {
+    const uint8_t *raw; const uint64_t *off; const uint32_t *len; uint32_t ns;
+    const uint8_t *qpacked; const uint32_t *qoff; const uint32_t *qlen; int q0, q1;
+    void *out; size_t out_stride; int out_mode;
+    int32_t *scratch; uint32_t max_cols;
+    int match, mismatch, goe, ge, limit, mode;
+    const unsigned *list_count; const uint2 *list; unsigned list_cap; int32_t *list_score;
+};
+
+__device__ __forceinline__ int score32_pair(const uint8_t *rp, int m, const uint8_t *cp, int n, int32_t *Hb,
+                                            int32_t *Gb, size_t nthreads, const Score32Args &a)
+{
+    // rows = (rp, m), columns = (cp, n), n <= max_cols
+    const int gb = a.goe > a.ge ? a.goe : a.ge;
+    for (int j = 0; j < n; ++j) { Hb[(size_t)j * nthreads] = 0; Gb[(size_t)j * nthreads] = gb; }
+    int best = 0;
+    for (int r0 = 0; r0 < m; r0 += kGR) {
+        const int nr = (m - r0 < kGR) ? (m - r0) : kGR;
+        uint32_t qw = 0;                               // 2-bit codes of the strip's rows
+        for (int r = 0; r < nr; ++r) {
+            const int i = r0 + r;
+            qw |= (uint32_t)((rp[i >> 2] >> ((i & 3) * 2)) & 3) << (2 * r);
+        }
+        int H[kGR], Gv[kGR];
+#pragma unroll
+        for (int r = 0; r < kGR; ++r) { H[r] = 0; Gv[r] = gb; }
+        int hd_top = 0;                                // H(r0-1, j-1)
+        int nx_h = n ? Hb[0] : 0, nx_g = n ? Gb[0] : gb;
+        for (int j = 0; j < n; ++j) {
+            const int tj = (cp[j >> 2] >> ((j & 3) * 2)) & 3;
+            const int top_h = nx_h, top_g = nx_g;      // H, G of row r0-1 in this column
+            if (j + 1 < n) { nx_h = Hb[(size_t)(j + 1) * nthreads]; nx_g = Gb[(size_t)(j + 1) * nthreads]; }
+            int diag = hd_top, gu = top_g;
+#pragma unroll
+            for (int r = 0; r < kGR; ++r) {
+                if (r < nr) {
+                    const int sc = ((int)((qw >> (2 * r)) & 3) == tj) ? a.match : a.mismatch;
+                    int mm = diag + sc;                             // v1.0.v:287
+                    mm = mm > 0 ? mm : 0;                           // v1.0.v:288
+                    if (a.limit && mm > a.limit) mm = 0;            // W-bit wrap-then-clamp
+                    const int ii = Gv[r] > gu ? Gv[r] : gu;         // v1.0.v:126-129, 291
+                    diag = H[r];
+                    const int a1 = mm + a.goe, a2 = ii + a.ge;
+                    gu = a1 > a2 ? a1 : a2;
+                    Gv[r] = gu;
+                    H[r] = mm > ii ? mm : ii;
+                    best = H[r] > best ? H[r] : best;               // v1.0.v:411-420
+                }
+            }
+            hd_top = top_h;
+            Hb[(size_t)j * nthreads] = H[kGR - 1];                  // used only below full strips
+            Gb[(size_t)j * nthreads] = Gv[kGR - 1];
+        }
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(128) score32_kernel(const Score32Args a)
 {
     const size_t nthreads = (size_t)gridDim.x * blockDim.x;
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int32_t *Hb = scratch + tid;                          // Hb[j * nthreads]: H(strip bottom, j)
-    int32_t *Gb = scratch + (size_t)max_t * nthreads + tid;
-    const int gb = goe > ge ? goe : ge;
-    const size_t njobs = (size_t)ns * (size_t)(q1 - q0);
+    int32_t *Hb = a.scratch + tid;                          // Hb[j * nthreads]: H(strip bottom, j)
+    int32_t *Gb = a.scratch + (size_t)a.max_cols * nthreads + tid;
+    size_t njobs;
+    if (a.mode == 2) {
+        const unsigned c = *a.list_count;
+        njobs = c < a.list_cap ? c : a.list_cap;
+    } else {
+        njobs = (size_t)a.ns * (size_t)(a.q1 - a.q0);
+    }
     for (size_t job = tid; job < njobs; job += nthreads) {
-        const uint32_t s = (uint32_t)(job % ns);
-        const int q = q0 + (int)(job / ns);
-        if (fix_only && out[(size_t)q * out_stride + s] != SW_OVERFLOW_SENTINEL) continue;
-        const int m = (int)qlen[q], n = (int)len[s];
-        const uint8_t *qp = qpacked + qoff[q];
-        const uint8_t *tpk = raw + off[s];
-        for (int j = 0; j < n; ++j) { Hb[(size_t)j * nthreads] = 0; Gb[(size_t)j * nthreads] = gb; }
-        int best = 0;
-        for (int r0 = 0; r0 < m; r0 += kGR) {
-            const int nr = (m - r0 < kGR) ? (m - r0) : kGR;
-            uint32_t qw = 0;                               // 2-bit codes of the strip's rows
-            for (int r = 0; r < nr; ++r) {
-                const int i = r0 + r;
-                qw |= (uint32_t)((qp[i >> 2] >> ((i & 3) * 2)) & 3) << (2 * r);
-            }
-            int H[kGR], Gv[kGR];
-#pragma unroll
-            for (int r = 0; r < kGR; ++r) { H[r] = 0; Gv[r] = gb; }
-            int hd_top = 0;                                // H(r0-1, j-1)
-            int nx_h = n ? Hb[0] : 0, nx_g = n ? Gb[0] : gb;
-            for (int j = 0; j < n; ++j) {
-                const int tj = (tpk[j >> 2] >> ((j & 3) * 2)) & 3;
-                const int top_h = nx_h, top_g = nx_g;      // H, G of row r0-1 in this column
-                if (j + 1 < n) { nx_h = Hb[(size_t)(j + 1) * nthreads]; nx_g = Gb[(size_t)(j + 1) * nthreads]; }
-                int diag = hd_top, gu = top_g;
-#pragma unroll
-                for (int r = 0; r < kGR; ++r) {
-                    if (r < nr) {
-                        const int sc = ((int)((qw >> (2 * r)) & 3) == tj) ? match : mismatch;
-                        int mm = diag + sc;                             // v1.0.v:287
-                        mm = mm > 0 ? mm : 0;                           // v1.0.v:288
-                        if (limit && mm > limit) mm = 0;                // W-bit wrap-then-clamp
-                        const int ii = Gv[r] > gu ? Gv[r] : gu;         // v1.0.v:126-129, 291
-                        diag = H[r];
-                        const int a1 = mm + goe, a2 = ii + ge;
-                        gu = a1 > a2 ? a1 : a2;
-                        Gv[r] = gu;
-                        H[r] = mm > ii ? mm : ii;
-                        best = H[r] > best ? H[r] : best;               // v1.0.v:411-420
-                    }
-                }
-                hd_top = top_h;
-                Hb[(size_t)j * nthreads] = H[kGR - 1];                  // used only below full strips
-                Gb[(size_t)j * nthreads] = Gv[kGR - 1];
-            }
+        uint32_t s; int q;
+        if (a.mode == 2) { q = (int)a.list[job].x; s = a.list[job].y; }
+        else { s = (uint32_t)(job % a.ns); q = a.q0 + (int)(job / a.ns); }
+        if (a.mode == 1) {
+            const bool flagged = a.out_mode == SW_OUT_I16 ? ((const int16_t *)a.out)[(size_t)q * a.out_stride + s] == SW_OVERFLOW_SENTINEL
+                                                          : ((const int32_t *)a.out)[(size_t)q * a.out_stride + s] == SW_OVERFLOW_SENTINEL;
+            if (!flagged) continue;
         }
-        out[(size_t)q * out_stride + s] = best;
+        const int m = (int)a.qlen[q], n = (int)a.len[s];
+        const uint8_t *qp = a.qpacked + a.qoff[q];
+        const uint8_t *tpk = a.raw + a.off[s];
+        const int best = (n <= m) ? score32_pair(qp, m, tpk, n, Hb, Gb, nthreads, a)
+                                  : score32_pair(tpk, n, qp, m, Hb, Gb, nthreads, a);
+        if (a.mode == 2 && a.list_score) a.list_score[job] = best;
+        if (a.out) {
+            // a 16-bit matrix keeps the sentinel for scores it cannot hold (they are on the list)
+            if (a.out_mode == SW_OUT_I16) { if (best <= 32767) ((int16_t *)a.out)[(size_t)q * a.out_stride + s] = (int16_t)best; }
+            else ((int32_t *)a.out)[(size_t)q * a.out_stride + s] = best;
+        }
     }
 }
 
@@ -579,136 +183,182 @@ __global__ void __launch_bounds__(1024) best_kernel(const int32_t *scores, size_
 }
 
 // ------------------------------------------------------------------------------------------
-// Variant table
+// Top-k merge: one block per query folds the per-block lists of the strip epilogue (nlists x k
+// keys, descending) and the recomputed overflow entries of this query into out_keys[q][0..k).
+// Keys are unique (they contain the subject index), so "largest key below the previous pick"
+// enumerates them in order: k rounds of a block-wide max.
 // ------------------------------------------------------------------------------------------
-constexpr int kBT = 128;
+__global__ void __launch_bounds__(256) topk_merge_kernel(const unsigned long long *keys, int nlists, int nq, int k,
+                                                        const unsigned *ovf_count, const uint2 *ovf_list,
+                                                        const int32_t *ovf_score, unsigned ovf_cap,
+                                                        unsigned long long *out_keys)
+{
+    const int q = blockIdx.x;
+    __shared__ unsigned long long s_red[8];
+    __shared__ unsigned long long s_pick;
+    const unsigned novf = ovf_count ? min(*ovf_count, ovf_cap) : 0u;
+    unsigned long long prev = ~0ull;
+    for (int round = 0; round < k; ++round) {
+        unsigned long long best = 0;
+        for (int i = threadIdx.x; i < nlists * k; i += blockDim.x) {
+            const unsigned long long v = keys[((size_t)(i / k) * nq + q) * k + (i % k)];
+            if (v < prev && v > best) best = v;
+        }
+        for (unsigned i = threadIdx.x; i < novf; i += blockDim.x) {
+            if ((int)ovf_list[i].x != q) continue;
+            const unsigned long long v = ((unsigned long long)(uint32_t)ovf_score[i] << 32) | (uint32_t)(~ovf_list[i].y);
+            if (v < prev && v > best) best = v;
+        }
+        for (int o = 16; o >= 1; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+            best = other > best ? other : best;
+        }
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long b = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) b = s_red[w] > b ? s_red[w] : b;
+            s_pick = b;
+            out_keys[(size_t)q * k + round] = b;
+        }
+        __syncthreads();
+        prev = s_pick;
+        if (prev == 0) {                       // nothing left: the remaining slots stay empty
+            for (int r = round + 1 + threadIdx.x; r < k; r += blockDim.x) out_keys[(size_t)q * k + r] = 0;
+            break;
+        }
+    }
+}
 
-typedef void (*StripFn)(const StripArgs);
+// ------------------------------------------------------------------------------------------
+// Variant table (assembled from the translation units that hold the instances)
+// ------------------------------------------------------------------------------------------
+static const std::vector<VariantEntry> &variants()
+{
+    static const std::vector<VariantEntry> all = [] {
+        std::vector<VariantEntry> v;
+        const VariantPart parts[] = {sw_variants_part_a(), sw_variants_part_b(), sw_variants_part_c(),
+                                     sw_variants_part_d(), sw_variants_part_e(), sw_variants_part_f()};
+        for (const VariantPart &p : parts) v.insert(v.end(), p.v, p.v + p.n);
+        return v;
+    }();
+    return all;
+}
 
-struct VariantEntry {
-    SwStripVariant info;
-    StripFn fn;        // exact arithmetic, run-time penalties
-    StripFn fn_w12;    // W-bit wrap-then-clamp
-    StripFn fn_fixed;  // exact arithmetic, gap penalties kFixedGoe / kFixedGe as immediates (or null)
-    StripFn fn_fixed2; // same for the second compiled-in set kFixed2Goe / kFixed2Ge (or null)
-};
+}  // namespace swk
 
-// the reference's default gap penalties: gap_open -12, gap_extend -4  =>  goe = -16, ge = -4
-constexpr int kFixedGoe = -16, kFixedGe = -4;
-// second compiled-in set: gap_open -8, gap_extend -4, the parameters of the reference's swalign
-// golden vectors (data/sw_testing.txt: first gap residue costs -12)
-constexpr int kFixed2Goe = -12, kFixed2Ge = -4;
-
-#define SW_VARIANT_S16(RS, S, G, MINB)                                                          \
-    { {RS * S, G, kBT, S, MINB, "strip_s16x2_R" #RS "x" #S "_G" #G},                            \
-      sw_strip_kernel<RS, S, G, ArithS16, false, kBT, MINB>, sw_strip_kernel<RS, S, G, ArithS16, true, kBT, MINB>, nullptr, nullptr }
-// + an instance with the default gap penalties as immediates
-#define SW_VARIANT_S16F(RS, S, G, MINB)                                                         \
-    { {RS * S, G, kBT, S, MINB, "strip_s16x2_R" #RS "x" #S "_G" #G},                            \
-      sw_strip_kernel<RS, S, G, ArithS16, false, kBT, MINB>, sw_strip_kernel<RS, S, G, ArithS16, true, kBT, MINB>, \
-      sw_strip_kernel<RS, S, G, ArithS16, false, kBT, MINB, kFixedGoe, kFixedGe>, nullptr }
-// + instances for both compiled-in gap penalty sets
-#define SW_VARIANT_S16F2(RS, S, G, MINB)                                                        \
-    { {RS * S, G, kBT, S, MINB, "strip_s16x2_R" #RS "x" #S "_G" #G},                            \
-      sw_strip_kernel<RS, S, G, ArithS16, false, kBT, MINB>, sw_strip_kernel<RS, S, G, ArithS16, true, kBT, MINB>, \
-      sw_strip_kernel<RS, S, G, ArithS16, false, kBT, MINB, kFixedGoe, kFixedGe>,               \
-      sw_strip_kernel<RS, S, G, ArithS16, false, kBT, MINB, kFixed2Goe, kFixed2Ge> }
-const VariantEntry g_variants[] = {
-    SW_VARIANT_S16F(30, 1, 1, 4),
-    SW_VARIANT_S16F(38, 1, 1, 4),
-    SW_VARIANT_S16F(75, 1, 1, 2),
-    // one lane per subject pair (inter-task): RS rows x S sub-strips per lane
-    SW_VARIANT_S16F(32, 1, 1, 4),
-    SW_VARIANT_S16F(50, 1, 1, 3),
-    SW_VARIANT_S16F2(25, 2, 1, 3),
-    SW_VARIANT_S16(19, 2, 1, 4),
-    SW_VARIANT_S16(15, 3, 1, 4),
-    SW_VARIANT_S16(30, 2, 1, 3),
-    SW_VARIANT_S16F(64, 1, 1, 2),
-    SW_VARIANT_S16F(32, 2, 1, 2),
-    SW_VARIANT_S16F2(25, 3, 1, 2),
-    SW_VARIANT_S16F2(38, 2, 1, 2),
-    SW_VARIANT_S16(25, 4, 1, 2),
-    // G lanes per subject pair (systolic group, shuffles): small databases / few long pairs
-    SW_VARIANT_S16(25, 1, 2, 5),
-    SW_VARIANT_S16(75, 1, 2, 2),
-    SW_VARIANT_S16(25, 3, 2, 2),
-    SW_VARIANT_S16F(38, 1, 4, 3),
-    SW_VARIANT_S16(19, 2, 4, 3),
-    SW_VARIANT_S16(32, 1, 4, 4),
-    SW_VARIANT_S16F(16, 1, 32, 3),
-    SW_VARIANT_S16F(8, 2, 32, 3),
-};
-constexpr int kNumVariants = sizeof(g_variants) / sizeof(g_variants[0]);
-
-}  // namespace
+using namespace swk;
 
 static bool g_no_fixed = false;     // testing: force the run-time-penalty instance
 void sw_strip_disable_fixed(bool off) { g_no_fixed = off; }
 
-int sw_strip_variant_count(void) { return kNumVariants; }
+int sw_strip_variant_count(void) { return (int)variants().size(); }
 
 const SwStripVariant *sw_strip_variant(int idx)
 {
-    return (idx >= 0 && idx < kNumVariants) ? &g_variants[idx].info : nullptr;
+    return (idx >= 0 && idx < (int)variants().size()) ? &variants()[idx].info : nullptr;
 }
 
 size_t sw_strip_smem_bytes(int idx, int chunk_passes)
 {
-    if (idx < 0 || idx >= kNumVariants) return 0;
-    const SwStripVariant &v = g_variants[idx].info;
-    const int rs = v.R / v.S;
-    return (size_t)chunk_passes * v.G * v.S * ((rs + 1) / 2) * kCodesPerRow * sizeof(uint2);
+    const SwStripVariant *v = sw_strip_variant(idx);
+    if (!v) return 0;
+    const int rs = v->R / v->S;
+    return (size_t)chunk_passes * v->G * v->S * ((rs + 1) / 2) * kCodesPerRow * sizeof(uint2);
 }
 
 cudaError_t sw_strip_occupancy(int idx, size_t smem_bytes, int *blocks_per_sm)
 {
-    if (idx < 0 || idx >= kNumVariants) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute((const void *)g_variants[idx].fn,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, (const void *)g_variants[idx].fn,
-                                                         g_variants[idx].info.block_threads, smem_bytes);
+    const SwStripVariant *v = sw_strip_variant(idx);
+    if (!v) return cudaErrorInvalidValue;
+    const void *fn = (const void *)variants()[idx].fn;
+    if (smem_bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, v->block_threads, smem_bytes);
 }
 
-cudaError_t sw_launch_strip(int idx, cudaStream_t st, const SwDevDb &db, const SwDevQueries &q,
-                            int q0, int q1, const SwScoring &sc, int32_t *out, size_t out_stride,
-                            uint2 *bnd, uint32_t bnd_cols, unsigned *counter, int grid, int chunk_passes)
+static StripFn pick_instance(const SwStripLaunch &L, const char **kind)
 {
-    if (idx < 0 || idx >= kNumVariants) return cudaErrorInvalidValue;
-    const VariantEntry &v = g_variants[idx];
-    StripFn fn = sc.limit ? v.fn_w12 : v.fn;
-    if (!sc.limit && v.fn_fixed && sc.goe == kFixedGoe && sc.ge == kFixedGe && !g_no_fixed) fn = v.fn_fixed;
-    if (!sc.limit && v.fn_fixed2 && sc.goe == kFixed2Goe && sc.ge == kFixed2Ge && !g_no_fixed) fn = v.fn_fixed2;
+    const VariantEntry &v = variants()[L.vidx];
+    const SwScoring &sc = L.sc;
+    if (L.direct) { *kind = "direct"; return sc.limit ? nullptr : v.fn_direct; }
+    if (sc.limit) { *kind = "w12"; return v.fn_w12; }
+    if (!g_no_fixed && v.fn_fixed && sc.goe == kFixedGoe && sc.ge == kFixedGe) { *kind = "fixed"; return v.fn_fixed; }
+    if (!g_no_fixed && v.fn_fixed2 && sc.goe == kFixed2Goe && sc.ge == kFixed2Ge) { *kind = "fixed"; return v.fn_fixed2; }
+    *kind = "runtime";
+    return v.fn;
+}
+
+const char *sw_strip_instance_kind(const SwStripLaunch &L)
+{
+    if (L.vidx < 0 || L.vidx >= (int)variants().size()) return "none";
+    if (L.jit_kernel && !L.direct && !L.sc.limit) return "jit";
+    const char *kind = "none";
+    pick_instance(L, &kind);
+    return kind;
+}
+
+cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L)
+{
+    if (L.vidx < 0 || L.vidx >= (int)variants().size()) return cudaErrorInvalidValue;
+    const VariantEntry &v = variants()[L.vidx];
+    const char *kind = "none";
+    StripFn fn = pick_instance(L, &kind);
     if (fn == nullptr) return cudaErrorInvalidValue;
     const int ppb = v.info.block_threads / v.info.G;
-    StripArgs a;
-    a.tp = db.tp; a.tile_woff = db.tile_woff; a.pair_len = db.pair_len; a.pair_subj = db.pair_subj;
-    a.npairs = db.npairs; a.npb = (db.npairs + ppb - 1) / ppb;
-    a.qpacked = q.packed; a.qoff = q.off; a.qlen = q.len; a.q0 = q0; a.q1 = q1;
-    a.out = out; a.out_stride = out_stride; a.bnd = bnd; a.bnd_cols = bnd_cols; a.counter = counter;
-    a.chunk_passes = chunk_passes;
+    const SwScoring &sc = L.sc;
+    StripArgs a{};
+    a.tp = L.db.tp; a.tile_woff = L.db.tile_woff; a.pair_len = L.db.pair_len; a.pair_subj = L.db.pair_subj;
+    a.npairs = L.db.npairs; a.npb = (L.db.npairs + ppb - 1) / ppb;
+    a.qpacked = L.q.packed; a.qoff = L.q.off; a.qlen = L.q.len; a.qidx = L.qidx; a.q0 = L.q0; a.nql = L.nql;
+    a.out = L.out; a.out_stride = L.out_stride; a.out_mode = L.out_mode;
+    a.bnd = L.bnd; a.bnd_cols = L.bnd_cols; a.counter = L.counter;
+    a.chunk_passes = L.chunk_passes;
     a.match = sc.match; a.mismatch = sc.mismatch; a.goe = sc.goe; a.ge = sc.ge; a.limit = sc.limit;
     a.goe2 = ((uint32_t)sc.goe & 0xFFFFu) * 0x10001u; a.ge2 = ((uint32_t)sc.ge & 0xFFFFu) * 0x10001u;
     a.ovf_limit = 32767 - sc.match - 1;
     a.zero = 0;
-    const size_t smem = sw_strip_smem_bytes(idx, chunk_passes);
-    cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    fn<<<grid, v.info.block_threads, smem, st>>>(a);
+    a.raw = L.db.raw; a.off = L.db.off;
+    a.ovf_count = L.ovf_count; a.ovf_list = L.ovf_list; a.ovf_cap = L.ovf_cap;
+    a.topk_keys = L.topk_keys; a.topk_k = L.topk_k; a.topk_nq = L.topk_nq;
+    a.dev_err = L.dev_err;
+#ifdef SW_BOUNDS_CHECK
+    a.tp_words = L.db.tp_words; a.bnd_elems = L.bnd_elems; a.out_elems = L.out_elems;
+#endif
+    if (L.out_mode == SW_OUT_TOPK && (L.topk_k < 1 || L.topk_k > kMaxTopK || !L.topk_keys)) return cudaErrorInvalidValue;
+    const size_t smem = sw_strip_smem_bytes(L.vidx, L.chunk_passes);
+    if (L.jit_kernel && !L.direct && !sc.limit) {
+        void *params[] = {&a};
+        cudaKernel_t k = (cudaKernel_t)L.jit_kernel;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaLaunchKernel((const void *)k, dim3(L.grid), dim3(v.info.block_threads), params, smem, st);
+    }
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    fn<<<L.grid, v.info.block_threads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t sw_launch_generic32(cudaStream_t st, const SwDevDb &db, const SwDevQueries &q, int q0, int q1,
-                                const SwScoring &sc, int32_t *out, size_t out_stride, int32_t *scratch,
-                                int threads_total, bool fix_only)
+cudaError_t sw_launch_score32(cudaStream_t st, const SwScore32Launch &L)
 {
     const int bt = 128;
-    const int grid = threads_total / bt;
+    const int grid = L.threads_total / bt;
     if (grid <= 0) return cudaErrorInvalidValue;
-    generic32_kernel<<<grid, bt, 0, st>>>(db.raw, db.off, db.len, db.ns, q.packed, q.off, q.len, q0, q1, out,
-                                          out_stride, scratch, db.max_len, sc.match, sc.mismatch, sc.goe,
-                                          sc.ge, sc.limit, fix_only ? 1 : 0);
+    Score32Args a{};
+    a.raw = L.db.raw; a.off = L.db.off; a.len = L.db.len; a.ns = L.db.ns;
+    a.qpacked = L.q.packed; a.qoff = L.q.off; a.qlen = L.q.len; a.q0 = L.q0; a.q1 = L.q1;
+    a.out = L.out; a.out_stride = L.out_stride; a.out_mode = L.out_mode;
+    a.scratch = L.scratch; a.max_cols = L.max_cols;
+    a.match = L.sc.match; a.mismatch = L.sc.mismatch; a.goe = L.sc.goe; a.ge = L.sc.ge; a.limit = L.sc.limit;
+    a.mode = L.mode; a.list_count = L.list_count; a.list = L.list; a.list_cap = L.list_cap; a.list_score = L.list_score;
+    score32_kernel<<<grid, bt, 0, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -728,5 +378,14 @@ cudaError_t sw_launch_best(cudaStream_t st, const int32_t *scores, size_t stride
 {
     if (nq <= 0) return cudaSuccess;
     best_kernel<<<nq, 1024, 0, st>>>(scores, stride, ns, best_score, best_index);
+    return cudaGetLastError();
+}
+
+cudaError_t sw_launch_topk_merge(cudaStream_t st, const unsigned long long *keys, int nlists, int nq, int k,
+                                 const unsigned *ovf_count, const uint2 *ovf_list, const int32_t *ovf_score,
+                                 unsigned ovf_cap, unsigned long long *out_keys)
+{
+    if (nq <= 0 || k <= 0) return cudaSuccess;
+    topk_merge_kernel<<<nq, 256, 0, st>>>(keys, nlists, nq, k, ovf_count, ovf_list, ovf_score, ovf_cap, out_keys);
     return cudaGetLastError();
 }

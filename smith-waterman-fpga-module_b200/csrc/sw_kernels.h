@@ -9,17 +9,21 @@
 #include <stdint.h>
 
 #define SW_NO_SUBJECT 0xFFFFFFFFu
-#define SW_OVERFLOW_SENTINEL (-1)   /* strip kernel: 16-bit range possibly exceeded, recompute in 32 bit */
+#define SW_OVERFLOW_SENTINEL (-1)   /* strip kernel: 16-bit range possibly exceeded, recomputed in 32 bit */
+#define SW_OUT_I32  0
+#define SW_OUT_I16  1
+#define SW_OUT_TOPK 2
+#define SW_MAX_TOPK 32
 
 /* Database shard resident in HBM.  Layout (DESIGN.md "data layout"):
  *   raw/off/len   : the caller's 2-bit packed records, as uploaded
  *   pair_subj     : [2*npairs] shard-local subject index of the low / high 16-bit
  *                   lane of pair p (SW_NO_SUBJECT = lane unused)
- *   pair_len      : [npairs] columns of the pair (both members have this length)
+ *   pair_len      : [2*npairs] columns of the two members (low lane = the longer one)
  *   tp            : column codes, one byte per column (0..15 = t_lo | t_hi << 2; 16..19 = the
  *                   shorter member has ended; 20 = no column), four columns per 32-bit
  *                   word, tiles of 32 pairs, word k of the 32 pairs of a tile contiguous:
- *                   tp[tile_woff[tile] + k*32 + slot]
+ *                   tp[tile_woff[tile] + k*32 + slot]   (null for DIRECT launches)
  */
 struct SwDevDb {
     const uint8_t  *raw;
@@ -30,6 +34,7 @@ struct SwDevDb {
     const uint32_t *pair_len;
     const uint64_t *tile_woff;
     uint32_t       *tp;
+    uint64_t        tp_words;
     uint32_t        npairs;
     uint32_t        max_len;
 };
@@ -54,6 +59,7 @@ struct SwStripVariant {
     int S;            /* independent sub-strips per lane (R = RS * S) */
     int min_blocks;   /* resident blocks per SM the kernel was compiled for */
     const char *name;
+    int has_direct;   /* a DIRECT instance exists (codes formed on the fly: small-batch path) */
 };
 
 int sw_strip_variant_count(void);
@@ -67,25 +73,72 @@ size_t sw_strip_smem_bytes(int idx, int chunk_passes);
 /* Resident blocks per SM of variant idx with smem_bytes of dynamic shared memory. */
 cudaError_t sw_strip_occupancy(int idx, size_t smem_bytes, int *blocks_per_sm);
 
-/* Scores queries [q0,q1) against all pairs of db.  out[(q)*out_stride + subj].
- * bnd: scratch for pass boundaries, grid * bnd_cols * (block_threads/G) uint2.
- * counter: zeroed device word (work queue).  chunk_passes: passes (of R*G rows) whose
- * query profile is held in shared memory at once. */
-cudaError_t sw_launch_strip(int idx, cudaStream_t st, const SwDevDb &db, const SwDevQueries &q,
-                            int q0, int q1, const SwScoring &sc, int32_t *out, size_t out_stride,
-                            uint2 *bnd, uint32_t bnd_cols, unsigned *counter, int grid,
-                            int chunk_passes);
+/* One strip-kernel launch: queries qidx[0..nql) (or q0 .. q0+nql-1 when qidx is null) against all
+ * pairs of db.  bnd: scratch for pass boundaries, grid * bnd_cols * (block_threads/G) uint2.
+ * counter: zeroed device word (work queue) or null for a static schedule.  chunk_passes: passes (of
+ * R*G rows) whose query profile is held in shared memory at once. */
+struct SwStripLaunch {
+    int vidx = -1;
+    bool direct = false;
+    SwDevDb db{};
+    SwDevQueries q{};
+    int q0 = 0, nql = 0;
+    const int *qidx = nullptr;
+    SwScoring sc{};
+    void *out = nullptr;
+    size_t out_stride = 0, out_elems = 0;
+    int out_mode = SW_OUT_I32;
+    uint2 *bnd = nullptr;
+    uint32_t bnd_cols = 0;
+    size_t bnd_elems = 0;
+    unsigned *counter = nullptr;
+    int grid = 0, chunk_passes = 1;
+    unsigned *ovf_count = nullptr;
+    uint2 *ovf_list = nullptr;
+    unsigned ovf_cap = 0;
+    unsigned long long *topk_keys = nullptr;
+    int topk_k = 0, topk_nq = 0;
+    unsigned *dev_err = nullptr;
+    void *jit_kernel = nullptr;   /* cudaKernel_t of a run-time specialised instance (sw_jit.cu), or null */
+};
+cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L);
+/* name of the instance sw_launch_strip would run ("fixed" / "runtime" / "w12" / "direct" / "jit") */
+const char *sw_strip_instance_kind(const SwStripLaunch &L);
 
-/* 32-bit kernel: any length, any score range.  scratch: 2 * (db.max_len) * threads int32.
- * fix_only: recompute only the entries the strip kernel marked SW_OVERFLOW_SENTINEL. */
-cudaError_t sw_launch_generic32(cudaStream_t st, const SwDevDb &db, const SwDevQueries &q,
-                                int q0, int q1, const SwScoring &sc, int32_t *out, size_t out_stride,
-                                int32_t *scratch, int threads_total, bool fix_only);
+/* 32-bit kernel: any length, any score range.  scratch: 2 * max_cols * threads_total int32 where
+ * max_cols = min(longest query, longest subject) (the recurrence is symmetric: the shorter sequence
+ * is walked as columns).  mode 0: every (query, subject) job of q0..q1; mode 1: only matrix entries
+ * equal to SW_OVERFLOW_SENTINEL; mode 2: the (query, subject) entries of the overflow list, results
+ * to the matrix (if out != null) and to list_score[i]. */
+struct SwScore32Launch {
+    SwDevDb db{};
+    SwDevQueries q{};
+    int q0 = 0, q1 = 0;
+    SwScoring sc{};
+    void *out = nullptr;
+    size_t out_stride = 0;
+    int out_mode = SW_OUT_I32;
+    int32_t *scratch = nullptr;
+    uint32_t max_cols = 0;
+    int threads_total = 0;
+    int mode = 0;
+    const unsigned *list_count = nullptr;
+    const uint2 *list = nullptr;
+    unsigned list_cap = 0;
+    int32_t *list_score = nullptr;
+};
+cudaError_t sw_launch_score32(cudaStream_t st, const SwScore32Launch &L);
 
 cudaError_t sw_launch_build_tp(cudaStream_t st, const SwDevDb &db);
 
-/* Per-query arg-max over subjects (first index reaching the max). */
+/* Per-query arg-max over subjects of a materialised int32 matrix (first index reaching the max). */
 cudaError_t sw_launch_best(cudaStream_t st, const int32_t *scores, size_t stride, uint32_t ns,
                            int nq, int32_t *best_score, uint32_t *best_index);
+
+/* Folds the per-block top-k lists (nlists x nq x k keys) and the recomputed overflow entries into
+ * out_keys[nq][k] (descending; key = score << 32 | ~subject, 0 = no entry). */
+cudaError_t sw_launch_topk_merge(cudaStream_t st, const unsigned long long *keys, int nlists, int nq, int k,
+                                 const unsigned *ovf_count, const uint2 *ovf_list, const int32_t *ovf_score,
+                                 unsigned ovf_cap, unsigned long long *out_keys);
 
 #endif

@@ -46,14 +46,24 @@ STRIP_VARIANTS = [
     "strip_s16x2_R38x2_G1", "strip_s16x2_R25x4_G1", "strip_s16x2_R25x1_G2", "strip_s16x2_R75x1_G2",
     "strip_s16x2_R25x3_G2", "strip_s16x2_R38x1_G4", "strip_s16x2_R19x2_G4", "strip_s16x2_R32x1_G4",
     "strip_s16x2_R16x1_G32", "strip_s16x2_R8x2_G32",
+    # small-R warp-wide variants of the latency path (P ~ query length)
+    "strip_s16x2_R1x1_G32", "strip_s16x2_R2x1_G32", "strip_s16x2_R4x1_G32", "strip_s16x2_R8x1_G32",
+    "strip_s16x2_R8x1_G16", "strip_s16x2_R16x1_G8",
 ]
+# variants that also exist as DIRECT instances (column codes formed on the fly: the small-batch path)
+DIRECT_VARIANTS = ["strip_s16x2_R16x1_G32", "strip_s16x2_R1x1_G32", "strip_s16x2_R2x1_G32", "strip_s16x2_R4x1_G32",
+                   "strip_s16x2_R8x1_G32", "strip_s16x2_R8x1_G16", "strip_s16x2_R16x1_G8"]
 S16_VARIANTS = [v for v in STRIP_VARIANTS if "s16x2" in v]
 VARIANTS = ["auto", "generic32"] + STRIP_VARIANTS
 
 
 def _choose(e, variant):
+    """auto = the library's own choice (small batches then take the latency path with its DIRECT
+    instances); a named variant is run through the regular path (code stream in HBM) -- the DIRECT
+    instances have their own tests in test_gpu_round2.py."""
     if variant == "auto":
         return
+    e.set_small_batch_path(False)
     if variant == "generic32":
         e.set_kernel_choice(0, 0, True, -1)
     else:

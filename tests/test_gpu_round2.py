@@ -1,0 +1,378 @@
+"""GPU parity tests of the round-2 paths, all through the C ABI: the small-batch latency path (DIRECT
+instances), int16 output + overflow side list, fused top-k, query groups, the list-driven 32-bit
+fix-up, run-time specialised penalties, virtual multi-shard handles, and the bounds-check build."""
+import os
+import random
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests.test_gpu_parity import DIRECT_VARIANTS, _mutate, _oracle_matrix, _rand
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _topk_want(mat, k):
+    """Oracle top-k: score descending, ties by ascending index; short rows padded with (-1, 2^64-1)."""
+    nq, ns = mat.shape
+    sc = np.full((nq, k), -1, dtype=np.int32)
+    ix = np.full((nq, k), np.iinfo(np.uint64).max, dtype=np.uint64)
+    for q in range(nq):
+        order = np.lexsort((np.arange(ns), -mat[q].astype(np.int64)))[:k]
+        sc[q, :len(order)] = mat[q, order]
+        ix[q, :len(order)] = order
+    return sc, ix
+
+
+@pytest.mark.parametrize("variant", ["auto"] + DIRECT_VARIANTS)
+def test_small_path_direct_variants_vs_oracle(oracle_mod, pkg, variant):
+    """Latency path: one staging copy, one DIRECT kernel, mapped output.  Ragged lengths, empty
+    subjects, odd counts, queries shorter / longer than one pass of the variant."""
+    rng = random.Random(500 + len(variant))
+    for qlens, nsub in (((1, 31, 32, 33), 61), ((128,), 499), ((150, 64), 300), ((600, 257), 40), ((32,), 1)):
+        queries = [_rand(rng, n) for n in qlens]
+        subjects = []
+        for _ in range(nsub):
+            if rng.random() < 0.4:
+                s = _mutate(rng, rng.choice(queries), 0.08, 0.06)
+                s = _rand(rng, rng.randint(0, 30)) + s + _rand(rng, rng.randint(0, 30))
+            else:
+                s = _rand(rng, rng.choice([0, 1, 2, 5, rng.randint(1, 300)]))
+            subjects.append(s)
+        if nsub == 1:
+            subjects = [_rand(rng, 128)]
+        want = _oracle_matrix(oracle_mod, pkg, queries, subjects)
+        with pkg.Engine() as e:
+            if variant != "auto":
+                e.set_kernel_name(variant)
+            got = e.score(queries, subjects)
+            assert e.last_kernel_name.endswith("+direct"), e.last_kernel_name
+            assert e.device_error_bits == 0
+        np.testing.assert_array_equal(got, want, err_msg=f"{variant} {qlens}")
+
+
+def test_small_path_golden_and_streaming(golden, oracle_mod, pkg):
+    """config 2 through the latency path == the reference's golden files; two small batches in
+    flight; the regular path gives the same matrix."""
+    q = golden["fasta"]["query100.fa"][0][1]
+    db = golden["fasta"]["data500.fa"]
+    ss = dict([x for x in golden["ssearch"] if x["file"] == "score500.txt"][0]["rows"])
+    rng = random.Random(8)
+    b2 = [_rand(rng, rng.randint(1, 200)) for _ in range(77)]
+    want2 = _oracle_matrix(oracle_mod, pkg, [q], b2)
+    with pkg.Engine() as e:
+        e.set_queries([q])
+        e.score_batch([s for _, s in db], ids=np.arange(len(db), dtype=np.uint64) + 100)
+        assert e.last_kernel_name.endswith("+direct")
+        e.score_batch(b2)
+        assert e.batches_in_flight == 2
+        got = e.fetch()
+        assert e.fetch_ids()[3] == 103
+        got2 = e.fetch()
+        assert e.last_kernel_ms > 0
+        e.set_small_batch_path(False)
+        ref = e.score([q], [s for _, s in db])
+        assert "+direct" not in e.last_kernel_name
+    assert dict(zip([n for n, _ in db], got[0].tolist())) == ss
+    np.testing.assert_array_equal(got, ref)
+    np.testing.assert_array_equal(got2, want2)
+
+
+def _overflow_case(rng):
+    s = _rand(rng, 6700)                      # identical pair scores 33500 > 32767
+    t = _mutate(rng, s, 0.004, 0.002)         # around the threshold
+    u = _mutate(rng, s, 0.10, 0.05)           # well inside 16 bit
+    others = [_rand(rng, rng.randint(100, 2000)) for _ in range(9)]
+    return s, [s, t, u, "ACGT", s[:6560], s[100:6652] + "A"] + others
+
+
+def test_output_i16_and_overflow_side_list(oracle_mod, pkg):
+    """int16 matrix: half the bytes; scores above 32767 are -1 in the matrix and exact in the side list."""
+    rng = random.Random(5)
+    s, subjects = _overflow_case(rng)
+    queries = [s, _rand(rng, 150)]
+    want = _oracle_matrix(oracle_mod, pkg, queries, subjects)
+    assert want[0, 0] == 33500 and (want > 32767).sum() >= 2
+    for resident in (False, True):
+        with pkg.Engine() as e:
+            e.set_output(pkg.SW_OUTPUT_I16)
+            e.set_queries(queries)
+            if resident:
+                e.load_db(subjects)
+                e.score_db()
+                got = e.fetch_db()
+            else:
+                e.score_batch(subjects)
+                got = e.fetch()
+            idx, sc = e.fetch_overflow()
+            assert e.device_error_bits == 0
+        assert got.dtype == np.int16
+        big = want > 32767
+        assert np.array_equal(got[~big].astype(np.int32), want[~big])
+        assert np.all(got[big] == -1)
+        flat = sorted(zip(idx.tolist(), sc.tolist()))
+        assert flat == sorted((int(i), int(want.reshape(-1)[i])) for i in np.nonzero(big.reshape(-1))[0])
+    # int32 output of the same batch is exact everywhere (list-driven 32-bit fix-up)
+    with pkg.Engine() as e:
+        np.testing.assert_array_equal(e.score(queries, subjects), want)
+    # plain case: no overflow possible, int16 == int32
+    q2 = [_rand(rng, 150) for _ in range(3)]
+    s2 = [_rand(rng, rng.randint(0, 300)) for _ in range(5000)]
+    w2 = _oracle_matrix(oracle_mod, pkg, q2, s2)
+    with pkg.Engine() as e:
+        e.set_output(pkg.SW_OUTPUT_I16)
+        g2 = e.score(q2, s2)
+        assert e.fetch_overflow()[0].size == 0
+    np.testing.assert_array_equal(g2.astype(np.int32), w2)
+
+
+@pytest.mark.parametrize("choice", ["auto", "strip_s16x2_R25x2_G1", "strip_s16x2_R16x1_G32", "strip_s16x2_R38x1_G4"])
+def test_topk_vs_oracle_argsort(oracle_mod, pkg, choice):
+    """Fused per-query top-k in the strip epilogue (ScoreBank_v2.v:42-43 max / vld_max, generalised):
+    equals the oracle's (score desc, index asc) ranking; no matrix is fetched.  Duplicated subjects
+    create ties; empty subjects score 0."""
+    rng = random.Random(1234)
+    queries = [_rand(rng, n) for n in (150, 40, 151, 300, 75)]
+    subjects = []
+    for i in range(3000):
+        r = rng.random()
+        if r < 0.15:
+            subjects.append(_mutate(rng, rng.choice(queries), 0.1, 0.05) or "A")
+        elif r < 0.25 and subjects:
+            subjects.append(rng.choice(subjects))            # exact duplicate: tie on score
+        elif r < 0.28:
+            subjects.append("")
+        else:
+            subjects.append(_rand(rng, rng.randint(1, 260)))
+    want = _oracle_matrix(oracle_mod, pkg, queries, subjects)
+    for k in (1, 5, 16, 32):
+        wsc, wix = _topk_want(want, k)
+        with pkg.Engine() as e:
+            if choice != "auto":
+                e.set_kernel_name(choice)
+            e.set_topk(k)
+            e.set_queries(queries)
+            e.load_db(subjects)
+            e.score_db()
+            sc, ix = e.fetch_db_topk()
+            assert e.device_error_bits == 0
+            with pytest.raises(pkg.SwError):
+                e.fetch_db()                                  # there is no matrix in top-k mode
+        np.testing.assert_array_equal(sc, wsc, err_msg=f"k={k}")
+        np.testing.assert_array_equal(ix, wix, err_msg=f"k={k}")
+
+
+def test_topk_streaming_small_and_sharded(oracle_mod, pkg):
+    """Top-k for streaming batches (two in flight), with fewer subjects than k, all-empty batches, and
+    one handle whose database is split in three shards (gather + merge across shards)."""
+    rng = random.Random(77)
+    queries = [_rand(rng, 120), _rand(rng, 33)]
+    batches = [[_rand(rng, rng.randint(0, 200)) for _ in range(n)] for n in (900, 3, 0, 450)]
+    batches.append(["", "", ""])
+    k = 8
+    for gpu_ids in ([0], [0, 0, 0]):
+        with pkg.Engine(gpu_ids=gpu_ids) as e:
+            e.set_topk(k)
+            e.set_queries(queries)
+            got = []
+            e.score_batch(batches[0])
+            for b in batches[1:]:
+                e.score_batch(b)
+                got.append(e.fetch_topk())
+            got.append(e.fetch_topk())
+        for b, (sc, ix) in zip(batches, got):
+            want = _oracle_matrix(oracle_mod, pkg, queries, b) if b else np.zeros((2, 0), np.int32)
+            wsc, wix = _topk_want(want, k)
+            np.testing.assert_array_equal(sc, wsc, err_msg=str((gpu_ids, len(b))))
+            np.testing.assert_array_equal(ix, wix, err_msg=str((gpu_ids, len(b))))
+
+
+def test_topk_with_scores_beyond_int16(oracle_mod, pkg):
+    rng = random.Random(5)
+    s, subjects = _overflow_case(rng)
+    want = _oracle_matrix(oracle_mod, pkg, [s], subjects)
+    wsc, wix = _topk_want(want, 4)
+    with pkg.Engine() as e:
+        e.set_topk(4)
+        e.set_queries([s])
+        e.score_batch(subjects)
+        sc, ix = e.fetch_topk()
+    assert sc[0, 0] == 33500
+    np.testing.assert_array_equal(sc, wsc)
+    np.testing.assert_array_equal(ix, wix)
+
+
+def test_virtual_multi_shard_handle(oracle_mod, pkg):
+    """One handle, database sharded over several per-GPU contexts with a host-side gather (SURVEY 8e;
+    ScoreBank_v2.v:78-139,162 at the GPU level).  The same GPU listed several times gives every
+    shard its own streams and buffers, so the shard plan, the per-shard sort and the column-range
+    gather run through the CUDA path on a one-GPU box as well; with more GPUs they are used too."""
+    rng = random.Random(4)
+    queries = [_rand(rng, 150) for _ in range(4)]
+    subjects = [_rand(rng, rng.randint(0, 300)) for _ in range(3001)]
+    subjects[1700] = queries[2]
+    want = _oracle_matrix(oracle_mod, pkg, queries, subjects)
+    n = pkg.device_count()
+    for gpu_ids in ([0, 0], [0, 0, 0, 0, 0], list(range(n)) + [0]):
+        with pkg.Engine(gpu_ids=gpu_ids) as e:
+            e.set_small_batch_path(False)
+            got = e.score(queries, subjects)
+            np.testing.assert_array_equal(got, want, err_msg=str(gpu_ids))
+            e.set_queries(queries)
+            e.load_db(subjects, ids=np.arange(len(subjects), dtype=np.uint64) * 3)
+            e.score_db()
+            e.wait()
+            np.testing.assert_array_equal(e.fetch_db(), want)
+            bs, bi = e.fetch_best()
+            assert bs.tolist() == want.max(axis=1).tolist() and bi.tolist() == want.argmax(axis=1).tolist()
+            assert int(bi[2]) == 1700 and e.fetch_ids()[1700] == 5100
+            st = e.stats()
+            assert st["kernel_ms_max"] >= st["kernel_ms_min"] > 0
+            e.set_output(pkg.SW_OUTPUT_I16)
+            e.score_db()
+            np.testing.assert_array_equal(e.fetch_db().astype(np.int32), want)
+
+
+def test_query_groups_get_their_own_variant(oracle_mod, pkg):
+    """Mixed query lengths (config 5): queries are grouped by the variant whose pass height fits them
+    and every group is launched with its own variant; the matrix stays in input order."""
+    rng = random.Random(55)
+    queries = [_rand(rng, n) for n in (32, 4096, 150, 1000, 31, 2049, 150)]
+    subjects = [_rand(rng, rng.randint(200, 900)) for _ in range(12000)]
+    for k in range(0, 12000, 97):
+        src = queries[k % len(queries)]
+        a = rng.randint(0, max(0, len(src) - 50))
+        subjects[k] = (_mutate(rng, src[a:a + 600], 0.05, 0.03) + _rand(rng, 300))[:700] or "A"
+    with pkg.Engine() as e:
+        got = e.score(queries, subjects)
+        name = e.last_kernel_name
+        assert e.device_error_bits == 0
+    assert "+groups" in name, name
+    # the oracle checks a sample of the columns (the full matrix would take minutes on the CPU)
+    cols = sorted(set(range(0, 12000, 97)) | set(rng.sample(range(12000), 300)))
+    want = _oracle_matrix(oracle_mod, pkg, queries, [subjects[c] for c in cols])
+    np.testing.assert_array_equal(got[:, cols], want)
+    with pkg.Engine() as e:
+        e.set_kernel_name("strip_s16x2_R25x3_G1")
+        one = e.score(queries, subjects)
+    np.testing.assert_array_equal(got, one)
+
+
+def test_load_db_right_after_async_score_db(oracle_mod, pkg):
+    """sw_score_db is asynchronous: a following sw_load_db / sw_score_batch must not overwrite the
+    slot's buffers under the running kernels (uploads wait for the slot's scoring to finish)."""
+    rng = random.Random(9)
+    q = pkg.random_packed_db(24, 150, seed=3)
+    db1 = pkg.random_packed_db(400000, 150, seed=4)
+    small = [_rand(rng, rng.randint(1, 200)) for _ in range(9000)]
+    with pkg.Engine() as e:
+        e.set_queries(q)
+        e.load_db(db1)
+        e.score_db()                      # ~30 ms of kernels in flight
+        e.load_db(small)                  # same slot, different shape
+        e.score_db()
+        got = e.fetch_db()
+        e.load_db(db1)
+        e.score_db()
+        e.score_batch(small)              # slot 0 again (nothing in flight in the fifo)
+        got2 = e.fetch()
+        assert e.device_error_bits == 0
+    o = oracle_mod.Oracle()
+    sp = pkg.pack_sequences(small)
+    want_small, _ = o.score_batch_packed(q[0], q[1], q[2], sp[0], sp[1], sp[2])
+    np.testing.assert_array_equal(got, want_small)
+    np.testing.assert_array_equal(got2, want_small)
+
+
+def test_long_subject_overflow_fixup_needs_little_scratch(oracle_mod, pkg):
+    """A 300 kb subject next to a 7 kb query whose copy it contains: the score leaves 16 bits, the
+    pair goes to the overflow list and the list-driven 32-bit kernel (shorter sequence as columns,
+    bounded scratch) recomputes it -- no allocation proportional to the longest subject x all threads."""
+    rng = random.Random(12)
+    q = _rand(rng, 7000)
+    genome = _rand(rng, 150000) + q + _rand(rng, 143000)
+    subjects = [genome, _rand(rng, 5000), _mutate(rng, q, 0.2, 0.1), "ACGT"]
+    want = _oracle_matrix(oracle_mod, pkg, [q], subjects)
+    assert want[0, 0] == 35000
+    with pkg.Engine() as e:
+        got = e.score([q], subjects)
+    np.testing.assert_array_equal(got, want)
+
+
+def test_runtime_specialised_penalties(oracle_mod, pkg):
+    """Any penalty set gets immediates: the variant a job uses is compiled at run time with the
+    handle's penalties (ld_penalties is a run-time bus in the reference, ScoreBank_v2.v:34,161)."""
+    if not pkg.load_library().sw_jit_is_available():
+        pytest.skip("NVRTC not loadable on this box")
+    params = dict(match=5, mismatch=-4, gap_open=-10, gap_extend=-3)
+    ok, msg = pkg.jit_compile_check("strip_s16x2_R25x2_G1", -10, -3)
+    assert ok == 1, msg
+    rng = random.Random(3)
+    queries = [_rand(rng, 150), _rand(rng, 90)]
+    subjects = [(_mutate(rng, rng.choice(queries), 0.15, 0.15) or "A") for _ in range(20000)]
+    want = _oracle_matrix(oracle_mod, pkg, queries, subjects, **params)
+    with pkg.Engine(**params) as e:
+        e.set_jit(2)
+        got = e.score(queries, subjects)
+        assert "+jit" in e.last_kernel_name, e.last_kernel_name
+        e.set_jit(0)
+        plain = e.score(queries, subjects)
+        assert "+jit" not in e.last_kernel_name
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(plain, want)
+
+
+def test_mixed_one_very_long_subject_with_many_short(oracle_mod, pkg):
+    """One 60 kb subject next to 10^5 short ones and a multi-pass query: the launch plan must not size
+    the pass-boundary scratch of every resident block by the longest subject."""
+    rng = random.Random(60)
+    query = _rand(rng, 400)
+    genome = _rand(rng, 30000) + _mutate(rng, query, 0.03, 0.02) + _rand(rng, 30000)
+    db = pkg.random_packed_db(100000, 150, seed=61)
+    gp = pkg.pack_sequences([genome])
+    nb = 38
+    packed = np.concatenate([db[0][:100000 * nb], gp[0]])
+    ln = np.concatenate([db[1], gp[1]]).astype(np.uint32)
+    off = np.concatenate([db[2], np.array([100000 * nb], dtype=np.uint64)])
+    qp = pkg.pack_sequences([query])
+    with pkg.Engine() as e:
+        got = e.score(qp, (packed, ln, off))
+        assert e.device_error_bits == 0
+    o = oracle_mod.Oracle()
+    idx = np.arange(0, 100000, 41)
+    sub = (np.concatenate([packed[i * nb:(i + 1) * nb] for i in idx] + [np.zeros(16, np.uint8)]),
+           ln[idx], (np.arange(len(idx), dtype=np.uint64) * nb))
+    want, _ = o.score_batch_packed(qp[0], qp[1], qp[2], sub[0], sub[1], sub[2])
+    np.testing.assert_array_equal(got[:, idx], want)
+    assert int(got[0, 100000]) == o.score(query, genome) > 1500
+
+
+def test_bounds_check_build_runs_clean(pkg):
+    """Stand-in for compute-sanitizer (closed on this pool): the same sources built with
+    -DSW_BOUNDS_CHECK (device-side index checks on tp / bnd / profile / out, canaries around every
+    device buffer) run the ragged parity tests; any violation turns into SW_EDEVICE."""
+    lib = os.path.join(ROOT, "smith-waterman-fpga-module_b200", "libsw_b200_check.so")
+    if not os.path.exists(lib):
+        pytest.skip("libsw_b200_check.so not built (make -C csrc CHECK=1)")
+    if pkg.is_check_build():
+        pytest.skip("already running the check build")
+    env = dict(os.environ, SW_B200_LIB=lib)
+    sel = ("test_random_mixed_lengths_vs_oracle or test_long_query_multi_pass_and_chunks or test_edge_cases or "
+           "test_small_path_direct_variants_vs_oracle or test_topk_vs_oracle_argsort or test_output_i16 or "
+           "test_very_long_subjects_short_queries or test_query_groups or test_is_check_build")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-x", "-q", "-m", "gpu", "-k", sel,
+                        "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout
+
+
+def test_is_check_build_flag(pkg):
+    """In the check build every fetch also verifies canaries and the device error word."""
+    want = os.environ.get("SW_B200_LIB", "").endswith("_check.so")
+    assert pkg.is_check_build() == want
+    with pkg.Engine() as e:
+        e.score(["ACGTACGT"], ["ACGTTCGT", "", "A"])
+        assert e.device_error_bits == 0

@@ -1,0 +1,17 @@
+"""CPU-side checks of the host-only ABI additions of round 2."""
+import ctypes as C
+
+
+def test_exact_domain_query(pkg):
+    """sw_params_in_exact_domain: match + gap_open <= 0 is the RTL's schedule-independent domain
+    (SW_ProcessingElement_v1.0.v:120 vs :131-141)."""
+    assert pkg.params_in_exact_domain() == 1                              # 5/-4/-12/-4
+    assert pkg.params_in_exact_domain(5, -4, -8, -4) == 1                 # the swalign vectors' set
+    assert pkg.params_in_exact_domain(5, -4, -5, -1) == 1                 # boundary: match + gap_open == 0
+    assert pkg.params_in_exact_domain(5, -4, -2, -1) == 0                 # accepted, RTL schedule-dependent
+    assert pkg.params_in_exact_domain(5, -4, -12, 3) == pkg.SW_EINVAL     # rejected by sw_init as well
+    assert pkg.load_library().sw_params_in_exact_domain(None) == 1
+
+
+def test_stats_struct_layout(pkg):
+    assert C.sizeof(pkg.SwStats) == 6 * 8
