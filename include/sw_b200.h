@@ -246,6 +246,9 @@ int sw_jit_compile_check(const char *variant_name, int gap_open, int gap_extend,
  * the reference's own data sets: data/data500.fa is 499 x 128 nt).  enable = 0 forces the regular
  * path (environment SW_B200_SMALL_PATH=0). */
 int sw_set_small_batch_path(sw_handle_t *h, int enable);
+/* The latency path records two CUDA events around its kernel so that sw_last_kernel_ms works
+ * (about 2 us of host time per batch); enable = 0 drops them (sw_last_kernel_ms then reports 0). */
+int sw_set_small_batch_timing(sw_handle_t *h, int enable);
 int sw_kernel_variant_count(void);
 const char *sw_kernel_variant_name(int idx);
 int sw_set_kernel_name(sw_handle_t *h, const char *name);

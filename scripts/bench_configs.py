@@ -111,6 +111,46 @@ def latency(pkg, name, queries, db, reps=300, check=True):
     return res
 
 
+def c_latency(pkg, name, nq, qlen, ns, slen, seed, iters=3000):
+    """The same job timed from C (bin/sw_b200_latency: sw_score_batch + sw_fetch in a loop, no Python in
+    the timed region), with and without the CUDA events of the latency path; the scores of the last
+    iteration are checked against the oracle."""
+    import subprocess
+    import tempfile
+    seqio = importlib.import_module("smith-waterman-fpga-module_b200.seqio")
+    exe = os.path.join(ROOT, "bin", "sw_b200_latency")
+    if not os.path.exists(exe):
+        return {"error": "bin/sw_b200_latency missing"}
+    q = pkg.random_packed_db(nq, qlen, seed)
+    db = pkg.random_packed_db(ns, slen, seed + 1)
+    qs = [seqio.unpack_to_str(q[0], qlen, int(o)) for o in q[2]]
+    ds = [seqio.unpack_to_str(db[0], slen, int(o)) for o in db[2]]
+    o = _oracle()
+    res = {"config": name, "timed_in": "C (bin/sw_b200_latency), clock_gettime around sw_score_batch + sw_fetch"}
+    with tempfile.TemporaryDirectory() as td:
+        qf, lf, sf = os.path.join(td, "q.fa"), os.path.join(td, "l.fa"), os.path.join(td, "s.txt")
+        open(qf, "w").write("".join(f">q{i}\n{s}\n" for i, s in enumerate(qs)))
+        open(lf, "w").write("".join(f">s{i}\n{s}\n" for i, s in enumerate(ds)))
+        for ev in (1, 0):
+            r = subprocess.run([exe, "-q", qf, "-l", lf, "-n", str(iters), "-e", str(ev), "-o", sf],
+                               capture_output=True, text=True, timeout=120)
+            if r.returncode != 0:
+                return {"config": name, "error": (r.stdout + r.stderr)[-300:]}
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            got = np.array([int(l.split()[2]) for l in open(sf)], dtype=np.int32).reshape(nq, ns)
+            want, _ = o.score_batch_packed(q[0], q[1], q[2], db[0], db[1], db[2])
+            assert np.array_equal(got, want), f"{name}: C-driver scores differ from the oracle"
+            key = "with_events" if ev else "without_events"
+            res[key] = {k: d[k] for k in ("e2e_us_median", "e2e_us_min", "e2e_us_p90", "e2e_us_p99", "device_us_mean")}
+            res["kernel"] = d["kernel"]
+            res["cells"] = d["cells"]
+    res["oracle_checked_pairs"] = nq * ns
+    res["e2e_us_median"] = res["without_events"]["e2e_us_median"]
+    res["device_us"] = res["with_events"]["device_us_mean"]
+    res["gcups_e2e"] = res["cells"] / res["e2e_us_median"] / 1e3
+    return res
+
+
 def case_latency(pkg):
     a = latency(pkg, "2 (latency): 1 x 128 nt query vs 499 x 128 nt, sw_score_batch + sw_fetch",
                 pkg.random_packed_db(1, 128, 1), pkg.random_packed_db(499, 128, 2))
@@ -118,7 +158,12 @@ def case_latency(pkg):
     b = latency(pkg, "1 pair (latency): 32 nt query vs one 128 nt subject (the CAPI sample's job)",
                 pkg.random_packed_db(1, 32, 1), pkg.random_packed_db(1, 128, 2))
     b["reference_simulated_us"] = REF_PAIR_US
-    return {"config2_499x128": a, "single_pair_32x128": b}
+    c = c_latency(pkg, "2 (latency, C driver): 1 x 128 nt query vs 499 x 128 nt", 1, 128, 499, 128, 1)
+    c["reference_simulated_us"] = REF_BANK_US_DATA500
+    d = c_latency(pkg, "1 pair (latency, C driver): 32 nt query vs one 128 nt subject", 1, 32, 1, 128, 3)
+    d["reference_simulated_us"] = REF_PAIR_US
+    return {"config2_499x128": c, "single_pair_32x128": d, "config2_499x128_python_ctypes": a,
+            "single_pair_32x128_python_ctypes": b}
 
 
 def case_4full(pkg):

@@ -80,7 +80,8 @@ def sass_functions(path):
 
 
 def demangle_params(fn):
-    m = re.search(r"sw_strip_kernelILi(\d+)ELi(\d+)ELi(\d+)ENS\w*8ArithS16ELb([01])ELi(\d+)ELi(\d+)ELi(n?\d+)ELi(n?\d+)ELb([01])", fn)
+    m = re.search(r"sw_strip_kernelILi(\d+)ELi(\d+)ELi(\d+)ENS\w*8ArithS16ELb([01])ELi(\d+)ELi(\d+)ELi(n?\d+)ELi(n?\d+)ELb([01])ELi(\d+)", fn)
+    U = int(m.group(10)) if m else 4
     if not m:
         m2 = re.search(r"sw_strip_kernelILi(\d+)ELi(\d+)ELi(\d+)ENS\w*8ArithS16ELb([01])ELi(\d+)ELi(\d+)ELi(n?\d+)ELi(n?\d+)ELi", fn)
         if not m2:
@@ -90,7 +91,7 @@ def demangle_params(fn):
         g = m.groups()
     num = lambda s: -int(s[1:]) if s.startswith("n") else int(s)
     return {"RS": int(g[0]), "S": int(g[1]), "G": int(g[2]), "w12": g[3] == "1", "BT": int(g[4]), "MINB": int(g[5]),
-            "goe": num(g[6]), "ge": num(g[7]), "direct": g[8] == "1"}
+            "goe": num(g[6]), "ge": num(g[7]), "direct": g[8] == "1", "U": U}
 
 
 def hot_loop(rows):
@@ -128,7 +129,7 @@ def analyse(path, pattern):
         p = demangle_params(fn)
         if not p:
             continue
-        name = "strip_s16x2_R%dx%d_G%d" % (p["RS"], p["S"], p["G"])
+        name = "strip_s16x2_R%dx%d_G%d" % (p["RS"], p["S"], p["G"]) + ("_U%d" % p["U"] if p["U"] != 4 else "")
         kind = "direct" if p["direct"] else "w12" if p["w12"] else ("fixed(%d,%d)" % (p["goe"], p["ge"])) if p["goe"] else "runtime"
         label = f"{name} [{kind}]"
         if pattern and not re.search(pattern, label):
@@ -140,9 +141,9 @@ def analyse(path, pattern):
         pipes = collections.Counter()
         for op, n in hist.items():
             pipes[pipe_of(op)] += n
-        pairs = 4 * p["RS"] * p["S"]
+        pairs = p["U"] * p["RS"] * p["S"]
         res[label] = {"variant": name, "instance": kind, "function": fn, "loop_instructions": len(body),
-                      "cell_pairs_per_trip": pairs, "by_pipe": dict(pipes),
+                      "cell_pairs_per_trip": pairs, "columns_per_trip": p["U"], "by_pipe": dict(pipes),
                       "alu_pipe_per_cell_pair": pipes["alu"] / pairs,
                       "fma_pipe_per_cell_pair": pipes["fma"] / pairs,
                       "issue_slots_per_cell_pair": len(body) / pairs,
@@ -154,7 +155,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--lib", default=DEFAULT_LIB)
     ap.add_argument("--cubin", default=None)
-    ap.add_argument("--match", default=r"R25x2_G1 \[fixed\(-16,-4\)\]|R25x3_G1 \[fixed\(-16,-4\)\]|R38x2_G1 \[fixed\(-16,-4\)\]|R25x2_G1 \[runtime\]|R16x1_G32 \[fixed")
+    ap.add_argument("--match", default=r"R25x2_G1\w* \[fixed\(-16,-4\)\]|R25x3_G1\w* \[fixed\(-16,-4\)\]|R38x2_G1\w* \[fixed\(-16,-4\)\]|R25x2_G1 \[runtime\]|R16x1_G32 \[fixed")
     ap.add_argument("--json", default=None)
     ap.add_argument("--txt", default=None)
     a = ap.parse_args()
@@ -162,8 +163,8 @@ def main():
     lines = []
     for label, r in sorted(res.items()):
         lines.append(f"== {label}")
-        lines.append(f"   hot loop: {r['loop_instructions']} instructions per trip = 4 columns x {r['cell_pairs_per_trip'] // 4} rows "
-                     f"= {r['cell_pairs_per_trip']} cell pairs")
+        lines.append(f"   hot loop: {r['loop_instructions']} instructions per trip = {r['columns_per_trip']} columns x "
+                     f"{r['cell_pairs_per_trip'] // r['columns_per_trip']} rows = {r['cell_pairs_per_trip']} cell pairs")
         lines.append(f"   per cell pair: ALU pipe {r['alu_pipe_per_cell_pair']:.3f}, FMA-side pipe {r['fma_pipe_per_cell_pair']:.3f}, "
                      f"issue slots {r['issue_slots_per_cell_pair']:.3f}")
         lines.append("   by pipe: " + ", ".join(f"{k} {v}" for k, v in sorted(r["by_pipe"].items(), key=lambda kv: -kv[1])))

@@ -122,8 +122,10 @@ struct Slot {
     int topk_k = 0;
     // small (latency) path: one staging buffer in, mapped scores out
     bool is_small = false;
-    PinnedBuf h_small_in, h_small_out;
-    DevBuf d_small_in;
+    PinnedBuf h_small_in, h_small_out, h_small_flag;
+    DevBuf d_small_in, d_small_done;
+    unsigned small_seq = 0;            // value the kernel writes to the completion flag
+    bool small_timed = false;          // events were recorded around the kernel
 };
 
 struct GpuCtx {
@@ -176,6 +178,7 @@ struct sw_handle {
     int out_mode = SW_OUT_I32;        // SW_OUTPUT_I32 / SW_OUTPUT_I16 for the next scoring
     int topk_k = 0;                   // > 0: fused top-k instead of a matrix
     bool small_path = true;
+    bool small_timing = true;         // record CUDA events around the latency path's kernel (sw_last_kernel_ms)
     int jit = 1;                      // run-time specialisation of gap penalties: 0 off, 1 large jobs, 2 always
     // bookkeeping
     std::atomic<int> last_cuda{0};    // written by the per-GPU worker threads as well
@@ -231,7 +234,7 @@ std::vector<DevBuf *> all_devbufs(GpuCtx &g)
                                &g.d_best_score, &g.d_best_index, &g.d_topk_keys, &g.d_err};
     for (Slot &b : g.slot) {
         DevBuf *bufs[] = {&b.d_raw, &b.d_off, &b.d_len, &b.d_pair_subj, &b.d_pair_len, &b.d_tile_woff, &b.d_tp, &b.d_out,
-                          &b.d_ovf_count, &b.d_ovf_list, &b.d_ovf_score, &b.d_topk_out, &b.d_small_in};
+                          &b.d_ovf_count, &b.d_ovf_list, &b.d_ovf_score, &b.d_topk_out, &b.d_small_in, &b.d_small_done};
         v.insert(v.end(), std::begin(bufs), std::end(bufs));
     }
     return v;
@@ -245,7 +248,8 @@ void free_gpu(GpuCtx &g)
         for (cudaEvent_t e : b.ev_pool) cudaEventDestroy(e);
         b.ev_pool.clear();
         b.chunks.clear();
-        PinnedBuf *pins[] = {&b.h_stage_a, &b.h_stage_b, &b.h_stage_c, &b.h_stage_d, &b.h_topk, &b.h_ovf, &b.h_small_in, &b.h_small_out};
+        PinnedBuf *pins[] = {&b.h_stage_a, &b.h_stage_b, &b.h_stage_c, &b.h_stage_d, &b.h_topk, &b.h_ovf, &b.h_small_in, &b.h_small_out,
+                             &b.h_small_flag};
         for (PinnedBuf *p : pins) p->release();
         if (b.ev_start) cudaEventDestroy(b.ev_start);
         if (b.ev_stop) cudaEventDestroy(b.ev_stop);
@@ -914,11 +918,24 @@ int fetch_slot(sw_handle *h, int si, FetchKind kind, void *scores, uint64_t *ind
     if (bt.small) {
         GpuCtx &g = h->gpus[0];
         Slot &b = g.slot[si];
-        int rc = wait_event(h, b.ev_stop, t_end, forever);
-        if (rc != SW_OK) return rc;
+        // poll the completion flag the kernel writes into mapped host memory
+        volatile unsigned *flag = (volatile unsigned *)b.h_small_flag.p;
+        unsigned spins = 0;
+        while (*flag != b.small_seq) {
+            if ((++spins & 0x3FF) == 0) {
+                if (!forever && std::chrono::steady_clock::now() >= t_end) return SW_ETIMEOUT;
+                cudaError_t qe = cudaStreamQuery(g.st_compute);          // a failed launch would never write the flag
+                if (qe != cudaSuccess && qe != cudaErrorNotReady) { h->last_cuda.store((int)qe); return SW_ECUDA; }
+                if (qe == cudaSuccess && *flag != b.small_seq) { h->last_cuda.store((int)cudaErrorUnknown); return SW_ECUDA; }
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
         std::memcpy(scores, b.h_small_out.p, nq * bt.ns * sizeof(int32_t));
         float ms = 0.f;
-        SW_CUDA(h, cudaEventElapsedTime(&ms, b.ev_start, b.ev_stop));
+        if (b.small_timed) {
+            SW_CUDA(h, cudaEventSynchronize(b.ev_stop));
+            SW_CUDA(h, cudaEventElapsedTime(&ms, b.ev_start, b.ev_stop));
+        }
         finish_timing(h, si, t_fetch0, std::chrono::steady_clock::now(), ms, ms);
 #ifdef SW_BOUNDS_CHECK
         if (device_error_bits(h)) return SW_EDEVICE;
@@ -1159,7 +1176,8 @@ int small_submit(sw_handle *h, int si, const uint8_t *packed, const uint32_t *le
         maxlen = std::max(maxlen, len[i]);
         sum += len[i];
     }
-    if (maxlen == 0 || bmax - bmin > (1u << 20) || maxlen > 65535) return SW_OK;
+    // the DIRECT instances stage a pair's code words in shared memory: subjects of up to 1024 bases
+    if (maxlen == 0 || bmax - bmin > (1u << 20) || maxlen > 1024) return SW_OK;
     const SwScoring sc = scoring_of(h);
     if ((uint64_t)sc.match * std::min<uint64_t>(h->q_max_len, maxlen) + (uint64_t)sc.match >= 32000ull) return SW_OK;
     GpuCtx &gc = h->gpus[0];
@@ -1167,6 +1185,12 @@ int small_submit(sw_handle *h, int si, const uint8_t *packed, const uint32_t *le
     const size_t np_max = (ns + 1) / 2;
     const int vidx = small_variant(h, h->q_max_len, np_max);
     if (vidx < 0) return SW_OK;
+    {
+        // DIRECT instances with a pass of fewer than 512 rows have no multi-pass code
+        const SwStripVariant *sv = sw_strip_variant(vidx);
+        const uint32_t P = (uint32_t)(sv->R * sv->G);
+        if (P < 512 && h->q_max_len > P) return SW_OK;
+    }
     *taken = true;
 
     SW_CUDA(h, cudaSetDevice(gc.dev));
@@ -1191,6 +1215,12 @@ int small_submit(sw_handle *h, int si, const uint8_t *packed, const uint32_t *le
     SW_CUDA(h, g.h_small_in.reserve(total));
     SW_CUDA(h, g.d_small_in.reserve(total));
     SW_CUDA(h, g.h_small_out.reserve((size_t)nq * ns * sizeof(int32_t), true));
+    if (!g.h_small_flag.p) {
+        SW_CUDA(h, g.h_small_flag.reserve(64, true));
+        std::memset(g.h_small_flag.p, 0, 64);
+        SW_CUDA(h, g.d_small_done.reserve(sizeof(unsigned)));
+        SW_CUDA(h, cudaMemset(g.d_small_done.p, 0, sizeof(unsigned)));
+    }
     // the staging buffer is reused: the previous copy out of it finished before its batch was fetched
     char *st = (char *)g.h_small_in.p;
     sort_by_length(g, len, ns, maxlen);
@@ -1232,9 +1262,15 @@ int small_submit(sw_handle *h, int si, const uint8_t *packed, const uint32_t *le
         L.bnd_elems = (size_t)L.grid * per_block / sizeof(uint2);
     }
     L.bnd = gc.d_bnd.as<uint2>();
-    SW_CUDA(h, cudaEventRecord(g.ev_start, cs));
+    // completion: the kernel's last block writes small_seq into a mapped host word the host polls
+    g.small_seq++;
+    if (g.small_seq == 0) g.small_seq = 1;
+    L.done_count = g.d_small_done.as<unsigned>(); L.done_flag = (unsigned *)g.h_small_flag.dptr; L.done_seq = g.small_seq;
+    g.small_timed = h->small_timing;
+    if (g.small_timed) SW_CUDA(h, cudaEventRecord(g.ev_start, cs));
     SW_CUDA(h, sw_launch_strip(cs, L));
     h->launches++;
+    // ev_stop is recorded in both modes: load_shard orders a later reuse of the slot after it
     SW_CUDA(h, cudaEventRecord(g.ev_stop, cs));
     g.scored = true;
     std::snprintf(h->last_kernel, sizeof h->last_kernel, "%s+direct", v->name);
@@ -1694,6 +1730,13 @@ int sw_set_small_batch_path(sw_handle_t *h, int enable)
 {
     if (!h) return SW_EINVAL;
     h->small_path = enable != 0;
+    return SW_OK;
+}
+
+int sw_set_small_batch_timing(sw_handle_t *h, int enable)
+{
+    if (!h) return SW_EINVAL;
+    h->small_timing = enable != 0;
     return SW_OK;
 }
 

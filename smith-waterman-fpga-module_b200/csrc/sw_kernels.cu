@@ -238,7 +238,8 @@ static const std::vector<VariantEntry> &variants()
     static const std::vector<VariantEntry> all = [] {
         std::vector<VariantEntry> v;
         const VariantPart parts[] = {sw_variants_part_a(), sw_variants_part_b(), sw_variants_part_c(),
-                                     sw_variants_part_d(), sw_variants_part_e(), sw_variants_part_f()};
+                                     sw_variants_part_d(), sw_variants_part_e(), sw_variants_part_f(),
+                                     sw_variants_part_g()};
         for (const VariantPart &p : parts) v.insert(v.end(), p.v, p.v + p.n);
         return v;
     }();
@@ -248,6 +249,10 @@ static const std::vector<VariantEntry> &variants()
 }  // namespace swk
 
 using namespace swk;
+
+// dynamic + static shared memory must stay below 48 KB unless the kernel opts in; the strip kernel has
+// a few KB of static shared memory (work item, top-k candidates), so opt in from 32 KB of dynamic on
+static const size_t kSmemOptIn = 32 * 1024;
 
 static bool g_no_fixed = false;     // testing: force the run-time-penalty instance
 void sw_strip_disable_fixed(bool off) { g_no_fixed = off; }
@@ -272,7 +277,7 @@ cudaError_t sw_strip_occupancy(int idx, size_t smem_bytes, int *blocks_per_sm)
     const SwStripVariant *v = sw_strip_variant(idx);
     if (!v) return cudaErrorInvalidValue;
     const void *fn = (const void *)variants()[idx].fn;
-    if (smem_bytes > 48 * 1024) {
+    if (smem_bytes > kSmemOptIn) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
         if (e != cudaSuccess) return e;
     }
@@ -324,6 +329,7 @@ cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L)
     a.ovf_count = L.ovf_count; a.ovf_list = L.ovf_list; a.ovf_cap = L.ovf_cap;
     a.topk_keys = L.topk_keys; a.topk_k = L.topk_k; a.topk_nq = L.topk_nq;
     a.dev_err = L.dev_err;
+    a.done_count = L.done_count; a.done_flag = L.done_flag; a.done_seq = L.done_seq;
 #ifdef SW_BOUNDS_CHECK
     a.tp_words = L.db.tp_words; a.bnd_elems = L.bnd_elems; a.out_elems = L.out_elems;
 #endif
@@ -332,13 +338,13 @@ cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L)
     if (L.jit_kernel && !L.direct && !sc.limit) {
         void *params[] = {&a};
         cudaKernel_t k = (cudaKernel_t)L.jit_kernel;
-        if (smem > 48 * 1024) {
+        if (smem > kSmemOptIn) {
             cudaError_t e = cudaFuncSetAttribute((const void *)k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
         return cudaLaunchKernel((const void *)k, dim3(L.grid), dim3(v.info.block_threads), params, smem, st);
     }
-    if (smem > 48 * 1024) {
+    if (smem > kSmemOptIn) {
         cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
     }

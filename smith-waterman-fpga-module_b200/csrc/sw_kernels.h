@@ -60,6 +60,7 @@ struct SwStripVariant {
     int min_blocks;   /* resident blocks per SM the kernel was compiled for */
     const char *name;
     int has_direct;   /* a DIRECT instance exists (codes formed on the fly: small-batch path) */
+    int U;            /* columns per trip of the step loop */
 };
 
 int sw_strip_variant_count(void);
@@ -99,6 +100,8 @@ struct SwStripLaunch {
     unsigned long long *topk_keys = nullptr;
     int topk_k = 0, topk_nq = 0;
     unsigned *dev_err = nullptr;
+    unsigned *done_count = nullptr, *done_flag = nullptr;   /* latency path: completion flag in mapped host memory */
+    unsigned done_seq = 0;
     void *jit_kernel = nullptr;   /* cudaKernel_t of a run-time specialised instance (sw_jit.cu), or null */
 };
 cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L);

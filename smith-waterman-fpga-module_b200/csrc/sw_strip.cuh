@@ -154,6 +154,11 @@ struct StripArgs {
     unsigned long long *topk_keys;
     int topk_k, topk_nq;
     unsigned *dev_err;         // device-side error word (bounds-check builds)
+    // completion flag of the latency path: the last block to finish writes done_seq to *done_flag
+    // (mapped host memory), which the host polls -- no event, no stream query on the critical path
+    unsigned *done_count;
+    unsigned *done_flag;
+    unsigned done_seq;
 #ifdef SW_BOUNDS_CHECK
     unsigned long long tp_words, bnd_elems, out_elems;
 #endif
@@ -195,21 +200,26 @@ __device__ __forceinline__ uint32_t make_code_word(uint32_t a, uint32_t b, uint3
 // is one column behind s-1): S independent dependency chains in one basic block, so a warp
 // always has an instruction whose operands are ready (the PE array's pipelining, inside one
 // thread).  H[s][r] / Gl[s][r] hold H and G of the previous column on entry and of this column
-// on exit; hd_top = H(row0-1, c-1), g_top = G(row0-1, c); prow[s] points at the profile entry
-// of (first row pair of the sub-strip, this column's code), one uint2 = two consecutive rows.
+// on exit; hd_top = H(row0-1, c-1), g_top = G(row0-1, c); sv[s][k] = the substitution scores of
+// rows 2k, 2k+1 of sub-strip s against this column's code (load_scores: one LDS.64 per row pair).
+template <int RS, int S, int G>
+__device__ __forceinline__ void load_scores(uint2 (&sv)[S][(RS + 1) / 2], const uint2 *prof_lane, const uint32_t (&code)[S])
+{
+    constexpr int RP = (RS + 1) / 2;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const uint2 *prow = prof_lane + (s * RP * kCodesPerRow + code[s]) * G;
+#pragma unroll
+        for (int k = 0; k < RP; ++k) sv[s][k] = prow[k * kCodesPerRow * G];
+    }
+}
+
 template <int RS, int S, int G, class AR, bool W12>
 __device__ __forceinline__ void column_step_multi(uint32_t (&H)[S][RS], uint32_t (&Gl)[S][RS], uint32_t &best,
                                                   const uint32_t (&hd_top)[S], const uint32_t (&g_top)[S],
-                                                  const uint2 *const (&prow)[S], uint32_t goe2,
+                                                  const uint2 (&sv)[S][(RS + 1) / 2], uint32_t goe2,
                                                   uint32_t ge2, uint32_t zero, uint32_t lim2)
 {
-    constexpr int RP = (RS + 1) / 2;
-    // substitution scores of this column: one LDS.64 per row pair
-    uint2 sv[S][RP];
-#pragma unroll
-    for (int s = 0; s < S; ++s)
-#pragma unroll
-        for (int k = 0; k < RP; ++k) sv[s][k] = prow[s][k * kCodesPerRow * G];
     if constexpr (!W12) {
         // Clamped, goe-shifted form (exact).  Every gap value is clamped at 0
         // (non-positive gap values can never reach H because M >= 0) and the register strip holds
@@ -321,6 +331,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
 {
     extern __shared__ uint2 s_prof[];
     __shared__ unsigned s_work, s_iter;
+    __shared__ uint32_t s_codes[DIRECT ? BT / G : 1][DIRECT ? 256 : 1];   // DIRECT: staged code words per pair slot
     constexpr int R = RS * S;
     constexpr int P = R * G;
     constexpr int RP = (RS + 1) / 2;
@@ -328,7 +339,17 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
     constexpr int PASS_ENTRIES = VPE * RP * kCodesPerRow;
     constexpr int PPB = BT / G;
     constexpr unsigned FULL = 0xFFFFFFFFu;
-    static_assert(U == 4, "the step loop consumes one 4-column code word per trip");
+    static_assert(U % 4 == 0, "the step loop consumes 4-column code words");
+    // EARLY (wide systolic groups): the column codes travel from lane to lane ONE STEP AHEAD of the
+    // (H, G) values, so the profile load of step t+1 is issued during step t and the per-step
+    // dependency chain is shuffle -> add -> max chain instead of shuffle -> LDS -> add -> max chain.
+    // These variants are latency-bound (one warp = one pair), so that is what sets their speed.
+    constexpr bool EARLY = (G >= 8);
+    constexpr int kDirectWords = 256;                // DIRECT: code words staged per pair slot (1024 columns)
+    // DIRECT instances with a short pass (P < 512 rows) are only used for queries of at most P rows
+    // (the host checks): no pass-boundary code at all in their step loop
+    constexpr bool MULTIPASS = !(DIRECT && P < 512);
+    static_assert(sizeof(s_codes[0]) == (DIRECT ? kDirectWords : 1) * sizeof(uint32_t), "s_codes row = kDirectWords");
 
     const int lane = threadIdx.x & 31;
     const int gl = (G == 1) ? 0 : (lane & (G - 1));
@@ -394,12 +415,20 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                 tpp += a.tile_woff[pair >> 5] + (pair & 31);
             }
         }
+        // DIRECT: the lanes of the group form the pair's code words in parallel, once, into shared
+        // memory (the host sends only subjects of up to 4 * kDirectWords bases down this path)
+        if constexpr (DIRECT) {
+            for (int k = gl; 4 * k < ncols && k < kDirectWords; k += G) {
+                const uint32_t ba = (uint32_t)__ldg(rlo + k);
+                const uint32_t bb = (rhi != nullptr && 4 * (uint32_t)k < nhi) ? (uint32_t)__ldg(rhi + k) : 0u;
+                s_codes[pslot][k] = make_code_word(ba, bb, (uint32_t)k, (uint32_t)ncols, nhi);
+            }
+            __syncwarp();
+        }
         // word k of the pair's column code stream (columns 4k .. 4k+3)
         auto code_word = [&](int k) -> uint32_t {
             if constexpr (DIRECT) {
-                const uint32_t ba = (4 * k < ncols) ? (uint32_t)__ldg(rlo + k) : 0u;
-                const uint32_t bb = (rhi != nullptr && 4 * (uint32_t)k < nhi) ? (uint32_t)__ldg(rhi + k) : 0u;
-                return make_code_word(ba, bb, (uint32_t)k, (uint32_t)ncols, nhi);
+                return s_codes[pslot][k & (kDirectWords - 1)];
             } else {
                 SW_CHECK((unsigned long long)(tpp - a.tp) + (unsigned long long)k * 32 < a.tp_words, SW_DEVERR_TP, a);
                 return __ldg(tpp + k * 32);
@@ -465,39 +494,73 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                 if (gl == 0 && ncols > 0) {
                     wcur = code_word(0);
                     if (ncols > 4) wnext = code_word(1);
-                    if (has_top) {
+                    if (MULTIPASS && has_top) {
                         SW_CHECK((unsigned long long)(bnd - a.bnd) < a.bnd_elems, SW_DEVERR_BND, a);
                         bcur = bnd_load(bnd, bnd_pol);
                         for (int c = 1; c < 4 && c < ncols; ++c) prefetch_l1(bnd + (size_t)c * PPB);
                     }
                 }
                 // what each sub-strip hands to the next virtual PE (the next sub-strip, or for
-                // s = S-1 the next lane): bottom H, bottom G and the column code it just used
+                // s = S-1 the next lane): bottom H, bottom G and a column code -- the code it just
+                // used, or in EARLY mode the code it uses in the CURRENT step (one step ahead of H, G)
                 uint32_t pub_h[S], pub_g[S], pub_t[S], hd_top[S];
 #pragma unroll
                 for (int s = 0; s < S; ++s) { pub_h[s] = h0; pub_g[s] = gb2; pub_t[s] = kPadCode; hd_top[s] = h0; }
+                uint2 sv[S][RP];                              // substitution scores of the current step
+                if constexpr (EARLY) {
+                    // step 0: the head PE is on column 0, every other virtual PE on PAD
+                    if (gl == 0 && ncols > 0) pub_t[0] = wcur & 255u;
+                    load_scores<RS, S, G>(sv, prof_lane, pub_t);
+                }
 
 #pragma unroll 1
                 for (int t2 = 0; t2 < nsteps; t2 += U) {
 #pragma unroll
-                  for (int u = 0; u < U; ++u) {
-                    const int t = t2 + u;
+                  for (int uu = 0; uu < U; ++uu) {
+                    const int t = t2 + uu;
+                    const int u = uu & 3;                 // column inside the current 4-column code word
+                    // in_t: the code of THIS step (of the NEXT step in EARLY mode) of each virtual PE
                     uint32_t in_h[S], in_g[S], in_t[S];
                     if (G > 1) {
                         in_h[0] = __shfl_up_sync(FULL, pub_h[S - 1], 1, G);
                         in_g[0] = __shfl_up_sync(FULL, pub_g[S - 1], 1, G);
                         in_t[0] = __shfl_up_sync(FULL, pub_t[S - 1], 1, G);
                     }
-                    if (G == 1 || gl == 0) {
+                    if constexpr (EARLY) {
+                        // head of the systolic group, written without divergent branches (these
+                        // variants are latency-bound): every lane evaluates the head's expressions
+                        // on its own (empty) word registers, the head lane keeps them
+                        const bool head = gl == 0;
+                        const uint32_t wsel = (u < 3) ? wcur : wnext;
+                        const uint32_t lead_t = (t + 1 < ncols) ? ((wsel >> (8 * ((u + 1) & 3))) & 255u) : (uint32_t)kPadCode;
+                        in_h[0] = head ? bcur.x : in_h[0];
+                        in_g[0] = head ? bcur.y : in_g[0];
+                        in_t[0] = head ? lead_t : in_t[0];
+                        if (u == 3) {
+                            wcur = wnext;
+                            const int k = (t >> 2) + 2;
+                            if (head && k * 4 < ncols) wnext = code_word(k);
+                            if (!DIRECT && head && (k + 1) * 4 < ncols) prefetch_l1(tpp + (k + 1) * 32);
+                        }
+                        if constexpr (MULTIPASS) {
+                            if (has_top && head) {
+                                if (t + 1 < ncols) {
+                                    SW_CHECK((unsigned long long)(bnd - a.bnd) + (unsigned long long)(t + 1) * PPB < a.bnd_elems, SW_DEVERR_BND, a);
+                                    bcur = bnd_load(bnd + (size_t)(t + 1) * PPB, bnd_pol);
+                                }
+                                if (t + 4 < ncols) prefetch_l1(bnd + (size_t)(t + 4) * PPB);
+                            }
+                        }
+                    } else if (G == 1 || gl == 0) {
                         // head of the systolic group: column t comes from the code stream, the row
                         // above from the previous pass (or the zero boundary)
                         const bool on = t < ncols;
                         in_h[0] = bcur.x;
                         in_g[0] = bcur.y;
-                        // U == 4 and t2 % 4 == 0: the four columns of this trip are the four bytes of wcur
+                        // t2 % 4 == 0: columns t2 + 4j .. t2 + 4j + 3 are the four bytes of one code word
                         in_t[0] = on ? ((wcur >> (8 * u)) & 255u) : (uint32_t)kPadCode;
                         if (on) {
-                            if (u == U - 1) {
+                            if (u == 3) {
                                 wcur = wnext;
                                 const int k = (t >> 2) + 2;
                                 if (k * 4 < ncols) wnext = code_word(k);
@@ -516,20 +579,28 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                     }
 #pragma unroll
                     for (int s = 1; s < S; ++s) { in_h[s] = pub_h[s - 1]; in_g[s] = pub_g[s - 1]; in_t[s] = pub_t[s - 1]; }
-
-                    const uint2 *prow[S];
 #pragma unroll
-                    for (int s = 0; s < S; ++s) {
-                        SW_CHECK(in_t[s] <= (uint32_t)kPadCode, SW_DEVERR_PROF, a);
-                        prow[s] = prof_lane + (s * RP * kCodesPerRow + in_t[s]) * G;
+                    for (int s = 0; s < S; ++s) SW_CHECK(in_t[s] <= (uint32_t)kPadCode, SW_DEVERR_PROF, a);
+
+                    if constexpr (EARLY) {
+                        // scores of step t + 1 are requested now and consumed one step later
+                        uint2 sv_next[S][RP];
+                        load_scores<RS, S, G>(sv_next, prof_lane, in_t);
+                        column_step_multi<RS, S, G, AR, W12>(H, Gl, best, hd_top, in_g, sv, goe2, ge2, zero, lim2);
+#pragma unroll
+                        for (int s = 0; s < S; ++s)
+#pragma unroll
+                            for (int k = 0; k < RP; ++k) sv[s][k] = sv_next[s][k];
+                    } else {
+                        load_scores<RS, S, G>(sv, prof_lane, in_t);
+                        column_step_multi<RS, S, G, AR, W12>(H, Gl, best, hd_top, in_g, sv, goe2, ge2, zero, lim2);
                     }
-                    column_step_multi<RS, S, G, AR, W12>(H, Gl, best, hd_top, in_g, prow, goe2, ge2, zero, lim2);
 #pragma unroll
                     for (int s = 0; s < S; ++s) {
                         hd_top[s] = in_h[s];
                         pub_h[s] = H[s][RS - 1]; pub_g[s] = Gl[s][RS - 1]; pub_t[s] = in_t[s];
                     }
-                    if (has_bottom && gl == G - 1) {
+                    if (MULTIPASS && has_bottom && gl == G - 1) {
                         const int cl = t - (VPE - 1);          // column the last virtual PE just finished
                         if (cl >= 0 && cl < ncols) {
                             SW_CHECK((unsigned long long)(bnd - a.bnd) + (unsigned long long)cl * PPB < a.bnd_elems, SW_DEVERR_BND, a);
@@ -593,6 +664,19 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                 if (k1 > thr) s_cand[atomicAdd(&s_ncand, 1)] = k1;
                 __syncthreads();
                 if (threadIdx.x < 32) topk_insert_warp(list, K, s_cand, s_ncand);
+            }
+        }
+    }
+    if (a.done_flag) {
+        // every thread's result stores (mapped host memory) are ordered before the flag: block
+        // barrier, then a system-scope fence by the thread that counts the block as finished
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            if (atomicAdd(a.done_count, 1u) == gridDim.x - 1) {
+                *a.done_count = 0;
+                __threadfence_system();
+                *(volatile unsigned *)a.done_flag = a.done_seq;
             }
         }
     }

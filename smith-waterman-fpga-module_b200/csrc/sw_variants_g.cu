@@ -1,0 +1,12 @@
+/* sw_variants_g.cu -- ahead-of-time instances of the strip kernel (one slice of the variant table). */
+#include "sw_variants.h"
+
+namespace swk {
+static const VariantEntry g_part[] = {
+    // 8 columns per trip of the step loop
+    SW_VARIANT_S16F_U(25, 2, 1, 3, 8),
+    SW_VARIANT_S16F_U(25, 3, 1, 2, 8),
+    SW_VARIANT_S16F_U(38, 2, 1, 2, 8),
+};
+VariantPart sw_variants_part_g() { return {g_part, (int)(sizeof(g_part) / sizeof(g_part[0]))}; }
+}  // namespace swk

@@ -32,7 +32,12 @@ def test_small_path_direct_variants_vs_oracle(oracle_mod, pkg, variant):
     """Latency path: one staging copy, one DIRECT kernel, mapped output.  Ragged lengths, empty
     subjects, odd counts, queries shorter / longer than one pass of the variant."""
     rng = random.Random(500 + len(variant))
-    for qlens, nsub in (((1, 31, 32, 33), 61), ((128,), 499), ((150, 64), 300), ((600, 257), 40), ((32,), 1)):
+    rows_per_pass = {"auto": 512, "strip_s16x2_R16x1_G32": 512, "strip_s16x2_R1x1_G32": 32, "strip_s16x2_R2x1_G32": 64,
+                     "strip_s16x2_R4x1_G32": 128, "strip_s16x2_R8x1_G32": 256, "strip_s16x2_R8x1_G16": 128,
+                     "strip_s16x2_R16x1_G8": 128}[variant]
+    for qlens, nsub in (((1, 31, 32, 17), 61), ((128,), 499), ((150, 64), 300), ((600, 257), 40), ((1300, 513), 12), ((32,), 1)):
+        if variant not in ("auto", "strip_s16x2_R16x1_G32") and max(qlens) > rows_per_pass:
+            continue            # small-P DIRECT instances are single-pass by construction (the host checks)
         queries = [_rand(rng, n) for n in qlens]
         subjects = []
         for _ in range(nsub):
@@ -41,7 +46,7 @@ def test_small_path_direct_variants_vs_oracle(oracle_mod, pkg, variant):
                 s = _rand(rng, rng.randint(0, 30)) + s + _rand(rng, rng.randint(0, 30))
             else:
                 s = _rand(rng, rng.choice([0, 1, 2, 5, rng.randint(1, 300)]))
-            subjects.append(s)
+            subjects.append(s[:1024])           # the latency path takes subjects of up to 1024 bases
         if nsub == 1:
             subjects = [_rand(rng, 128)]
         want = _oracle_matrix(oracle_mod, pkg, queries, subjects)
@@ -240,24 +245,41 @@ def test_query_groups_get_their_own_variant(oracle_mod, pkg):
     """Mixed query lengths (config 5): queries are grouped by the variant whose pass height fits them
     and every group is launched with its own variant; the matrix stays in input order."""
     rng = random.Random(55)
+    nrng = np.random.default_rng(55)
     queries = [_rand(rng, n) for n in (32, 4096, 150, 1000, 31, 2049, 150)]
-    subjects = [_rand(rng, rng.randint(200, 900)) for _ in range(12000)]
-    for k in range(0, 12000, 97):
-        src = queries[k % len(queries)]
-        a = rng.randint(0, max(0, len(src) - 50))
-        subjects[k] = (_mutate(rng, src[a:a + 600], 0.05, 0.03) + _rand(rng, 300))[:700] or "A"
+    ns = 120000
+    lens = nrng.integers(200, 900, size=ns).astype(np.uint32)
+    nbytes = (lens.astype(np.uint64) + 3) // 4
+    off = np.concatenate([[0], np.cumsum(nbytes)[:-1]]).astype(np.uint64)
+    packed = nrng.integers(0, 256, size=int(nbytes.sum()) + 16, dtype=np.uint8)
+    tail = (lens % 4).astype(np.int64)
+    last = (off + nbytes - 1).astype(np.int64)
+    m = tail > 0
+    packed[last[m]] &= ((1 << (2 * tail[m])) - 1).astype(np.uint8)
+    # plant homologs of the queries (byte-aligned copies of query stretches)
+    qp = pkg.pack_sequences(queries)
+    for k in range(0, ns, 997):
+        qi = (k // 997) % len(queries)
+        qb = int((qp[1][qi] + 3) // 4)
+        n = min(int(nbytes[k]) - 1, qb - 1)
+        if n > 4:
+            packed[int(off[k]): int(off[k]) + n] = qp[0][int(qp[2][qi]): int(qp[2][qi]) + n]
+    db = (packed, lens, off)
     with pkg.Engine() as e:
-        got = e.score(queries, subjects)
+        got = e.score(qp, db)
         name = e.last_kernel_name
         assert e.device_error_bits == 0
     assert "+groups" in name, name
     # the oracle checks a sample of the columns (the full matrix would take minutes on the CPU)
-    cols = sorted(set(range(0, 12000, 97)) | set(rng.sample(range(12000), 300)))
-    want = _oracle_matrix(oracle_mod, pkg, queries, [subjects[c] for c in cols])
+    cols = np.array(sorted(set(range(0, ns, 997)) | set(rng.sample(range(ns), 250))))
+    sub = (np.concatenate([packed[int(off[c]): int(off[c]) + int(nbytes[c])] for c in cols] + [np.zeros(16, np.uint8)]),
+           lens[cols], np.concatenate([[0], np.cumsum(nbytes[cols])[:-1]]).astype(np.uint64))
+    want, _ = oracle_mod.Oracle().score_batch_packed(qp[0], qp[1], qp[2], sub[0], sub[1], sub[2])
     np.testing.assert_array_equal(got[:, cols], want)
+    assert want.max() > 1000
     with pkg.Engine() as e:
         e.set_kernel_name("strip_s16x2_R25x3_G1")
-        one = e.score(queries, subjects)
+        one = e.score(qp, db)
     np.testing.assert_array_equal(got, one)
 
 
