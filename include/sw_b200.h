@@ -249,6 +249,13 @@ int sw_set_small_batch_path(sw_handle_t *h, int enable);
 /* The latency path records two CUDA events around its kernel so that sw_last_kernel_ms works
  * (about 2 us of host time per batch); enable = 0 drops them (sw_last_kernel_ms then reports 0). */
 int sw_set_small_batch_timing(sw_handle_t *h, int enable);
+/* Few, long pairs (a long query against a handful of subjects, down to ONE pair): the 512-row bands
+ * of the query become separate work items that run concurrently on different warps / SMs, each
+ * band consuming the bottom row of the band above as it is produced -- the module chaining the
+ * reference left "for future use" (ScoringModule_v1.1.v:36-39, 49-54).  mode 0 = never,
+ * 1 = automatic (default: <= 1536 subject pairs and a query of >= 1024 rows, or <= 64 pairs and a
+ * query of > 512 rows), 2 = whenever the query has more than one band (environment SW_B200_WAVE). */
+int sw_set_wave_mode(sw_handle_t *h, int mode);
 int sw_kernel_variant_count(void);
 const char *sw_kernel_variant_name(int idx);
 int sw_set_kernel_name(sw_handle_t *h, const char *name);

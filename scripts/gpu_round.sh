@@ -1,16 +1,25 @@
 #!/bin/bash
-# One GPU session: parity tests, latency / config benches, kernel A/B.  Outputs under gpurun_out/.
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv > gpurun_out/smi.txt 2>&1
-timeout 2400 python -m pytest tests -m gpu -q --maxfail=15 --timeout=900 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+timeout 600 python -m pytest tests -m gpu -q -k "wave" --timeout=240 -p no:cacheprovider > gpurun_out/pytest_wave.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/pytest_wave.log
+tail -30 gpurun_out/pytest_wave.log
+timeout 2400 python -m pytest tests -m gpu -q -k "not wave" --maxfail=15 --timeout=900 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
 tail -25 gpurun_out/pytest_gpu.log
-timeout 300 python scripts/bench_configs.py lat 4w 5 > gpurun_out/configs.jsonl 2> gpurun_out/configs.err
-cat gpurun_out/configs.jsonl
-: > gpurun_out/ab.jsonl
-for k in strip_s16x2_R25x2_G1 strip_s16x2_R25x2_G1_U8 strip_s16x2_R25x3_G1 strip_s16x2_R25x3_G1_U8 strip_s16x2_R38x2_G1 strip_s16x2_R38x2_G1_U8; do
-  timeout 300 python bench.py --steps 3 --warmup 2 --subjects 4000000 --no-e2e --no-cpu --no-configs --kernel $k 2>> gpurun_out/ab.err | python -c "
-import json,sys
-d=json.loads(sys.stdin.read()); print(json.dumps({'kernel': d['detail']['kernel'], 'gcups': d['value'], 'clocks': d['clocks']['sm_mhz']}))" >> gpurun_out/ab.jsonl
+timeout 400 python scripts/bench_configs.py 4w pair 5 4 > gpurun_out/configs_wave.jsonl 2> gpurun_out/configs_wave.err
+cat gpurun_out/configs_wave.jsonl; tail -3 gpurun_out/configs_wave.err
+# true kernel durations of the latency path
+python - <<'PY'
+import importlib, os, sys
+sys.path.insert(0, os.getcwd())
+seqio = importlib.import_module("smith-waterman-fpga-module_b200.seqio")
+pkg = importlib.import_module("smith-waterman-fpga-module_b200")
+for name, nq, ql, ns, sl, seed in (("c2", 1, 128, 499, 128, 1), ("p1", 1, 32, 1, 128, 3)):
+    q = pkg.random_packed_db(nq, ql, seed); db = pkg.random_packed_db(ns, sl, seed + 1)
+    open(f"/tmp/{name}_q.fa", "w").write("".join(f">q{i}\n{seqio.unpack_to_str(q[0], ql, int(o))}\n" for i, o in enumerate(q[2])))
+    open(f"/tmp/{name}_l.fa", "w").write("".join(f">s{i}\n{seqio.unpack_to_str(db[0], sl, int(o))}\n" for i, o in enumerate(db[2])))
+PY
+for n in c2 p1; do
+  timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none -c 70 --csv --log-file gpurun_out/ncu_lat_$n.csv bin/sw_b200_latency -q /tmp/${n}_q.fa -l /tmp/${n}_l.fa -n 10 > gpurun_out/ncu_lat_$n.log 2>&1
+  tail -4 gpurun_out/ncu_lat_$n.csv
 done
-cat gpurun_out/ab.jsonl

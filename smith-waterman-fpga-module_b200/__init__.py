@@ -110,6 +110,8 @@ def load_library():
     L.sw_jit_is_available.restype = i32
     L.sw_jit_compile_check.argtypes = [C.c_char_p, i32, i32, C.c_char_p, sz]
     L.sw_set_small_batch_path.argtypes = [vp, i32]
+    L.sw_set_small_batch_timing.argtypes = [vp, i32]
+    L.sw_set_wave_mode.argtypes = [vp, i32]
     L.sw_get_stats.argtypes = [vp, C.POINTER(SwStats)]
     L.sw_params_in_exact_domain.argtypes = [C.POINTER(SwParams)]
     L.sw_device_count.restype = i32
@@ -249,6 +251,10 @@ class Engine:
 
     def set_jit(self, mode):
         self._check(self.lib.sw_set_jit(self.h, mode))
+
+    def set_wave_mode(self, mode):
+        """Band-pipelined kernel for few long pairs: 0 never, 1 automatic, 2 whenever possible."""
+        self._check(self.lib.sw_set_wave_mode(self.h, mode))
 
     def set_small_batch_path(self, enable):
         self._check(self.lib.sw_set_small_batch_path(self.h, int(bool(enable))))

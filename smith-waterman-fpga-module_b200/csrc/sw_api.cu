@@ -99,6 +99,14 @@ struct DevBuf {
 
 struct QueryChunk { int q0, q1; cudaEvent_t done; };
 
+// A length group of the sorted pair list: pairs [p0, p1) (p0 a multiple of 32), subjects at most
+// max_len long.  The bank's arbitration (PrioEncoder.v:18-21 + SM_Feeder2.v:104-205) hands every
+// target to the first free module; here every length group gets its own launch, kernel variant and
+// pass-boundary scratch, so one very long subject does not size the scratch of every block.
+struct Seg { uint32_t p0, p1, max_len; uint64_t sum_len; };
+
+constexpr int kStreams = 4;              // concurrent launch streams per GPU (the compute stream + 3)
+
 constexpr unsigned kOvfCap = 1u << 20;   // entries of the 16-bit-overflow side list
 
 // Everything that belongs to one database batch on one GPU.  Two slots per GPU: while the
@@ -116,6 +124,8 @@ struct Slot {
     std::vector<QueryChunk> chunks;
     std::vector<uint32_t> order, hist; // host scratch of the length sort (capacity is kept)
     std::vector<uint32_t> empties;     // first few zero-length subjects (they score 0; top-k fill)
+    std::vector<Seg> segs;             // length groups of the sorted pair list (launch planning)
+    std::vector<int> qidx_host;        // query lists of the last launch plan (source of an async upload)
     bool scored = false;
     bool ovf_used = false;
     int out_mode = SW_OUT_I32;         // of the last scoring
@@ -132,11 +142,16 @@ struct GpuCtx {
     int dev = 0;
     int num_sms = 0;
     cudaStream_t st_compute = nullptr, st_copy = nullptr;
+    cudaStream_t st_aux[kStreams - 1] = {nullptr, nullptr, nullptr};   // launches of a plan run concurrently
+    cudaEvent_t ev_fork = nullptr, ev_join[kStreams - 1] = {nullptr, nullptr, nullptr};
+    DevBuf d_bnd_aux[kStreams - 1];
     // queries
     DevBuf d_qpacked, d_qoff, d_qlen, d_qidx;
     Slot slot[2];
     // scratch shared by both slots (kernels of one GPU run in stream order)
     DevBuf d_bnd, d_counters, d_scratch32, d_best_score, d_best_index, d_topk_keys, d_err;
+    DevBuf d_wave_bnd, d_wave_state;  // band-pipelined kernel: boundary rows; progress / best / done words
+    int wave_bps = 0;                 // its resident blocks per SM (0 = not asked yet)
     unsigned counter_next = 0;        // next unused work-queue counter
     // autotune: timing events and the cached decision, per GPU (shards differ in shape)
     cudaEvent_t ev_tune0 = nullptr, ev_tune1 = nullptr;
@@ -180,6 +195,7 @@ struct sw_handle {
     bool small_path = true;
     bool small_timing = true;         // record CUDA events around the latency path's kernel (sw_last_kernel_ms)
     int jit = 1;                      // run-time specialisation of gap penalties: 0 off, 1 large jobs, 2 always
+    int wave = 1;                     // band-pipelined kernel for few long pairs: 0 off, 1 automatic, 2 whenever possible
     // bookkeeping
     std::atomic<int> last_cuda{0};    // written by the per-GPU worker threads as well
     std::atomic<uint64_t> launches{0};
@@ -231,7 +247,8 @@ SwScoring scoring_of(const sw_handle *h)
 std::vector<DevBuf *> all_devbufs(GpuCtx &g)
 {
     std::vector<DevBuf *> v = {&g.d_qpacked, &g.d_qoff, &g.d_qlen, &g.d_qidx, &g.d_bnd, &g.d_counters, &g.d_scratch32,
-                               &g.d_best_score, &g.d_best_index, &g.d_topk_keys, &g.d_err};
+                               &g.d_best_score, &g.d_best_index, &g.d_topk_keys, &g.d_err, &g.d_wave_bnd, &g.d_wave_state,
+                               &g.d_bnd_aux[0], &g.d_bnd_aux[1], &g.d_bnd_aux[2]};
     for (Slot &b : g.slot) {
         DevBuf *bufs[] = {&b.d_raw, &b.d_off, &b.d_len, &b.d_pair_subj, &b.d_pair_len, &b.d_tile_woff, &b.d_tp, &b.d_out,
                           &b.d_ovf_count, &b.d_ovf_list, &b.d_ovf_score, &b.d_topk_out, &b.d_small_in, &b.d_small_done};
@@ -255,6 +272,9 @@ void free_gpu(GpuCtx &g)
         if (b.ev_stop) cudaEventDestroy(b.ev_stop);
         if (b.ev_upload) cudaEventDestroy(b.ev_upload);
     }
+    for (cudaStream_t st : g.st_aux) if (st) cudaStreamDestroy(st);
+    if (g.ev_fork) cudaEventDestroy(g.ev_fork);
+    for (cudaEvent_t e : g.ev_join) if (e) cudaEventDestroy(e);
     if (g.ev_tune0) cudaEventDestroy(g.ev_tune0);
     if (g.ev_tune1) cudaEventDestroy(g.ev_tune1);
     if (g.st_compute) cudaStreamDestroy(g.st_compute);
@@ -320,6 +340,31 @@ size_t make_pairs(const Slot &g, const uint32_t *ln, size_t n, uint32_t *pair_su
     return np;
 }
 
+// Length groups: from the longest pair down, a group ends where the length has halved (boundaries on
+// 32-pair tiles); at most 16 groups.
+void build_segments(Slot &g, const uint32_t *pair_len, size_t np)
+{
+    g.segs.clear();
+    size_t hi = np;
+    while (hi > 0 && g.segs.size() < 15) {
+        const uint32_t lmax = pair_len[2 * (hi - 1)];
+        size_t lo = hi;
+        // first pair (ascending order) longer than lmax / 2, by binary search
+        size_t a = 0, b = hi;
+        while (a < b) { const size_t mid = (a + b) / 2; if (pair_len[2 * mid] * 2u > lmax) b = mid; else a = mid + 1; }
+        lo = a & ~(size_t)31;
+        Seg sg{(uint32_t)lo, (uint32_t)hi, lmax, 0};
+        for (size_t p = lo; p < hi; ++p) sg.sum_len += (uint64_t)pair_len[2 * p] + pair_len[2 * p + 1];
+        g.segs.push_back(sg);
+        hi = lo;
+    }
+    if (hi > 0) {
+        Seg sg{0, (uint32_t)hi, pair_len[2 * (hi - 1)], 0};
+        for (size_t p = 0; p < hi; ++p) sg.sum_len += (uint64_t)pair_len[2 * p] + pair_len[2 * p + 1];
+        g.segs.push_back(sg);
+    }
+}
+
 // Length-sorts the shard's subjects, pairs neighbours in length order, lays out 32-pair tiles, uploads.
 int load_shard(sw_handle *h, GpuCtx &gc, Slot &g, const uint8_t *packed, const uint32_t *len, const uint64_t *off)
 {
@@ -364,6 +409,7 @@ int load_shard(sw_handle *h, GpuCtx &gc, Slot &g, const uint8_t *packed, const u
     tile_woff[ntiles] = w;
     g.npairs = (uint32_t)np;
     g.tp_words = w;
+    build_segments(g, pair_len, np);
 
     // --- local byte offsets
     SW_CUDA(h, g.h_stage_d.reserve(n * sizeof(uint64_t)));
@@ -507,7 +553,7 @@ int cached_occupancy(sw_handle *h, GpuCtx &gc, int vidx, int chunk_passes, int *
 
 // Launch geometry of a strip variant for `npairs` pairs with subjects up to max_len and queries up to
 // maxq rows; also grows the pass-boundary scratch.
-int strip_setup(sw_handle *h, GpuCtx &gc, uint32_t npairs, uint32_t max_len, uint32_t maxq, int vidx, int *grid,
+int strip_setup(sw_handle *h, GpuCtx &gc, DevBuf &bnd_buf, uint32_t npairs, uint32_t max_len, uint32_t maxq, int vidx, int *grid,
                 int *chunk_passes, size_t *bnd_elems)
 {
     const SwStripVariant *v = sw_strip_variant(vidx);
@@ -532,7 +578,12 @@ int strip_setup(sw_handle *h, GpuCtx &gc, uint32_t npairs, uint32_t max_len, uin
         const size_t budget = (size_t)16 << 30;
         if (per_block > budget) return SW_ENOMEM;
         *grid = (int)std::min<size_t>((size_t)*grid, std::max<size_t>(1, budget / per_block));
-        SW_CUDA(h, gc.d_bnd.reserve((size_t)*grid * per_block));
+        // (a buffer shared by the launches of one stream only ever grows: earlier launches keep fitting)
+        if (bnd_buf.cap < (size_t)*grid * per_block) {
+            SW_CUDA(h, cudaStreamSynchronize(gc.st_compute));
+            for (cudaStream_t st : gc.st_aux) if (st) SW_CUDA(h, cudaStreamSynchronize(st));
+            SW_CUDA(h, bnd_buf.reserve((size_t)*grid * per_block));
+        }
         *bnd_elems = (size_t)*grid * per_block / sizeof(uint2);
     }
     return SW_OK;
@@ -573,7 +624,7 @@ int autotune_variant(sw_handle *h, GpuCtx &gc, Slot &g, SwStripLaunch base, cons
     float best_ms = 0.f;
     for (int c = 0; c < ncand; ++c) {
         base.vidx = ranked[c];
-        int rc = strip_setup(h, gc, base.db.npairs, g.max_len, h->q_max_len, base.vidx, &base.grid, &base.chunk_passes, &base.bnd_elems);
+        int rc = strip_setup(h, gc, gc.d_bnd, base.db.npairs, g.max_len, h->q_max_len, base.vidx, &base.grid, &base.chunk_passes, &base.bnd_elems);
         if (rc != SW_OK) return rc;
         base.bnd = gc.d_bnd.as<uint2>();
         float ms = 0.f;
@@ -650,46 +701,40 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
     const bool may_overflow = !sc.limit && (smax + (uint64_t)sc.match >= 32000ull);
     SW_CUDA(h, gc.d_counters.reserve(kMaxCounters * sizeof(unsigned)));
 
-    // ---- which variant for which query -------------------------------------------------------
-    std::vector<QueryGroup> groups;
-    std::vector<int> ranked;
-    int vall = -1;
-    if (!h->force32) {
-        vall = choose_variant(h, gc, g, h->q_len.data(), h->q_len.size(), h->q_max_len, &ranked);
-        if (vall < 0) return SW_EINVAL;
-        if (variant_forced(h) || nq == 1) {
-            groups.push_back({vall, {}, h->q_sum_len});
-        } else {
-            // per query: the variant whose pass height fits its length best.  Small groups are folded
-            // into the overall choice (every launch has its own tail).
-            std::map<int, QueryGroup> by_variant;
-            for (int q = 0; q < nq; ++q) {
-                const uint32_t ql = h->q_len[q];
-                const int v = choose_variant(h, gc, g, &ql, 1, ql);
-                QueryGroup &gr = by_variant[v];
-                gr.vidx = v; gr.q.push_back(q); gr.rows += ql;
+    // ---- few, long pairs: the bands of a long query become concurrent work items (sw_wave.cuh) ----
+    std::vector<int> wave_q, strip_q;
+    {
+        const bool wave_ok = h->wave && !topk && !sc.limit && !h->force32 && !variant_forced(h);
+        for (int q = 0; q < nq; ++q) {
+            const uint32_t ql = h->q_len[q];
+            bool w = false;
+            if (wave_ok && ql > SW_WAVE_ROWS_PER_BAND) {
+                if (h->wave >= 2) w = true;
+                else w = (g.npairs <= 1536 && ql >= 2 * SW_WAVE_ROWS_PER_BAND) || g.npairs <= 64;
             }
-            QueryGroup rest{vall, {}, 0};
-            for (auto &kv : by_variant) {
-                QueryGroup &gr = kv.second;
-                const double est_ms = (double)g.sum_len * (double)gr.rows / 6.0e9;
-                if (gr.vidx == vall || est_ms < 5.0 || (double)gr.rows < 0.03 * (double)h->q_sum_len) {
-                    rest.q.insert(rest.q.end(), gr.q.begin(), gr.q.end());
-                    rest.rows += gr.rows;
-                } else {
-                    groups.push_back(gr);
-                }
-            }
-            if (!rest.q.empty()) { std::sort(rest.q.begin(), rest.q.end()); groups.push_back(rest); }
-            if (groups.size() == 1) groups[0].q.clear();      // all queries, contiguous
+            (w ? wave_q : strip_q).push_back(q);
         }
     }
-    const bool single_group = groups.size() == 1 && groups[0].q.empty();
+
+    // ---- launch plan ---------------------------------------------------------------------------
+    // Simple case (one length group, every query on one variant -- the bulk case, config 3): query
+    // chunks on the compute stream, D2H of finished rows overlapping the next chunk, the model's top
+    // candidates timed on a sample.  General case: every (length group, query group) gets its own
+    // launch and variant; launches run on several streams so that the tail of one overlaps the
+    // start of the next, longest work items first.
+    struct Planned { SwStripLaunch L; int q0, q1; int stream; double item_s; };
+    std::vector<Planned> plan;
+    std::vector<int> &qidx_host = g.qidx_host;     // stays alive until this slot is scored again
+    qidx_host.clear();
+    std::vector<int> ranked;
+    int max_grid = 0;
+    bool simple = false, jit_used = false;
+    int label_v = -1;
+    size_t n_groups_total = 0;
 
     SwStripLaunch base;
     base.db = db; base.q = dq; base.sc = sc;
     base.out = topk ? nullptr : g.d_out.p; base.out_stride = n; base.out_elems = (size_t)nq * n; base.out_mode = g.out_mode;
-    base.bnd_cols = g.max_len;
     base.dev_err = gc.d_err.as<unsigned>();
     if (may_overflow) {
         SW_CUDA(h, g.d_ovf_count.reserve(sizeof(unsigned)));
@@ -699,89 +744,199 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
         base.ovf_count = g.d_ovf_count.as<unsigned>(); base.ovf_list = g.d_ovf_list.as<uint2>(); base.ovf_cap = kOvfCap;
         g.ovf_used = true;
     }
-    // large jobs: let the GPU pick among the model's top candidates (decision cached per workload shape)
-    const double est_ms_all = (double)g.sum_len * (double)h->q_sum_len / 6.0e9;
-    if (single_group && !topk && h->autotune && !variant_forced(h) && est_ms_all >= 400.0 && ranked.size() > 1) {
-        uint64_t key = 1469598103934665603ull;
-        auto log2b = [](uint64_t x) { uint64_t b = 0; while (x >>= 1) ++b; return b; };
-        const uint64_t parts[] = {h->q_max_len, h->q_sum_len, (uint64_t)nq, g.max_len, log2b(g.npairs), log2b(g.sum_len),
-                                  (uint64_t)(uint16_t)h->params.match, (uint64_t)(uint16_t)h->params.mismatch,
-                                  (uint64_t)(uint16_t)h->params.gap_open, (uint64_t)(uint16_t)h->params.gap_extend,
-                                  (uint64_t)h->params.score_width, (uint64_t)g.out_mode};
-        for (uint64_t x : parts) { key ^= x; key *= 1099511628211ull; }
-        if (gc.tune_key != key || gc.tune_choice < 0) {
-            int choice = vall;
-            rc = autotune_variant(h, gc, g, base, ranked, nq, &choice);
-            if (rc != SW_OK) return rc;
-            gc.tune_choice = choice;
-            gc.tune_key = key;
-        }
-        groups[0].vidx = gc.tune_choice;
-    }
 
-    // ---- launch plan --------------------------------------------------------------------------
-    struct Planned { SwStripLaunch L; int q0, q1; };
-    std::vector<Planned> plan;
-    std::vector<int> qidx_host;
-    int max_grid = 0;
-    if (!groups.empty()) {
-        size_t total_idx = 0;
-        for (auto &gr : groups) total_idx += gr.q.size();
-        if (total_idx) SW_CUDA(h, gc.d_qidx.reserve(total_idx * sizeof(int)));
-        size_t idx_off = 0;
-        size_t big = 0;
-        for (size_t gi = 0; gi < groups.size(); ++gi) {
-            QueryGroup &gr = groups[gi];
-            const bool all = gr.q.empty();
-            const int gq = all ? nq : (int)gr.q.size();
-            uint32_t gmaxq = 0;
-            if (all) { gmaxq = h->q_max_len; gr.rows = h->q_sum_len; }
-            else for (int q : gr.q) gmaxq = std::max(gmaxq, h->q_len[q]);
-            if (gr.rows > groups[big].rows) big = gi;
+    if (!h->force32 && !strip_q.empty()) {
+        std::vector<uint32_t> sl;
+        uint32_t smaxq = 0;
+        uint64_t srows = 0;
+        for (int q : strip_q) { sl.push_back(h->q_len[q]); smaxq = std::max(smaxq, h->q_len[q]); srows += h->q_len[q]; }
+        const bool all_strip = (int)strip_q.size() == nq;
+        const bool same_len = std::all_of(sl.begin(), sl.end(), [&](uint32_t x) { return x == sl[0]; });
+        std::vector<Seg> segs = g.segs;
+        if (segs.empty() || variant_forced(h)) segs.assign(1, Seg{0, g.npairs, g.max_len, g.sum_len});
+        simple = all_strip && segs.size() == 1 && (variant_forced(h) || same_len || strip_q.size() == 1);
+
+        if (simple) {
+            int vidx = choose_variant(h, gc, g, sl.data(), sl.size(), smaxq, &ranked);
+            if (vidx < 0) return SW_EINVAL;
+            // large jobs: let the GPU pick among the model's top candidates (decision cached per workload shape)
+            const double est_ms_all = (double)g.sum_len * (double)srows / 6.0e9;
+            base.bnd_cols = g.max_len;
+            if (!topk && h->autotune && !variant_forced(h) && est_ms_all >= 400.0 && ranked.size() > 1) {
+                uint64_t key = 1469598103934665603ull;
+                auto log2b = [](uint64_t x) { uint64_t b = 0; while (x >>= 1) ++b; return b; };
+                const uint64_t parts[] = {h->q_max_len, h->q_sum_len, (uint64_t)nq, g.max_len, log2b(g.npairs), log2b(g.sum_len),
+                                          (uint64_t)(uint16_t)h->params.match, (uint64_t)(uint16_t)h->params.mismatch,
+                                          (uint64_t)(uint16_t)h->params.gap_open, (uint64_t)(uint16_t)h->params.gap_extend,
+                                          (uint64_t)h->params.score_width, (uint64_t)g.out_mode};
+                for (uint64_t x : parts) { key ^= x; key *= 1099511628211ull; }
+                if (gc.tune_key != key || gc.tune_choice < 0) {
+                    int choice = vidx;
+                    rc = autotune_variant(h, gc, g, base, ranked, nq, &choice);
+                    if (rc != SW_OK) return rc;
+                    gc.tune_choice = choice;
+                    gc.tune_key = key;
+                }
+                vidx = gc.tune_choice;
+            }
             SwStripLaunch L = base;
-            L.vidx = gr.vidx;
-            rc = strip_setup(h, gc, g.npairs, g.max_len, gmaxq, gr.vidx, &L.grid, &L.chunk_passes, &L.bnd_elems);
+            L.vidx = vidx;
+            rc = strip_setup(h, gc, gc.d_bnd, g.npairs, g.max_len, smaxq, vidx, &L.grid, &L.chunk_passes, &L.bnd_elems);
             if (rc != SW_OK) return rc;
-            max_grid = std::max(max_grid, L.grid);
-            // run-time specialisation of the gap penalties for jobs that are worth a compile
-            const double est_ms = (double)g.sum_len * (double)gr.rows / 6.0e9;
-            if (h->jit && !sc.limit && (est_ms >= 2000.0 || h->jit >= 2) && std::strcmp(sw_strip_instance_kind(L), "runtime") == 0)
-                L.jit_kernel = sw_jit_strip_kernel(sw_strip_variant(gr.vidx), sc.goe, sc.ge, nullptr, 0);
+            max_grid = L.grid;
+            label_v = vidx;
+            n_groups_total = 1;
+            if (h->jit && !sc.limit && (est_ms_all >= 2000.0 || h->jit >= 2) && std::strcmp(sw_strip_instance_kind(L), "runtime") == 0) {
+                L.jit_kernel = sw_jit_strip_kernel(sw_strip_variant(vidx), sc.goe, sc.ge, nullptr, 0);
+                jit_used = L.jit_kernel != nullptr;
+            }
             // query chunks: a handful of launches so that D2H of finished rows overlaps compute
             // (each launch has its own tail: aim for >= ~50 ms of work per launch, at ~6 TCUPS)
-            int nchunks = std::max(1, std::min(std::min(gq, 8), (int)(est_ms / 50.0)));
-            if (!single_group || topk || may_overflow) nchunks = 1;
+            int nchunks = std::max(1, std::min(std::min(nq, 8), (int)(est_ms_all / 50.0)));
+            if (topk || may_overflow || !wave_q.empty()) nchunks = 1;
             // the device work counter is 32-bit: (pair blocks) x (queries per launch) must stay below 2^31
-            while (nchunks < gq && (uint64_t)(g.npairs / 4 + 1) * (uint64_t)((gq + nchunks - 1) / nchunks) >= (1ull << 31)) nchunks *= 2;
-            nchunks = std::min(nchunks, gq);
-            if (!all) qidx_host.insert(qidx_host.end(), gr.q.begin(), gr.q.end());
+            while (nchunks < nq && (uint64_t)(g.npairs / 4 + 1) * (uint64_t)((nq + nchunks - 1) / nchunks) >= (1ull << 31)) nchunks *= 2;
+            nchunks = std::min(nchunks, nq);
             for (int c = 0; c < nchunks; ++c) {
-                const int a0 = (int)((long long)gq * c / nchunks), a1 = (int)((long long)gq * (c + 1) / nchunks);
+                const int a0 = (int)((long long)nq * c / nchunks), a1 = (int)((long long)nq * (c + 1) / nchunks);
                 if (a1 <= a0) continue;
-                Planned p{L, a0, a1};
-                p.L.nql = a1 - a0;
-                if (all) { p.L.q0 = a0; p.L.qidx = nullptr; }
-                else { p.L.q0 = 0; p.L.qidx = gc.d_qidx.as<int>() + idx_off + a0; }
+                Planned p{L, a0, a1, 0, 0.0};
+                p.L.q0 = a0; p.L.nql = a1 - a0; p.L.qidx = nullptr;
                 plan.push_back(p);
             }
-            if (!all) idx_off += gr.q.size();
-        }
-        if (!qidx_host.empty()) {
+        } else {
+            // lanes needed to keep the GPU busy decide the least lanes per pair; the time budget of a
+            // single work item decides when a length group needs more lanes per pair than that
+            const double fill = (double)gc.num_sms * 3 * 128;
+            int gmin = 1;
+            while (gmin < 32 && (double)g.npairs * gmin < 0.6 * fill) gmin *= 2;
+            const double t_total = (double)g.sum_len * (double)srows / 8.0e12;          // seconds, optimistic
+            const double tau = std::max(0.5 * t_total, 1.0e-3);      // the longest items start first
+            const int nv = sw_strip_variant_count();
+            auto pick = [&](const Seg &sg, const uint32_t *ql, size_t nql, uint32_t maxq, double *item_s) {
+                int best = -1, best_any = -1;
+                double best_thr = 0, best_any_cost = 0, best_item = 0, best_any_item = 0;
+                const double cols_avg = std::max(1.0, (double)sg.sum_len / (2.0 * std::max<uint32_t>(sg.p1 - sg.p0, 1)));
+                for (int i = 0; i < nv; ++i) {
+                    const SwStripVariant *v = sw_strip_variant(i);
+                    if (v->U != 4) continue;                                     // experimental instances: by name only
+                    const int P = v->R * v->G, vpe = v->G * v->S;
+                    double rows = 0;
+                    for (size_t k = 0; k < nql; ++k) rows += (double)((ql[k] + P - 1) / P) * P;
+                    const double speed = variant_speed(v) * 1e9;
+                    const double thr = rows * (double)sg.sum_len * (cols_avg + vpe - 1) / cols_avg / speed;
+                    const double qrows = (double)((maxq + P - 1) / P) * P;
+                    const int ppb = v->block_threads / v->G;
+                    const double item = qrows * ((double)sg.max_len + vpe - 1) * 2.0 * ppb * ((double)gc.num_sms * v->min_blocks) / speed;
+                    const double any_cost = thr + item + (v->G < gmin ? 10.0 * thr : 0.0);
+                    if (best_any < 0 || any_cost < best_any_cost) { best_any = i; best_any_cost = any_cost; best_any_item = item; }
+                    if (v->G < gmin || item > tau) continue;
+                    if (best < 0 || thr < best_thr) { best = i; best_thr = thr; best_item = item; }
+                }
+                *item_s = best >= 0 ? best_item : best_any_item;
+                return best >= 0 ? best : best_any;
+            };
+            std::map<int, uint64_t> rows_by_variant;
+            for (const Seg &sg : segs) {
+                if (sg.p1 <= sg.p0) continue;
+                // queries of this length group, grouped by the variant that suits them
+                std::map<int, std::vector<int>> by_variant;
+                std::map<int, double> item_of;
+                for (int q : strip_q) {
+                    const uint32_t ql = h->q_len[q];
+                    double it = 0;
+                    const int v = pick(sg, &ql, 1, ql, &it);
+                    by_variant[v].push_back(q);
+                    item_of[v] = std::max(item_of[v], it);
+                }
+                // fold small groups into the largest one of this length group (every launch has a tail)
+                int big = -1;
+                uint64_t big_rows = 0, all_rows = 0;
+                std::map<int, uint64_t> vrows;
+                for (auto &kv : by_variant) {
+                    uint64_t r = 0;
+                    for (int q : kv.second) r += h->q_len[q];
+                    vrows[kv.first] = r;
+                    all_rows += r;
+                    if (r >= big_rows) { big_rows = r; big = kv.first; }
+                }
+                for (auto it = by_variant.begin(); it != by_variant.end();) {
+                    const double ms = (double)sg.sum_len * (double)vrows[it->first] / 8.0e9;
+                    if (it->first != big && (ms < 2.0 || (double)vrows[it->first] < 0.03 * (double)all_rows)) {
+                        std::vector<int> &dst = by_variant[big];
+                        dst.insert(dst.end(), it->second.begin(), it->second.end());
+                        vrows[big] += vrows[it->first];
+                        it = by_variant.erase(it);
+                    } else {
+                        ++it;
+                    }
+                }
+                for (auto &kv : by_variant) {
+                    std::vector<int> &ql = kv.second;
+                    std::sort(ql.begin(), ql.end());
+                    uint32_t gmaxq = 0;
+                    for (int q : ql) gmaxq = std::max(gmaxq, h->q_len[q]);
+                    Planned p{base, 0, 0, 0, item_of[kv.first]};
+                    SwStripLaunch &L = p.L;
+                    L.vidx = kv.first;
+                    // this length group's window of the pair list
+                    L.db.pair_subj = db.pair_subj + 2 * (size_t)sg.p0;
+                    L.db.pair_len = db.pair_len + 2 * (size_t)sg.p0;
+                    L.db.tile_woff = db.tile_woff + sg.p0 / 32;
+                    L.db.npairs = sg.p1 - sg.p0;
+                    L.db.max_len = sg.max_len;
+                    L.bnd_cols = sg.max_len;
+                    L.q0 = 0; L.nql = (int)ql.size();
+                    L.qidx = (const int *)(uintptr_t)qidx_host.size();          // offset for now, pointer after the upload
+                    qidx_host.insert(qidx_host.end(), ql.begin(), ql.end());
+                    rows_by_variant[kv.first] += vrows[kv.first] * (sg.sum_len >> 8);
+                    plan.push_back(p);
+                    ++n_groups_total;
+                }
+            }
+            // longest work items first, round-robin over the streams
+            std::stable_sort(plan.begin(), plan.end(), [](const Planned &x, const Planned &y) { return x.item_s > y.item_s; });
+            const int ns_used = topk ? 1 : kStreams;       // top-k lists are per block index: one kernel at a time
+            for (size_t i = 0; i < plan.size(); ++i) plan[i].stream = (int)(i % ns_used);
+            SW_CUDA(h, gc.d_qidx.reserve(std::max<size_t>(1, qidx_host.size()) * sizeof(int)));
+            for (Planned &p : plan) {
+                SwStripLaunch &L = p.L;
+                const size_t off = (size_t)(uintptr_t)L.qidx;
+                L.qidx = gc.d_qidx.as<int>() + off;
+                uint32_t gmaxq = 0;
+                for (int k = 0; k < L.nql; ++k) gmaxq = std::max(gmaxq, h->q_len[qidx_host[off + k]]);
+                DevBuf &bb = p.stream == 0 ? gc.d_bnd : gc.d_bnd_aux[p.stream - 1];
+                rc = strip_setup(h, gc, bb, L.db.npairs, L.db.max_len, gmaxq, L.vidx, &L.grid, &L.chunk_passes, &L.bnd_elems);
+                if (rc != SW_OK) return rc;
+                // more work items than the 32-bit work counter can address: does not happen per length group
+                max_grid = std::max(max_grid, L.grid);
+                if (h->jit >= 2 && !sc.limit && std::strcmp(sw_strip_instance_kind(L), "runtime") == 0) {
+                    L.jit_kernel = sw_jit_strip_kernel(sw_strip_variant(L.vidx), sc.goe, sc.ge, nullptr, 0);
+                    jit_used |= L.jit_kernel != nullptr;
+                }
+            }
+            uint64_t lr = 0;
+            for (auto &kv : rows_by_variant) if (kv.second >= lr) { lr = kv.second; label_v = kv.first; }
             SW_CUDA(h, cudaMemcpyAsync(gc.d_qidx.p, qidx_host.data(), qidx_host.size() * sizeof(int), cudaMemcpyHostToDevice, gc.st_compute));
-            SW_CUDA(h, cudaStreamSynchronize(gc.st_compute));      // qidx_host is a local
         }
-        // label: the variant that does most of the work
-        bool jit_used = false;
-        for (auto &p : plan) if (p.L.vidx == groups[big].vidx && p.L.jit_kernel) jit_used = true;
-        if (&gc == &h->gpus[0])      // one writer: the per-GPU workers run concurrently
-            std::snprintf(h->last_kernel, sizeof h->last_kernel, "%s%s%s", sw_strip_variant(groups[big].vidx)->name,
-                          jit_used ? "+jit" : "", groups.size() > 1 ? "+groups" : "");
-    } else if (&gc == &h->gpus[0]) {
-        std::snprintf(h->last_kernel, sizeof h->last_kernel, "generic32");
     }
+    if (&gc == &h->gpus[0]) {      // one writer: the per-GPU workers run concurrently
+        if (label_v >= 0)
+            std::snprintf(h->last_kernel, sizeof h->last_kernel, "%s%s%s", sw_strip_variant(label_v)->name, jit_used ? "+jit" : "",
+                          n_groups_total > 1 ? "+groups" : "");
+        else
+            std::snprintf(h->last_kernel, sizeof h->last_kernel, "%s", wave_q.empty() ? "generic32" : sw_wave_kernel_name());
+        if (!wave_q.empty() && label_v >= 0) {
+            uint64_t wrows = 0;
+            for (int q : wave_q) wrows += h->q_len[q];
+            if (2 * wrows > h->q_sum_len) std::snprintf(h->last_kernel, sizeof h->last_kernel, "%s+groups", sw_wave_kernel_name());
+        }
+    }
+    const bool have_strip = !plan.empty();
 
+    const bool use32 = !have_strip && wave_q.empty();        // forced 32-bit scorer
     if (topk) {
-        if (groups.empty()) return SW_EINVAL;                 // the 32-bit scorer has no top-k epilogue
+        if (!have_strip) return SW_EINVAL;                    // the 32-bit scorer has no top-k epilogue
         const size_t bytes = (size_t)max_grid * nq * g.topk_k * sizeof(unsigned long long);
         SW_CUDA(h, gc.d_topk_keys.reserve(bytes));
         SW_CUDA(h, cudaMemsetAsync(gc.d_topk_keys.p, 0, bytes, gc.st_compute));
@@ -790,10 +945,10 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
     // 32-bit scratch (force32, or the overflow fix-up of the few listed pairs)
     const uint32_t max_cols = std::max<uint32_t>(1, std::min<uint32_t>(h->q_max_len, g.max_len));
     int threads32 = 0;
-    if (groups.empty() || may_overflow) {
+    if (use32 || may_overflow) {
         const size_t budget = (size_t)1 << 30;
         size_t t = budget / ((size_t)2 * max_cols * sizeof(int32_t));
-        t = std::min<size_t>(t, groups.empty() ? (size_t)gc.num_sms * 2 * 128 : 4096);
+        t = std::min<size_t>(t, use32 ? (size_t)gc.num_sms * 2 * 128 : 4096);
         t = std::max<size_t>(128, t / 128 * 128);
         threads32 = (int)t;
         SW_CUDA(h, gc.d_scratch32.reserve((size_t)2 * max_cols * threads32 * sizeof(int32_t)));
@@ -803,21 +958,70 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
     s32.scratch = gc.d_scratch32.as<int32_t>(); s32.max_cols = max_cols; s32.threads_total = threads32;
 
     size_t nev = 0;
-    if (!groups.empty()) {
-        const bool chunk_events = single_group && plan.size() > 1 && !may_overflow && !topk;
+    if (!use32) {
+        const bool chunk_events = simple && plan.size() > 1 && !may_overflow && !topk;
+        bool forked[kStreams] = {false, false, false, false};
         for (size_t i = 0; i < plan.size(); ++i) {
             Planned &p = plan[i];
-            p.L.bnd = gc.d_bnd.as<uint2>();
+            cudaStream_t st = gc.st_compute;
+            if (p.stream > 0) {
+                st = gc.st_aux[p.stream - 1];
+                if (!forked[p.stream]) {
+                    // the side streams start after everything queued on the compute stream so far
+                    // (output memset, query lists, an earlier batch's kernels)
+                    if (!forked[0]) { SW_CUDA(h, cudaEventRecord(gc.ev_fork, gc.st_compute)); forked[0] = true; }
+                    SW_CUDA(h, cudaStreamWaitEvent(st, gc.ev_fork, 0));
+                    forked[p.stream] = true;
+                }
+            }
+            p.L.bnd = (p.stream == 0 ? gc.d_bnd : gc.d_bnd_aux[p.stream - 1]).as<uint2>();
             p.L.counter = next_counter(gc);
-            SW_CUDA(h, cudaMemsetAsync(p.L.counter, 0, sizeof(unsigned), gc.st_compute));
+            SW_CUDA(h, cudaMemsetAsync(p.L.counter, 0, sizeof(unsigned), st));
             if (topk) { p.L.topk_keys = gc.d_topk_keys.as<unsigned long long>(); p.L.topk_k = g.topk_k; p.L.topk_nq = nq; }
-            SW_CUDA(h, sw_launch_strip(gc.st_compute, p.L));
+            SW_CUDA(h, sw_launch_strip(st, p.L));
             h->launches++;
             if (chunk_events) {
                 QueryChunk qc{p.q0, p.q1, pool_event(h, g, nev++, &rc)};
                 if (rc != SW_OK) return rc;
                 SW_CUDA(h, cudaEventRecord(qc.done, gc.st_compute));
                 g.chunks.push_back(qc);
+            }
+        }
+        for (int k = 1; k < kStreams; ++k) {
+            if (!forked[k]) continue;
+            SW_CUDA(h, cudaEventRecord(gc.ev_join[k - 1], gc.st_aux[k - 1]));
+            SW_CUDA(h, cudaStreamWaitEvent(gc.st_compute, gc.ev_join[k - 1], 0));
+        }
+        // ---- band-pipelined launches, one per long query ----------------------------------------
+        if (!wave_q.empty()) {
+            if (!gc.wave_bps) SW_CUDA(h, sw_wave_occupancy(&gc.wave_bps));
+            if (gc.wave_bps < 1) return SW_ECUDA;
+            const uint32_t cols_stride = (g.max_len + 31u) & ~31u;
+            uint32_t wmaxq = 0;
+            for (int q : wave_q) wmaxq = std::max(wmaxq, h->q_len[q]);
+            const int max_pass = (int)((wmaxq + SW_WAVE_ROWS_PER_BAND - 1) / SW_WAVE_ROWS_PER_BAND);
+            SW_CUDA(h, gc.d_wave_bnd.reserve((size_t)g.npairs * 2 * cols_stride * sizeof(uint2)));
+            // state words: prog [npairs * max_pass] | best [2 * npairs] | done [npairs]
+            const size_t n_prog = (size_t)g.npairs * max_pass, n_state = n_prog + 3 * (size_t)g.npairs;
+            SW_CUDA(h, gc.d_wave_state.reserve(n_state * sizeof(unsigned)));
+            for (int q : wave_q) {
+                SwWaveLaunch W;
+                W.db = db; W.q = dq; W.query = q; W.sc = sc;
+                W.npass = (int)((h->q_len[q] + SW_WAVE_ROWS_PER_BAND - 1) / SW_WAVE_ROWS_PER_BAND);
+                W.out = g.d_out.p; W.out_stride = n; W.out_mode = g.out_mode;
+                W.bnd = gc.d_wave_bnd.as<uint2>(); W.cols_stride = cols_stride;
+                W.prog = gc.d_wave_state.as<unsigned>();
+                W.best = (int *)(gc.d_wave_state.as<unsigned>() + n_prog);
+                W.done = gc.d_wave_state.as<unsigned>() + n_prog + 2 * (size_t)g.npairs;
+                W.counter = next_counter(gc);
+                const size_t items = (size_t)W.npass * ((g.npairs + 3) / 4);
+                W.grid = (int)std::min<size_t>(items, (size_t)gc.num_sms * gc.wave_bps);
+                W.ovf_count = base.ovf_count; W.ovf_list = base.ovf_list; W.ovf_cap = base.ovf_cap;
+                W.dev_err = gc.d_err.as<unsigned>();
+                SW_CUDA(h, cudaMemsetAsync(gc.d_wave_state.p, 0, n_state * sizeof(unsigned), gc.st_compute));
+                SW_CUDA(h, cudaMemsetAsync(W.counter, 0, sizeof(unsigned), gc.st_compute));
+                SW_CUDA(h, sw_launch_wave(gc.st_compute, W));
+                h->launches++;
             }
         }
         if (may_overflow) {
@@ -1385,6 +1589,7 @@ int sw_init(sw_handle_t **out, const sw_params_t *p, const int *gpu_ids, int n_g
     if (const char *e = std::getenv("SW_B200_AUTOTUNE")) h->autotune = (e[0] != '0');
     if (const char *e = std::getenv("SW_B200_JIT")) h->jit = std::atoi(e);
     if (const char *e = std::getenv("SW_B200_SMALL_PATH")) h->small_path = (e[0] != '0');
+    if (const char *e = std::getenv("SW_B200_WAVE")) h->wave = std::atoi(e);
     h->gpus.resize(ids.size());
     for (size_t i = 0; i < ids.size(); ++i) {
         GpuCtx &g = h->gpus[i];
@@ -1398,6 +1603,11 @@ int sw_init(sw_handle_t **out, const sw_params_t *p, const int *gpu_ids, int n_g
         }
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g.st_compute, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g.st_copy, cudaStreamNonBlocking);
+        for (int k = 0; k < kStreams - 1; ++k) {
+            if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g.st_aux[k], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g.ev_join[k], cudaEventDisableTiming);
+        }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g.ev_fork, cudaEventDisableTiming);
         for (Slot &b : g.slot) {
             if (e == cudaSuccess) e = cudaEventCreate(&b.ev_start);
             if (e == cudaSuccess) e = cudaEventCreate(&b.ev_stop);
@@ -1711,6 +1921,13 @@ int sw_set_jit(sw_handle_t *h, int mode)
 {
     if (!h || mode < 0 || mode > 2) return SW_EINVAL;
     h->jit = mode;
+    return SW_OK;
+}
+
+int sw_set_wave_mode(sw_handle_t *h, int mode)
+{
+    if (!h || mode < 0 || mode > 2) return SW_EINVAL;
+    h->wave = mode;
     return SW_OK;
 }
 

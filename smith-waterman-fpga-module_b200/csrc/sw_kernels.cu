@@ -3,6 +3,7 @@
  * scorer / overflow fix-up, best-hit and top-k merge; the variant table and the launchers.
  */
 #include "sw_variants.h"
+#include "sw_wave.cuh"
 
 #include <stdint.h>
 
@@ -349,6 +350,49 @@ cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L)
         if (e != cudaSuccess) return e;
     }
     fn<<<L.grid, v.info.block_threads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// ---- band-pipelined kernel: 8 rows x 2 sub-strips x 32 lanes = 512 rows per band ------------------
+namespace {
+constexpr int kWaveRS = 8, kWaveS = 2, kWaveMinB = 3;
+static_assert(kWaveRS * kWaveS * 32 == SW_WAVE_ROWS_PER_BAND, "band height");
+typedef void (*WaveFn)(const WaveArgs);
+const WaveFn g_wave_fn = sw_wave_kernel<kWaveRS, kWaveS, ArithS16, kBT, kWaveMinB>;
+const WaveFn g_wave_fn_fixed = sw_wave_kernel<kWaveRS, kWaveS, ArithS16, kBT, kWaveMinB, kFixedGoe, kFixedGe>;
+constexpr size_t kWaveSmem = (size_t)32 * kWaveS * ((kWaveRS + 1) / 2) * kCodesPerRow * sizeof(uint2);
+}  // namespace
+
+const char *sw_wave_kernel_name(void) { return "wave_s16x2_R8x2_G32"; }
+
+cudaError_t sw_wave_occupancy(int *blocks_per_sm)
+{
+    cudaError_t e = cudaFuncSetAttribute((const void *)g_wave_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWaveSmem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, (const void *)g_wave_fn, kBT, kWaveSmem);
+}
+
+cudaError_t sw_launch_wave(cudaStream_t st, const SwWaveLaunch &L)
+{
+    const SwScoring &sc = L.sc;
+    if (sc.limit) return cudaErrorInvalidValue;            // exact arithmetic only
+    WaveFn fn = (!g_no_fixed && sc.goe == kFixedGoe && sc.ge == kFixedGe) ? g_wave_fn_fixed : g_wave_fn;
+    WaveArgs a{};
+    a.tp = L.db.tp; a.tile_woff = L.db.tile_woff; a.pair_len = L.db.pair_len; a.pair_subj = L.db.pair_subj;
+    a.npairs = L.db.npairs; a.npb = (L.db.npairs + 3) / 4;
+    a.qpacked = L.q.packed; a.qoff = L.q.off; a.qlen = L.q.len; a.q = L.query; a.npass = L.npass;
+    a.out = L.out; a.out_stride = L.out_stride; a.out_mode = L.out_mode;
+    a.bnd = L.bnd; a.cols_stride = L.cols_stride; a.prog = L.prog; a.best = L.best; a.done = L.done; a.counter = L.counter;
+    a.match = sc.match; a.mismatch = sc.mismatch; a.goe = sc.goe; a.ge = sc.ge;
+    a.goe2 = ((uint32_t)sc.goe & 0xFFFFu) * 0x10001u; a.ge2 = ((uint32_t)sc.ge & 0xFFFFu) * 0x10001u;
+    a.ovf_limit = 32767 - sc.match - 1;
+    a.zero = 0;
+    a.ovf_count = L.ovf_count; a.ovf_list = L.ovf_list; a.ovf_cap = L.ovf_cap;
+    a.dev_err = L.dev_err;
+    a.spin_limit = 1u << 24;
+    cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWaveSmem);
+    if (e != cudaSuccess) return e;
+    fn<<<L.grid, kBT, kWaveSmem, st>>>(a);
     return cudaGetLastError();
 }
 

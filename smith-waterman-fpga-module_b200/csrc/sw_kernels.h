@@ -108,6 +108,36 @@ cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L);
 /* name of the instance sw_launch_strip would run ("fixed" / "runtime" / "w12" / "direct" / "jit") */
 const char *sw_strip_instance_kind(const SwStripLaunch &L);
 
+/* Band-pipelined kernel for few, long pairs (sw_wave.cuh): ONE query per launch, its bands are
+ * separate work items that run concurrently on different warps.  bnd: npairs * 2 * cols_stride uint2;
+ * prog: npairs * npass words, best: 2 * npairs ints, done: npairs words -- all zeroed before the
+ * launch; counter: zeroed work-queue word. */
+#define SW_WAVE_ROWS_PER_BAND 512
+struct SwWaveLaunch {
+    SwDevDb db{};
+    SwDevQueries q{};
+    int query = 0;
+    int npass = 0;
+    SwScoring sc{};
+    void *out = nullptr;
+    size_t out_stride = 0;
+    int out_mode = SW_OUT_I32;
+    uint2 *bnd = nullptr;
+    uint32_t cols_stride = 0;
+    unsigned *prog = nullptr;
+    int *best = nullptr;
+    unsigned *done = nullptr;
+    unsigned *counter = nullptr;
+    int grid = 0;
+    unsigned *ovf_count = nullptr;
+    uint2 *ovf_list = nullptr;
+    unsigned ovf_cap = 0;
+    unsigned *dev_err = nullptr;
+};
+cudaError_t sw_wave_occupancy(int *blocks_per_sm);
+cudaError_t sw_launch_wave(cudaStream_t st, const SwWaveLaunch &L);
+const char *sw_wave_kernel_name(void);
+
 /* 32-bit kernel: any length, any score range.  scratch: 2 * max_cols * threads_total int32 where
  * max_cols = min(longest query, longest subject) (the recurrence is symmetric: the shorter sequence
  * is walked as columns).  mode 0: every (query, subject) job of q0..q1; mode 1: only matrix entries

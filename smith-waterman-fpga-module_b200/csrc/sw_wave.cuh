@@ -1,0 +1,296 @@
+/*
+ * sw_wave.cuh -- band-pipelined ("wavefront over warps") strip kernel for few, long pairs.
+ *
+ * The strip kernel gives one warp (G = 32 lanes x R rows = P rows per pass) to a pair and walks the
+ * passes of a long query one after the other, so with few pairs most of the GPU idles, and a single
+ * pair runs on a single warp.  Here the passes ("bands") of one pair are DIFFERENT work items: band
+ * b of a pair can start as soon as band b-1 has produced the first columns of its bottom row, so
+ * the bands of one pair run concurrently on different warps / SMs, staggered by a few dozen
+ * columns -- the module-chaining ports the reference left "for future use"
+ * (ScoringModule_v1.1.v:36-39, 49-54: M_in / I_in / High_in of one module fed by the outputs of
+ * another), with HBM/L2 as the wire and a progress counter as the valid signal.
+ *
+ *   work item  = (band, block of 4 pairs); items are claimed from an atomic counter in band-major
+ *                order, so the item a band waits for (same pairs, band - 1) was always claimed
+ *                earlier by a block that is resident and running: no deadlock by construction.
+ *   boundary   = bottom row (H, G) of a band, per pair and band parity: bnd[pair][band & 1][column],
+ *                written with st.cg by the last lane, published every 32 columns through
+ *                prog[pair][band] (release / acquire), read by the next band 32 columns at a time
+ *                (coalesced ld.cg by the whole warp into shared memory, one LDS per step).
+ *   result     = max over the bands: atomicMax per pair; the band that finishes last writes the score.
+ * Arithmetic, profile layout and the one-step-ahead code pipeline are those of the strip kernel
+ * (sw_strip.cuh); exact arithmetic only (the W-bit mode keeps the strip kernel).
+ */
+#ifndef SW_WAVE_CUH_
+#define SW_WAVE_CUH_
+
+#include "sw_strip.cuh"
+
+namespace swk {
+
+struct WaveArgs {
+    const uint32_t *tp;
+    const uint64_t *tile_woff;
+    const uint32_t *pair_len;
+    const uint32_t *pair_subj;
+    uint32_t npairs, npb;      // npb = ceil(npairs / 4)
+    const uint8_t *qpacked;
+    const uint32_t *qoff;
+    const uint32_t *qlen;
+    int q;                     // the query of this launch
+    int npass;                 // bands of that query
+    void *out;
+    size_t out_stride;
+    int out_mode;              // SW_OUT_I32 / SW_OUT_I16
+    uint2 *bnd;                // [pair][2][cols_stride]
+    uint32_t cols_stride;
+    unsigned *prog;            // [pair][npass]: columns of the band's bottom row that are published
+    int *best;                 // [pair][2]: running maximum of the two members, INT_MAX = 16-bit overflow
+    unsigned *done;            // [pair]: bands finished
+    unsigned *counter;
+    int match, mismatch, goe, ge;
+    uint32_t goe2, ge2;
+    int ovf_limit;
+    uint32_t zero;
+    unsigned *ovf_count;
+    uint2 *ovf_list;
+    unsigned ovf_cap;
+    unsigned *dev_err;
+    unsigned spin_limit;       // polls of a progress counter before the watchdog gives up
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// One band of one pair (one warp).  Returns the band's running maximum (K representation).
+template <int RS, int S, class AR, bool HAS_TOP, bool HAS_BOTTOM>
+__device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *prof_lane, uint2 (&s_top)[32], const uint32_t *tpp,
+                                              int ncols, const uint2 *top, uint2 *bot, const unsigned *prog_top, unsigned *prog_bot,
+                                              uint32_t goe2, uint32_t ge2, uint32_t h0, uint32_t gb2, uint32_t zero)
+{
+    constexpr int G = 32, RP = (RS + 1) / 2, VPE = G * S, U = 4;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const int lane = threadIdx.x & 31;
+    const bool head = lane == 0;
+    uint32_t best = h0;
+    uint32_t H[S][RS], Gl[S][RS];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int r = 0; r < RS; ++r) { H[s][r] = h0; Gl[s][r] = gb2; }
+    uint32_t wcur = 0, wnext = 0;
+    if (head && ncols > 0) {
+        wcur = __ldg(tpp);
+        if (ncols > 4) wnext = __ldg(tpp + 32);
+    }
+    uint32_t pub_h[S], pub_g[S], pub_t[S], hd_top[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) { pub_h[s] = h0; pub_g[s] = gb2; pub_t[s] = kPadCode; hd_top[s] = h0; }
+    if (head && ncols > 0) pub_t[0] = wcur & 255u;
+    uint2 sv[S][RP];
+    load_scores<RS, S, G>(sv, prof_lane, pub_t);
+    uint2 bcur = make_uint2(h0, gb2);
+    unsigned avail = 0;                                   // published columns of the band above (as last seen)
+    const int nsteps = ncols > 0 ? (ncols + (VPE - 1) + U - 1) / U * U : 0;
+
+#pragma unroll 1
+    for (int t2 = 0; t2 < nsteps; t2 += U) {
+        if constexpr (HAS_TOP) {
+            if ((t2 & 31) == 0 && t2 < ncols) {
+                // stage columns t2 .. t2 + 31 of the bottom row of the band above
+                const unsigned need = (unsigned)min(t2 + 32, ncols);
+                if (avail < need) {
+                    if (head) {
+                        unsigned spins = 0;
+                        while ((avail = ld_acquire_u32(prog_top)) < need) {
+                            __nanosleep(40);
+                            if (++spins > a.spin_limit) {          // watchdog: never hang the GPU
+                                if (a.dev_err) atomicOr(a.dev_err, SW_DEVERR_SPIN);
+                                avail = need;
+                                break;
+                            }
+                        }
+                    }
+                    avail = __shfl_sync(FULL, avail, 0);
+                    __syncwarp();                              // orders the other lanes' loads after the acquire
+                }
+                const int c = t2 + lane;
+                uint2 v = make_uint2(h0, gb2);
+                if (c < ncols) v = __ldcg(top + c);
+                __syncwarp();                                  // the head lane is done with the previous 32 columns
+                s_top[lane] = v;
+                __syncwarp();
+            }
+        }
+#pragma unroll
+        for (int uu = 0; uu < U; ++uu) {
+            const int t = t2 + uu;
+            const int u = uu & 3;
+            uint32_t in_h[S], in_g[S], in_t[S];
+            in_h[0] = __shfl_up_sync(FULL, pub_h[S - 1], 1, G);
+            in_g[0] = __shfl_up_sync(FULL, pub_g[S - 1], 1, G);
+            in_t[0] = __shfl_up_sync(FULL, pub_t[S - 1], 1, G);
+            if constexpr (HAS_TOP) bcur = s_top[t & 31];
+            const uint32_t wsel = (u < 3) ? wcur : wnext;
+            const uint32_t lead_t = (t + 1 < ncols) ? ((wsel >> (8 * ((u + 1) & 3))) & 255u) : (uint32_t)kPadCode;
+            in_h[0] = head ? bcur.x : in_h[0];
+            in_g[0] = head ? bcur.y : in_g[0];
+            in_t[0] = head ? lead_t : in_t[0];
+            if (u == 3) {
+                wcur = wnext;
+                const int k = (t >> 2) + 2;
+                if (head && k * 4 < ncols) wnext = __ldg(tpp + k * 32);
+                if (head && (k + 1) * 4 < ncols) prefetch_l1(tpp + (k + 1) * 32);
+            }
+#pragma unroll
+            for (int s = 1; s < S; ++s) { in_h[s] = pub_h[s - 1]; in_g[s] = pub_g[s - 1]; in_t[s] = pub_t[s - 1]; }
+            uint2 sv_next[S][RP];
+            load_scores<RS, S, G>(sv_next, prof_lane, in_t);
+            column_step_multi<RS, S, G, AR, false>(H, Gl, best, hd_top, in_g, sv, goe2, ge2, zero, 0u);
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+#pragma unroll
+                for (int k = 0; k < RP; ++k) sv[s][k] = sv_next[s][k];
+                hd_top[s] = in_h[s];
+                pub_h[s] = H[s][RS - 1]; pub_g[s] = Gl[s][RS - 1]; pub_t[s] = in_t[s];
+            }
+            if constexpr (HAS_BOTTOM) {
+                if (lane == G - 1) {
+                    const int cl = t - (VPE - 1);              // column the last virtual PE just finished
+                    if (cl >= 0 && cl < ncols) {
+                        __stcg(bot + cl, make_uint2(pub_h[S - 1], pub_g[S - 1]));
+                        if ((cl & 31) == 31 || cl == ncols - 1) st_release_u32(prog_bot, (unsigned)(cl + 1));
+                    }
+                }
+            }
+        }
+    }
+    return best;
+}
+
+template <int RS, int S, class AR, int BT, int MINB, int CGOE = 0, int CGE = 0>
+__global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
+{
+    extern __shared__ uint2 s_prof[];
+    __shared__ unsigned s_work;
+    constexpr int G = 32, R = RS * S, P = R * G, RP = (RS + 1) / 2, VPE = G * S;
+    constexpr int PASS_ENTRIES = VPE * RP * kCodesPerRow;
+    constexpr int PPB = BT / G;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    __shared__ uint2 s_top[PPB][32];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t zero = a.zero;
+    const uint32_t goe2 = CGOE ? ((uint32_t)(CGOE & 0xFFFF) * 0x10001u) : a.goe2;
+    const uint32_t ge2 = CGOE ? ((uint32_t)(CGE & 0xFFFF) * 0x10001u) : a.ge2;
+    const uint32_t gb2 = 0u;               // clamped form: boundary gap value 0
+    const uint32_t h0 = goe2;              // "H = 0" in the K = H + goe representation
+    const int q = a.q;
+    const int m = (int)a.qlen[q];
+    const uint8_t *qp = a.qpacked + a.qoff[q];
+    const unsigned nitems = (unsigned)a.npass * a.npb;
+
+    int prof_pass = -1;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_work = atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const unsigned work = s_work;
+        if (work >= nitems) break;
+        // band-major, longest pairs first inside a band
+        const int pass = (int)(work / a.npb);
+        const unsigned pb = a.npb - 1u - (work % a.npb);
+        const unsigned pair = pb * PPB + (unsigned)warp;
+        const bool valid = pair < a.npairs;
+        const int ncols = valid ? (int)a.pair_len[2 * pair] : 0;
+        const uint32_t *tpp = a.tp;
+        if (valid) tpp += a.tile_woff[pair >> 5] + (pair & 31);
+
+        if (prof_pass != pass) {
+            prof_pass = pass;
+            __syncthreads();
+            for (int idx = threadIdx.x; idx < PASS_ENTRIES; idx += BT) {
+                // layout as in the strip kernel: ((s * RP + rp) * 32 + code) * G + lane
+                const int lg = idx % G;
+                const int code = (idx / G) & (kCodesPerRow - 1);
+                if (code > kPadCode) continue;
+                const int rp = (idx / (G * kCodesPerRow)) % RP;
+                const int ss = (idx / (G * kCodesPerRow * RP)) % S;
+                const int vpe = lg * S + ss;
+                uint32_t e[2];
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    const int rr = 2 * rp + k;
+                    const int i = pass * P + vpe * RS + rr;
+                    int lo = AR::kPad, hi = AR::kPad;
+                    if (rr < RS && i < m && code < kPadCode) {
+                        const int qi = (qp[i >> 2] >> ((i & 3) * 2)) & 3;
+                        lo = (qi == (code & 3)) ? a.match : a.mismatch;   // v1.0.v:119
+                        if (code < kHiEndedCode) hi = (qi == (code >> 2)) ? a.match : a.mismatch;
+                    }
+                    e[k] = AR::pack_score(lo, hi);
+                }
+                s_prof[idx] = make_uint2(e[0], e[1]);
+            }
+            __syncthreads();
+        }
+        const uint2 *prof_lane = s_prof + lane;
+        const bool has_top = pass > 0, has_bottom = pass + 1 < a.npass;
+        const size_t prow = (size_t)pair * 2;
+        const uint2 *top = a.bnd + (prow + (size_t)((pass - 1) & 1)) * a.cols_stride;
+        uint2 *bot = a.bnd + (prow + (size_t)(pass & 1)) * a.cols_stride;
+        const unsigned *prog_top = a.prog + (size_t)pair * a.npass + (pass > 0 ? pass - 1 : 0);
+        unsigned *prog_bot = a.prog + (size_t)pair * a.npass + pass;
+
+        uint32_t best;
+        if (has_top) {
+            if (has_bottom) best = wave_band<RS, S, AR, true, true>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, prog_top, prog_bot, goe2, ge2, h0, gb2, zero);
+            else best = wave_band<RS, S, AR, true, false>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, prog_top, prog_bot, goe2, ge2, h0, gb2, zero);
+        } else {
+            if (has_bottom) best = wave_band<RS, S, AR, false, true>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, prog_top, prog_bot, goe2, ge2, h0, gb2, zero);
+            else best = wave_band<RS, S, AR, false, false>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, prog_top, prog_bot, goe2, ge2, h0, gb2, zero);
+        }
+
+#pragma unroll
+        for (int o = G / 2; o >= 1; o >>= 1) best = AR::max2(best, __shfl_xor_sync(FULL, best, o));
+        if (lane == 0 && valid) {
+            const int b0 = AR::extract(best, 0), b1 = AR::extract(best, 1);
+            // a running maximum above the threshold means a 16-bit wrap may have happened in this band
+            atomicMax(a.best + 2 * pair, b0 > a.ovf_limit ? 0x7FFFFFFF : b0 - a.goe);
+            atomicMax(a.best + 2 * pair + 1, b1 > a.ovf_limit ? 0x7FFFFFFF : b1 - a.goe);
+            __threadfence();
+            if (atomicAdd(a.done + pair, 1u) == (unsigned)a.npass - 1u) {
+                // last band of this pair: the maximum over all bands is final
+                __threadfence();
+                const int f0 = atomicMax(a.best + 2 * pair, 0), f1 = atomicMax(a.best + 2 * pair + 1, 0);
+                const uint32_t subj_lo = a.pair_subj[2 * pair], subj_hi = a.pair_subj[2 * pair + 1];
+                const bool ov0 = f0 == 0x7FFFFFFF, ov1 = f1 == 0x7FFFFFFF, has1 = subj_hi != SW_NO_SUBJECT;
+                if (a.ovf_list) {
+                    if (ov0) { const unsigned p = atomicAdd(a.ovf_count, 1u); if (p < a.ovf_cap) a.ovf_list[p] = make_uint2((unsigned)q, subj_lo); }
+                    if (has1 && ov1) { const unsigned p = atomicAdd(a.ovf_count, 1u); if (p < a.ovf_cap) a.ovf_list[p] = make_uint2((unsigned)q, subj_hi); }
+                }
+                if (a.out_mode == SW_OUT_I16) {
+                    int16_t *orow = (int16_t *)a.out + (size_t)q * a.out_stride;
+                    orow[subj_lo] = (int16_t)(ov0 ? SW_OVERFLOW_SENTINEL : f0);
+                    if (has1) orow[subj_hi] = (int16_t)(ov1 ? SW_OVERFLOW_SENTINEL : f1);
+                } else {
+                    int32_t *orow = (int32_t *)a.out + (size_t)q * a.out_stride;
+                    orow[subj_lo] = ov0 ? SW_OVERFLOW_SENTINEL : f0;
+                    if (has1) orow[subj_hi] = ov1 ? SW_OVERFLOW_SENTINEL : f1;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace swk
+
+#endif  /* SW_WAVE_CUH_ */

@@ -398,3 +398,59 @@ def test_is_check_build_flag(pkg):
     with pkg.Engine() as e:
         e.score(["ACGTACGT"], ["ACGTTCGT", "", "A"])
         assert e.device_error_bits == 0
+
+
+def test_wave_kernel_few_long_pairs_vs_oracle(oracle_mod, pkg):
+    """Band-pipelined kernel (sw_wave.cuh): the 512-row bands of a long query run concurrently on
+    different warps, each consuming the bottom row of the band above as it is produced
+    (ScoringModule_v1.1.v:36-39,49-54: the module-chaining ports left "for future use")."""
+    rng = random.Random(404)
+    q = _rand(rng, 3000)                                    # 6 bands
+    q2 = _rand(rng, 1100)                                   # 3 bands, the last one almost empty
+    subjects = []
+    for k in range(61):                                     # odd count: one pair has a single member
+        L = rng.choice([1, 5, 31, 32, 33, 64, 100, 511, 700, 1000, rng.randint(1, 1200)])
+        if k % 3 == 0:
+            a = rng.randint(0, 2000)
+            s = (_mutate(rng, q[a:a + L], 0.05, 0.03) + _rand(rng, L))[:L]
+        else:
+            s = _rand(rng, L)
+        subjects.append(s or "A")
+    subjects += ["", q[500:2500], _mutate(rng, q, 0.02, 0.01)]
+    want = _oracle_matrix(oracle_mod, pkg, [q, q2, q[:600]], subjects)
+    assert want.max() > 9000
+    for mode, out_mode in ((2, pkg.SW_OUTPUT_I32), (2, pkg.SW_OUTPUT_I16), (1, pkg.SW_OUTPUT_I32)):
+        with pkg.Engine() as e:
+            e.set_small_batch_path(False)
+            e.set_wave_mode(mode)
+            e.set_output(out_mode)
+            got = e.score([q, q2, q[:600]], subjects)
+            assert "wave" in e.last_kernel_name, e.last_kernel_name
+            assert e.device_error_bits == 0
+        np.testing.assert_array_equal(got.astype(np.int32), want, err_msg=str((mode, out_mode)))
+    # the strip kernel alone gives the same matrix
+    with pkg.Engine() as e:
+        e.set_small_batch_path(False)
+        e.set_wave_mode(0)
+        np.testing.assert_array_equal(e.score([q, q2, q[:600]], subjects), want)
+        assert "wave" not in e.last_kernel_name
+
+
+def test_wave_kernel_single_long_pair_and_overflow(oracle_mod, pkg):
+    """One long pair spread over many warps; and a pair whose score leaves the 16-bit range inside
+    the wave kernel (flagged per band, recomputed in 32 bit from the overflow list)."""
+    rng = random.Random(405)
+    a = _rand(rng, 6000)
+    b = _mutate(rng, a, 0.03, 0.02)                         # score ~ 25 000: still 16-bit
+    c = _rand(rng, 5000)
+    o = oracle_mod.Oracle()
+    with pkg.Engine() as e:
+        got = e.score([a], [b])
+        assert "wave" in e.last_kernel_name
+        assert int(got[0, 0]) == o.score(a, b) > 20000
+        got = e.score([a], [c])
+        assert int(got[0, 0]) == o.score(a, c)
+        big = _rand(rng, 7000)
+        got = e.score([big], [big, c, big[:6900]])
+        assert got[0].tolist() == [35000, o.score(big, c), 34500]
+        assert e.device_error_bits == 0
