@@ -256,6 +256,16 @@ int sw_set_small_batch_timing(sw_handle_t *h, int enable);
  * 1 = automatic (default: <= 1536 subject pairs and a query of >= 1024 rows, or <= 64 pairs and a
  * query of > 512 rows), 2 = whenever the query has more than one band (environment SW_B200_WAVE). */
 int sw_set_wave_mode(sw_handle_t *h, int mode);
+/* Launch plan of a scoring call.  The bank hands every target to the first free module
+ * (PrioEncoder.v:18-21, SM_Feeder2.v:104-205); here the sorted pair list can be cut into length
+ * groups (a group ends where the length has halved), each with its own launch, kernel variant and
+ * pass-boundary scratch, running on concurrent streams.  length_groups: 0 = one launch over all
+ * lengths, 1 = always one launch per length group, 2 = automatic (default): length groups only when
+ * one launch would need more than 4 GB of pass-boundary scratch (a few very long subjects next to
+ * many short ones).  query_groups != 0: additionally choose the variant per query length (default
+ * off: on the mixed-length config the extra launches cost more than the better fit gains --
+ * measured 7.3 vs 8.2 TCUPS). */
+int sw_set_launch_plan(sw_handle_t *h, int length_groups, int query_groups);
 int sw_kernel_variant_count(void);
 const char *sw_kernel_variant_name(int idx);
 int sw_set_kernel_name(sw_handle_t *h, const char *name);

@@ -192,12 +192,48 @@ def case_pair(pkg, n=100000):
                reps=2, check=0)
 
 
+def case_penalties(pkg, n=2_000_000):
+    """Run-time loadable penalties (ld_penalties, ScoreBank_v2.v:34,161): an arbitrary set with run-time
+    operands, the same set specialised at run time (NVRTC), and the compiled-in default set, all on the
+    same variant and the same 150-nt workload."""
+    q = pkg.random_packed_db(100, 150, 11)
+    db = pkg.random_packed_db(n, 150, 12)
+    custom = dict(match=5, mismatch=-4, gap_open=-10, gap_extend=-3)
+    out = {"workload": f"{n} x 150 nt subjects vs 100 x 150 nt queries, strip_s16x2_R25x2_G1"}
+    for label, params, jit in (("default_set_compiled_in", {}, 0), ("custom_set_runtime_operands", custom, 0),
+                               ("custom_set_specialised_at_run_time", custom, 2)):
+        with pkg.Engine(**params) as e:
+            e.set_jit(jit)
+            e.set_kernel_name("strip_s16x2_R25x2_G1")
+            e.set_queries(q)
+            e.load_db(db)
+            ms = []
+            for _ in range(4):
+                e.score_db()
+                e.wait()
+                ms.append(e.last_kernel_ms)
+            best = min(ms[1:])
+            got = e.fetch_db()
+            idx = np.arange(0, n, max(1, n // 400))
+            sub = _subset(db, idx)
+            from oracle import oracle as om
+            want, _ = om.Oracle(**params).score_batch_packed(q[0], q[1], q[2], sub[0], sub[1], sub[2])
+            assert np.array_equal(got[:, idx], want), f"penalties {label}: GPU scores differ from the oracle"
+            out[label] = {"kernel": e.last_kernel_name, "gcups": e.last_cells / best / 1e6, "kernel_ms": best,
+                          "oracle_checked_pairs": int(want.size)}
+    d = out["default_set_compiled_in"]["gcups"]
+    out["custom_runtime_vs_default"] = out["custom_set_runtime_operands"]["gcups"] / d
+    out["custom_jit_vs_default"] = out["custom_set_specialised_at_run_time"]["gcups"] / d
+    return out
+
+
 def bench_blocks(pkg, log=lambda *a: None):
     """What bench.py adds to its JSON line (rank 0, N = 1): ~60 s in total."""
     out = {"configs": {}, "latency": None}
     t0 = time.perf_counter()
     for key, fn in (("latency", case_latency), ("config4_full", case_4full), ("config4_200k", case_4),
-                    ("config4_2000_subjects", case_4w), ("config5_mixed", case_5)):
+                    ("config4_2000_subjects", case_4w), ("config5_mixed", case_5), ("single_pair_100kb", case_pair),
+                    ("run_time_penalties", case_penalties)):
         try:
             r = fn(pkg)
         except Exception as ex:
@@ -224,6 +260,8 @@ if __name__ == "__main__":
             print(json.dumps(case_4full(pkg)), flush=True)
         elif w == "pair":
             print(json.dumps(case_pair(pkg)), flush=True)
+        elif w == "pen":
+            print(json.dumps(case_penalties(pkg)), flush=True)
         elif w in ("4", "4w", "5"):
             for k in kernels:
                 print(json.dumps({"4": case_4, "4w": case_4w, "5": case_5}[w](pkg, k)), flush=True)

@@ -112,6 +112,7 @@ def load_library():
     L.sw_set_small_batch_path.argtypes = [vp, i32]
     L.sw_set_small_batch_timing.argtypes = [vp, i32]
     L.sw_set_wave_mode.argtypes = [vp, i32]
+    L.sw_set_launch_plan.argtypes = [vp, i32, i32]
     L.sw_get_stats.argtypes = [vp, C.POINTER(SwStats)]
     L.sw_params_in_exact_domain.argtypes = [C.POINTER(SwParams)]
     L.sw_device_count.restype = i32
@@ -255,6 +256,10 @@ class Engine:
     def set_wave_mode(self, mode):
         """Band-pipelined kernel for few long pairs: 0 never, 1 automatic, 2 whenever possible."""
         self._check(self.lib.sw_set_wave_mode(self.h, mode))
+
+    def set_launch_plan(self, length_groups=2, query_groups=False):
+        """length_groups: 0 one launch, 1 one launch per length group, 2 automatic; query_groups: variant per query length."""
+        self._check(self.lib.sw_set_launch_plan(self.h, length_groups, int(bool(query_groups))))
 
     def set_small_batch_path(self, enable):
         self._check(self.lib.sw_set_small_batch_path(self.h, int(bool(enable))))

@@ -151,7 +151,7 @@ struct GpuCtx {
     // scratch shared by both slots (kernels of one GPU run in stream order)
     DevBuf d_bnd, d_counters, d_scratch32, d_best_score, d_best_index, d_topk_keys, d_err;
     DevBuf d_wave_bnd, d_wave_state;  // band-pipelined kernel: boundary rows; progress / best / done words
-    int wave_bps = 0;                 // its resident blocks per SM (0 = not asked yet)
+    int wave_bps[2] = {0, 0};         // resident blocks per SM of its two instances (0 = not asked yet)
     unsigned counter_next = 0;        // next unused work-queue counter
     // autotune: timing events and the cached decision, per GPU (shards differ in shape)
     cudaEvent_t ev_tune0 = nullptr, ev_tune1 = nullptr;
@@ -196,6 +196,11 @@ struct sw_handle {
     bool small_timing = true;         // record CUDA events around the latency path's kernel (sw_last_kernel_ms)
     int jit = 1;                      // run-time specialisation of gap penalties: 0 off, 1 large jobs, 2 always
     int wave = 1;                     // band-pipelined kernel for few long pairs: 0 off, 1 automatic, 2 whenever possible
+    // launch-planner knobs (environment SW_B200_PLAN_SEGS / _QGROUPS / _STREAMS / _TAU): experiments
+    int plan_segs = 2;                // 0 never, 1 always, 2 when one launch would need a huge pass-boundary scratch
+    bool plan_qgroups = false;        // per-query variant choice (measured: the extra launches cost more than they gain)
+    int plan_streams = kStreams;
+    double plan_tau = 0.5;
     // bookkeeping
     std::atomic<int> last_cuda{0};    // written by the per-GPU worker threads as well
     std::atomic<uint64_t> launches{0};
@@ -484,6 +489,7 @@ double variant_speed(const SwStripVariant *v)
         // small-R latency variants: estimates (shuffle-bound), they are chosen for latency, not throughput
         {"strip_s16x2_R1x1_G32", 900}, {"strip_s16x2_R2x1_G32", 1700}, {"strip_s16x2_R4x1_G32", 3000},
         {"strip_s16x2_R8x1_G32", 4500}, {"strip_s16x2_R8x1_G16", 4600}, {"strip_s16x2_R16x1_G8", 5900},
+        {"strip_s16x2_R2x2_G32", 2900},
     };
     for (auto &t : tab) if (std::strcmp(t.name, v->name) == 0) return t.gcups;
     return 5000.0;
@@ -499,7 +505,8 @@ double variant_cost(const GpuCtx &gc, const Slot &g, const SwStripVariant *v, co
     double rows = 0;                      // padded rows over all queries
     for (size_t i = 0; i < nql; ++i) rows += (double)((qlens[i] + P - 1) / P) * P;
     if (rows == 0) rows = (double)((maxq + P - 1) / P) * P;
-    const double lanes = (double)g.npairs * v->G;
+    // parallel work = lanes of all (pair, query) items of a launch
+    const double lanes = (double)g.npairs * v->G * (double)std::max<size_t>(nql, 1);
     const double fill = (double)gc.num_sms * v->min_blocks * v->block_threads;
     const double util = std::min(1.0, lanes / fill);
     const double cols = (double)std::max<uint32_t>(g.max_len, 1);
@@ -553,8 +560,8 @@ int cached_occupancy(sw_handle *h, GpuCtx &gc, int vidx, int chunk_passes, int *
 
 // Launch geometry of a strip variant for `npairs` pairs with subjects up to max_len and queries up to
 // maxq rows; also grows the pass-boundary scratch.
-int strip_setup(sw_handle *h, GpuCtx &gc, DevBuf &bnd_buf, uint32_t npairs, uint32_t max_len, uint32_t maxq, int vidx, int *grid,
-                int *chunk_passes, size_t *bnd_elems)
+int strip_setup(sw_handle *h, GpuCtx &gc, DevBuf &bnd_buf, uint32_t npairs, uint32_t max_len, uint32_t maxq, int nql, int vidx,
+                int *grid, int *chunk_passes, size_t *bnd_elems)
 {
     const SwStripVariant *v = sw_strip_variant(vidx);
     const int P = v->R * v->G;
@@ -568,7 +575,8 @@ int strip_setup(sw_handle *h, GpuCtx &gc, DevBuf &bnd_buf, uint32_t npairs, uint
     if (bps < 1) return SW_ECUDA;
     const int ppb = v->block_threads / v->G;
     const uint32_t npb = (npairs + ppb - 1) / ppb;
-    *grid = (int)std::min<uint64_t>(std::max<uint32_t>(npb, 1), (uint64_t)gc.num_sms * bps);
+    // persistent blocks: as many as there are work items (pair blocks x queries), at most a full GPU
+    *grid = (int)std::min<uint64_t>(std::max<uint64_t>((uint64_t)npb * (uint64_t)std::max(nql, 1), 1), (uint64_t)gc.num_sms * bps);
     *bnd_elems = 0;
     if (need_passes > 1) {
         // pass-boundary scratch: one (H, G) per column of the longest subject, per pair slot, per
@@ -624,7 +632,7 @@ int autotune_variant(sw_handle *h, GpuCtx &gc, Slot &g, SwStripLaunch base, cons
     float best_ms = 0.f;
     for (int c = 0; c < ncand; ++c) {
         base.vidx = ranked[c];
-        int rc = strip_setup(h, gc, gc.d_bnd, base.db.npairs, g.max_len, h->q_max_len, base.vidx, &base.grid, &base.chunk_passes, &base.bnd_elems);
+        int rc = strip_setup(h, gc, gc.d_bnd, base.db.npairs, g.max_len, h->q_max_len, nqs, base.vidx, &base.grid, &base.chunk_passes, &base.bnd_elems);
         if (rc != SW_OK) return rc;
         base.bnd = gc.d_bnd.as<uint2>();
         float ms = 0.f;
@@ -753,7 +761,13 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
         const bool all_strip = (int)strip_q.size() == nq;
         const bool same_len = std::all_of(sl.begin(), sl.end(), [&](uint32_t x) { return x == sl[0]; });
         std::vector<Seg> segs = g.segs;
-        if (segs.empty() || variant_forced(h)) segs.assign(1, Seg{0, g.npairs, g.max_len, g.sum_len});
+        bool use_segs = h->plan_segs == 1;
+        if (h->plan_segs == 2 && segs.size() > 1) {
+            // one launch over everything sizes every block's pass-boundary scratch by the longest subject
+            const size_t worst = (size_t)gc.num_sms * 4 * 128 * (size_t)g.max_len * sizeof(uint2);
+            use_segs = smaxq > 64 && worst > ((size_t)4 << 30);
+        }
+        if (segs.empty() || variant_forced(h) || !use_segs) segs.assign(1, Seg{0, g.npairs, g.max_len, g.sum_len});
         simple = all_strip && segs.size() == 1 && (variant_forced(h) || same_len || strip_q.size() == 1);
 
         if (simple) {
@@ -779,9 +793,16 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 }
                 vidx = gc.tune_choice;
             }
+            // query chunks: a handful of launches so that D2H of finished rows overlaps compute
+            // (each launch has its own tail: aim for >= ~50 ms of work per launch, at ~6 TCUPS)
+            int nchunks = std::max(1, std::min(std::min(nq, 8), (int)(est_ms_all / 50.0)));
+            if (topk || may_overflow || !wave_q.empty()) nchunks = 1;
+            // the device work counter is 32-bit: (pair blocks) x (queries per launch) must stay below 2^31
+            while (nchunks < nq && (uint64_t)(g.npairs / 4 + 1) * (uint64_t)((nq + nchunks - 1) / nchunks) >= (1ull << 31)) nchunks *= 2;
+            nchunks = std::min(nchunks, nq);
             SwStripLaunch L = base;
             L.vidx = vidx;
-            rc = strip_setup(h, gc, gc.d_bnd, g.npairs, g.max_len, smaxq, vidx, &L.grid, &L.chunk_passes, &L.bnd_elems);
+            rc = strip_setup(h, gc, gc.d_bnd, g.npairs, g.max_len, smaxq, nq / nchunks, vidx, &L.grid, &L.chunk_passes, &L.bnd_elems);
             if (rc != SW_OK) return rc;
             max_grid = L.grid;
             label_v = vidx;
@@ -790,13 +811,6 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 L.jit_kernel = sw_jit_strip_kernel(sw_strip_variant(vidx), sc.goe, sc.ge, nullptr, 0);
                 jit_used = L.jit_kernel != nullptr;
             }
-            // query chunks: a handful of launches so that D2H of finished rows overlaps compute
-            // (each launch has its own tail: aim for >= ~50 ms of work per launch, at ~6 TCUPS)
-            int nchunks = std::max(1, std::min(std::min(nq, 8), (int)(est_ms_all / 50.0)));
-            if (topk || may_overflow || !wave_q.empty()) nchunks = 1;
-            // the device work counter is 32-bit: (pair blocks) x (queries per launch) must stay below 2^31
-            while (nchunks < nq && (uint64_t)(g.npairs / 4 + 1) * (uint64_t)((nq + nchunks - 1) / nchunks) >= (1ull << 31)) nchunks *= 2;
-            nchunks = std::min(nchunks, nq);
             for (int c = 0; c < nchunks; ++c) {
                 const int a0 = (int)((long long)nq * c / nchunks), a1 = (int)((long long)nq * (c + 1) / nchunks);
                 if (a1 <= a0) continue;
@@ -809,9 +823,9 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
             // single work item decides when a length group needs more lanes per pair than that
             const double fill = (double)gc.num_sms * 3 * 128;
             int gmin = 1;
-            while (gmin < 32 && (double)g.npairs * gmin < 0.6 * fill) gmin *= 2;
+            while (gmin < 32 && (double)g.npairs * gmin * (double)strip_q.size() < 0.6 * fill) gmin *= 2;
             const double t_total = (double)g.sum_len * (double)srows / 8.0e12;          // seconds, optimistic
-            const double tau = std::max(0.5 * t_total, 1.0e-3);      // the longest items start first
+            const double tau = std::max(h->plan_tau * t_total, 1.0e-3);      // the longest items start first
             const int nv = sw_strip_variant_count();
             auto pick = [&](const Seg &sg, const uint32_t *ql, size_t nql, uint32_t maxq, double *item_s) {
                 int best = -1, best_any = -1;
@@ -842,12 +856,19 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 // queries of this length group, grouped by the variant that suits them
                 std::map<int, std::vector<int>> by_variant;
                 std::map<int, double> item_of;
-                for (int q : strip_q) {
-                    const uint32_t ql = h->q_len[q];
+                if (h->plan_qgroups) {
+                    for (int q : strip_q) {
+                        const uint32_t ql = h->q_len[q];
+                        double it = 0;
+                        const int v = pick(sg, &ql, 1, ql, &it);
+                        by_variant[v].push_back(q);
+                        item_of[v] = std::max(item_of[v], it);
+                    }
+                } else {
                     double it = 0;
-                    const int v = pick(sg, &ql, 1, ql, &it);
-                    by_variant[v].push_back(q);
-                    item_of[v] = std::max(item_of[v], it);
+                    const int v = pick(sg, sl.data(), sl.size(), smaxq, &it);
+                    by_variant[v] = strip_q;
+                    item_of[v] = it;
                 }
                 // fold small groups into the largest one of this length group (every launch has a tail)
                 int big = -1;
@@ -896,7 +917,7 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
             }
             // longest work items first, round-robin over the streams
             std::stable_sort(plan.begin(), plan.end(), [](const Planned &x, const Planned &y) { return x.item_s > y.item_s; });
-            const int ns_used = topk ? 1 : kStreams;       // top-k lists are per block index: one kernel at a time
+            const int ns_used = topk ? 1 : h->plan_streams;   // top-k lists are per block index: one kernel at a time
             for (size_t i = 0; i < plan.size(); ++i) plan[i].stream = (int)(i % ns_used);
             SW_CUDA(h, gc.d_qidx.reserve(std::max<size_t>(1, qidx_host.size()) * sizeof(int)));
             for (Planned &p : plan) {
@@ -906,7 +927,7 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 uint32_t gmaxq = 0;
                 for (int k = 0; k < L.nql; ++k) gmaxq = std::max(gmaxq, h->q_len[qidx_host[off + k]]);
                 DevBuf &bb = p.stream == 0 ? gc.d_bnd : gc.d_bnd_aux[p.stream - 1];
-                rc = strip_setup(h, gc, bb, L.db.npairs, L.db.max_len, gmaxq, L.vidx, &L.grid, &L.chunk_passes, &L.bnd_elems);
+                rc = strip_setup(h, gc, bb, L.db.npairs, L.db.max_len, gmaxq, L.nql, L.vidx, &L.grid, &L.chunk_passes, &L.bnd_elems);
                 if (rc != SW_OK) return rc;
                 // more work items than the 32-bit work counter can address: does not happen per length group
                 max_grid = std::max(max_grid, L.grid);
@@ -925,11 +946,11 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
             std::snprintf(h->last_kernel, sizeof h->last_kernel, "%s%s%s", sw_strip_variant(label_v)->name, jit_used ? "+jit" : "",
                           n_groups_total > 1 ? "+groups" : "");
         else
-            std::snprintf(h->last_kernel, sizeof h->last_kernel, "%s", wave_q.empty() ? "generic32" : sw_wave_kernel_name());
+            std::snprintf(h->last_kernel, sizeof h->last_kernel, "%s", wave_q.empty() ? "generic32" : sw_wave_kernel_name(0));
         if (!wave_q.empty() && label_v >= 0) {
             uint64_t wrows = 0;
             for (int q : wave_q) wrows += h->q_len[q];
-            if (2 * wrows > h->q_sum_len) std::snprintf(h->last_kernel, sizeof h->last_kernel, "%s+groups", sw_wave_kernel_name());
+            if (2 * wrows > h->q_sum_len) std::snprintf(h->last_kernel, sizeof h->last_kernel, "%s+groups", sw_wave_kernel_name(0));
         }
     }
     const bool have_strip = !plan.empty();
@@ -994,20 +1015,24 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
         }
         // ---- band-pipelined launches, one per long query ----------------------------------------
         if (!wave_q.empty()) {
-            if (!gc.wave_bps) SW_CUDA(h, sw_wave_occupancy(&gc.wave_bps));
-            if (gc.wave_bps < 1) return SW_ECUDA;
             const uint32_t cols_stride = (g.max_len + 31u) & ~31u;
             uint32_t wmaxq = 0;
             for (int q : wave_q) wmaxq = std::max(wmaxq, h->q_len[q]);
-            const int max_pass = (int)((wmaxq + SW_WAVE_ROWS_PER_BAND - 1) / SW_WAVE_ROWS_PER_BAND);
+            const int max_pass = (int)((wmaxq + 255) / 256);
             SW_CUDA(h, gc.d_wave_bnd.reserve((size_t)g.npairs * 2 * cols_stride * sizeof(uint2)));
             // state words: prog [npairs * max_pass] | best [2 * npairs] | done [npairs]
             const size_t n_prog = (size_t)g.npairs * max_pass, n_state = n_prog + 3 * (size_t)g.npairs;
             SW_CUDA(h, gc.d_wave_state.reserve(n_state * sizeof(unsigned)));
             for (int q : wave_q) {
                 SwWaveLaunch W;
+                // 512-row bands unless they leave most of the GPU idle: then 256-row bands
+                const size_t warps512 = (size_t)g.npairs * ((h->q_len[q] + 511) / 512);
+                W.instance = warps512 < (size_t)gc.num_sms * 6 ? 1 : 0;
+                if (!gc.wave_bps[W.instance]) SW_CUDA(h, sw_wave_occupancy(W.instance, &gc.wave_bps[W.instance]));
+                if (gc.wave_bps[W.instance] < 1) return SW_ECUDA;
+                const int rows = sw_wave_rows_per_band(W.instance);
                 W.db = db; W.q = dq; W.query = q; W.sc = sc;
-                W.npass = (int)((h->q_len[q] + SW_WAVE_ROWS_PER_BAND - 1) / SW_WAVE_ROWS_PER_BAND);
+                W.npass = (int)((h->q_len[q] + rows - 1) / rows);
                 W.out = g.d_out.p; W.out_stride = n; W.out_mode = g.out_mode;
                 W.bnd = gc.d_wave_bnd.as<uint2>(); W.cols_stride = cols_stride;
                 W.prog = gc.d_wave_state.as<unsigned>();
@@ -1015,13 +1040,15 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 W.done = gc.d_wave_state.as<unsigned>() + n_prog + 2 * (size_t)g.npairs;
                 W.counter = next_counter(gc);
                 const size_t items = (size_t)W.npass * ((g.npairs + 3) / 4);
-                W.grid = (int)std::min<size_t>(items, (size_t)gc.num_sms * gc.wave_bps);
+                W.grid = (int)std::min<size_t>(items, (size_t)gc.num_sms * gc.wave_bps[W.instance]);
                 W.ovf_count = base.ovf_count; W.ovf_list = base.ovf_list; W.ovf_cap = base.ovf_cap;
                 W.dev_err = gc.d_err.as<unsigned>();
                 SW_CUDA(h, cudaMemsetAsync(gc.d_wave_state.p, 0, n_state * sizeof(unsigned), gc.st_compute));
                 SW_CUDA(h, cudaMemsetAsync(W.counter, 0, sizeof(unsigned), gc.st_compute));
                 SW_CUDA(h, sw_launch_wave(gc.st_compute, W));
                 h->launches++;
+                if (&gc == &h->gpus[0] && label_v < 0)
+                    std::snprintf(h->last_kernel, sizeof h->last_kernel, "%s", sw_wave_kernel_name(W.instance));
             }
         }
         if (may_overflow) {
@@ -1354,6 +1381,11 @@ int small_variant(const sw_handle *h, uint32_t qmax, size_t npairs)
     if (h->force_variant >= 0) return sw_strip_variant(h->force_variant)->has_direct ? h->force_variant : -1;
     if (h->force_R || h->force_G || h->force32) return -1;
     const char *want;
+    if (const char *e = std::getenv("SW_B200_SMALL_VARIANT")) {          // A/B measurements
+        for (int i = 0; i < sw_strip_variant_count(); ++i)
+            if (std::strcmp(sw_strip_variant(i)->name, e) == 0 && sw_strip_variant(i)->has_direct &&
+                (uint32_t)(sw_strip_variant(i)->R * sw_strip_variant(i)->G) >= qmax) return i;
+    }
     if (qmax <= 32) want = "strip_s16x2_R1x1_G32";
     else if (qmax <= 64) want = "strip_s16x2_R2x1_G32";
     else if (qmax <= 128) want = npairs <= 1500 ? "strip_s16x2_R4x1_G32" : npairs <= 3000 ? "strip_s16x2_R8x1_G16" : "strip_s16x2_R16x1_G8";
@@ -1590,6 +1622,10 @@ int sw_init(sw_handle_t **out, const sw_params_t *p, const int *gpu_ids, int n_g
     if (const char *e = std::getenv("SW_B200_JIT")) h->jit = std::atoi(e);
     if (const char *e = std::getenv("SW_B200_SMALL_PATH")) h->small_path = (e[0] != '0');
     if (const char *e = std::getenv("SW_B200_WAVE")) h->wave = std::atoi(e);
+    if (const char *e = std::getenv("SW_B200_PLAN_SEGS")) h->plan_segs = std::atoi(e);
+    if (const char *e = std::getenv("SW_B200_PLAN_QGROUPS")) h->plan_qgroups = (e[0] != '0');
+    if (const char *e = std::getenv("SW_B200_STREAMS")) h->plan_streams = std::max(1, std::min(kStreams, std::atoi(e)));
+    if (const char *e = std::getenv("SW_B200_TAU")) h->plan_tau = std::atof(e);
     h->gpus.resize(ids.size());
     for (size_t i = 0; i < ids.size(); ++i) {
         GpuCtx &g = h->gpus[i];
@@ -1921,6 +1957,14 @@ int sw_set_jit(sw_handle_t *h, int mode)
 {
     if (!h || mode < 0 || mode > 2) return SW_EINVAL;
     h->jit = mode;
+    return SW_OK;
+}
+
+int sw_set_launch_plan(sw_handle_t *h, int length_groups, int query_groups)
+{
+    if (!h || length_groups < 0 || length_groups > 2) return SW_EINVAL;
+    h->plan_segs = length_groups;
+    h->plan_qgroups = query_groups != 0;
     return SW_OK;
 }
 

@@ -353,30 +353,40 @@ cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L)
     return cudaGetLastError();
 }
 
-// ---- band-pipelined kernel: 8 rows x 2 sub-strips x 32 lanes = 512 rows per band ------------------
+// ---- band-pipelined kernel ---------------------------------------------------------------------
+// Two instances: bands of 512 rows (8 rows x 2 sub-strips x 32 lanes) for a few hundred pairs, and
+// bands of 256 rows (8 rows x 1 x 32 lanes: twice the bands, shorter band-to-band lag, shorter
+// dependency chain per step) when even the 512-row bands of all pairs do not fill the GPU -- down
+// to one single pair.
 namespace {
-constexpr int kWaveRS = 8, kWaveS = 2, kWaveMinB = 3;
-static_assert(kWaveRS * kWaveS * 32 == SW_WAVE_ROWS_PER_BAND, "band height");
 typedef void (*WaveFn)(const WaveArgs);
-const WaveFn g_wave_fn = sw_wave_kernel<kWaveRS, kWaveS, ArithS16, kBT, kWaveMinB>;
-const WaveFn g_wave_fn_fixed = sw_wave_kernel<kWaveRS, kWaveS, ArithS16, kBT, kWaveMinB, kFixedGoe, kFixedGe>;
-constexpr size_t kWaveSmem = (size_t)32 * kWaveS * ((kWaveRS + 1) / 2) * kCodesPerRow * sizeof(uint2);
+struct WaveInstance { int rows; size_t smem; WaveFn fn, fn_fixed; const char *name; };
+constexpr size_t wave_smem(int rs, int s) { return (size_t)32 * s * ((rs + 1) / 2) * kCodesPerRow * sizeof(uint2); }
+const WaveInstance g_wave[2] = {
+    {512, wave_smem(8, 2), sw_wave_kernel<8, 2, ArithS16, kBT, 3>, sw_wave_kernel<8, 2, ArithS16, kBT, 3, kFixedGoe, kFixedGe>,
+     "wave_s16x2_R8x2_G32"},
+    {256, wave_smem(8, 1), sw_wave_kernel<8, 1, ArithS16, kBT, 4>, sw_wave_kernel<8, 1, ArithS16, kBT, 4, kFixedGoe, kFixedGe>,
+     "wave_s16x2_R8x1_G32"},
+};
 }  // namespace
 
-const char *sw_wave_kernel_name(void) { return "wave_s16x2_R8x2_G32"; }
+const char *sw_wave_kernel_name(int inst) { return g_wave[inst ? 1 : 0].name; }
+int sw_wave_rows_per_band(int inst) { return g_wave[inst ? 1 : 0].rows; }
 
-cudaError_t sw_wave_occupancy(int *blocks_per_sm)
+cudaError_t sw_wave_occupancy(int inst, int *blocks_per_sm)
 {
-    cudaError_t e = cudaFuncSetAttribute((const void *)g_wave_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWaveSmem);
+    const WaveInstance &w = g_wave[inst ? 1 : 0];
+    cudaError_t e = cudaFuncSetAttribute((const void *)w.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, (const void *)g_wave_fn, kBT, kWaveSmem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, (const void *)w.fn, kBT, w.smem);
 }
 
 cudaError_t sw_launch_wave(cudaStream_t st, const SwWaveLaunch &L)
 {
     const SwScoring &sc = L.sc;
     if (sc.limit) return cudaErrorInvalidValue;            // exact arithmetic only
-    WaveFn fn = (!g_no_fixed && sc.goe == kFixedGoe && sc.ge == kFixedGe) ? g_wave_fn_fixed : g_wave_fn;
+    const WaveInstance &w = g_wave[L.instance ? 1 : 0];
+    WaveFn fn = (!g_no_fixed && sc.goe == kFixedGoe && sc.ge == kFixedGe) ? w.fn_fixed : w.fn;
     WaveArgs a{};
     a.tp = L.db.tp; a.tile_woff = L.db.tile_woff; a.pair_len = L.db.pair_len; a.pair_subj = L.db.pair_subj;
     a.npairs = L.db.npairs; a.npb = (L.db.npairs + 3) / 4;
@@ -390,9 +400,9 @@ cudaError_t sw_launch_wave(cudaStream_t st, const SwWaveLaunch &L)
     a.ovf_count = L.ovf_count; a.ovf_list = L.ovf_list; a.ovf_cap = L.ovf_cap;
     a.dev_err = L.dev_err;
     a.spin_limit = 1u << 24;
-    cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kWaveSmem);
+    cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem);
     if (e != cudaSuccess) return e;
-    fn<<<L.grid, kBT, kWaveSmem, st>>>(a);
+    fn<<<L.grid, kBT, w.smem, st>>>(a);
     return cudaGetLastError();
 }
 

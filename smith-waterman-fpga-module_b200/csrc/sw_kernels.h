@@ -112,8 +112,9 @@ const char *sw_strip_instance_kind(const SwStripLaunch &L);
  * separate work items that run concurrently on different warps.  bnd: npairs * 2 * cols_stride uint2;
  * prog: npairs * npass words, best: 2 * npairs ints, done: npairs words -- all zeroed before the
  * launch; counter: zeroed work-queue word. */
-#define SW_WAVE_ROWS_PER_BAND 512
+#define SW_WAVE_ROWS_PER_BAND 512     /* instance 0; instance 1 has bands of 256 rows */
 struct SwWaveLaunch {
+    int instance = 0;
     SwDevDb db{};
     SwDevQueries q{};
     int query = 0;
@@ -134,9 +135,10 @@ struct SwWaveLaunch {
     unsigned ovf_cap = 0;
     unsigned *dev_err = nullptr;
 };
-cudaError_t sw_wave_occupancy(int *blocks_per_sm);
+cudaError_t sw_wave_occupancy(int instance, int *blocks_per_sm);
 cudaError_t sw_launch_wave(cudaStream_t st, const SwWaveLaunch &L);
-const char *sw_wave_kernel_name(void);
+const char *sw_wave_kernel_name(int instance);
+int sw_wave_rows_per_band(int instance);
 
 /* 32-bit kernel: any length, any score range.  scratch: 2 * max_cols * threads_total int32 where
  * max_cols = min(longest query, longest subject) (the recurrence is symmetric: the shorter sequence

@@ -179,6 +179,7 @@ constexpr int kHiEndedCode = 16;
 constexpr int kPadCode = 20;
 constexpr int kCodesPerRow = 32;    // profile entries per row pair (codes 0..20 used): 256 bytes
 constexpr int kMaxTopK = 32;
+constexpr int kQueryBytes = 512;    // packed query bytes staged per profile chunk (2048 rows; host-checked)
 
 // The four column codes of columns 4k .. 4k+3 of a pair: a / b = the packed byte k of the longer /
 // shorter member (0 past its end), nlo >= nhi their lengths.  Used by build_tp_kernel (code stream
@@ -331,6 +332,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
 {
     extern __shared__ uint2 s_prof[];
     __shared__ unsigned s_work, s_iter;
+    __shared__ uint8_t s_qb[kQueryBytes];             // packed query bytes of the resident profile chunk
     __shared__ uint32_t s_codes[DIRECT ? BT / G : 1][DIRECT ? 256 : 1];   // DIRECT: staged code words per pair slot
     constexpr int R = RS * S;
     constexpr int P = R * G;
@@ -452,6 +454,13 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                     // rows 2k, 2k+1 of that virtual PE against column code = t_lo | t_hi << 2
                     __syncthreads();
                     const int npc = min(a.chunk_passes, npass - pass);
+                    // the chunk's query bytes first (one coalesced load): the entry loop below would
+                    // otherwise pay a global-memory round trip per entry, which is what a small
+                    // (latency-bound) launch consists of
+                    const int qb0 = (pass * P) >> 2;
+                    const int qnb = ((min((pass + npc) * P, m) + 3) >> 2) - qb0;
+                    for (int i = threadIdx.x; i < qnb && i < kQueryBytes; i += BT) s_qb[i] = qp[qb0 + i];
+                    __syncthreads();
                     for (int idx = threadIdx.x; idx < npc * PASS_ENTRIES; idx += BT) {
                         // layout: (((pass * S + s) * RP + rp) * 32 + code) * G + gl -- the G lanes of a
                         // group sit in consecutive 8-byte slots, so a warp-wide group reads 32 banks
@@ -469,7 +478,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                             const int i = (pass + pc) * P + vpe * RS + rr;
                             int lo = AR::kPad, hi = AR::kPad;
                             if (rr < RS && i < m && code < kPadCode) {
-                                const int qi = (qp[i >> 2] >> ((i & 3) * 2)) & 3;
+                                const int qi = (s_qb[(i >> 2) - qb0] >> ((i & 3) * 2)) & 3;
                                 lo = (qi == (code & 3)) ? a.match : a.mismatch;   // v1.0.v:119
                                 if (code < kHiEndedCode) hi = (qi == (code >> 2)) ? a.match : a.mismatch;
                             }

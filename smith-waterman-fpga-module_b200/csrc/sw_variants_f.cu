@@ -12,6 +12,7 @@ static const VariantEntry g_part[] = {
     SW_VARIANT_S16D(8, 1, 32, 4),
     SW_VARIANT_S16D(8, 1, 16, 4),
     SW_VARIANT_S16D(16, 1, 8, 4),
+    SW_VARIANT_S16D(2, 2, 32, 4),
 };
 VariantPart sw_variants_part_f() { return {g_part, (int)(sizeof(g_part) / sizeof(g_part[0]))}; }
 }  // namespace swk

@@ -14,9 +14,9 @@
  *                order, so the item a band waits for (same pairs, band - 1) was always claimed
  *                earlier by a block that is resident and running: no deadlock by construction.
  *   boundary   = bottom row (H, G) of a band, per pair and band parity: bnd[pair][band & 1][column],
- *                written with st.cg by the last lane, published every 32 columns through
- *                prog[pair][band] (release / acquire), read by the next band 32 columns at a time
- *                (coalesced ld.cg by the whole warp into shared memory, one LDS per step).
+ *                written with st.cg by the last lane, published every kWaveBlock columns through
+ *                prog[pair][band] (release / acquire), read by the next band one block at a time
+ *                (coalesced ld.cg into shared memory, one LDS per step); the block size is kWaveBlock.
  *   result     = max over the bands: atomicMax per pair; the band that finishes last writes the score.
  * Arithmetic, profile layout and the one-step-ahead code pipeline are those of the strip kernel
  * (sw_strip.cuh); exact arithmetic only (the W-bit mode keeps the strip kernel).
@@ -38,7 +38,7 @@ struct WaveArgs {
     const uint32_t *qoff;
     const uint32_t *qlen;
     int q;                     // the query of this launch
-    int npass;                 // bands of that query
+    int npass;                 // bands of that query (of R * 32 rows each)
     void *out;
     size_t out_stride;
     int out_mode;              // SW_OUT_I32 / SW_OUT_I16
@@ -59,6 +59,8 @@ struct WaveArgs {
     unsigned spin_limit;       // polls of a progress counter before the watchdog gives up
 };
 
+constexpr int kWaveBlock = 32;       // columns per publication of a band's bottom row (a power of two <= 32)
+
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
 {
     unsigned v;
@@ -72,11 +74,12 @@ __device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
 
 // One band of one pair (one warp).  Returns the band's running maximum (K representation).
 template <int RS, int S, class AR, bool HAS_TOP, bool HAS_BOTTOM>
-__device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *prof_lane, uint2 (&s_top)[32], const uint32_t *tpp,
+__device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *prof_lane, uint2 (&s_top)[kWaveBlock], const uint32_t *tpp,
                                               int ncols, const uint2 *top, uint2 *bot, const unsigned *prog_top, unsigned *prog_bot,
                                               uint32_t goe2, uint32_t ge2, uint32_t h0, uint32_t gb2, uint32_t zero)
 {
     constexpr int G = 32, RP = (RS + 1) / 2, VPE = G * S, U = 4;
+    constexpr int BLK = kWaveBlock;                       // columns per publication / staging block
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const bool head = lane == 0;
@@ -104,9 +107,9 @@ __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *pr
 #pragma unroll 1
     for (int t2 = 0; t2 < nsteps; t2 += U) {
         if constexpr (HAS_TOP) {
-            if ((t2 & 31) == 0 && t2 < ncols) {
-                // stage columns t2 .. t2 + 31 of the bottom row of the band above
-                const unsigned need = (unsigned)min(t2 + 32, ncols);
+            if ((t2 & (BLK - 1)) == 0 && t2 < ncols) {
+                // stage columns t2 .. t2 + BLK - 1 of the bottom row of the band above
+                const unsigned need = (unsigned)min(t2 + BLK, ncols);
                 if (avail < need) {
                     if (head) {
                         unsigned spins = 0;
@@ -124,9 +127,9 @@ __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *pr
                 }
                 const int c = t2 + lane;
                 uint2 v = make_uint2(h0, gb2);
-                if (c < ncols) v = __ldcg(top + c);
-                __syncwarp();                                  // the head lane is done with the previous 32 columns
-                s_top[lane] = v;
+                if (lane < BLK && c < ncols) v = __ldcg(top + c);
+                __syncwarp();                                  // the head lane is done with the previous block
+                if (lane < BLK) s_top[lane] = v;
                 __syncwarp();
             }
         }
@@ -138,7 +141,7 @@ __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *pr
             in_h[0] = __shfl_up_sync(FULL, pub_h[S - 1], 1, G);
             in_g[0] = __shfl_up_sync(FULL, pub_g[S - 1], 1, G);
             in_t[0] = __shfl_up_sync(FULL, pub_t[S - 1], 1, G);
-            if constexpr (HAS_TOP) bcur = s_top[t & 31];
+            if constexpr (HAS_TOP) bcur = s_top[t & (BLK - 1)];
             const uint32_t wsel = (u < 3) ? wcur : wnext;
             const uint32_t lead_t = (t + 1 < ncols) ? ((wsel >> (8 * ((u + 1) & 3))) & 255u) : (uint32_t)kPadCode;
             in_h[0] = head ? bcur.x : in_h[0];
@@ -167,7 +170,7 @@ __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *pr
                     const int cl = t - (VPE - 1);              // column the last virtual PE just finished
                     if (cl >= 0 && cl < ncols) {
                         __stcg(bot + cl, make_uint2(pub_h[S - 1], pub_g[S - 1]));
-                        if ((cl & 31) == 31 || cl == ncols - 1) st_release_u32(prog_bot, (unsigned)(cl + 1));
+                        if ((cl & (BLK - 1)) == BLK - 1 || cl == ncols - 1) st_release_u32(prog_bot, (unsigned)(cl + 1));
                     }
                 }
             }
@@ -185,7 +188,8 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
     constexpr int PASS_ENTRIES = VPE * RP * kCodesPerRow;
     constexpr int PPB = BT / G;
     constexpr unsigned FULL = 0xFFFFFFFFu;
-    __shared__ uint2 s_top[PPB][32];
+    __shared__ uint2 s_top[PPB][kWaveBlock];
+    __shared__ uint8_t s_qb[P / 4 + 4];                // packed query bytes of the band
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t zero = a.zero;
@@ -217,6 +221,10 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
         if (prof_pass != pass) {
             prof_pass = pass;
             __syncthreads();
+            const int qb0 = (pass * P) >> 2;
+            const int qnb = ((min((pass + 1) * P, m) + 3) >> 2) - qb0;
+            for (int i = threadIdx.x; i < qnb; i += BT) s_qb[i] = qp[qb0 + i];
+            __syncthreads();
             for (int idx = threadIdx.x; idx < PASS_ENTRIES; idx += BT) {
                 // layout as in the strip kernel: ((s * RP + rp) * 32 + code) * G + lane
                 const int lg = idx % G;
@@ -232,7 +240,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
                     const int i = pass * P + vpe * RS + rr;
                     int lo = AR::kPad, hi = AR::kPad;
                     if (rr < RS && i < m && code < kPadCode) {
-                        const int qi = (qp[i >> 2] >> ((i & 3) * 2)) & 3;
+                        const int qi = (s_qb[(i >> 2) - qb0] >> ((i & 3) * 2)) & 3;
                         lo = (qi == (code & 3)) ? a.match : a.mismatch;   // v1.0.v:119
                         if (code < kHiEndedCode) hi = (qi == (code >> 2)) ? a.match : a.mismatch;
                     }

@@ -48,13 +48,13 @@ STRIP_VARIANTS = [
     "strip_s16x2_R16x1_G32", "strip_s16x2_R8x2_G32",
     # small-R warp-wide variants of the latency path (P ~ query length)
     "strip_s16x2_R1x1_G32", "strip_s16x2_R2x1_G32", "strip_s16x2_R4x1_G32", "strip_s16x2_R8x1_G32",
-    "strip_s16x2_R8x1_G16", "strip_s16x2_R16x1_G8",
+    "strip_s16x2_R8x1_G16", "strip_s16x2_R16x1_G8", "strip_s16x2_R2x2_G32",
     # experimental: 8 columns per trip of the step loop (A/B against the 4-column instances)
     "strip_s16x2_R25x2_G1_U8", "strip_s16x2_R25x3_G1_U8", "strip_s16x2_R38x2_G1_U8",
 ]
 # variants that also exist as DIRECT instances (column codes formed on the fly: the small-batch path)
 DIRECT_VARIANTS = ["strip_s16x2_R16x1_G32", "strip_s16x2_R1x1_G32", "strip_s16x2_R2x1_G32", "strip_s16x2_R4x1_G32",
-                   "strip_s16x2_R8x1_G32", "strip_s16x2_R8x1_G16", "strip_s16x2_R16x1_G8"]
+                   "strip_s16x2_R8x1_G32", "strip_s16x2_R8x1_G16", "strip_s16x2_R16x1_G8", "strip_s16x2_R2x2_G32"]
 S16_VARIANTS = [v for v in STRIP_VARIANTS if "s16x2" in v]
 VARIANTS = ["auto", "generic32"] + STRIP_VARIANTS
 

@@ -34,7 +34,7 @@ def test_small_path_direct_variants_vs_oracle(oracle_mod, pkg, variant):
     rng = random.Random(500 + len(variant))
     rows_per_pass = {"auto": 512, "strip_s16x2_R16x1_G32": 512, "strip_s16x2_R1x1_G32": 32, "strip_s16x2_R2x1_G32": 64,
                      "strip_s16x2_R4x1_G32": 128, "strip_s16x2_R8x1_G32": 256, "strip_s16x2_R8x1_G16": 128,
-                     "strip_s16x2_R16x1_G8": 128}[variant]
+                     "strip_s16x2_R16x1_G8": 128, "strip_s16x2_R2x2_G32": 128}[variant]
     for qlens, nsub in (((1, 31, 32, 17), 61), ((128,), 499), ((150, 64), 300), ((600, 257), 40), ((1300, 513), 12), ((32,), 1)):
         if variant not in ("auto", "strip_s16x2_R16x1_G32") and max(qlens) > rows_per_pass:
             continue            # small-P DIRECT instances are single-pass by construction (the host checks)
@@ -266,6 +266,7 @@ def test_query_groups_get_their_own_variant(oracle_mod, pkg):
             packed[int(off[k]): int(off[k]) + n] = qp[0][int(qp[2][qi]): int(qp[2][qi]) + n]
     db = (packed, lens, off)
     with pkg.Engine() as e:
+        e.set_launch_plan(1, True)           # one launch per (length group, query group), concurrent streams
         got = e.score(qp, db)
         name = e.last_kernel_name
         assert e.device_error_bits == 0
@@ -280,7 +281,16 @@ def test_query_groups_get_their_own_variant(oracle_mod, pkg):
     with pkg.Engine() as e:
         e.set_kernel_name("strip_s16x2_R25x3_G1")
         one = e.score(qp, db)
+        e.set_kernel_name("")
+        e.set_launch_plan(1, False)
+        two = e.score(qp, db)
+        assert "+groups" in e.last_kernel_name
+        e.set_launch_plan(2, False)          # the default: one launch here
+        three = e.score(qp, db)
+        assert "+groups" not in e.last_kernel_name
     np.testing.assert_array_equal(got, one)
+    np.testing.assert_array_equal(got, two)
+    np.testing.assert_array_equal(got, three)
 
 
 def test_load_db_right_after_async_score_db(oracle_mod, pkg):
