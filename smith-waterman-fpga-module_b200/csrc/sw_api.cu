@@ -490,6 +490,9 @@ double variant_speed(const SwStripVariant *v)
         {"strip_s16x2_R1x1_G32", 900}, {"strip_s16x2_R2x1_G32", 1700}, {"strip_s16x2_R4x1_G32", 3000},
         {"strip_s16x2_R8x1_G32", 4500}, {"strip_s16x2_R8x1_G16", 4600}, {"strip_s16x2_R16x1_G8", 5900},
         {"strip_s16x2_R2x2_G32", 2900},
+        // 8 columns per trip: measured +1.6 % on 150-nt reads (profiles/r02_variant_ab_u8.jsonl); the
+        // R25x3 / R38x2 counterparts lose 15 % (their loop bodies outgrow the instruction cache)
+        {"strip_s16x2_R25x2_G1_U8", 8840}, {"strip_s16x2_R25x3_G1_U8", 7320}, {"strip_s16x2_R38x2_G1_U8", 7390},
     };
     for (auto &t : tab) if (std::strcmp(t.name, v->name) == 0) return t.gcups;
     return 5000.0;
