@@ -152,6 +152,7 @@ struct GpuCtx {
     DevBuf d_bnd, d_counters, d_scratch32, d_best_score, d_best_index, d_topk_keys, d_err;
     DevBuf d_wave_bnd, d_wave_state;  // band-pipelined kernel: boundary rows; progress / best / done words
     int wave_bps[2] = {0, 0};         // resident blocks per SM of its two instances (0 = not asked yet)
+    uint32_t wave_epoch = 0;          // launches so far: the tag of the boundary elements (20 bits)
     unsigned counter_next = 0;        // next unused work-queue counter
     // autotune: timing events and the cached decision, per GPU (shards differ in shape)
     cudaEvent_t ev_tune0 = nullptr, ev_tune1 = nullptr;
@@ -600,6 +601,22 @@ int strip_setup(sw_handle *h, GpuCtx &gc, DevBuf &bnd_buf, uint32_t npairs, uint
     return SW_OK;
 }
 
+// Pair blocks per super-block of the work order: inside a super-block the queries of a launch pass
+// over the same pair blocks one after the other, so its code stream should stay in L2 (about a
+// quarter of it: the pass-boundary scratch and the scores live there too) -- but not fewer blocks
+// than two full grids, or consecutive items of a thread block stop sharing the query profile.
+uint32_t superblock_for(const SwStripVariant *v, uint32_t npairs, uint64_t tp_words, int grid)
+{
+    const uint32_t ppb = (uint32_t)(v->block_threads / v->G);
+    const uint32_t npb = (npairs + ppb - 1) / ppb;
+    if (npb == 0 || tp_words == 0) return 0;
+    const double bytes_per_block = (double)tp_words * 4.0 / (double)npb;
+    uint32_t b = (uint32_t)std::max(1.0, (24.0 * 1024 * 1024) / std::max(bytes_per_block, 1.0));
+    b = std::max<uint32_t>(b, 2u * (uint32_t)std::max(grid, 1));
+    b = std::min<uint32_t>(b, std::max<uint32_t>(1u, npb >> 3));
+    return std::max<uint32_t>(b, 1u);
+}
+
 unsigned *next_counter(GpuCtx &gc)
 {
     unsigned *c = gc.d_counters.as<unsigned>() + (gc.counter_next % kMaxCounters);
@@ -719,7 +736,7 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
         for (int q = 0; q < nq; ++q) {
             const uint32_t ql = h->q_len[q];
             bool w = false;
-            if (wave_ok && ql > SW_WAVE_ROWS_PER_BAND) {
+            if (wave_ok && ql > SW_WAVE_ROWS_PER_BAND && ql <= 4000u * 256u) {
                 if (h->wave >= 2) w = true;
                 else w = (g.npairs <= 1536 && ql >= 2 * SW_WAVE_ROWS_PER_BAND) || g.npairs <= 64;
             }
@@ -807,6 +824,7 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
             L.vidx = vidx;
             rc = strip_setup(h, gc, gc.d_bnd, g.npairs, g.max_len, smaxq, nq / nchunks, vidx, &L.grid, &L.chunk_passes, &L.bnd_elems);
             if (rc != SW_OK) return rc;
+            L.superblock = superblock_for(sw_strip_variant(vidx), g.npairs, g.tp_words, L.grid);
             max_grid = L.grid;
             label_v = vidx;
             n_groups_total = 1;
@@ -1021,10 +1039,19 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
             const uint32_t cols_stride = (g.max_len + 31u) & ~31u;
             uint32_t wmaxq = 0;
             for (int q : wave_q) wmaxq = std::max(wmaxq, h->q_len[q]);
-            const int max_pass = (int)((wmaxq + 255) / 256);
-            SW_CUDA(h, gc.d_wave_bnd.reserve((size_t)g.npairs * 2 * cols_stride * sizeof(uint2)));
-            // state words: prog [npairs * max_pass] | best [2 * npairs] | done [npairs]
-            const size_t n_prog = (size_t)g.npairs * max_pass, n_state = n_prog + 3 * (size_t)g.npairs;
+            (void)wmaxq;
+            {
+                // tagged 16-byte boundary elements; zeroed once (tag 0 is never used), later launches
+                // are told apart by the epoch in the tag
+                const size_t bytes = (size_t)g.npairs * 2 * cols_stride * 16;
+                if (gc.d_wave_bnd.cap < bytes || !gc.d_wave_bnd.p) {
+                    SW_CUDA(h, cudaStreamSynchronize(gc.st_compute));
+                    SW_CUDA(h, gc.d_wave_bnd.reserve(bytes));
+                    SW_CUDA(h, cudaMemsetAsync(gc.d_wave_bnd.p, 0, gc.d_wave_bnd.cap, gc.st_compute));
+                }
+            }
+            // state words: best [2 * npairs] | done [npairs]
+            const size_t n_state = 3 * (size_t)g.npairs;
             SW_CUDA(h, gc.d_wave_state.reserve(n_state * sizeof(unsigned)));
             for (int q : wave_q) {
                 SwWaveLaunch W;
@@ -1037,10 +1064,15 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 W.db = db; W.q = dq; W.query = q; W.sc = sc;
                 W.npass = (int)((h->q_len[q] + rows - 1) / rows);
                 W.out = g.d_out.p; W.out_stride = n; W.out_mode = g.out_mode;
-                W.bnd = gc.d_wave_bnd.as<uint2>(); W.cols_stride = cols_stride;
-                W.prog = gc.d_wave_state.as<unsigned>();
-                W.best = (int *)(gc.d_wave_state.as<unsigned>() + n_prog);
-                W.done = gc.d_wave_state.as<unsigned>() + n_prog + 2 * (size_t)g.npairs;
+                W.bnd = gc.d_wave_bnd.p; W.cols_stride = cols_stride;
+                gc.wave_epoch = (gc.wave_epoch % 0xFFFFEu) + 1u;            // 1 .. 2^20 - 2
+                if (gc.wave_epoch == 1u && gc.counter_next > 0) {
+                    // the epoch wrapped (or first use): stale tags must not match again
+                    SW_CUDA(h, cudaMemsetAsync(gc.d_wave_bnd.p, 0, gc.d_wave_bnd.cap, gc.st_compute));
+                }
+                W.epoch = gc.wave_epoch;
+                W.best = (int *)gc.d_wave_state.as<unsigned>();
+                W.done = gc.d_wave_state.as<unsigned>() + 2 * (size_t)g.npairs;
                 W.counter = next_counter(gc);
                 const size_t items = (size_t)W.npass * ((g.npairs + 3) / 4);
                 W.grid = (int)std::min<size_t>(items, (size_t)gc.num_sms * gc.wave_bps[W.instance]);

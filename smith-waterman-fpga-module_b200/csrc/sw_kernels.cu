@@ -317,7 +317,7 @@ cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L)
     const SwScoring &sc = L.sc;
     StripArgs a{};
     a.tp = L.db.tp; a.tile_woff = L.db.tile_woff; a.pair_len = L.db.pair_len; a.pair_subj = L.db.pair_subj;
-    a.npairs = L.db.npairs; a.npb = (L.db.npairs + ppb - 1) / ppb;
+    a.npairs = L.db.npairs; a.npb = (L.db.npairs + ppb - 1) / ppb; a.superblock = L.superblock;
     a.qpacked = L.q.packed; a.qoff = L.q.off; a.qlen = L.q.len; a.qidx = L.qidx; a.q0 = L.q0; a.nql = L.nql;
     a.out = L.out; a.out_stride = L.out_stride; a.out_mode = L.out_mode;
     a.bnd = L.bnd; a.bnd_cols = L.bnd_cols; a.counter = L.counter;
@@ -361,9 +361,9 @@ cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L)
 namespace {
 typedef void (*WaveFn)(const WaveArgs);
 struct WaveInstance { int rows; size_t smem; WaveFn fn, fn_fixed; const char *name; };
-constexpr size_t wave_smem(int rs, int s) { return (size_t)32 * s * ((rs + 1) / 2) * kCodesPerRow * sizeof(uint2); }
+constexpr size_t wave_smem(int rs, int s) { return (size_t)32 * s * ((rs + 1) / 2) * kWaveCodes * sizeof(uint2); }
 const WaveInstance g_wave[2] = {
-    {512, wave_smem(8, 2), sw_wave_kernel<8, 2, ArithS16, kBT, 3>, sw_wave_kernel<8, 2, ArithS16, kBT, 3, kFixedGoe, kFixedGe>,
+    {512, wave_smem(8, 2), sw_wave_kernel<8, 2, ArithS16, kBT, 4>, sw_wave_kernel<8, 2, ArithS16, kBT, 4, kFixedGoe, kFixedGe>,
      "wave_s16x2_R8x2_G32"},
     {256, wave_smem(8, 1), sw_wave_kernel<8, 1, ArithS16, kBT, 4>, sw_wave_kernel<8, 1, ArithS16, kBT, 4, kFixedGoe, kFixedGe>,
      "wave_s16x2_R8x1_G32"},
@@ -392,7 +392,7 @@ cudaError_t sw_launch_wave(cudaStream_t st, const SwWaveLaunch &L)
     a.npairs = L.db.npairs; a.npb = (L.db.npairs + 3) / 4;
     a.qpacked = L.q.packed; a.qoff = L.q.off; a.qlen = L.q.len; a.q = L.query; a.npass = L.npass;
     a.out = L.out; a.out_stride = L.out_stride; a.out_mode = L.out_mode;
-    a.bnd = L.bnd; a.cols_stride = L.cols_stride; a.prog = L.prog; a.best = L.best; a.done = L.done; a.counter = L.counter;
+    a.bnd = (ulonglong2 *)L.bnd; a.cols_stride = L.cols_stride; a.epoch = L.epoch; a.best = L.best; a.done = L.done; a.counter = L.counter;
     a.match = sc.match; a.mismatch = sc.mismatch; a.goe = sc.goe; a.ge = sc.ge;
     a.goe2 = ((uint32_t)sc.goe & 0xFFFFu) * 0x10001u; a.ge2 = ((uint32_t)sc.ge & 0xFFFFu) * 0x10001u;
     a.ovf_limit = 32767 - sc.match - 1;

@@ -94,6 +94,7 @@ struct SwStripLaunch {
     size_t bnd_elems = 0;
     unsigned *counter = nullptr;
     int grid = 0, chunk_passes = 1;
+    uint32_t superblock = 0;      /* pair blocks per super-block of the work order (0 = a tenth... npb / 8) */
     unsigned *ovf_count = nullptr;
     uint2 *ovf_list = nullptr;
     unsigned ovf_cap = 0;
@@ -109,9 +110,10 @@ cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L);
 const char *sw_strip_instance_kind(const SwStripLaunch &L);
 
 /* Band-pipelined kernel for few, long pairs (sw_wave.cuh): ONE query per launch, its bands are
- * separate work items that run concurrently on different warps.  bnd: npairs * 2 * cols_stride uint2;
- * prog: npairs * npass words, best: 2 * npairs ints, done: npairs words -- all zeroed before the
- * launch; counter: zeroed work-queue word. */
+ * separate work items that run concurrently on different warps.  bnd: npairs * 2 * cols_stride
+ * 16-byte tagged elements (zeroed once when allocated; epoch makes the tags of earlier launches
+ * stale); best: 2 * npairs ints, done: npairs words -- zeroed before the launch; counter: zeroed
+ * work-queue word. */
 #define SW_WAVE_ROWS_PER_BAND 512     /* instance 0; instance 1 has bands of 256 rows */
 struct SwWaveLaunch {
     int instance = 0;
@@ -123,9 +125,9 @@ struct SwWaveLaunch {
     void *out = nullptr;
     size_t out_stride = 0;
     int out_mode = SW_OUT_I32;
-    uint2 *bnd = nullptr;
+    void *bnd = nullptr;
     uint32_t cols_stride = 0;
-    unsigned *prog = nullptr;
+    uint32_t epoch = 1;
     int *best = nullptr;
     unsigned *done = nullptr;
     unsigned *counter = nullptr;

@@ -127,6 +127,7 @@ struct StripArgs {
     const uint32_t *pair_subj;
     uint32_t npairs;
     uint32_t npb;              // pair blocks = ceil(npairs / pairs-per-block)
+    uint32_t superblock;       // pair blocks per super-block of the work order (0 = npb / 8)
     const uint8_t *qpacked;
     const uint32_t *qoff;
     const uint32_t *qlen;
@@ -203,15 +204,15 @@ __device__ __forceinline__ uint32_t make_code_word(uint32_t a, uint32_t b, uint3
 // thread).  H[s][r] / Gl[s][r] hold H and G of the previous column on entry and of this column
 // on exit; hd_top = H(row0-1, c-1), g_top = G(row0-1, c); sv[s][k] = the substitution scores of
 // rows 2k, 2k+1 of sub-strip s against this column's code (load_scores: one LDS.64 per row pair).
-template <int RS, int S, int G>
+template <int RS, int S, int G, int CODES = kCodesPerRow>
 __device__ __forceinline__ void load_scores(uint2 (&sv)[S][(RS + 1) / 2], const uint2 *prof_lane, const uint32_t (&code)[S])
 {
     constexpr int RP = (RS + 1) / 2;
 #pragma unroll
     for (int s = 0; s < S; ++s) {
-        const uint2 *prow = prof_lane + (s * RP * kCodesPerRow + code[s]) * G;
+        const uint2 *prow = prof_lane + (s * RP * CODES + code[s]) * G;
 #pragma unroll
-        for (int k = 0; k < RP; ++k) sv[s][k] = prow[k * kCodesPerRow * G];
+        for (int k = 0; k < RP; ++k) sv[s][k] = prow[k * CODES * G];
     }
 }
 
@@ -371,13 +372,14 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
     // work item -> (pair block, query).  Pairs are sorted by ascending length: the longest blocks go
     // first so that the tail is made of short items.  Order: super-blocks of B pair blocks, longest
     // first; inside a super-block query-major.  With B >> grid (large databases) consecutive items
-    // of a thread block share the query and the profile in shared memory is reused; with B small
-    // the order degenerates to longest-first over everything, which is what short launches need for
-    // their tail.  (Decoded twice per item -- before the column loops and again in the epilogue --
+    // of a thread block share the query and the profile in shared memory is reused, and the host
+    // sizes B so that a super-block's code stream stays in L2 while its queries pass over it; with B
+    // small the order degenerates to longest-first over everything, which is what short launches
+    // need for their tail.  (Decoded twice per item -- before the column loops and again in the epilogue --
     // so that nothing but s_work has to stay live across the hot loop.)
     auto decode = [&](unsigned work, unsigned &pair, int &q) {
         const unsigned nql = (unsigned)a.nql;
-        const unsigned B = max(1u, a.npb >> 3);
+        const unsigned B = a.superblock ? a.superblock : max(1u, a.npb >> 3);
         const unsigned sb = work / (nql * B);
         const unsigned rem = work - sb * nql * B;
         const unsigned bcur = min(B, a.npb - sb * B);

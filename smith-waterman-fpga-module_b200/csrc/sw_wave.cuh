@@ -8,18 +8,24 @@
  * the bands of one pair run concurrently on different warps / SMs, staggered by a few dozen
  * columns -- the module-chaining ports the reference left "for future use"
  * (ScoringModule_v1.1.v:36-39, 49-54: M_in / I_in / High_in of one module fed by the outputs of
- * another), with HBM/L2 as the wire and a progress counter as the valid signal.
+ * another), with L2 as the wire and a tag inside every boundary element as the valid signal.
  *
  *   work item  = (band, block of 4 pairs); items are claimed from an atomic counter in band-major
  *                order, so the item a band waits for (same pairs, band - 1) was always claimed
- *                earlier by a block that is resident and running: no deadlock by construction.
+ *                earlier by a block that is resident and running: no deadlock by construction
+ *                (plus a watchdog that raises SW_DEVERR_SPIN instead of hanging the GPU).
  *   boundary   = bottom row (H, G) of a band, per pair and band parity: bnd[pair][band & 1][column],
- *                written with st.cg by the last lane, published every kWaveBlock columns through
- *                prog[pair][band] (release / acquire), read by the next band one block at a time
- *                (coalesced ld.cg into shared memory, one LDS per step); the block size is kWaveBlock.
+ *                one 16-byte element {tag:H, tag:G} per column: two 64-bit words, each stored
+ *                atomically, each carrying tag = (launch epoch, band).  The consumer loads 32
+ *                columns at a time (coalesced ld.cg) and simply retries until every element carries
+ *                the tag it expects -- no fence, no separate progress counter on the producer's path.
+ *                Band b+2 reuses the slots of band b, but only behind band b+1's read position
+ *                (band b+2 lags band b+1 by at least 32 columns plus the 32 S - 1 steps of the
+ *                systolic skew, and band b+1 has staged a column before it uses it).
  *   result     = max over the bands: atomicMax per pair; the band that finishes last writes the score.
- * Arithmetic, profile layout and the one-step-ahead code pipeline are those of the strip kernel
- * (sw_strip.cuh); exact arithmetic only (the W-bit mode keeps the strip kernel).
+ * Arithmetic and the one-step-ahead code pipeline are those of the strip kernel (sw_strip.cuh); the
+ * profile uses 24 code slots per row pair instead of 32 (48 KB per block: four resident blocks per
+ * SM).  Exact arithmetic only (the W-bit mode keeps the strip kernel).
  */
 #ifndef SW_WAVE_CUH_
 #define SW_WAVE_CUH_
@@ -27,6 +33,9 @@
 #include "sw_strip.cuh"
 
 namespace swk {
+
+constexpr int kWaveBlock = 32;       // columns staged per block by the consuming band
+constexpr int kWaveCodes = 24;       // profile slots per row pair (codes 0 .. 20 are used)
 
 struct WaveArgs {
     const uint32_t *tp;
@@ -38,13 +47,13 @@ struct WaveArgs {
     const uint32_t *qoff;
     const uint32_t *qlen;
     int q;                     // the query of this launch
-    int npass;                 // bands of that query (of R * 32 rows each)
+    int npass;                 // bands of that query (of R * 32 rows each), <= 4095
     void *out;
     size_t out_stride;
     int out_mode;              // SW_OUT_I32 / SW_OUT_I16
-    uint2 *bnd;                // [pair][2][cols_stride]
+    ulonglong2 *bnd;           // [pair][2][cols_stride] tagged boundary elements
     uint32_t cols_stride;
-    unsigned *prog;            // [pair][npass]: columns of the band's bottom row that are published
+    uint32_t epoch;            // launch number (tags of earlier launches never match), 1 .. 2^20 - 1
     int *best;                 // [pair][2]: running maximum of the two members, INT_MAX = 16-bit overflow
     unsigned *done;            // [pair]: bands finished
     unsigned *counter;
@@ -56,30 +65,17 @@ struct WaveArgs {
     uint2 *ovf_list;
     unsigned ovf_cap;
     unsigned *dev_err;
-    unsigned spin_limit;       // polls of a progress counter before the watchdog gives up
+    unsigned spin_limit;       // polls of a boundary block before the watchdog gives up
 };
-
-constexpr int kWaveBlock = 32;       // columns per publication of a band's bottom row (a power of two <= 32)
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned *p, unsigned v)
-{
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
 
 // One band of one pair (one warp).  Returns the band's running maximum (K representation).
 template <int RS, int S, class AR, bool HAS_TOP, bool HAS_BOTTOM>
 __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *prof_lane, uint2 (&s_top)[kWaveBlock], const uint32_t *tpp,
-                                              int ncols, const uint2 *top, uint2 *bot, const unsigned *prog_top, unsigned *prog_bot,
+                                              int ncols, const ulonglong2 *top, ulonglong2 *bot, uint32_t tag_top, uint32_t tag_bot,
                                               uint32_t goe2, uint32_t ge2, uint32_t h0, uint32_t gb2, uint32_t zero)
 {
     constexpr int G = 32, RP = (RS + 1) / 2, VPE = G * S, U = 4;
-    constexpr int BLK = kWaveBlock;                       // columns per publication / staging block
+    constexpr int BLK = kWaveBlock;
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const bool head = lane == 0;
@@ -99,35 +95,35 @@ __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *pr
     for (int s = 0; s < S; ++s) { pub_h[s] = h0; pub_g[s] = gb2; pub_t[s] = kPadCode; hd_top[s] = h0; }
     if (head && ncols > 0) pub_t[0] = wcur & 255u;
     uint2 sv[S][RP];
-    load_scores<RS, S, G>(sv, prof_lane, pub_t);
+    load_scores<RS, S, G, kWaveCodes>(sv, prof_lane, pub_t);
     uint2 bcur = make_uint2(h0, gb2);
-    unsigned avail = 0;                                   // published columns of the band above (as last seen)
+    const unsigned long long tag_hi = (unsigned long long)tag_bot << 32;
     const int nsteps = ncols > 0 ? (ncols + (VPE - 1) + U - 1) / U * U : 0;
 
 #pragma unroll 1
     for (int t2 = 0; t2 < nsteps; t2 += U) {
         if constexpr (HAS_TOP) {
             if ((t2 & (BLK - 1)) == 0 && t2 < ncols) {
-                // stage columns t2 .. t2 + BLK - 1 of the bottom row of the band above
-                const unsigned need = (unsigned)min(t2 + BLK, ncols);
-                if (avail < need) {
-                    if (head) {
-                        unsigned spins = 0;
-                        while ((avail = ld_acquire_u32(prog_top)) < need) {
-                            __nanosleep(40);
-                            if (++spins > a.spin_limit) {          // watchdog: never hang the GPU
-                                if (a.dev_err) atomicOr(a.dev_err, SW_DEVERR_SPIN);
-                                avail = need;
-                                break;
-                            }
-                        }
-                    }
-                    avail = __shfl_sync(FULL, avail, 0);
-                    __syncwarp();                              // orders the other lanes' loads after the acquire
-                }
+                // stage columns t2 .. t2 + BLK - 1 of the bottom row of the band above: every lane
+                // loads one element and retries until both of its words carry the producer's tag
                 const int c = t2 + lane;
+                const bool mine = lane < BLK && c < ncols;
                 uint2 v = make_uint2(h0, gb2);
-                if (lane < BLK && c < ncols) v = __ldcg(top + c);
+                unsigned spins = 0;
+                for (;;) {
+                    bool ok = true;
+                    if (mine) {
+                        const ulonglong2 e = __ldcg(top + c);
+                        ok = (uint32_t)(e.x >> 32) == tag_top && (uint32_t)(e.y >> 32) == tag_top;
+                        v = make_uint2((uint32_t)e.x, (uint32_t)e.y);
+                    }
+                    if (__all_sync(FULL, ok)) break;
+                    __nanosleep(64);
+                    if (++spins > a.spin_limit) {              // watchdog: never hang the GPU
+                        if (head && a.dev_err) atomicOr(a.dev_err, SW_DEVERR_SPIN);
+                        break;
+                    }
+                }
                 __syncwarp();                                  // the head lane is done with the previous block
                 if (lane < BLK) s_top[lane] = v;
                 __syncwarp();
@@ -156,7 +152,7 @@ __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *pr
 #pragma unroll
             for (int s = 1; s < S; ++s) { in_h[s] = pub_h[s - 1]; in_g[s] = pub_g[s - 1]; in_t[s] = pub_t[s - 1]; }
             uint2 sv_next[S][RP];
-            load_scores<RS, S, G>(sv_next, prof_lane, in_t);
+            load_scores<RS, S, G, kWaveCodes>(sv_next, prof_lane, in_t);
             column_step_multi<RS, S, G, AR, false>(H, Gl, best, hd_top, in_g, sv, goe2, ge2, zero, 0u);
 #pragma unroll
             for (int s = 0; s < S; ++s) {
@@ -168,10 +164,8 @@ __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *pr
             if constexpr (HAS_BOTTOM) {
                 if (lane == G - 1) {
                     const int cl = t - (VPE - 1);              // column the last virtual PE just finished
-                    if (cl >= 0 && cl < ncols) {
-                        __stcg(bot + cl, make_uint2(pub_h[S - 1], pub_g[S - 1]));
-                        if ((cl & (BLK - 1)) == BLK - 1 || cl == ncols - 1) st_release_u32(prog_bot, (unsigned)(cl + 1));
-                    }
+                    if (cl >= 0 && cl < ncols)
+                        __stcg(bot + cl, make_ulonglong2(tag_hi | pub_h[S - 1], tag_hi | pub_g[S - 1]));
                 }
             }
         }
@@ -185,7 +179,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
     extern __shared__ uint2 s_prof[];
     __shared__ unsigned s_work;
     constexpr int G = 32, R = RS * S, P = R * G, RP = (RS + 1) / 2, VPE = G * S;
-    constexpr int PASS_ENTRIES = VPE * RP * kCodesPerRow;
+    constexpr int PASS_ENTRIES = VPE * RP * kWaveCodes;
     constexpr int PPB = BT / G;
     constexpr unsigned FULL = 0xFFFFFFFFu;
     __shared__ uint2 s_top[PPB][kWaveBlock];
@@ -226,12 +220,12 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
             for (int i = threadIdx.x; i < qnb; i += BT) s_qb[i] = qp[qb0 + i];
             __syncthreads();
             for (int idx = threadIdx.x; idx < PASS_ENTRIES; idx += BT) {
-                // layout as in the strip kernel: ((s * RP + rp) * 32 + code) * G + lane
+                // layout: ((s * RP + rp) * kWaveCodes + code) * G + lane
                 const int lg = idx % G;
-                const int code = (idx / G) & (kCodesPerRow - 1);
+                const int code = (idx / G) % kWaveCodes;
                 if (code > kPadCode) continue;
-                const int rp = (idx / (G * kCodesPerRow)) % RP;
-                const int ss = (idx / (G * kCodesPerRow * RP)) % S;
+                const int rp = (idx / (G * kWaveCodes)) % RP;
+                const int ss = (idx / (G * kWaveCodes * RP)) % S;
                 const int vpe = lg * S + ss;
                 uint32_t e[2];
 #pragma unroll
@@ -253,18 +247,17 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
         const uint2 *prof_lane = s_prof + lane;
         const bool has_top = pass > 0, has_bottom = pass + 1 < a.npass;
         const size_t prow = (size_t)pair * 2;
-        const uint2 *top = a.bnd + (prow + (size_t)((pass - 1) & 1)) * a.cols_stride;
-        uint2 *bot = a.bnd + (prow + (size_t)(pass & 1)) * a.cols_stride;
-        const unsigned *prog_top = a.prog + (size_t)pair * a.npass + (pass > 0 ? pass - 1 : 0);
-        unsigned *prog_bot = a.prog + (size_t)pair * a.npass + pass;
+        const ulonglong2 *top = a.bnd + (prow + (size_t)((pass - 1) & 1)) * a.cols_stride;
+        ulonglong2 *bot = a.bnd + (prow + (size_t)(pass & 1)) * a.cols_stride;
+        const uint32_t tag_bot = (a.epoch << 12) | (uint32_t)pass, tag_top = tag_bot - 1u;
 
         uint32_t best;
         if (has_top) {
-            if (has_bottom) best = wave_band<RS, S, AR, true, true>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, prog_top, prog_bot, goe2, ge2, h0, gb2, zero);
-            else best = wave_band<RS, S, AR, true, false>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, prog_top, prog_bot, goe2, ge2, h0, gb2, zero);
+            if (has_bottom) best = wave_band<RS, S, AR, true, true>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero);
+            else best = wave_band<RS, S, AR, true, false>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero);
         } else {
-            if (has_bottom) best = wave_band<RS, S, AR, false, true>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, prog_top, prog_bot, goe2, ge2, h0, gb2, zero);
-            else best = wave_band<RS, S, AR, false, false>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, prog_top, prog_bot, goe2, ge2, h0, gb2, zero);
+            if (has_bottom) best = wave_band<RS, S, AR, false, true>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero);
+            else best = wave_band<RS, S, AR, false, false>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero);
         }
 
 #pragma unroll
