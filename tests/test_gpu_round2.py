@@ -394,7 +394,8 @@ def test_bounds_check_build_runs_clean(pkg):
     env = dict(os.environ, SW_B200_LIB=lib)
     sel = ("test_random_mixed_lengths_vs_oracle or test_long_query_multi_pass_and_chunks or test_edge_cases or "
            "test_small_path_direct_variants_vs_oracle or test_topk_vs_oracle_argsort or test_output_i16 or "
-           "test_very_long_subjects_short_queries or test_query_groups or test_is_check_build")
+           "test_very_long_subjects_short_queries or test_query_groups or test_is_check_build or test_wave_kernel or "
+           "test_randomised_modes_stress or test_virtual_multi_shard")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-x", "-q", "-m", "gpu", "-k", sel,
                         "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
@@ -464,3 +465,57 @@ def test_wave_kernel_single_long_pair_and_overflow(oracle_mod, pkg):
         got = e.score([big], [big, c, big[:6900]])
         assert got[0].tolist() == [35000, o.score(big, c), 34500]
         assert e.device_error_bits == 0
+
+
+def test_randomised_modes_stress_vs_oracle(oracle_mod, pkg):
+    """Seeded property test over the round-2 switches: output mode (int32 / int16 / top-k), launch plan
+    (one launch / length groups / query groups), band-pipelined kernel on or forced, latency path on
+    or off, one or three shards, resident or streaming -- against the oracle."""
+    rng = random.Random(20161018)
+    for it in range(36):
+        match = rng.randint(1, 7)
+        mismatch = -rng.randint(0, 6)
+        gap_extend = -rng.randint(0, 4)
+        gap_open = -rng.randint(0, 12)
+        params = dict(match=match, mismatch=mismatch, gap_open=gap_open, gap_extend=gap_extend)
+        nq = rng.randint(1, 4)
+        queries = [_rand(rng, rng.choice([1, 17, 32, 150, 513, 700, rng.randint(1, 1400)])) for _ in range(nq)]
+        ns = rng.choice([1, 2, 7, 60, 300, 900])
+        subjects = []
+        for _ in range(ns):
+            if rng.random() < 0.3:
+                src = rng.choice(queries)
+                s = _rand(rng, rng.randint(0, 20)) + _mutate(rng, src, 0.1, 0.1) + _rand(rng, rng.randint(0, 20))
+            else:
+                s = _rand(rng, rng.choice([0, 1, 3, rng.randint(1, 400), rng.randint(1, 1500)]))
+            subjects.append(s)
+        want = _oracle_matrix(oracle_mod, pkg, queries, subjects, **params)
+        mode = rng.choice(["i32", "i32", "i16", "topk"])
+        k = rng.choice([1, 3, 16, 32])
+        shards = rng.choice([[0], [0], [0, 0, 0]])
+        resident = rng.random() < 0.5
+        desc = f"it {it}: {params} nq={nq} ns={ns} mode={mode} k={k} shards={len(shards)} resident={resident}"
+        with pkg.Engine(gpu_ids=shards, **params) as e:
+            e.set_small_batch_path(rng.random() < 0.6)
+            e.set_wave_mode(rng.choice([0, 1, 2]))
+            e.set_launch_plan(rng.choice([0, 1, 2]), rng.random() < 0.5)
+            if mode == "i16":
+                e.set_output(pkg.SW_OUTPUT_I16)
+            if mode == "topk":
+                e.set_topk(k)
+            e.set_queries(queries)
+            if resident:
+                e.load_db(subjects)
+                e.score_db()
+                got = e.fetch_db_topk() if mode == "topk" else e.fetch_db()
+            else:
+                e.score_batch(subjects)
+                got = e.fetch_topk() if mode == "topk" else e.fetch()
+            desc += " " + e.last_kernel_name
+            assert e.device_error_bits == 0, desc
+        if mode == "topk":
+            wsc, wix = _topk_want(want, k)
+            np.testing.assert_array_equal(got[0], wsc, err_msg=desc)
+            np.testing.assert_array_equal(got[1], wix, err_msg=desc)
+        else:
+            np.testing.assert_array_equal(got.astype(np.int32), want, err_msg=desc)
