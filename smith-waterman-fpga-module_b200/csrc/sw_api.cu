@@ -151,7 +151,7 @@ struct GpuCtx {
     // scratch shared by both slots (kernels of one GPU run in stream order)
     DevBuf d_bnd, d_counters, d_scratch32, d_best_score, d_best_index, d_topk_keys, d_err;
     DevBuf d_wave_bnd, d_wave_state;  // band-pipelined kernel: boundary rows; progress / best / done words
-    int wave_bps[2] = {0, 0};         // resident blocks per SM of its two instances (0 = not asked yet)
+    int wave_bps[16] = {0};           // resident blocks per SM of its instances (0 = not asked yet)
     uint32_t wave_epoch = 0;          // launches so far: the tag of the boundary elements (20 bits)
     unsigned counter_next = 0;        // next unused work-queue counter
     // autotune: timing events and the cached decision, per GPU (shards differ in shape)
@@ -1058,6 +1058,10 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 // 512-row bands unless they leave most of the GPU idle: then 256-row bands
                 const size_t warps512 = (size_t)g.npairs * ((h->q_len[q] + 511) / 512);
                 W.instance = warps512 < (size_t)gc.num_sms * 6 ? 1 : 0;
+                if (const char *e = std::getenv("SW_B200_WAVE_INSTANCE")) {       // A/B measurements
+                    const int wi = std::atoi(e);
+                    if (wi >= 0 && wi < sw_wave_instance_count() && wi < 16) W.instance = wi;
+                }
                 if (!gc.wave_bps[W.instance]) SW_CUDA(h, sw_wave_occupancy(W.instance, &gc.wave_bps[W.instance]));
                 if (gc.wave_bps[W.instance] < 1) return SW_ECUDA;
                 const int rows = sw_wave_rows_per_band(W.instance);

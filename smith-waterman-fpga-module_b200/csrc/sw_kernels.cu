@@ -362,20 +362,26 @@ namespace {
 typedef void (*WaveFn)(const WaveArgs);
 struct WaveInstance { int rows; size_t smem; WaveFn fn, fn_fixed; const char *name; };
 constexpr size_t wave_smem(int rs, int s) { return (size_t)32 * s * ((rs + 1) / 2) * kWaveCodes * sizeof(uint2); }
-const WaveInstance g_wave[2] = {
-    {512, wave_smem(8, 2), sw_wave_kernel<8, 2, ArithS16, kBT, 4>, sw_wave_kernel<8, 2, ArithS16, kBT, 4, kFixedGoe, kFixedGe>,
-     "wave_s16x2_R8x2_G32"},
-    {256, wave_smem(8, 1), sw_wave_kernel<8, 1, ArithS16, kBT, 4>, sw_wave_kernel<8, 1, ArithS16, kBT, 4, kFixedGoe, kFixedGe>,
-     "wave_s16x2_R8x1_G32"},
+#define SW_WAVE(RS, S, MINB, BLK, NAME) \
+    {RS * S * 32, wave_smem(RS, S), sw_wave_kernel<RS, S, ArithS16, kBT, MINB, 0, 0, BLK>, \
+     sw_wave_kernel<RS, S, ArithS16, kBT, MINB, kFixedGoe, kFixedGe, BLK>, NAME}
+const WaveInstance g_wave[] = {
+    SW_WAVE(8, 2, 4, 32, "wave_s16x2_R8x2_G32"),          // 0: default for a few hundred pairs
+    SW_WAVE(8, 1, 4, 32, "wave_s16x2_R8x1_G32"),          // 1: default when even those do not fill the GPU
+    // measured and dropped (profiles/r02_wave_instance_ab.jsonl): 16-column blocks (R8x1 668, R8x2 634 GCUPS
+    // for one pair), 128-row bands (R4x1: 413 / 451 GCUPS), R4x2 (669)
 };
+constexpr int kNumWave = sizeof(g_wave) / sizeof(g_wave[0]);
+inline int wave_index(int inst) { return (inst >= 0 && inst < kNumWave) ? inst : 0; }
 }  // namespace
 
-const char *sw_wave_kernel_name(int inst) { return g_wave[inst ? 1 : 0].name; }
-int sw_wave_rows_per_band(int inst) { return g_wave[inst ? 1 : 0].rows; }
+const char *sw_wave_kernel_name(int inst) { return g_wave[wave_index(inst)].name; }
+int sw_wave_rows_per_band(int inst) { return g_wave[wave_index(inst)].rows; }
+int sw_wave_instance_count(void) { return kNumWave; }
 
 cudaError_t sw_wave_occupancy(int inst, int *blocks_per_sm)
 {
-    const WaveInstance &w = g_wave[inst ? 1 : 0];
+    const WaveInstance &w = g_wave[wave_index(inst)];
     cudaError_t e = cudaFuncSetAttribute((const void *)w.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem);
     if (e != cudaSuccess) return e;
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, (const void *)w.fn, kBT, w.smem);
@@ -385,7 +391,7 @@ cudaError_t sw_launch_wave(cudaStream_t st, const SwWaveLaunch &L)
 {
     const SwScoring &sc = L.sc;
     if (sc.limit) return cudaErrorInvalidValue;            // exact arithmetic only
-    const WaveInstance &w = g_wave[L.instance ? 1 : 0];
+    const WaveInstance &w = g_wave[wave_index(L.instance)];
     WaveFn fn = (!g_no_fixed && sc.goe == kFixedGoe && sc.ge == kFixedGe) ? w.fn_fixed : w.fn;
     WaveArgs a{};
     a.tp = L.db.tp; a.tile_woff = L.db.tile_woff; a.pair_len = L.db.pair_len; a.pair_subj = L.db.pair_subj;

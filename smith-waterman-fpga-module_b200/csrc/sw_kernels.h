@@ -141,6 +141,7 @@ cudaError_t sw_wave_occupancy(int instance, int *blocks_per_sm);
 cudaError_t sw_launch_wave(cudaStream_t st, const SwWaveLaunch &L);
 const char *sw_wave_kernel_name(int instance);
 int sw_wave_rows_per_band(int instance);
+int sw_wave_instance_count(void);
 
 /* 32-bit kernel: any length, any score range.  scratch: 2 * max_cols * threads_total int32 where
  * max_cols = min(longest query, longest subject) (the recurrence is symmetric: the shorter sequence

@@ -34,7 +34,7 @@
 
 namespace swk {
 
-constexpr int kWaveBlock = 32;       // columns staged per block by the consuming band
+constexpr int kWaveBlock = 32;       // default number of columns staged per block by the consuming band
 constexpr int kWaveCodes = 24;       // profile slots per row pair (codes 0 .. 20 are used)
 
 struct WaveArgs {
@@ -69,13 +69,12 @@ struct WaveArgs {
 };
 
 // One band of one pair (one warp).  Returns the band's running maximum (K representation).
-template <int RS, int S, class AR, bool HAS_TOP, bool HAS_BOTTOM>
-__device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *prof_lane, uint2 (&s_top)[kWaveBlock], const uint32_t *tpp,
+template <int RS, int S, class AR, int BLK, bool HAS_TOP, bool HAS_BOTTOM>
+__device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *prof_lane, uint2 (&s_top)[BLK], const uint32_t *tpp,
                                               int ncols, const ulonglong2 *top, ulonglong2 *bot, uint32_t tag_top, uint32_t tag_bot,
                                               uint32_t goe2, uint32_t ge2, uint32_t h0, uint32_t gb2, uint32_t zero)
 {
     constexpr int G = 32, RP = (RS + 1) / 2, VPE = G * S, U = 4;
-    constexpr int BLK = kWaveBlock;
     constexpr unsigned FULL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const bool head = lane == 0;
@@ -173,7 +172,7 @@ __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *pr
     return best;
 }
 
-template <int RS, int S, class AR, int BT, int MINB, int CGOE = 0, int CGE = 0>
+template <int RS, int S, class AR, int BT, int MINB, int CGOE = 0, int CGE = 0, int BLK = kWaveBlock>
 __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
 {
     extern __shared__ uint2 s_prof[];
@@ -182,7 +181,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
     constexpr int PASS_ENTRIES = VPE * RP * kWaveCodes;
     constexpr int PPB = BT / G;
     constexpr unsigned FULL = 0xFFFFFFFFu;
-    __shared__ uint2 s_top[PPB][kWaveBlock];
+    __shared__ uint2 s_top[PPB][BLK];
     __shared__ uint8_t s_qb[P / 4 + 4];                // packed query bytes of the band
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -253,11 +252,11 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
 
         uint32_t best;
         if (has_top) {
-            if (has_bottom) best = wave_band<RS, S, AR, true, true>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero);
-            else best = wave_band<RS, S, AR, true, false>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero);
+            if (has_bottom) best = wave_band<RS, S, AR, BLK, true, true>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero);
+            else best = wave_band<RS, S, AR, BLK, true, false>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero);
         } else {
-            if (has_bottom) best = wave_band<RS, S, AR, false, true>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero);
-            else best = wave_band<RS, S, AR, false, false>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero);
+            if (has_bottom) best = wave_band<RS, S, AR, BLK, false, true>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero);
+            else best = wave_band<RS, S, AR, BLK, false, false>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero);
         }
 
 #pragma unroll
