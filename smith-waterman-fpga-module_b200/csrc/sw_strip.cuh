@@ -352,6 +352,9 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
     // DIRECT instances with a short pass (P < 512 rows) are only used for queries of at most P rows
     // (the host checks): no pass-boundary code at all in their step loop
     constexpr bool MULTIPASS = !(DIRECT && P < 512);
+    // (A column-blocked schedule for these instances -- four columns per trip and one shuffle round
+    // trip per block -- was measured and dropped: 25.0 vs 23.0 us for config 2, 19.8 vs 16.4 us for
+    // one pair: the extra fill / drain costs more than the shuffles it saves.)
     static_assert(sizeof(s_codes[0]) == (DIRECT ? kDirectWords : 1) * sizeof(uint32_t), "s_codes row = kDirectWords");
 
     const int lane = threadIdx.x & 31;
