@@ -126,6 +126,7 @@ struct Slot {
     std::vector<uint32_t> empties;     // first few zero-length subjects (they score 0; top-k fill)
     std::vector<Seg> segs;             // length groups of the sorted pair list (launch planning)
     std::vector<int> qidx_host;        // query lists of the last launch plan (source of an async upload)
+    std::vector<uint32_t> pair_tmp;    // latency path: pairing scratch before the descriptors are written
     bool scored = false;
     bool ovf_used = false;
     int out_mode = SW_OUT_I32;         // of the last scoring
@@ -1479,12 +1480,10 @@ int small_submit(sw_handle *h, int si, const uint8_t *packed, const uint32_t *le
     for (auto &gg : h->gpus) { gg.slot[si].s0 = 0; gg.slot[si].s1 = 0; gg.slot[si].chunks.clear(); gg.slot[si].ovf_used = false; }
     g.s0 = 0; g.s1 = ns; g.is_small = true; g.max_len = maxlen; g.sum_len = sum; g.out_mode = SW_OUT_I32; g.topk_k = 0;
 
-    // ---- staging layout
+    // ---- staging layout: [pair descriptors (32 bytes each) | raw bases]
     const size_t ntiles = (np_max + 31) / 32;
-    const size_t o_subj = 0;
-    const size_t o_len = o_subj + ntiles * 32 * 2 * sizeof(uint32_t);
-    const size_t o_off = o_len + ntiles * 32 * 2 * sizeof(uint32_t);
-    const size_t o_raw = o_off + ns * sizeof(uint64_t);
+    const size_t o_desc = 0;
+    const size_t o_raw = o_desc + ntiles * 32 * 32;
     const size_t raw_bytes = (size_t)(bmax - bmin);
     const size_t total = o_raw + raw_bytes + 16;
     SW_CUDA(h, g.h_small_in.reserve(total));
@@ -1499,10 +1498,19 @@ int small_submit(sw_handle *h, int si, const uint8_t *packed, const uint32_t *le
     // the staging buffer is reused: the previous copy out of it finished before its batch was fetched
     char *st = (char *)g.h_small_in.p;
     sort_by_length(g, len, ns, maxlen);
-    const size_t np = make_pairs(g, len, ns, (uint32_t *)(st + o_subj), (uint32_t *)(st + o_len));
+    g.pair_tmp.resize(ntiles * 32 * 4);
+    uint32_t *t_subj = g.pair_tmp.data(), *t_len = t_subj + ntiles * 32 * 2;
+    const size_t np = make_pairs(g, len, ns, t_subj, t_len);
     g.npairs = (uint32_t)np;
-    uint64_t *loc_off = (uint64_t *)(st + o_off);
-    for (size_t k = 0; k < ns; ++k) loc_off[k] = len[k] ? off[k] - bmin : 0;
+    uint32_t *desc = (uint32_t *)(st + o_desc);
+    for (size_t p = 0; p < np; ++p) {
+        const uint32_t slo = t_subj[2 * p], shi = t_subj[2 * p + 1];
+        uint32_t *d = desc + 8 * p;
+        d[0] = t_len[2 * p]; d[1] = t_len[2 * p + 1]; d[2] = slo; d[3] = shi;
+        d[4] = (uint32_t)(off[slo] - bmin);
+        d[5] = shi != SW_NO_SUBJECT ? (uint32_t)(off[shi] - bmin) : 0u;
+        d[6] = 0; d[7] = 0;
+    }
     std::memcpy(st + o_raw, packed + bmin, raw_bytes);
     std::memset(st + o_raw + raw_bytes, 0, 16);
     // scores of empty subjects (never touched by the kernel)
@@ -1517,8 +1525,8 @@ int small_submit(sw_handle *h, int si, const uint8_t *packed, const uint32_t *le
     SwStripLaunch L;
     char *d = (char *)g.d_small_in.p;
     L.vidx = vidx; L.direct = true;
-    L.db.raw = (const uint8_t *)(d + o_raw); L.db.off = (const uint64_t *)(d + o_off); L.db.len = nullptr;
-    L.db.ns = (uint32_t)ns; L.db.pair_subj = (const uint32_t *)(d + o_subj); L.db.pair_len = (const uint32_t *)(d + o_len);
+    L.db.raw = (const uint8_t *)(d + o_raw); L.db.off = nullptr; L.db.len = nullptr;
+    L.db.ns = (uint32_t)ns; L.db.pair_subj = nullptr; L.db.pair_len = nullptr; L.db.pair_desc = (const uint4 *)(d + o_desc);
     L.db.tile_woff = nullptr; L.db.tp = nullptr; L.db.tp_words = 0; L.db.npairs = (uint32_t)np; L.db.max_len = maxlen;
     L.q = dev_queries(h, gc); L.q0 = 0; L.nql = nq; L.qidx = nullptr; L.sc = sc;
     L.out = g.h_small_out.dptr; L.out_stride = ns; L.out_elems = (size_t)nq * ns; L.out_mode = SW_OUT_I32;

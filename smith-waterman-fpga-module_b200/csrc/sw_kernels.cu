@@ -326,7 +326,7 @@ cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L)
     a.goe2 = ((uint32_t)sc.goe & 0xFFFFu) * 0x10001u; a.ge2 = ((uint32_t)sc.ge & 0xFFFFu) * 0x10001u;
     a.ovf_limit = 32767 - sc.match - 1;
     a.zero = 0;
-    a.raw = L.db.raw; a.off = L.db.off;
+    a.raw = L.db.raw; a.off = L.db.off; a.pair_desc = L.db.pair_desc;
     a.ovf_count = L.ovf_count; a.ovf_list = L.ovf_list; a.ovf_cap = L.ovf_cap;
     a.topk_keys = L.topk_keys; a.topk_k = L.topk_k; a.topk_nq = L.topk_nq;
     a.dev_err = L.dev_err;

@@ -32,6 +32,7 @@ struct SwDevDb {
     uint32_t        ns;
     const uint32_t *pair_subj;
     const uint32_t *pair_len;
+    const uint4    *pair_desc;   /* DIRECT launches: {n_lo, n_hi, subj_lo, subj_hi | off_lo, off_hi, 0, 0} per pair */
     const uint64_t *tile_woff;
     uint32_t       *tp;
     uint64_t        tp_words;

@@ -147,6 +147,10 @@ struct StripArgs {
     // DIRECT instances: column codes are formed on the fly from the uploaded 2-bit records
     const uint8_t *raw;
     const uint64_t *off;
+    // DIRECT: one 32-byte descriptor per pair {n_lo, n_hi, subj_lo, subj_hi | off_lo, off_hi, 0, 0}: one
+    // load gives a pair's lengths, subjects and record offsets (the latency path pays a memory round
+    // trip per DEPENDENT load, so the chain pair table -> offsets -> bases is cut to two links)
+    const uint4 *pair_desc;
     // pairs whose score may have left the 16-bit range: (query, subject) appended here
     unsigned *ovf_count;
     uint2 *ovf_list;
@@ -408,19 +412,31 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
         decode(s_work, pair, q);
 
         const bool valid = pair < a.npairs;
-        const int ncols = valid ? (int)a.pair_len[2 * pair] : 0;          // longer member (low lane)
+        int ncols_v = 0;                                                   // longer member (low lane)
         const uint32_t *tpp = a.tp;
         const uint8_t *rlo = nullptr, *rhi = nullptr;
         uint32_t nhi = 0;
+        // the query's length / offset are requested now, so that their round trip overlaps the pair's
+        const int m = (int)a.qlen[q];
+        const uint8_t *qp = a.qpacked + a.qoff[q];
         if (valid) {
             if constexpr (DIRECT) {
-                const uint32_t s_lo = a.pair_subj[2 * pair], s_hi = a.pair_subj[2 * pair + 1];
-                nhi = a.pair_len[2 * pair + 1];
-                rlo = a.raw + a.off[s_lo];
-                if (s_hi != SW_NO_SUBJECT) rhi = a.raw + a.off[s_hi];
+                const uint4 d0 = __ldg(a.pair_desc + 2 * pair), d1 = __ldg(a.pair_desc + 2 * pair + 1);
+                ncols_v = (int)d0.x;
+                nhi = d0.y;
+                rlo = a.raw + d1.x;
+                if (d0.w != SW_NO_SUBJECT) rhi = a.raw + d1.y;
             } else {
+                ncols_v = (int)a.pair_len[2 * pair];
                 tpp += a.tile_woff[pair >> 5] + (pair & 31);
             }
+        }
+        const int ncols = ncols_v;
+        // single-pass DIRECT instances: this thread's byte of the packed query, requested before the
+        // code staging below waits for the subject bytes (the profile build stores it to shared memory)
+        uint32_t my_qbyte = 0;
+        if constexpr (!MULTIPASS) {
+            if ((int)threadIdx.x < ((m + 3) >> 2)) my_qbyte = qp[threadIdx.x];
         }
         // DIRECT: the lanes of the group form the pair's code words in parallel, once, into shared
         // memory (the host sends only subjects of up to 4 * kDirectWords bases down this path)
@@ -446,8 +462,6 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
 
         uint32_t best = h0;
         {
-            const int m = (int)a.qlen[q];
-            const uint8_t *qp = a.qpacked + a.qoff[q];
             const int npass = (m + P - 1) / P;
 
             for (int pass = 0; pass < npass; ++pass) {
@@ -464,7 +478,11 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                     // (latency-bound) launch consists of
                     const int qb0 = (pass * P) >> 2;
                     const int qnb = ((min((pass + npc) * P, m) + 3) >> 2) - qb0;
-                    for (int i = threadIdx.x; i < qnb && i < kQueryBytes; i += BT) s_qb[i] = qp[qb0 + i];
+                    if constexpr (!MULTIPASS) {
+                        if ((int)threadIdx.x < qnb) s_qb[threadIdx.x] = (uint8_t)my_qbyte;     // P < 512: qnb <= BT
+                    } else {
+                        for (int i = threadIdx.x; i < qnb && i < kQueryBytes; i += BT) s_qb[i] = qp[qb0 + i];
+                    }
                     __syncthreads();
                     for (int idx = threadIdx.x; idx < npc * PASS_ENTRIES; idx += BT) {
                         // layout: (((pass * S + s) * RP + rp) * 32 + code) * G + gl -- the G lanes of a
@@ -639,7 +657,10 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
         decode(s_work, epair, eq);
         const bool owner = gl == 0 && epair < a.npairs;
         uint32_t subj_lo = SW_NO_SUBJECT, subj_hi = SW_NO_SUBJECT;
-        if (owner) { subj_lo = a.pair_subj[2 * epair]; subj_hi = a.pair_subj[2 * epair + 1]; }
+        if (owner) {
+            if constexpr (DIRECT) { const uint4 d0 = __ldg(a.pair_desc + 2 * epair); subj_lo = d0.z; subj_hi = d0.w; }
+            else { subj_lo = a.pair_subj[2 * epair]; subj_hi = a.pair_subj[2 * epair + 1]; }
+        }
         int sc0 = AR::extract(best, 0) , sc1 = AR::extract(best, 1);
         const bool ov0 = !W12 && sc0 > a.ovf_limit, ov1 = !W12 && sc1 > a.ovf_limit;
         sc0 -= shift; sc1 -= shift;
@@ -648,7 +669,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
             if (ov0) { const unsigned p = atomicAdd(a.ovf_count, 1u); if (p < a.ovf_cap) a.ovf_list[p] = make_uint2((unsigned)eq, subj_lo); }
             if (has1 && ov1) { const unsigned p = atomicAdd(a.ovf_count, 1u); if (p < a.ovf_cap) a.ovf_list[p] = make_uint2((unsigned)eq, subj_hi); }
         }
-        if (a.out_mode == SW_OUT_I32) {
+        if (DIRECT || a.out_mode == SW_OUT_I32) {            // (the latency path delivers int32 matrices only)
             if (owner) {
                 int32_t *orow = (int32_t *)a.out + (size_t)eq * a.out_stride;
                 SW_CHECK((unsigned long long)eq * a.out_stride + subj_lo < a.out_elems, SW_DEVERR_OUT, a);
@@ -687,7 +708,9 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence_system();
-            if (atomicAdd(a.done_count, 1u) == gridDim.x - 1) {
+            if (gridDim.x == 1) {
+                *(volatile unsigned *)a.done_flag = a.done_seq;      // one block: its own fence is enough
+            } else if (atomicAdd(a.done_count, 1u) == gridDim.x - 1) {
                 *a.done_count = 0;
                 __threadfence_system();
                 *(volatile unsigned *)a.done_flag = a.done_seq;
