@@ -1,5 +1,11 @@
 #!/bin/bash
+# Final evidence run of the round: full GPU test suite, smoke, bench (our arm + reference arm).
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -k "small_path or config2 or randomised_modes or streaming or edge_cases or bounds_check or golden" --timeout=800 -p no:cacheprovider 2>&1 | tail -12
-timeout 300 python scripts/bench_configs.py lat > gpurun_out/lat3.jsonl 2> gpurun_out/lat3.err
-cut -c1-700 gpurun_out/lat3.jsonl; tail -3 gpurun_out/lat3.err
+timeout 2400 python -m pytest tests -m gpu -q --maxfail=15 --timeout=900 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -6 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+( time timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err ) 2>&1 | tail -3
+cut -c1-600 gpurun_out/bench_ref.json
+( time timeout 1200 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err ) 2>&1 | tail -3
+cut -c1-1200 gpurun_out/bench_full.json; grep "\[bench\]" gpurun_out/bench_full.err | cut -c1-260
