@@ -1,6 +1,10 @@
 #!/bin/bash
-# whole GPU suite against the bounds-check build (device-side index checks + canaries)
+# Round evidence run on one B200: GPU tests, smoke, reference arm, headline bench.
+# Usage: gpurun --timeout 3000 -- bash scripts/gpu_round.sh
 mkdir -p gpurun_out
-SW_B200_LIB=$PWD/smith-waterman-fpga-module_b200/libsw_b200_check.so timeout 3000 python -m pytest tests -m gpu -q --maxfail=15 --timeout=1200 -p no:cacheprovider --deselect tests/test_gpu_round2.py::test_bounds_check_build_runs_clean > gpurun_out/pytest_gpu_checkbuild.log 2>&1
-echo "pytest rc=$?" >> gpurun_out/pytest_gpu_checkbuild.log
-tail -8 gpurun_out/pytest_gpu_checkbuild.log
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=10 --timeout=900 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; tail -c 600 gpurun_out/bench_reference.json
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err; tail -c 1500 gpurun_out/bench_1gpu.json
