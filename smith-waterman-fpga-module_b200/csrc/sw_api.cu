@@ -1037,7 +1037,7 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
         }
         // ---- band-pipelined launches, one per long query ----------------------------------------
         if (!wave_q.empty()) {
-            const uint32_t cols_stride = (g.max_len + 31u) & ~31u;
+            const uint32_t cols_stride = ((g.max_len + 31u) & ~31u) + 32u;    // + slack for the batched boundary stores (kWaveSlack)
             uint32_t wmaxq = 0;
             for (int q : wave_q) wmaxq = std::max(wmaxq, h->q_len[q]);
             (void)wmaxq;
@@ -1056,9 +1056,11 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
             SW_CUDA(h, gc.d_wave_state.reserve(n_state * sizeof(unsigned)));
             for (int q : wave_q) {
                 SwWaveLaunch W;
-                // 512-row bands unless they leave most of the GPU idle: then 256-row bands
-                const size_t warps512 = (size_t)g.npairs * ((h->q_len[q] + 511) / 512);
-                W.instance = warps512 < (size_t)gc.num_sms * 6 ? 1 : 0;
+                // pair-bands of 256 rows in this launch: many -> throughput-bound (512-row bands,
+                // four pairs per block); fewer -> one pair per block, four columns per step; a
+                // handful -> two columns per step (measured crossovers)
+                const size_t warps256 = (size_t)g.npairs * ((h->q_len[q] + 255) / 256);
+                W.instance = warps256 < 1200 ? 2 : warps256 < 15000 ? 1 : 0;
                 if (const char *e = std::getenv("SW_B200_WAVE_INSTANCE")) {       // A/B measurements
                     const int wi = std::atoi(e);
                     if (wi >= 0 && wi < sw_wave_instance_count() && wi < 16) W.instance = wi;
@@ -1070,6 +1072,7 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 W.npass = (int)((h->q_len[q] + rows - 1) / rows);
                 W.out = g.d_out.p; W.out_stride = n; W.out_mode = g.out_mode;
                 W.bnd = gc.d_wave_bnd.p; W.cols_stride = cols_stride;
+                W.bnd_elems = (size_t)g.npairs * 2 * cols_stride; W.out_elems = (size_t)nq * n;
                 gc.wave_epoch = (gc.wave_epoch % 0xFFFFEu) + 1u;            // 1 .. 2^20 - 2
                 if (gc.wave_epoch == 1u && gc.counter_next > 0) {
                     // the epoch wrapped (or first use): stale tags must not match again
@@ -1079,7 +1082,8 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 W.best = (int *)gc.d_wave_state.as<unsigned>();
                 W.done = gc.d_wave_state.as<unsigned>() + 2 * (size_t)g.npairs;
                 W.counter = next_counter(gc);
-                const size_t items = (size_t)W.npass * ((g.npairs + 3) / 4);
+                const size_t ppb = (size_t)sw_wave_pairs_per_block(W.instance);
+                const size_t items = (size_t)W.npass * ((g.npairs + ppb - 1) / ppb);
                 W.grid = (int)std::min<size_t>(items, (size_t)gc.num_sms * gc.wave_bps[W.instance]);
                 W.ovf_count = base.ovf_count; W.ovf_list = base.ovf_list; W.ovf_cap = base.ovf_cap;
                 W.dev_err = gc.d_err.as<unsigned>();

@@ -354,22 +354,29 @@ cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L)
 }
 
 // ---- band-pipelined kernel ---------------------------------------------------------------------
-// Two instances: bands of 512 rows (8 rows x 2 sub-strips x 32 lanes) for a few hundred pairs, and
-// bands of 256 rows (8 rows x 1 x 32 lanes: twice the bands, shorter band-to-band lag, shorter
-// dependency chain per step) when even the 512-row bands of all pairs do not fill the GPU -- down
-// to one single pair.
+// Three instances (measured over few-long-pair shapes, profiles/r02_wave_instance_ab2.txt):
+//   0  R8x2        bands of 512 rows, one column per step, four pairs per block: many pairs (the
+//                  GPU is full of pair-bands; throughput-bound)
+//   1  R8x1 C4     bands of 256 rows, four columns per step, ONE pair per block: a few dozen to a
+//                  few hundred pairs
+//   2  R8x1 C2     bands of 256 rows, two columns per step, one pair per block: a handful of pairs
+//                  down to a single one (latency-bound: one warp per band; with one pair per block
+//                  the active warps spread over the four schedulers of an SM instead of all being
+//                  warp 0 of a four-warp block)
 namespace {
 typedef void (*WaveFn)(const WaveArgs);
-struct WaveInstance { int rows; size_t smem; WaveFn fn, fn_fixed; const char *name; };
+struct WaveInstance { int rows, bt; size_t smem; WaveFn fn, fn_fixed; const char *name; };
 constexpr size_t wave_smem(int rs, int s) { return (size_t)32 * s * ((rs + 1) / 2) * kWaveCodes * sizeof(uint2); }
-#define SW_WAVE(RS, S, MINB, BLK, NAME) \
-    {RS * S * 32, wave_smem(RS, S), sw_wave_kernel<RS, S, ArithS16, kBT, MINB, 0, 0, BLK>, \
-     sw_wave_kernel<RS, S, ArithS16, kBT, MINB, kFixedGoe, kFixedGe, BLK>, NAME}
+#define SW_WAVE(RS, S, BT, MINB, BLK, C, NAME) \
+    {RS * S * 32, BT, wave_smem(RS, S), sw_wave_kernel<RS, S, ArithS16, BT, MINB, 0, 0, BLK, C>, \
+     sw_wave_kernel<RS, S, ArithS16, BT, MINB, kFixedGoe, kFixedGe, BLK, C>, NAME}
 const WaveInstance g_wave[] = {
-    SW_WAVE(8, 2, 4, 32, "wave_s16x2_R8x2_G32"),          // 0: default for a few hundred pairs
-    SW_WAVE(8, 1, 4, 32, "wave_s16x2_R8x1_G32"),          // 1: default when even those do not fill the GPU
-    // measured and dropped (profiles/r02_wave_instance_ab.jsonl): 16-column blocks (R8x1 668, R8x2 634 GCUPS
-    // for one pair), 128-row bands (R4x1: 413 / 451 GCUPS), R4x2 (669)
+    SW_WAVE(8, 2, 128, 4, 32, 1, "wave_s16x2_R8x2_G32"),
+    SW_WAVE(8, 1, 32, 8, 32, 4, "wave_s16x2_R8x1_G32_C4"),
+    SW_WAVE(8, 1, 32, 16, 32, 2, "wave_s16x2_R8x1_G32_C2"),
+    // measured and dropped (profiles/r02_wave_instance_ab.jsonl, r02_wave_instance_ab2.txt): 16-column
+    // blocks, 128-row bands (R4x1 with 1 / 2 / 4 columns per step, R4x2), R8x1 with one column per
+    // step, four-pair blocks for the multi-column instances
 };
 constexpr int kNumWave = sizeof(g_wave) / sizeof(g_wave[0]);
 inline int wave_index(int inst) { return (inst >= 0 && inst < kNumWave) ? inst : 0; }
@@ -378,13 +385,14 @@ inline int wave_index(int inst) { return (inst >= 0 && inst < kNumWave) ? inst :
 const char *sw_wave_kernel_name(int inst) { return g_wave[wave_index(inst)].name; }
 int sw_wave_rows_per_band(int inst) { return g_wave[wave_index(inst)].rows; }
 int sw_wave_instance_count(void) { return kNumWave; }
+int sw_wave_pairs_per_block(int inst) { return g_wave[wave_index(inst)].bt / 32; }
 
 cudaError_t sw_wave_occupancy(int inst, int *blocks_per_sm)
 {
     const WaveInstance &w = g_wave[wave_index(inst)];
     cudaError_t e = cudaFuncSetAttribute((const void *)w.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem);
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, (const void *)w.fn, kBT, w.smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, (const void *)w.fn, w.bt, w.smem);
 }
 
 cudaError_t sw_launch_wave(cudaStream_t st, const SwWaveLaunch &L)
@@ -395,7 +403,7 @@ cudaError_t sw_launch_wave(cudaStream_t st, const SwWaveLaunch &L)
     WaveFn fn = (!g_no_fixed && sc.goe == kFixedGoe && sc.ge == kFixedGe) ? w.fn_fixed : w.fn;
     WaveArgs a{};
     a.tp = L.db.tp; a.tile_woff = L.db.tile_woff; a.pair_len = L.db.pair_len; a.pair_subj = L.db.pair_subj;
-    a.npairs = L.db.npairs; a.npb = (L.db.npairs + 3) / 4;
+    a.npairs = L.db.npairs; a.npb = (L.db.npairs + (uint32_t)(w.bt / 32) - 1u) / (uint32_t)(w.bt / 32);
     a.qpacked = L.q.packed; a.qoff = L.q.off; a.qlen = L.q.len; a.q = L.query; a.npass = L.npass;
     a.out = L.out; a.out_stride = L.out_stride; a.out_mode = L.out_mode;
     a.bnd = (ulonglong2 *)L.bnd; a.cols_stride = L.cols_stride; a.epoch = L.epoch; a.best = L.best; a.done = L.done; a.counter = L.counter;
@@ -406,9 +414,10 @@ cudaError_t sw_launch_wave(cudaStream_t st, const SwWaveLaunch &L)
     a.ovf_count = L.ovf_count; a.ovf_list = L.ovf_list; a.ovf_cap = L.ovf_cap;
     a.dev_err = L.dev_err;
     a.spin_limit = 1u << 24;
+    a.tp_words = L.db.tp_words; a.bnd_elems = L.bnd_elems; a.out_elems = L.out_elems;
     cudaError_t e = cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem);
     if (e != cudaSuccess) return e;
-    fn<<<L.grid, kBT, w.smem, st>>>(a);
+    fn<<<L.grid, w.bt, w.smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -115,7 +115,7 @@ const char *sw_strip_instance_kind(const SwStripLaunch &L);
  * 16-byte tagged elements (zeroed once when allocated; epoch makes the tags of earlier launches
  * stale); best: 2 * npairs ints, done: npairs words -- zeroed before the launch; counter: zeroed
  * work-queue word. */
-#define SW_WAVE_ROWS_PER_BAND 512     /* instance 0; instance 1 has bands of 256 rows */
+#define SW_WAVE_ROWS_PER_BAND 512     /* instance 0; instances 1 and 2 have bands of 256 rows */
 struct SwWaveLaunch {
     int instance = 0;
     SwDevDb db{};
@@ -128,6 +128,7 @@ struct SwWaveLaunch {
     int out_mode = SW_OUT_I32;
     void *bnd = nullptr;
     uint32_t cols_stride = 0;
+    size_t bnd_elems = 0, out_elems = 0;      /* sizes of bnd (16-byte elements) and out, for the check build */
     uint32_t epoch = 1;
     int *best = nullptr;
     unsigned *done = nullptr;
@@ -143,6 +144,7 @@ cudaError_t sw_launch_wave(cudaStream_t st, const SwWaveLaunch &L);
 const char *sw_wave_kernel_name(int instance);
 int sw_wave_rows_per_band(int instance);
 int sw_wave_instance_count(void);
+int sw_wave_pairs_per_block(int instance);
 
 /* 32-bit kernel: any length, any score range.  scratch: 2 * max_cols * threads_total int32 where
  * max_cols = min(longest query, longest subject) (the recurrence is symmetric: the shorter sequence

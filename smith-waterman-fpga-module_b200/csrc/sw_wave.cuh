@@ -36,13 +36,15 @@ namespace swk {
 
 constexpr int kWaveBlock = 32;       // default number of columns staged per block by the consuming band
 constexpr int kWaveCodes = 24;       // profile slots per row pair (codes 0 .. 20 are used)
+constexpr int kWaveSlack = 8;        // boundary elements of slack on either side of a row (batched stores)
+constexpr int kWavePrefetch = 8;     // steps between the prefetch of a boundary block and its use
 
 struct WaveArgs {
     const uint32_t *tp;
     const uint64_t *tile_woff;
     const uint32_t *pair_len;
     const uint32_t *pair_subj;
-    uint32_t npairs, npb;      // npb = ceil(npairs / 4)
+    uint32_t npairs, npb;      // npb = ceil(npairs / pairs per block)
     const uint8_t *qpacked;
     const uint32_t *qoff;
     const uint32_t *qlen;
@@ -66,6 +68,7 @@ struct WaveArgs {
     unsigned ovf_cap;
     unsigned *dev_err;
     unsigned spin_limit;       // polls of a boundary block before the watchdog gives up
+    uint64_t tp_words, bnd_elems, out_elems;   // buffer sizes (only read by the -DSW_BOUNDS_CHECK build)
 };
 
 // One band of one pair (one warp).  Returns the band's running maximum (K representation).
@@ -84,11 +87,15 @@ __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *pr
     for (int s = 0; s < S; ++s)
 #pragma unroll
         for (int r = 0; r < RS; ++r) { H[s][r] = h0; Gl[s][r] = gb2; }
-    uint32_t wcur = 0, wnext = 0;
-    if (head && ncols > 0) {
-        wcur = __ldg(tpp);
-        if (ncols > 4) wnext = __ldg(tpp + 32);
-    }
+    // code words (4 columns each): lane i holds word 32 B + i of the current / next block of 128
+    // columns, loaded 128 columns ahead; the step loop takes one word per four steps by shuffle
+    auto bulk = [&](int blk) -> uint32_t {
+        const int w = blk * 32 + lane;
+        if (4 * w < ncols) SW_CHECK((unsigned long long)(tpp - a.tp) + (unsigned long long)w * 32 < a.tp_words, SW_DEVERR_TP, a);
+        return 4 * w < ncols ? __ldg(tpp + (size_t)w * 32) : kPadCode * 0x01010101u;
+    };
+    uint32_t cw_cur = bulk(0), cw_nxt = bulk(1);
+    uint32_t wcur = __shfl_sync(FULL, cw_cur, 0), wnext = __shfl_sync(FULL, cw_cur, 1);
     uint32_t pub_h[S], pub_g[S], pub_t[S], hd_top[S];
 #pragma unroll
     for (int s = 0; s < S; ++s) { pub_h[s] = h0; pub_g[s] = gb2; pub_t[s] = kPadCode; hd_top[s] = h0; }
@@ -96,6 +103,8 @@ __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *pr
     uint2 sv[S][RP];
     load_scores<RS, S, G, kWaveCodes>(sv, prof_lane, pub_t);
     uint2 bcur = make_uint2(h0, gb2);
+    ulonglong2 pre = make_ulonglong2(0ull, 0ull);
+    uint32_t sto_h[U], sto_g[U];
     const unsigned long long tag_hi = (unsigned long long)tag_bot << 32;
     const int nsteps = ncols > 0 ? (ncols + (VPE - 1) + U - 1) / U * U : 0;
 
@@ -104,28 +113,35 @@ __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *pr
         if constexpr (HAS_TOP) {
             if ((t2 & (BLK - 1)) == 0 && t2 < ncols) {
                 // stage columns t2 .. t2 + BLK - 1 of the bottom row of the band above: every lane
-                // loads one element and retries until both of its words carry the producer's tag
+                // takes one element (prefetched eight steps ago, see below) and retries the load
+                // until both of its words carry the producer's tag
                 const int c = t2 + lane;
                 const bool mine = lane < BLK && c < ncols;
-                uint2 v = make_uint2(h0, gb2);
+                ulonglong2 e = pre;
+                bool have = t2 != 0;
                 unsigned spins = 0;
                 for (;;) {
-                    bool ok = true;
-                    if (mine) {
-                        const ulonglong2 e = __ldcg(top + c);
-                        ok = (uint32_t)(e.x >> 32) == tag_top && (uint32_t)(e.y >> 32) == tag_top;
-                        v = make_uint2((uint32_t)e.x, (uint32_t)e.y);
-                    }
+                    if (mine) SW_CHECK((unsigned long long)(top + c - a.bnd) < a.bnd_elems, SW_DEVERR_BND, a);
+                    if (!have && mine) e = __ldcg(top + c);
+                    const bool ok = !mine || ((uint32_t)(e.x >> 32) == tag_top && (uint32_t)(e.y >> 32) == tag_top);
                     if (__all_sync(FULL, ok)) break;
+                    have = false;
                     __nanosleep(64);
                     if (++spins > a.spin_limit) {              // watchdog: never hang the GPU
                         if (head && a.dev_err) atomicOr(a.dev_err, SW_DEVERR_SPIN);
                         break;
                     }
                 }
+                const uint2 v = mine ? make_uint2((uint32_t)e.x, (uint32_t)e.y) : make_uint2(h0, gb2);
                 __syncwarp();                                  // the head lane is done with the previous block
                 if (lane < BLK) s_top[lane] = v;
                 __syncwarp();
+            }
+            if ((t2 & (BLK - 1)) == BLK - kWavePrefetch && t2 + kWavePrefetch < ncols) {
+                // the next block's elements, a few steps before they are needed: the L2 round trip
+                // overlaps the steps in between; a stale element fails the tag check above and is re-read
+                const int c = t2 + kWavePrefetch + lane;
+                if (lane < BLK && c < ncols) pre = __ldcg(top + c);
             }
         }
 #pragma unroll
@@ -145,11 +161,12 @@ __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *pr
             if (u == 3) {
                 wcur = wnext;
                 const int k = (t >> 2) + 2;
-                if (head && k * 4 < ncols) wnext = __ldg(tpp + k * 32);
-                if (head && (k + 1) * 4 < ncols) prefetch_l1(tpp + (k + 1) * 32);
+                if ((k & 31) == 0) { cw_cur = cw_nxt; cw_nxt = bulk((k >> 5) + 1); }
+                wnext = __shfl_sync(FULL, cw_cur, k & 31);
             }
 #pragma unroll
             for (int s = 1; s < S; ++s) { in_h[s] = pub_h[s - 1]; in_g[s] = pub_g[s - 1]; in_t[s] = pub_t[s - 1]; }
+            SW_CHECK(in_t[0] <= (uint32_t)kPadCode, SW_DEVERR_PROF, a);
             uint2 sv_next[S][RP];
             load_scores<RS, S, G, kWaveCodes>(sv_next, prof_lane, in_t);
             column_step_multi<RS, S, G, AR, false>(H, Gl, best, hd_top, in_g, sv, goe2, ge2, zero, 0u);
@@ -160,11 +177,19 @@ __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *pr
                 hd_top[s] = in_h[s];
                 pub_h[s] = H[s][RS - 1]; pub_g[s] = Gl[s][RS - 1]; pub_t[s] = in_t[s];
             }
-            if constexpr (HAS_BOTTOM) {
-                if (lane == G - 1) {
-                    const int cl = t - (VPE - 1);              // column the last virtual PE just finished
-                    if (cl >= 0 && cl < ncols)
-                        __stcg(bot + cl, make_ulonglong2(tag_hi | pub_h[S - 1], tag_hi | pub_g[S - 1]));
+            sto_h[uu] = pub_h[S - 1];
+            sto_g[uu] = pub_g[S - 1];
+        }
+        if constexpr (HAS_BOTTOM) {
+            // the last virtual PE finished columns cl0 .. cl0 + 3 in these four steps: one branch,
+            // four 16-byte stores.  Columns outside 0 .. ncols - 1 land in the row's slack
+            // (kWaveSlack elements on either side) and are never read.
+            const int cl0 = t2 - (VPE - 1);
+            if (lane == G - 1 && cl0 + (U - 1) >= 0 && cl0 < ncols) {
+#pragma unroll
+                for (int uu = 0; uu < U; ++uu) {
+                    SW_CHECK((unsigned long long)(bot + cl0 + uu - a.bnd) < a.bnd_elems, SW_DEVERR_BND, a);
+                    __stcg(bot + cl0 + uu, make_ulonglong2(tag_hi | sto_h[uu], tag_hi | sto_g[uu]));
                 }
             }
         }
@@ -172,7 +197,165 @@ __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *pr
     return best;
 }
 
-template <int RS, int S, class AR, int BT, int MINB, int CGOE = 0, int CGE = 0, int BLK = kWaveBlock>
+// The same band with C columns per systolic step (S = 1): a lane finishes the C x RS tile of its
+// rows before it hands (H, G) of its bottom row -- C columns at once -- to the next lane, so the
+// lanes are skewed by C columns, a band needs ncols / C + 31 steps instead of ncols + 31, and the
+// fixed cost of a step (shuffles, selects, the profile address, loop control) is paid once per C
+// columns.  Inside the tile column j + 1 of row r only needs column j of row r and column j + 1
+// of row r - 1: C interleaved dependency chains, which is what a lone warp on its scheduler needs
+// (one long pair = one warp per band: latency-bound, not throughput-bound).
+// Codes travel as one word of C bytes, one step ahead of H / G, exactly as in wave_band.
+template <int RS, int C, class AR, int BLK, bool HAS_TOP, bool HAS_BOTTOM>
+__device__ __forceinline__ uint32_t wave_band_c(const WaveArgs &a, const uint2 *prof_lane, uint2 (&s_top)[BLK], const uint32_t *tpp,
+                                                int ncols, const ulonglong2 *top, ulonglong2 *bot, uint32_t tag_top, uint32_t tag_bot,
+                                                uint32_t goe2, uint32_t ge2, uint32_t h0, uint32_t gb2, uint32_t zero)
+{
+    static_assert(C == 2 || C == 4, "2 or 4 columns per step");
+    constexpr int G = 32, RP = (RS + 1) / 2, TC = 8, U = TC / C;      // a loop trip = 8 columns = U steps
+    constexpr int PF = 16;                                            // columns between prefetch and use of a boundary block
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    constexpr uint32_t PADW = kPadCode * 0x01010101u;
+    constexpr uint32_t CMASK = C == 4 ? 0xFFFFFFFFu : 0xFFFFu;
+    static_assert(BLK % TC == 0 && BLK == 32, "boundary blocks of 32 columns");
+    const int lane = threadIdx.x & 31;
+    const bool head = lane == 0;
+    uint32_t best = h0;
+    uint32_t H[1][RS], Gl[1][RS];
+#pragma unroll
+    for (int r = 0; r < RS; ++r) { H[0][r] = h0; Gl[0][r] = gb2; }
+
+    // Code words (4 columns each): the warp keeps 2 x 32 of them in one register per lane -- lane i
+    // holds word 32 B + i of the current / next block of 128 columns, loaded 128 columns before they
+    // are needed (the stream of a lone pair comes from DRAM: a load issued one trip ahead would
+    // bound the trip by the memory latency) -- and a trip takes its two words by shuffle.
+    auto bulk = [&](int blk) -> uint32_t {
+        const int w = blk * 32 + lane;
+        if (4 * w < ncols) SW_CHECK((unsigned long long)(tpp - a.tp) + (unsigned long long)w * 32 < a.tp_words, SW_DEVERR_TP, a);
+        return 4 * w < ncols ? __ldg(tpp + (size_t)w * 32) : PADW;
+    };
+    uint32_t cw_cur = bulk(0), cw_nxt = bulk(1);
+    uint32_t tc0 = __shfl_sync(FULL, cw_cur, 0), tc1 = __shfl_sync(FULL, cw_cur, 1);
+    uint32_t tn0 = __shfl_sync(FULL, cw_cur, 2), tn1 = __shfl_sync(FULL, cw_cur, 3);
+
+    uint32_t pub_h[C], pub_g[C], pub_t = head ? (tc0 & CMASK) : (PADW & CMASK), hd_carry = h0;
+#pragma unroll
+    for (int j = 0; j < C; ++j) { pub_h[j] = h0; pub_g[j] = gb2; }
+    auto load_sv = [&](uint2 (&sv)[C][RP], uint32_t tw) {
+#pragma unroll
+        for (int j = 0; j < C; ++j) {
+            const uint2 *prow = prof_lane + ((tw >> (8 * j)) & 255u) * G;
+#pragma unroll
+            for (int k = 0; k < RP; ++k) sv[j][k] = prow[k * kWaveCodes * G];
+        }
+    };
+    uint2 sv[C][RP];
+    load_sv(sv, pub_t);
+    ulonglong2 pre = make_ulonglong2(0ull, 0ull);
+    uint32_t sto_h[TC], sto_g[TC];
+    const unsigned long long tag_hi = (unsigned long long)tag_bot << 32;
+    const int nsteps = ncols > 0 ? ((ncols + C - 1) / C + (G - 1) + U - 1) / U * U : 0;
+
+#pragma unroll 1
+    for (int k0 = 0; k0 < nsteps; k0 += U) {
+        const int c0 = k0 * C;                                 // the head lane's first column of this trip
+        const int wq = (c0 >> 2) + 4;                          // the words of the trip after next
+        if ((wq & 31) == 0) { cw_cur = cw_nxt; cw_nxt = bulk((wq >> 5) + 1); }
+        const uint32_t tnn0 = __shfl_sync(FULL, cw_cur, wq & 31), tnn1 = __shfl_sync(FULL, cw_cur, (wq & 31) + 1);
+        if constexpr (HAS_TOP) {
+            if ((c0 & (BLK - 1)) == 0 && c0 < ncols) {
+                const int c = c0 + lane;
+                const bool mine = c < ncols;
+                ulonglong2 e = pre;
+                bool have = c0 != 0;
+                unsigned spins = 0;
+                for (;;) {
+                    if (mine) SW_CHECK((unsigned long long)(top + c - a.bnd) < a.bnd_elems, SW_DEVERR_BND, a);
+                    if (!have && mine) e = __ldcg(top + c);
+                    const bool ok = !mine || ((uint32_t)(e.x >> 32) == tag_top && (uint32_t)(e.y >> 32) == tag_top);
+                    if (__all_sync(FULL, ok)) break;
+                    have = false;
+                    __nanosleep(64);
+                    if (++spins > a.spin_limit) {              // watchdog: never hang the GPU
+                        if (head && a.dev_err) atomicOr(a.dev_err, SW_DEVERR_SPIN);
+                        break;
+                    }
+                }
+                const uint2 v = mine ? make_uint2((uint32_t)e.x, (uint32_t)e.y) : make_uint2(h0, gb2);
+                __syncwarp();                                  // the head lane is done with the previous block
+                s_top[lane] = v;
+                __syncwarp();
+            }
+            if ((c0 & (BLK - 1)) == BLK - PF && c0 + PF < ncols) {
+                const int c = c0 + PF + lane;
+                if (c < ncols) pre = __ldcg(top + c);
+            }
+        }
+        const uint2 *stp = s_top + (c0 & (BLK - 1));
+#pragma unroll
+        for (int uu = 0; uu < U; ++uu) {
+            uint32_t in_h[C], in_g[C];
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                in_h[j] = __shfl_up_sync(FULL, pub_h[j], 1, G);
+                in_g[j] = __shfl_up_sync(FULL, pub_g[j], 1, G);
+            }
+            uint32_t in_t = __shfl_up_sync(FULL, pub_t, 1, G);
+            // head lane: the band above (or the matrix edge) and the codes of its NEXT step's columns
+            const int nb = C * (uu + 1);                       // first byte of those codes inside this trip's 8
+            uint32_t lead;
+            if (nb >= TC) lead = tn0;
+            else if (C == 4) lead = tc1;
+            else lead = nb == 2 ? (tc0 >> 16) : nb == 4 ? tc1 : (tc1 >> 16);
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                uint2 b = make_uint2(h0, gb2);
+                if constexpr (HAS_TOP) b = stp[uu * C + j];
+                in_h[j] = head ? b.x : in_h[j];
+                in_g[j] = head ? b.y : in_g[j];
+            }
+            in_t = head ? (lead & CMASK) : in_t;
+#pragma unroll
+            for (int j = 0; j < C; ++j) SW_CHECK(((in_t >> (8 * j)) & 255u) <= (uint32_t)kPadCode, SW_DEVERR_PROF, a);
+            uint2 sv_next[C][RP];
+            load_sv(sv_next, in_t);
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                const uint32_t hd[1] = {j == 0 ? hd_carry : in_h[j - 1]};
+                const uint32_t gt[1] = {in_g[j]};
+                uint2 svj[1][RP];
+#pragma unroll
+                for (int k = 0; k < RP; ++k) svj[0][k] = sv[j][k];
+                column_step_multi<RS, 1, G, AR, false>(H, Gl, best, hd, gt, svj, goe2, ge2, zero, 0u);
+                pub_h[j] = H[0][RS - 1];
+                pub_g[j] = Gl[0][RS - 1];
+                sto_h[uu * C + j] = pub_h[j];
+                sto_g[uu * C + j] = pub_g[j];
+            }
+            hd_carry = in_h[C - 1];
+            pub_t = in_t;
+#pragma unroll
+            for (int j = 0; j < C; ++j)
+#pragma unroll
+                for (int k = 0; k < RP; ++k) sv[j][k] = sv_next[j][k];
+        }
+        tc0 = tn0; tc1 = tn1; tn0 = tnn0; tn1 = tnn1;
+        if constexpr (HAS_BOTTOM) {
+            // the last lane finished columns cl0 .. cl0 + 7 in this trip; columns outside
+            // 0 .. ncols - 1 land in the row's slack and are never read
+            const int cl0 = c0 - C * (G - 1);
+            if (lane == G - 1 && cl0 + (TC - 1) >= 0 && cl0 < ncols) {
+#pragma unroll
+                for (int i = 0; i < TC; ++i) {
+                    SW_CHECK((unsigned long long)(bot + cl0 + i - a.bnd) < a.bnd_elems, SW_DEVERR_BND, a);
+                    __stcg(bot + cl0 + i, make_ulonglong2(tag_hi | sto_h[i], tag_hi | sto_g[i]));
+                }
+            }
+        }
+    }
+    return best;
+}
+
+template <int RS, int S, class AR, int BT, int MINB, int CGOE = 0, int CGE = 0, int BLK = kWaveBlock, int C = 1>
 __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
 {
     extern __shared__ uint2 s_prof[];
@@ -181,7 +364,8 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
     constexpr int PASS_ENTRIES = VPE * RP * kWaveCodes;
     constexpr int PPB = BT / G;
     constexpr unsigned FULL = 0xFFFFFFFFu;
-    __shared__ uint2 s_top[PPB][BLK];
+    static_assert(C == 1 || S == 1, "several columns per step: one sub-strip");
+    __shared__ __align__(16) uint2 s_top[PPB][BLK];
     __shared__ uint8_t s_qb[P / 4 + 4];                // packed query bytes of the band
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -246,18 +430,21 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
         const uint2 *prof_lane = s_prof + lane;
         const bool has_top = pass > 0, has_bottom = pass + 1 < a.npass;
         const size_t prow = (size_t)pair * 2;
-        const ulonglong2 *top = a.bnd + (prow + (size_t)((pass - 1) & 1)) * a.cols_stride;
-        ulonglong2 *bot = a.bnd + (prow + (size_t)(pass & 1)) * a.cols_stride;
+        const ulonglong2 *top = a.bnd + (prow + (size_t)((pass - 1) & 1)) * a.cols_stride + kWaveSlack;
+        ulonglong2 *bot = a.bnd + (prow + (size_t)(pass & 1)) * a.cols_stride + kWaveSlack;
         const uint32_t tag_bot = (a.epoch << 12) | (uint32_t)pass, tag_top = tag_bot - 1u;
 
         uint32_t best;
-        if (has_top) {
-            if (has_bottom) best = wave_band<RS, S, AR, BLK, true, true>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero);
-            else best = wave_band<RS, S, AR, BLK, true, false>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero);
-        } else {
-            if (has_bottom) best = wave_band<RS, S, AR, BLK, false, true>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero);
-            else best = wave_band<RS, S, AR, BLK, false, false>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero);
-        }
+#define SW_WAVE_BAND(T, B)                                                                                                   \
+        do {                                                                                                                 \
+            if constexpr (C > 1)                                                                                             \
+                best = wave_band_c<RS, C, AR, BLK, T, B>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero); \
+            else                                                                                                             \
+                best = wave_band<RS, S, AR, BLK, T, B>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero); \
+        } while (0)
+        if (has_top) { if (has_bottom) SW_WAVE_BAND(true, true); else SW_WAVE_BAND(true, false); }
+        else { if (has_bottom) SW_WAVE_BAND(false, true); else SW_WAVE_BAND(false, false); }
+#undef SW_WAVE_BAND
 
 #pragma unroll
         for (int o = G / 2; o >= 1; o >>= 1) best = AR::max2(best, __shfl_xor_sync(FULL, best, o));
@@ -277,6 +464,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
                     if (ov0) { const unsigned p = atomicAdd(a.ovf_count, 1u); if (p < a.ovf_cap) a.ovf_list[p] = make_uint2((unsigned)q, subj_lo); }
                     if (has1 && ov1) { const unsigned p = atomicAdd(a.ovf_count, 1u); if (p < a.ovf_cap) a.ovf_list[p] = make_uint2((unsigned)q, subj_hi); }
                 }
+                SW_CHECK((unsigned long long)q * a.out_stride + subj_lo < a.out_elems && (!has1 || (unsigned long long)q * a.out_stride + subj_hi < a.out_elems), SW_DEVERR_OUT, a);
                 if (a.out_mode == SW_OUT_I16) {
                     int16_t *orow = (int16_t *)a.out + (size_t)q * a.out_stride;
                     orow[subj_lo] = (int16_t)(ov0 ? SW_OVERFLOW_SENTINEL : f0);

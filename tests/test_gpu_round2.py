@@ -447,6 +447,35 @@ def test_wave_kernel_few_long_pairs_vs_oracle(oracle_mod, pkg):
         assert "wave" not in e.last_kernel_name
 
 
+@pytest.mark.parametrize("instance", [0, 1, 2])
+def test_wave_kernel_every_instance_vs_oracle(oracle_mod, pkg, monkeypatch, instance):
+    """Each instance of the band-pipelined kernel (512-row bands, one column per step; 256-row bands
+    with four / two columns per step and one pair per block) forced in turn over ragged lengths:
+    subject lengths around the 4- and 8-column trip, the 32-column boundary block and the 128-column
+    code-word block; query lengths that leave the last band almost empty or exactly full."""
+    monkeypatch.setenv("SW_B200_WAVE_INSTANCE", str(instance))
+    rng = random.Random(4100 + instance)
+    q = _rand(rng, 2049)
+    queries = [q, q[:1024], q[:769], _rand(rng, 513)]
+    subjects = []
+    for L in (1, 2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 128, 129, 255, 256, 257, 500, 777, 1031):
+        a = rng.randint(0, 1000)
+        s = (_mutate(rng, q[a:a + L], 0.05, 0.03) + _rand(rng, L))[:L] if L % 2 else _rand(rng, L)
+        subjects.append(s)
+    subjects += ["", q[100:1900], _mutate(rng, q, 0.02, 0.01)]
+    want = _oracle_matrix(oracle_mod, pkg, queries, subjects)
+    with pkg.Engine() as e:
+        e.set_small_batch_path(False)
+        e.set_wave_mode(2)
+        got = e.score(queries, subjects)
+        assert "wave" in e.last_kernel_name, e.last_kernel_name
+        assert e.device_error_bits == 0
+        np.testing.assert_array_equal(got, want)
+        # a second call on the same handle: the boundary tags of the first launches must not match
+        got = e.score(queries[::-1], subjects)
+        np.testing.assert_array_equal(got, want[::-1])
+
+
 def test_wave_kernel_single_long_pair_and_overflow(oracle_mod, pkg):
     """One long pair spread over many warps; and a pair whose score leaves the 16-bit range inside
     the wave kernel (flagged per band, recomputed in 32 bit from the overflow list)."""
