@@ -112,6 +112,7 @@ def load_library():
     L.sw_set_small_batch_path.argtypes = [vp, i32]
     L.sw_set_small_batch_timing.argtypes = [vp, i32]
     L.sw_set_wave_mode.argtypes = [vp, i32]
+    L.sw_set_overflow_wave.argtypes = [vp, i32, C.c_ulonglong]
     L.sw_set_launch_plan.argtypes = [vp, i32, i32]
     L.sw_get_stats.argtypes = [vp, C.POINTER(SwStats)]
     L.sw_params_in_exact_domain.argtypes = [C.POINTER(SwParams)]
@@ -256,6 +257,10 @@ class Engine:
     def set_wave_mode(self, mode):
         """Band-pipelined kernel for few long pairs: 0 never, 1 automatic, 2 whenever possible."""
         self._check(self.lib.sw_set_wave_mode(self.h, mode))
+
+    def set_overflow_wave(self, enable=True, min_cells=1000000):
+        """Overflow list: entries of >= min_cells cells are scored by bands on many warps (32-bit)."""
+        self._check(self.lib.sw_set_overflow_wave(self.h, int(bool(enable)), int(min_cells)))
 
     def set_launch_plan(self, length_groups=2, query_groups=False):
         """length_groups: 0 one launch, 1 one launch per length group, 2 automatic; query_groups: variant per query length."""

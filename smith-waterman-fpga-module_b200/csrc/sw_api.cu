@@ -153,6 +153,9 @@ struct GpuCtx {
     DevBuf d_bnd, d_counters, d_scratch32, d_best_score, d_best_index, d_topk_keys, d_err;
     DevBuf d_wave_bnd, d_wave_state;  // band-pipelined kernel: boundary rows; progress / best / done words
     int wave_bps[16] = {0};           // resident blocks per SM of its instances (0 = not asked yet)
+    DevBuf d_wave32_bnd, d_wave32_state;   // 32-bit band-pipelined scorer of the overflow list
+    uint32_t wave32_epoch = 0;        // 8-bit tag field: 1 .. 255, boundary rows zeroed when it restarts
+    int wave32_bps = 0;
     uint32_t wave_epoch = 0;          // launches so far: the tag of the boundary elements (20 bits)
     unsigned counter_next = 0;        // next unused work-queue counter
     // autotune: timing events and the cached decision, per GPU (shards differ in shape)
@@ -198,6 +201,8 @@ struct sw_handle {
     bool small_timing = true;         // record CUDA events around the latency path's kernel (sw_last_kernel_ms)
     int jit = 1;                      // run-time specialisation of gap penalties: 0 off, 1 large jobs, 2 always
     int wave = 1;                     // band-pipelined kernel for few long pairs: 0 off, 1 automatic, 2 whenever possible
+    int wave32 = 1;                   // overflow list: long entries go to the band-pipelined 32-bit scorer
+    unsigned long long wave32_min_cells = 1000000ull;
     // launch-planner knobs (environment SW_B200_PLAN_SEGS / _QGROUPS / _STREAMS / _TAU): experiments
     int plan_segs = 2;                // 0 never, 1 always, 2 when one launch would need a huge pass-boundary scratch
     bool plan_qgroups = false;        // per-query variant choice (measured: the extra launches cost more than they gain)
@@ -254,7 +259,7 @@ SwScoring scoring_of(const sw_handle *h)
 std::vector<DevBuf *> all_devbufs(GpuCtx &g)
 {
     std::vector<DevBuf *> v = {&g.d_qpacked, &g.d_qoff, &g.d_qlen, &g.d_qidx, &g.d_bnd, &g.d_counters, &g.d_scratch32,
-                               &g.d_best_score, &g.d_best_index, &g.d_topk_keys, &g.d_err, &g.d_wave_bnd, &g.d_wave_state,
+                               &g.d_best_score, &g.d_best_index, &g.d_topk_keys, &g.d_err, &g.d_wave_bnd, &g.d_wave_state, &g.d_wave32_bnd, &g.d_wave32_state,
                                &g.d_bnd_aux[0], &g.d_bnd_aux[1], &g.d_bnd_aux[2]};
     for (Slot &b : g.slot) {
         DevBuf *bufs[] = {&b.d_raw, &b.d_off, &b.d_len, &b.d_pair_subj, &b.d_pair_len, &b.d_tile_woff, &b.d_tp, &b.d_out,
@@ -1098,6 +1103,45 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
         if (may_overflow) {
             s32.mode = 2; s32.list_count = g.d_ovf_count.as<unsigned>(); s32.list = g.d_ovf_list.as<uint2>();
             s32.list_cap = kOvfCap; s32.list_score = g.d_ovf_score.as<int32_t>();
+            if (h->wave32) {
+                // long entries (with the default scoring every entry is >= 6 400 x 6 400 nt) are scored
+                // by bands on many warps; the launch is list-driven, so nothing is read back here
+                SwWave32Launch W;
+                W.db = db; W.q = dq; W.sc = sc;
+                W.list_count = s32.list_count; W.list = s32.list; W.list_cap = kOvfCap; W.list_score = s32.list_score;
+                W.out = s32.out; W.out_stride = n; W.out_elems = (size_t)nq * n; W.out_mode = g.out_mode;
+                W.cols_stride = ((g.max_len + 31u) & ~31u) + 32u;
+                const size_t per_slot = (size_t)2 * W.cols_stride * 16;
+                W.nslots = (uint32_t)std::min<size_t>(64, std::max<size_t>(2, ((size_t)64 << 20) / per_slot));
+                W.bnd_elems = (size_t)W.nslots * 2 * W.cols_stride;
+                bool fresh = false;
+                if (gc.d_wave32_bnd.cap < W.bnd_elems * 16 || !gc.d_wave32_bnd.p) {
+                    SW_CUDA(h, cudaStreamSynchronize(gc.st_compute));
+                    SW_CUDA(h, gc.d_wave32_bnd.reserve(W.bnd_elems * 16));
+                    fresh = true;
+                }
+                gc.wave32_epoch = gc.wave32_epoch % 255u + 1u;
+                if (fresh || gc.wave32_epoch == 1u)          // stale tags must never match
+                    SW_CUDA(h, cudaMemsetAsync(gc.d_wave32_bnd.p, 0, gc.d_wave32_bnd.cap, gc.st_compute));
+                W.bnd = gc.d_wave32_bnd.p; W.epoch = gc.wave32_epoch;
+                const size_t state_bytes = (size_t)3 * SW_WAVE32_MAX_ENTRIES * sizeof(unsigned);
+                SW_CUDA(h, gc.d_wave32_state.reserve(state_bytes));
+                SW_CUDA(h, cudaMemsetAsync(gc.d_wave32_state.p, 0, state_bytes, gc.st_compute));
+                W.state = gc.d_wave32_state.as<unsigned>();
+                W.counter = next_counter(gc);
+                SW_CUDA(h, cudaMemsetAsync(W.counter, 0, sizeof(unsigned), gc.st_compute));
+                W.maxb = (h->q_max_len + SW_WAVE32_ROWS - 1) / SW_WAVE32_ROWS;
+                W.min_cells = h->wave32_min_cells;
+                if (!gc.wave32_bps) SW_CUDA(h, sw_wave32_occupancy(&gc.wave32_bps));
+                if (gc.wave32_bps < 1) return SW_ECUDA;
+                // one warp per scheduler: a larger grid lets the first (few hundred) claiming blocks pile
+                // up on a few SMs (measured: 16 blocks per SM = 2.3x slower for one 100 kb entry)
+                W.grid = gc.num_sms * std::min(gc.wave32_bps, 4);
+                W.dev_err = gc.d_err.as<unsigned>();
+                SW_CUDA(h, sw_launch_wave32(gc.st_compute, W));
+                h->launches++;
+                s32.wave32_min_cells = W.min_cells;
+            }
             SW_CUDA(h, sw_launch_score32(gc.st_compute, s32));
             h->launches++;
         }
@@ -1673,6 +1717,7 @@ int sw_init(sw_handle_t **out, const sw_params_t *p, const int *gpu_ids, int n_g
     if (const char *e = std::getenv("SW_B200_JIT")) h->jit = std::atoi(e);
     if (const char *e = std::getenv("SW_B200_SMALL_PATH")) h->small_path = (e[0] != '0');
     if (const char *e = std::getenv("SW_B200_WAVE")) h->wave = std::atoi(e);
+    if (const char *e = std::getenv("SW_B200_WAVE32")) h->wave32 = (e[0] != '0');
     if (const char *e = std::getenv("SW_B200_PLAN_SEGS")) h->plan_segs = std::atoi(e);
     if (const char *e = std::getenv("SW_B200_PLAN_QGROUPS")) h->plan_qgroups = (e[0] != '0');
     if (const char *e = std::getenv("SW_B200_STREAMS")) h->plan_streams = std::max(1, std::min(kStreams, std::atoi(e)));
@@ -2023,6 +2068,14 @@ int sw_set_wave_mode(sw_handle_t *h, int mode)
 {
     if (!h || mode < 0 || mode > 2) return SW_EINVAL;
     h->wave = mode;
+    return SW_OK;
+}
+
+int sw_set_overflow_wave(sw_handle_t *h, int enable, unsigned long long min_cells)
+{
+    if (!h) return SW_EINVAL;
+    h->wave32 = enable != 0;
+    h->wave32_min_cells = min_cells ? min_cells : 1ull;
     return SW_OK;
 }
 

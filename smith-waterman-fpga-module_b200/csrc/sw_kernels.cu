@@ -63,6 +63,7 @@ struct Score32Args {
     int32_t *scratch; uint32_t max_cols;
     int match, mismatch, goe, ge, limit, mode;
     const unsigned *list_count; const uint2 *list; unsigned list_cap; int32_t *list_score;
+    unsigned long long wave32_min_cells;
 };
 
 __device__ __forceinline__ int score32_pair(const uint8_t *rp, int m, const uint8_t *cp, int n, int32_t *Hb,
@@ -136,6 +137,8 @@ __global__ void __launch_bounds__(128) score32_kernel(const Score32Args a)
             if (!flagged) continue;
         }
         const int m = (int)a.qlen[q], n = (int)a.len[s];
+        // long entries at the head of the list belong to the band-pipelined 32-bit scorer
+        if (a.mode == 2 && a.wave32_min_cells && wave32_takes((unsigned)job, (uint32_t)m, (uint32_t)n, a.wave32_min_cells)) continue;
         const uint8_t *qp = a.qpacked + a.qoff[q];
         const uint8_t *tpk = a.raw + a.off[s];
         const int best = (n <= m) ? score32_pair(qp, m, tpk, n, Hb, Gb, nthreads, a)
@@ -421,6 +424,35 @@ cudaError_t sw_launch_wave(cudaStream_t st, const SwWaveLaunch &L)
     return cudaGetLastError();
 }
 
+static_assert(SW_WAVE32_MAX_ENTRIES == kWave32MaxEntries && SW_WAVE32_ROWS == kWave32Rows, "sw_kernels.h / sw_wave.cuh");
+namespace {
+constexpr int kWave32MinBlocks = 16;
+const auto g_wave32 = sw_wave32_kernel<8, 2, kWave32MinBlocks>;
+}
+
+cudaError_t sw_wave32_occupancy(int *blocks_per_sm)
+{
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, (const void *)g_wave32, 32, 0);
+}
+
+cudaError_t sw_launch_wave32(cudaStream_t st, const SwWave32Launch &L)
+{
+    if (L.sc.limit || L.grid <= 0 || L.nslots == 0) return cudaErrorInvalidValue;    // exact arithmetic only
+    Wave32Args a{};
+    a.raw = L.db.raw; a.off = L.db.off; a.len = L.db.len;
+    a.qpacked = L.q.packed; a.qoff = L.q.off; a.qlen = L.q.len;
+    a.list_count = L.list_count; a.list = L.list; a.list_cap = L.list_cap; a.list_score = L.list_score;
+    a.out = L.out; a.out_stride = L.out_stride; a.out_mode = L.out_mode; a.out_elems = L.out_elems;
+    a.bnd = (ulonglong2 *)L.bnd; a.cols_stride = L.cols_stride; a.nslots = L.nslots; a.epoch = L.epoch; a.bnd_elems = L.bnd_elems;
+    a.best = (int *)L.state; a.done = L.state + kWave32MaxEntries; a.flag = L.state + 2 * kWave32MaxEntries;
+    a.counter = L.counter; a.maxb = L.maxb ? L.maxb : 1u; a.min_cells = L.min_cells;
+    a.match = L.sc.match; a.mismatch = L.sc.mismatch; a.goe = L.sc.goe; a.ge = L.sc.ge;
+    a.dev_err = L.dev_err;
+    a.spin_limit = 1u << 24;
+    g_wave32<<<L.grid, 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t sw_launch_score32(cudaStream_t st, const SwScore32Launch &L)
 {
     const int bt = 128;
@@ -433,6 +465,7 @@ cudaError_t sw_launch_score32(cudaStream_t st, const SwScore32Launch &L)
     a.scratch = L.scratch; a.max_cols = L.max_cols;
     a.match = L.sc.match; a.mismatch = L.sc.mismatch; a.goe = L.sc.goe; a.ge = L.sc.ge; a.limit = L.sc.limit;
     a.mode = L.mode; a.list_count = L.list_count; a.list = L.list; a.list_cap = L.list_cap; a.list_score = L.list_score;
+    a.wave32_min_cells = L.wave32_min_cells;
     score32_kernel<<<grid, bt, 0, st>>>(a);
     return cudaGetLastError();
 }

@@ -146,6 +146,36 @@ int sw_wave_rows_per_band(int instance);
 int sw_wave_instance_count(void);
 int sw_wave_pairs_per_block(int instance);
 
+/* 32-bit band-pipelined scorer of the overflow list (sw_wave.cuh, sw_wave32_kernel): the first
+ * SW_WAVE32_MAX_ENTRIES entries with at least min_cells cells; score32 (mode 2) with the same
+ * wave32_min_cells skips exactly those.  bnd: nslots * 2 * cols_stride 16-byte elements (zeroed once
+ * and whenever epoch restarts at 1); state: 3 * SW_WAVE32_MAX_ENTRIES zeroed words per launch. */
+#define SW_WAVE32_MAX_ENTRIES 4096
+#define SW_WAVE32_ROWS 256
+struct SwWave32Launch {
+    SwDevDb db{};
+    SwDevQueries q{};
+    SwScoring sc{};
+    const unsigned *list_count = nullptr;
+    const uint2 *list = nullptr;
+    unsigned list_cap = 0;
+    int32_t *list_score = nullptr;
+    void *out = nullptr;
+    size_t out_stride = 0, out_elems = 0;
+    int out_mode = SW_OUT_I32;
+    void *bnd = nullptr;
+    uint32_t cols_stride = 0, nslots = 0, epoch = 1;
+    size_t bnd_elems = 0;
+    unsigned *state = nullptr;
+    unsigned *counter = nullptr;
+    uint32_t maxb = 1;
+    unsigned long long min_cells = 0;
+    int grid = 0;
+    unsigned *dev_err = nullptr;
+};
+cudaError_t sw_wave32_occupancy(int *blocks_per_sm);
+cudaError_t sw_launch_wave32(cudaStream_t st, const SwWave32Launch &L);
+
 /* 32-bit kernel: any length, any score range.  scratch: 2 * max_cols * threads_total int32 where
  * max_cols = min(longest query, longest subject) (the recurrence is symmetric: the shorter sequence
  * is walked as columns).  mode 0: every (query, subject) job of q0..q1; mode 1: only matrix entries
@@ -167,6 +197,7 @@ struct SwScore32Launch {
     const uint2 *list = nullptr;
     unsigned list_cap = 0;
     int32_t *list_score = nullptr;
+    unsigned long long wave32_min_cells = 0;   /* mode 2: entries sw_wave32_kernel takes are skipped (0 = none) */
 };
 cudaError_t sw_launch_score32(cudaStream_t st, const SwScore32Launch &L);
 

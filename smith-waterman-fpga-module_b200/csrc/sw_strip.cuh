@@ -93,6 +93,24 @@ struct ArithS16 {
     }
 };
 
+// Plain signed 32-bit arithmetic, one subject per register: the band-pipelined 32-bit scorer of
+// the overflow list (sw_wave.cuh, sw_wave32_kernel).  Same DPX instruction per operation.
+struct ArithS32 {
+    static constexpr int kPad = -(1 << 28);
+    static __device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) {
+        return (uint32_t)__viaddmax_s32_relu((int)a, (int)b, (int)c);
+    }
+    static __device__ __forceinline__ uint32_t pack_score(int lo, int) { return (uint32_t)lo; }
+    static __device__ __forceinline__ int extract(uint32_t v, int) { return (int)v; }
+    static __device__ __forceinline__ uint32_t add_relu(uint32_t a, uint32_t b, uint32_t) { return (uint32_t)max((int)(a + b), 0); }
+    static __device__ __forceinline__ uint32_t wrap_clamp(uint32_t m, uint32_t) { return m; }   // exact mode only
+    static __device__ __forceinline__ uint32_t add(uint32_t a, uint32_t b) { return a + b; }
+    static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { return (uint32_t)max((int)a, (int)b); }
+    static __device__ __forceinline__ uint32_t addmax(uint32_t a, uint32_t b, uint32_t c) {
+        return (uint32_t)__viaddmax_s32((int)a, (int)b, (int)c);
+    }
+};
+
 // Pass-boundary scratch accesses, tagged evict_last so that the scratch lines, which are rewritten
 // every pass, stay resident in L2 instead of being written back to HBM between passes.  A slot is
 // written and read by the same warp only (lane G-1 / lane 0), so L1 is coherent for it: loads are

@@ -205,8 +205,26 @@ __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *pr
 // of row r - 1: C interleaved dependency chains, which is what a lone warp on its scheduler needs
 // (one long pair = one warp per band: latency-bound, not throughput-bound).
 // Codes travel as one word of C bytes, one step ahead of H / G, exactly as in wave_band.
-template <int RS, int C, class AR, int BLK, bool HAS_TOP, bool HAS_BOTTOM>
-__device__ __forceinline__ uint32_t wave_band_c(const WaveArgs &a, const uint2 *prof_lane, uint2 (&s_top)[BLK], const uint32_t *tpp,
+// Code sources of wave_band_c: word(w) = the codes of columns 4 w .. 4 w + 3, one byte each.
+struct TiledCodes {                  // a pair's column of the tiled code stream (build_tp_kernel)
+    static constexpr int kCodes = kWaveCodes, kPad = kPadCode;
+    const uint32_t *tpp;
+    __device__ __forceinline__ uint32_t word(int w, int) const { return __ldg(tpp + (size_t)w * 32); }
+};
+struct RawCodes {                    // one subject's packed 2-bit record: code = nucleotide, 4 = past its end
+    static constexpr int kCodes = 8, kPad = 4;
+    const uint8_t *raw;
+    __device__ __forceinline__ uint32_t word(int w, int ncols) const {
+        const uint32_t b = __ldg(raw + w);
+        uint32_t x = (b & 3u) | ((b & 12u) << 6) | ((b & 48u) << 12) | ((b & 192u) << 18);
+        const int rem = ncols - 4 * w;                         // >= 1 (the caller checks 4 w < ncols)
+        if (rem < 4) x = (x & ((1u << (8 * rem)) - 1u)) | ((kPad * 0x01010101u) << (8 * rem));
+        return x;
+    }
+};
+
+template <int RS, int C, class AR, int BLK, bool HAS_TOP, bool HAS_BOTTOM, class ARGS, class SRC>
+__device__ __forceinline__ uint32_t wave_band_c(const ARGS &a, const uint2 *prof_lane, uint2 (&s_top)[BLK], const SRC src,
                                                 int ncols, const ulonglong2 *top, ulonglong2 *bot, uint32_t tag_top, uint32_t tag_bot,
                                                 uint32_t goe2, uint32_t ge2, uint32_t h0, uint32_t gb2, uint32_t zero)
 {
@@ -214,7 +232,7 @@ __device__ __forceinline__ uint32_t wave_band_c(const WaveArgs &a, const uint2 *
     constexpr int G = 32, RP = (RS + 1) / 2, TC = 8, U = TC / C;      // a loop trip = 8 columns = U steps
     constexpr int PF = 16;                                            // columns between prefetch and use of a boundary block
     constexpr unsigned FULL = 0xFFFFFFFFu;
-    constexpr uint32_t PADW = kPadCode * 0x01010101u;
+    constexpr uint32_t PADW = SRC::kPad * 0x01010101u;
     constexpr uint32_t CMASK = C == 4 ? 0xFFFFFFFFu : 0xFFFFu;
     static_assert(BLK % TC == 0 && BLK == 32, "boundary blocks of 32 columns");
     const int lane = threadIdx.x & 31;
@@ -230,8 +248,7 @@ __device__ __forceinline__ uint32_t wave_band_c(const WaveArgs &a, const uint2 *
     // bound the trip by the memory latency) -- and a trip takes its two words by shuffle.
     auto bulk = [&](int blk) -> uint32_t {
         const int w = blk * 32 + lane;
-        if (4 * w < ncols) SW_CHECK((unsigned long long)(tpp - a.tp) + (unsigned long long)w * 32 < a.tp_words, SW_DEVERR_TP, a);
-        return 4 * w < ncols ? __ldg(tpp + (size_t)w * 32) : PADW;
+        return 4 * w < ncols ? src.word(w, ncols) : PADW;
     };
     uint32_t cw_cur = bulk(0), cw_nxt = bulk(1);
     uint32_t tc0 = __shfl_sync(FULL, cw_cur, 0), tc1 = __shfl_sync(FULL, cw_cur, 1);
@@ -245,7 +262,7 @@ __device__ __forceinline__ uint32_t wave_band_c(const WaveArgs &a, const uint2 *
         for (int j = 0; j < C; ++j) {
             const uint2 *prow = prof_lane + ((tw >> (8 * j)) & 255u) * G;
 #pragma unroll
-            for (int k = 0; k < RP; ++k) sv[j][k] = prow[k * kWaveCodes * G];
+            for (int k = 0; k < RP; ++k) sv[j][k] = prow[k * SRC::kCodes * G];
         }
     };
     uint2 sv[C][RP];
@@ -315,7 +332,7 @@ __device__ __forceinline__ uint32_t wave_band_c(const WaveArgs &a, const uint2 *
             }
             in_t = head ? (lead & CMASK) : in_t;
 #pragma unroll
-            for (int j = 0; j < C; ++j) SW_CHECK(((in_t >> (8 * j)) & 255u) <= (uint32_t)kPadCode, SW_DEVERR_PROF, a);
+            for (int j = 0; j < C; ++j) SW_CHECK(((in_t >> (8 * j)) & 255u) <= (uint32_t)SRC::kPad, SW_DEVERR_PROF, a);
             uint2 sv_next[C][RP];
             load_sv(sv_next, in_t);
 #pragma unroll
@@ -394,6 +411,8 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
         const int ncols = valid ? (int)a.pair_len[2 * pair] : 0;
         const uint32_t *tpp = a.tp;
         if (valid) tpp += a.tile_woff[pair >> 5] + (pair & 31);
+        if (valid && ncols > 0)
+            SW_CHECK((unsigned long long)(tpp - a.tp) + (unsigned long long)((ncols - 1) >> 2) * 32 < a.tp_words, SW_DEVERR_TP, a);
 
         if (prof_pass != pass) {
             prof_pass = pass;
@@ -438,7 +457,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
 #define SW_WAVE_BAND(T, B)                                                                                                   \
         do {                                                                                                                 \
             if constexpr (C > 1)                                                                                             \
-                best = wave_band_c<RS, C, AR, BLK, T, B>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero); \
+                best = wave_band_c<RS, C, AR, BLK, T, B>(a, prof_lane, s_top[warp], TiledCodes{tpp}, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero); \
             else                                                                                                             \
                 best = wave_band<RS, S, AR, BLK, T, B>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero); \
         } while (0)
@@ -474,6 +493,167 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
                     orow[subj_lo] = ov0 ? SW_OVERFLOW_SENTINEL : f0;
                     if (has1) orow[subj_hi] = ov1 ? SW_OVERFLOW_SENTINEL : f1;
                 }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 32-bit band-pipelined scorer of the overflow list.  The packed 16-bit kernels flag the (query,
+// subject) entries whose score may leave the 16-bit range; with the default scoring those are
+// pairs of at least 6 400 x 6 400 nt, and one thread of score32_kernel per entry takes seconds
+// to minutes for them.  Here the bands (256 rows) of an entry are work items exactly as in
+// sw_wave_kernel -- same band function, ArithS32 instead of ArithS16, codes straight from the
+// subject's 2-bit record -- and the kernel is list-driven: the entry count is read on the device,
+// so the launch stays asynchronous.
+//   item      = (entry e, band b), index e * maxb + b, claimed in increasing order: the band an
+//               item waits for was claimed earlier by a running block (no deadlock by construction)
+//   boundary  = bnd[e % nslots][b & 1][column], tag = (epoch : 8, e : 12, b : 12); entry e may only
+//               start when entry e - nslots has finished (flag[e - nslots], set by its last band, or
+//               by band 0 of an entry this kernel leaves to score32_kernel)
+//   entries   = the first kWave32MaxEntries of the list that satisfy wave32_takes(); score32_kernel
+//               (mode 2) skips exactly those.
+// ------------------------------------------------------------------------------------------
+constexpr unsigned kWave32MaxEntries = 4096;
+constexpr int kWave32Rows = 256;
+
+__host__ __device__ inline bool wave32_takes(unsigned e, uint32_t m, uint32_t n, unsigned long long min_cells)
+{
+    return e < kWave32MaxEntries && (unsigned long long)m * n >= min_cells && n > 0 &&
+           (m + kWave32Rows - 1) / kWave32Rows <= 4095u;
+}
+
+struct Wave32Args {
+    const uint8_t *raw;            // subjects: packed 2-bit records
+    const uint64_t *off;
+    const uint32_t *len;
+    const uint8_t *qpacked;
+    const uint32_t *qoff;
+    const uint32_t *qlen;
+    const unsigned *list_count;
+    const uint2 *list;             // (query, subject)
+    unsigned list_cap;
+    int32_t *list_score;
+    void *out;                     // score matrix (may be null), as for score32_kernel
+    size_t out_stride;
+    int out_mode;
+    ulonglong2 *bnd;               // [nslots][2][cols_stride]
+    uint32_t cols_stride, nslots, epoch;
+    int *best;                     // [kWave32MaxEntries], zeroed
+    unsigned *done;                // [kWave32MaxEntries], zeroed: bands finished
+    unsigned *flag;                // [kWave32MaxEntries], zeroed: entry finished (or not taken)
+    unsigned *counter;
+    uint32_t maxb;                 // bands of the longest query
+    unsigned long long min_cells;
+    int match, mismatch, goe, ge;
+    unsigned *dev_err;
+    unsigned spin_limit;
+    uint64_t bnd_elems, out_elems;
+};
+
+template <int RS, int C, int MINB>
+__global__ void __launch_bounds__(32, MINB) sw_wave32_kernel(const Wave32Args a)
+{
+    constexpr int G = 32, P = RS * G, RP = (RS + 1) / 2, CODES = RawCodes::kCodes, BLK = 32;
+    static_assert(P == kWave32Rows, "band height");
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    __shared__ uint2 s_prof[G * RP * CODES];
+    __shared__ __align__(16) uint2 s_top[BLK];
+    __shared__ uint8_t s_qb[P / 4 + 4];
+    const int lane = threadIdx.x;
+    const unsigned listed = min(min(*a.list_count, a.list_cap), kWave32MaxEntries);
+    const uint32_t goe = (uint32_t)a.goe, ge = (uint32_t)a.ge, h0 = goe, gb = 0u;
+
+    for (;;) {
+        unsigned work = 0;
+        if (lane == 0) work = atomicAdd(a.counter, 1u);
+        work = __shfl_sync(FULL, work, 0);
+        const unsigned e = work / a.maxb;
+        const int b = (int)(work % a.maxb);
+        if (e >= listed) break;
+        const uint2 ent = a.list[e];
+        const int q = (int)ent.x;
+        const uint32_t subj = ent.y;
+        const int m = (int)a.qlen[q], n = (int)a.len[subj];
+        const int npass = (m + P - 1) / P;
+        const bool take = wave32_takes(e, (uint32_t)m, (uint32_t)n, a.min_cells);
+        if (e >= a.nslots) {
+            // the boundary rows of this slot are free once entry e - nslots has finished (every item
+            // of the entry waits here, so that the waits inside a band stay pipeline-short)
+            const volatile unsigned *f = a.flag + (e - a.nslots);
+            unsigned spins = 0;
+            while (*f == 0u) {
+                __nanosleep(256);
+                if (++spins > (1u << 28)) {                    // ~ a minute: never hang the GPU
+                    if (lane == 0 && a.dev_err) atomicOr(a.dev_err, SW_DEVERR_SPIN);
+                    break;
+                }
+            }
+            __threadfence();
+        }
+        if (b == 0 && !take) {
+            // left to score32_kernel: the slot chain must not stop here
+            if (lane == 0) { __threadfence(); atomicExch(a.flag + e, 1u); }
+            continue;
+        }
+        if (!take || b >= npass) continue;
+
+        // profile of the band: s_prof[(rp * CODES + code) * G + lane] = scores of rows 2 rp, 2 rp + 1
+        __syncwarp();
+        const uint8_t *qp = a.qpacked + a.qoff[q];
+        const int qb0 = (b * P) >> 2;
+        const int qnb = ((min((b + 1) * P, m) + 3) >> 2) - qb0;
+        for (int i = lane; i < qnb; i += G) s_qb[i] = qp[qb0 + i];
+        __syncwarp();
+        for (int idx = lane; idx < G * RP * CODES; idx += G) {
+            const int code = (idx / G) % CODES;
+            const int rp = idx / (G * CODES);
+            uint32_t sc[2];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const int rr = 2 * rp + k;
+                const int i = b * P + lane * RS + rr;
+                int v = ArithS32::kPad;
+                if (rr < RS && i < m && code < RawCodes::kPad) {
+                    const int qi = (s_qb[(i >> 2) - qb0] >> ((i & 3) * 2)) & 3;
+                    v = (qi == code) ? a.match : a.mismatch;       // v1.0.v:119
+                }
+                sc[k] = (uint32_t)v;
+            }
+            s_prof[idx] = make_uint2(sc[0], sc[1]);
+        }
+        __syncwarp();
+
+        const bool has_top = b > 0, has_bottom = b + 1 < npass;
+        const size_t slot = (size_t)(e % a.nslots) * 2;
+        const ulonglong2 *top = a.bnd + (slot + (size_t)((b - 1) & 1)) * a.cols_stride + kWaveSlack;
+        ulonglong2 *bot = a.bnd + (slot + (size_t)(b & 1)) * a.cols_stride + kWaveSlack;
+        const uint32_t tag_bot = ((a.epoch & 255u) << 24) | (e << 12) | (uint32_t)b, tag_top = tag_bot - 1u;
+        const RawCodes src{a.raw + a.off[subj]};
+        const uint2 *prof_lane = s_prof + lane;
+        uint32_t best;
+#define SW_WAVE32_BAND(T, B) \
+        best = wave_band_c<RS, C, ArithS32, BLK, T, B>(a, prof_lane, s_top, src, n, top, bot, tag_top, tag_bot, goe, ge, h0, gb, 0u)
+        if (has_top) { if (has_bottom) SW_WAVE32_BAND(true, true); else SW_WAVE32_BAND(true, false); }
+        else { if (has_bottom) SW_WAVE32_BAND(false, true); else SW_WAVE32_BAND(false, false); }
+#undef SW_WAVE32_BAND
+#pragma unroll
+        for (int o = G / 2; o >= 1; o >>= 1) best = ArithS32::max2(best, __shfl_xor_sync(FULL, best, o));
+        if (lane == 0) {
+            atomicMax(a.best + e, (int)best - a.goe);
+            __threadfence();
+            if (atomicAdd(a.done + e, 1u) == (unsigned)npass - 1u) {
+                __threadfence();
+                const int f = atomicMax(a.best + e, 0);
+                if (a.list_score) a.list_score[e] = f;
+                if (a.out) {
+                    SW_CHECK((unsigned long long)q * a.out_stride + subj < a.out_elems, SW_DEVERR_OUT, a);
+                    // a 16-bit matrix keeps the sentinel for scores it cannot hold (they are on the list)
+                    if (a.out_mode == SW_OUT_I16) { if (f <= 32767) ((int16_t *)a.out)[(size_t)q * a.out_stride + subj] = (int16_t)f; }
+                    else ((int32_t *)a.out)[(size_t)q * a.out_stride + subj] = f;
+                }
+                __threadfence();
+                atomicExch(a.flag + e, 1u);
             }
         }
     }

@@ -496,6 +496,70 @@ def test_wave_kernel_single_long_pair_and_overflow(oracle_mod, pkg):
         assert e.device_error_bits == 0
 
 
+def test_overflow_list_scored_by_32bit_bands(oracle_mod, pkg):
+    """Scores beyond 16 bits: the long entries of the overflow list go to the band-pipelined 32-bit
+    scorer (sw_wave32_kernel: 256-row bands on many warps, list-driven, slots of boundary rows reused
+    by later entries), short ones to the one-thread scorer -- same numbers either way, in the int32
+    matrix, the int16 side list and the top-k lists."""
+    rng = random.Random(77)
+    big = _rand(rng, 7000)
+    # 150 exact substrings of the query, 6 600 .. 7 000 nt: score = 5 x length, every one overflows;
+    # more entries than boundary-row slots (64), so the slot chain is exercised
+    subs, want = [], []
+    for k in range(150):
+        L = rng.randint(6600, 7000)
+        a0 = rng.randint(0, 7000 - L)
+        subs.append(big[a0:a0 + L])
+        want.append(5 * L)
+    subs += [_rand(rng, 3000), "", _mutate(rng, big, 0.3, 0.1)]
+    o = oracle_mod.Oracle()
+    want += [o.score(big, subs[-3]), 0, o.score(big, subs[-1])]
+    want = np.array([want], dtype=np.int32)
+    assert (want > 32767).sum() == 150
+    for enable in (True, False):
+        with pkg.Engine() as e:
+            e.set_overflow_wave(enable)
+            got = e.score([big], subs)
+            assert e.device_error_bits == 0
+            np.testing.assert_array_equal(got, want, err_msg=f"wave32={enable}")
+    with pkg.Engine() as e:                                   # int16 matrix + side list
+        e.set_output(pkg.SW_OUTPUT_I16)
+        got = e.score([big], subs)
+        idx, sc = e.fetch_overflow()
+        assert np.all(got[0, :150] == -1) and np.array_equal(got[0, 150:].astype(np.int32), want[0, 150:])
+        assert sorted(zip(idx.tolist(), sc.tolist())) == [(i, int(want[0, i])) for i in range(150)]
+    with pkg.Engine() as e:                                   # top-k sees the recomputed scores
+        e.set_topk(5)
+        e.set_queries([big])
+        e.score_batch(subs)
+        sc, ix = e.fetch_topk()
+        order = sorted(range(len(subs)), key=lambda i: (-int(want[0, i]), i))[:5]
+        assert ix[0].tolist() == order and sc[0].tolist() == [int(want[0, i]) for i in order]
+
+
+def test_overflow_list_mixed_long_and_short_entries(oracle_mod, pkg):
+    """match = 100: a 330-nt identity already leaves 16 bits, so the list mixes entries below and
+    above the cell threshold of the 32-bit band scorer; both scorers share one list and one call."""
+    rng = random.Random(78)
+    q1 = _rand(rng, 2100)
+    q2 = _rand(rng, 400)
+    subs = []
+    for k in range(120):
+        src = q1 if k % 2 else q2
+        L = rng.randint(340, len(src))
+        a0 = rng.randint(0, len(src) - L)
+        subs.append(src[a0:a0 + L])
+    subs += [_rand(rng, 500), _mutate(rng, q1, 0.05, 0.02)]
+    with pkg.Engine(match=100, mismatch=-40, gap_open=-120, gap_extend=-20) as e:
+        want = _oracle_matrix(oracle_mod, pkg, [q1, q2], subs, match=100, mismatch=-40, gap_open=-120, gap_extend=-20)
+        assert (want > 32767).sum() >= 120
+        for enable, cells in ((True, 1000000), (True, 1), (False, 1000000)):
+            e.set_overflow_wave(enable, cells)
+            got = e.score([q1, q2], subs)
+            assert e.device_error_bits == 0
+            np.testing.assert_array_equal(got, want, err_msg=str((enable, cells)))
+
+
 def test_randomised_modes_stress_vs_oracle(oracle_mod, pkg):
     """Seeded property test over the round-2 switches: output mode (int32 / int16 / top-k), launch plan
     (one launch / length groups / query groups), band-pipelined kernel on or forced, latency path on
