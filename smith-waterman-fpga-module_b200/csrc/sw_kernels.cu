@@ -370,13 +370,13 @@ namespace {
 typedef void (*WaveFn)(const WaveArgs);
 struct WaveInstance { int rows, bt; size_t smem; WaveFn fn, fn_fixed; const char *name; };
 constexpr size_t wave_smem(int rs, int s) { return (size_t)32 * s * ((rs + 1) / 2) * kWaveCodes * sizeof(uint2); }
-#define SW_WAVE(RS, S, BT, MINB, BLK, C, NAME) \
-    {RS * S * 32, BT, wave_smem(RS, S), sw_wave_kernel<RS, S, ArithS16, BT, MINB, 0, 0, BLK, C>, \
-     sw_wave_kernel<RS, S, ArithS16, BT, MINB, kFixedGoe, kFixedGe, BLK, C>, NAME}
+#define SW_WAVE(RS, S, BT, MINB, BLK, C, LS, NAME) \
+    {RS * S * 32, BT, wave_smem(RS, S), sw_wave_kernel<RS, S, ArithS16, BT, MINB, 0, 0, BLK, C, LS>, \
+     sw_wave_kernel<RS, S, ArithS16, BT, MINB, kFixedGoe, kFixedGe, BLK, C, LS>, NAME}
 const WaveInstance g_wave[] = {
-    SW_WAVE(8, 2, 128, 4, 32, 1, "wave_s16x2_R8x2_G32"),
-    SW_WAVE(8, 1, 32, 8, 32, 4, "wave_s16x2_R8x1_G32_C4"),
-    SW_WAVE(8, 1, 32, 16, 32, 2, "wave_s16x2_R8x1_G32_C2"),
+    SW_WAVE(8, 2, 128, 4, 32, 1, false, "wave_s16x2_R8x2_G32"),
+    SW_WAVE(8, 1, 32, 8, 32, 4, false, "wave_s16x2_R8x1_G32_C4"),
+    SW_WAVE(8, 1, 32, 16, 32, 2, true, "wave_s16x2_R8x1_G32_C2"),
     // measured and dropped (profiles/r02_wave_instance_ab.jsonl, r02_wave_instance_ab2.txt): 16-column
     // blocks, 128-row bands (R4x1 with 1 / 2 / 4 columns per step, R4x2), R8x1 with one column per
     // step, four-pair blocks for the multi-column instances

@@ -38,6 +38,7 @@ constexpr int kWaveBlock = 32;       // default number of columns staged per blo
 constexpr int kWaveCodes = 24;       // profile slots per row pair (codes 0 .. 20 are used)
 constexpr int kWaveSlack = 8;        // boundary elements of slack on either side of a row (batched stores)
 constexpr int kWavePrefetch = 8;     // steps between the prefetch of a boundary block and its use
+constexpr int kWaveBotSlots = 8;     // shared-memory slots for the bottom-row values of one loop trip (LS)
 
 struct WaveArgs {
     const uint32_t *tp;
@@ -73,7 +74,7 @@ struct WaveArgs {
 
 // One band of one pair (one warp).  Returns the band's running maximum (K representation).
 template <int RS, int S, class AR, int BLK, bool HAS_TOP, bool HAS_BOTTOM>
-__device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *prof_lane, uint2 (&s_top)[BLK], const uint32_t *tpp,
+__device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *prof_lane, uint2 *s_top, const uint32_t *tpp,
                                               int ncols, const ulonglong2 *top, ulonglong2 *bot, uint32_t tag_top, uint32_t tag_bot,
                                               uint32_t goe2, uint32_t ge2, uint32_t h0, uint32_t gb2, uint32_t zero)
 {
@@ -223,8 +224,8 @@ struct RawCodes {                    // one subject's packed 2-bit record: code 
     }
 };
 
-template <int RS, int C, class AR, int BLK, bool HAS_TOP, bool HAS_BOTTOM, class ARGS, class SRC>
-__device__ __forceinline__ uint32_t wave_band_c(const ARGS &a, const uint2 *prof_lane, uint2 (&s_top)[BLK], const SRC src,
+template <int RS, int C, class AR, int BLK, bool HAS_TOP, bool HAS_BOTTOM, bool LS, class ARGS, class SRC>
+__device__ __forceinline__ uint32_t wave_band_c(const ARGS &a, const uint2 *prof_lane, uint2 *s_top, const SRC src,
                                                 int ncols, const ulonglong2 *top, ulonglong2 *bot, uint32_t tag_top, uint32_t tag_bot,
                                                 uint32_t goe2, uint32_t ge2, uint32_t h0, uint32_t gb2, uint32_t zero)
 {
@@ -269,6 +270,7 @@ __device__ __forceinline__ uint32_t wave_band_c(const ARGS &a, const uint2 *prof
     load_sv(sv, pub_t);
     ulonglong2 pre = make_ulonglong2(0ull, 0ull);
     uint32_t sto_h[TC], sto_g[TC];
+    uint2 *s_bot = s_top + BLK;            // LS: the last lane's bottom-row values of this trip
     const unsigned long long tag_hi = (unsigned long long)tag_bot << 32;
     const int nsteps = ncols > 0 ? ((ncols + C - 1) / C + (G - 1) + U - 1) / U * U : 0;
 
@@ -345,8 +347,12 @@ __device__ __forceinline__ uint32_t wave_band_c(const ARGS &a, const uint2 *prof
                 column_step_multi<RS, 1, G, AR, false>(H, Gl, best, hd, gt, svj, goe2, ge2, zero, 0u);
                 pub_h[j] = H[0][RS - 1];
                 pub_g[j] = Gl[0][RS - 1];
-                sto_h[uu * C + j] = pub_h[j];
-                sto_g[uu * C + j] = pub_g[j];
+                if constexpr (HAS_BOTTOM && LS) {
+                    if (lane == G - 1) s_bot[uu * C + j] = make_uint2(pub_h[j], pub_g[j]);
+                } else {
+                    sto_h[uu * C + j] = pub_h[j];
+                    sto_g[uu * C + j] = pub_g[j];
+                }
             }
             hd_carry = in_h[C - 1];
             pub_t = in_t;
@@ -360,7 +366,20 @@ __device__ __forceinline__ uint32_t wave_band_c(const ARGS &a, const uint2 *prof
             // the last lane finished columns cl0 .. cl0 + 7 in this trip; columns outside
             // 0 .. ncols - 1 land in the row's slack and are never read
             const int cl0 = c0 - C * (G - 1);
-            if (lane == G - 1 && cl0 + (TC - 1) >= 0 && cl0 < ncols) {
+            if constexpr (LS) {
+                // LS (latency-bound instances: one warp per scheduler): stored by TC lanes, one element
+                // each, through shared memory.  A single lane storing TC elements reuses one register
+                // quad for the 16-byte stores and waits on every store for the previous one to have
+                // read it -- 9 % of a lone warp's time; with several warps per scheduler that wait is
+                // hidden and the extra shared-memory round trip costs 1-7 % instead.
+                __syncwarp();
+                if (lane < TC && cl0 + (TC - 1) >= 0 && cl0 < ncols) {
+                    const uint2 v = s_bot[lane];
+                    SW_CHECK((unsigned long long)(bot + cl0 + lane - a.bnd) < a.bnd_elems, SW_DEVERR_BND, a);
+                    __stcg(bot + cl0 + lane, make_ulonglong2(tag_hi | v.x, tag_hi | v.y));
+                }
+                __syncwarp();
+            } else if (lane == G - 1 && cl0 + (TC - 1) >= 0 && cl0 < ncols) {
 #pragma unroll
                 for (int i = 0; i < TC; ++i) {
                     SW_CHECK((unsigned long long)(bot + cl0 + i - a.bnd) < a.bnd_elems, SW_DEVERR_BND, a);
@@ -372,7 +391,7 @@ __device__ __forceinline__ uint32_t wave_band_c(const ARGS &a, const uint2 *prof
     return best;
 }
 
-template <int RS, int S, class AR, int BT, int MINB, int CGOE = 0, int CGE = 0, int BLK = kWaveBlock, int C = 1>
+template <int RS, int S, class AR, int BT, int MINB, int CGOE = 0, int CGE = 0, int BLK = kWaveBlock, int C = 1, bool LS = false>
 __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
 {
     extern __shared__ uint2 s_prof[];
@@ -382,7 +401,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
     constexpr int PPB = BT / G;
     constexpr unsigned FULL = 0xFFFFFFFFu;
     static_assert(C == 1 || S == 1, "several columns per step: one sub-strip");
-    __shared__ __align__(16) uint2 s_top[PPB][BLK];
+    __shared__ __align__(16) uint2 s_top[PPB][BLK + kWaveBotSlots];
     __shared__ uint8_t s_qb[P / 4 + 4];                // packed query bytes of the band
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -457,7 +476,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
 #define SW_WAVE_BAND(T, B)                                                                                                   \
         do {                                                                                                                 \
             if constexpr (C > 1)                                                                                             \
-                best = wave_band_c<RS, C, AR, BLK, T, B>(a, prof_lane, s_top[warp], TiledCodes{tpp}, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero); \
+                best = wave_band_c<RS, C, AR, BLK, T, B, LS>(a, prof_lane, s_top[warp], TiledCodes{tpp}, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero); \
             else                                                                                                             \
                 best = wave_band<RS, S, AR, BLK, T, B>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero); \
         } while (0)
@@ -558,7 +577,7 @@ __global__ void __launch_bounds__(32, MINB) sw_wave32_kernel(const Wave32Args a)
     static_assert(P == kWave32Rows, "band height");
     constexpr unsigned FULL = 0xFFFFFFFFu;
     __shared__ uint2 s_prof[G * RP * CODES];
-    __shared__ __align__(16) uint2 s_top[BLK];
+    __shared__ __align__(16) uint2 s_top[BLK + kWaveBotSlots];
     __shared__ uint8_t s_qb[P / 4 + 4];
     const int lane = threadIdx.x;
     const unsigned listed = min(min(*a.list_count, a.list_cap), kWave32MaxEntries);
@@ -633,7 +652,7 @@ __global__ void __launch_bounds__(32, MINB) sw_wave32_kernel(const Wave32Args a)
         const uint2 *prof_lane = s_prof + lane;
         uint32_t best;
 #define SW_WAVE32_BAND(T, B) \
-        best = wave_band_c<RS, C, ArithS32, BLK, T, B>(a, prof_lane, s_top, src, n, top, bot, tag_top, tag_bot, goe, ge, h0, gb, 0u)
+        best = wave_band_c<RS, C, ArithS32, BLK, T, B, true>(a, prof_lane, s_top, src, n, top, bot, tag_top, tag_bot, goe, ge, h0, gb, 0u)
         if (has_top) { if (has_bottom) SW_WAVE32_BAND(true, true); else SW_WAVE32_BAND(true, false); }
         else { if (has_bottom) SW_WAVE32_BAND(false, true); else SW_WAVE32_BAND(false, false); }
 #undef SW_WAVE32_BAND
