@@ -136,6 +136,7 @@ struct Slot {
     PinnedBuf h_small_in, h_small_out, h_small_flag;
     DevBuf d_small_in, d_small_done;
     unsigned small_seq = 0;            // value the kernel writes to the completion flag
+    bool small_by_flag = false;        // this batch completes by flag (else: every result word replaces a sentinel)
     bool small_timed = false;          // events were recorded around the kernel
 };
 
@@ -202,6 +203,7 @@ struct sw_handle {
     int jit = 1;                      // run-time specialisation of gap penalties: 0 off, 1 large jobs, 2 always
     int wave = 1;                     // band-pipelined kernel for few long pairs: 0 off, 1 automatic, 2 whenever possible
     int wave32 = 1;                   // overflow list: long entries go to the band-pipelined 32-bit scorer
+    bool small_sentinel = true;       // latency path: completion seen in the result words themselves (no fence, no flag)
     unsigned long long wave32_min_cells = 1000000ull;
     // launch-planner knobs (environment SW_B200_PLAN_SEGS / _QGROUPS / _STREAMS / _TAU): experiments
     int plan_segs = 2;                // 0 never, 1 always, 2 when one launch would need a huge pass-boundary scratch
@@ -1214,6 +1216,9 @@ unsigned device_error_bits(sw_handle *h)
     return bits;
 }
 
+// latency path: value of a result word the kernel has not written yet (scores are >= -1)
+constexpr int32_t kSmallSentinel = INT32_MIN;
+
 // what a fetch delivers
 enum FetchKind { FETCH_I32, FETCH_I16, FETCH_TOPK };
 
@@ -1237,15 +1242,27 @@ int fetch_slot(sw_handle *h, int si, FetchKind kind, void *scores, uint64_t *ind
     if (bt.small) {
         GpuCtx &g = h->gpus[0];
         Slot &b = g.slot[si];
-        // poll the completion flag the kernel writes into mapped host memory
+        // Completion is read from mapped host memory.  Default: every result word replaces the
+        // sentinel the host wrote before the launch (4-byte stores arrive whole), so the kernel needs
+        // no system-scope fence and no flag -- its fence.sys alone was a quarter of the warp time of
+        // the config-2 kernel -- and the host sees the last score one PCIe write after it was stored.
+        // Otherwise: the flag the kernel's last block writes after its fence.
         volatile unsigned *flag = (volatile unsigned *)b.h_small_flag.p;
+        const volatile int32_t *res = (const volatile int32_t *)b.h_small_out.p;
+        const size_t nres = nq * bt.ns;
+        size_t seen = 0;                                           // results [0, seen) have arrived
         unsigned spins = 0;
-        while (*flag != b.small_seq) {
+        auto complete = [&]() -> bool {
+            if (b.small_by_flag) return *flag == b.small_seq;
+            while (seen < nres && res[seen] != kSmallSentinel) ++seen;
+            return seen == nres;
+        };
+        while (!complete()) {
             if ((++spins & 0x3FF) == 0) {
                 if (!forever && std::chrono::steady_clock::now() >= t_end) return SW_ETIMEOUT;
-                cudaError_t qe = cudaStreamQuery(g.st_compute);          // a failed launch would never write the flag
+                cudaError_t qe = cudaStreamQuery(g.st_compute);          // a failed launch would never finish the buffer
                 if (qe != cudaSuccess && qe != cudaErrorNotReady) { h->last_cuda.store((int)qe); return SW_ECUDA; }
-                if (qe == cudaSuccess && *flag != b.small_seq) { h->last_cuda.store((int)cudaErrorUnknown); return SW_ECUDA; }
+                if (qe == cudaSuccess && !complete()) { h->last_cuda.store((int)cudaErrorUnknown); return SW_ECUDA; }
             }
         }
         std::atomic_thread_fence(std::memory_order_acquire);
@@ -1563,6 +1580,9 @@ int small_submit(sw_handle *h, int si, const uint8_t *packed, const uint32_t *le
     std::memset(st + o_raw + raw_bytes, 0, 16);
     // scores of empty subjects (never touched by the kernel)
     int32_t *hout = (int32_t *)g.h_small_out.p;
+    g.small_by_flag = !h->small_sentinel;
+    for (uint32_t l : h->q_len) if (l == 0) g.small_by_flag = true;       // be safe: rows the kernel may not write
+    if (!g.small_by_flag) std::fill(hout, hout + (size_t)nq * ns, kSmallSentinel);
     if (np * 2 != ns)
         for (size_t k = 0; k < ns; ++k) if (len[k] == 0) for (int q = 0; q < nq; ++q) hout[(size_t)q * ns + k] = 0;
 
@@ -1596,7 +1616,7 @@ int small_submit(sw_handle *h, int si, const uint8_t *packed, const uint32_t *le
     // completion: the kernel's last block writes small_seq into a mapped host word the host polls
     g.small_seq++;
     if (g.small_seq == 0) g.small_seq = 1;
-    L.done_count = g.d_small_done.as<unsigned>(); L.done_flag = (unsigned *)g.h_small_flag.dptr; L.done_seq = g.small_seq;
+    if (g.small_by_flag) { L.done_count = g.d_small_done.as<unsigned>(); L.done_flag = (unsigned *)g.h_small_flag.dptr; L.done_seq = g.small_seq; }
     g.small_timed = h->small_timing;
     if (g.small_timed) SW_CUDA(h, cudaEventRecord(g.ev_start, cs));
     SW_CUDA(h, sw_launch_strip(cs, L));
@@ -1718,6 +1738,7 @@ int sw_init(sw_handle_t **out, const sw_params_t *p, const int *gpu_ids, int n_g
     if (const char *e = std::getenv("SW_B200_SMALL_PATH")) h->small_path = (e[0] != '0');
     if (const char *e = std::getenv("SW_B200_WAVE")) h->wave = std::atoi(e);
     if (const char *e = std::getenv("SW_B200_WAVE32")) h->wave32 = (e[0] != '0');
+    if (const char *e = std::getenv("SW_B200_SMALL_SENTINEL")) h->small_sentinel = (e[0] != '0');
     if (const char *e = std::getenv("SW_B200_PLAN_SEGS")) h->plan_segs = std::atoi(e);
     if (const char *e = std::getenv("SW_B200_PLAN_QGROUPS")) h->plan_qgroups = (e[0] != '0');
     if (const char *e = std::getenv("SW_B200_STREAMS")) h->plan_streams = std::max(1, std::min(kStreams, std::atoi(e)));
