@@ -204,6 +204,7 @@ struct sw_handle {
     int wave = 1;                     // band-pipelined kernel for few long pairs: 0 off, 1 automatic, 2 whenever possible
     int wave32 = 1;                   // overflow list: long entries go to the band-pipelined 32-bit scorer
     bool small_sentinel = true;       // latency path: completion seen in the result words themselves (no fence, no flag)
+    bool small_zero_copy = true;      // latency path: staging buffers of <= 64 KB are read by the kernel from mapped host memory (no H2D copy)
     unsigned long long wave32_min_cells = 1000000ull;
     // launch-planner knobs (environment SW_B200_PLAN_SEGS / _QGROUPS / _STREAMS / _TAU): experiments
     int plan_segs = 2;                // 0 never, 1 always, 2 when one launch would need a huge pass-boundary scratch
@@ -1551,7 +1552,7 @@ int small_submit(sw_handle *h, int si, const uint8_t *packed, const uint32_t *le
     const size_t o_raw = o_desc + ntiles * 32 * 32;
     const size_t raw_bytes = (size_t)(bmax - bmin);
     const size_t total = o_raw + raw_bytes + 16;
-    SW_CUDA(h, g.h_small_in.reserve(total));
+    SW_CUDA(h, g.h_small_in.reserve(total, true));
     SW_CUDA(h, g.d_small_in.reserve(total));
     SW_CUDA(h, g.h_small_out.reserve((size_t)nq * ns * sizeof(int32_t), true));
     if (!g.h_small_flag.p) {
@@ -1588,10 +1589,11 @@ int small_submit(sw_handle *h, int si, const uint8_t *packed, const uint32_t *le
 
     // ---- one copy, one kernel
     cudaStream_t cs = gc.st_compute;
-    SW_CUDA(h, cudaMemcpyAsync(g.d_small_in.p, st, total, cudaMemcpyHostToDevice, cs));
+    const bool zero_copy = h->small_zero_copy && total <= (64u << 10);
+    if (!zero_copy) SW_CUDA(h, cudaMemcpyAsync(g.d_small_in.p, st, total, cudaMemcpyHostToDevice, cs));
     const SwStripVariant *v = sw_strip_variant(vidx);
     SwStripLaunch L;
-    char *d = (char *)g.d_small_in.p;
+    char *d = zero_copy ? (char *)g.h_small_in.dptr : (char *)g.d_small_in.p;
     L.vidx = vidx; L.direct = true;
     L.db.raw = (const uint8_t *)(d + o_raw); L.db.off = nullptr; L.db.len = nullptr;
     L.db.ns = (uint32_t)ns; L.db.pair_subj = nullptr; L.db.pair_len = nullptr; L.db.pair_desc = (const uint4 *)(d + o_desc);
@@ -1739,6 +1741,7 @@ int sw_init(sw_handle_t **out, const sw_params_t *p, const int *gpu_ids, int n_g
     if (const char *e = std::getenv("SW_B200_WAVE")) h->wave = std::atoi(e);
     if (const char *e = std::getenv("SW_B200_WAVE32")) h->wave32 = (e[0] != '0');
     if (const char *e = std::getenv("SW_B200_SMALL_SENTINEL")) h->small_sentinel = (e[0] != '0');
+    if (const char *e = std::getenv("SW_B200_SMALL_ZEROCOPY")) h->small_zero_copy = (e[0] != '0');
     if (const char *e = std::getenv("SW_B200_PLAN_SEGS")) h->plan_segs = std::atoi(e);
     if (const char *e = std::getenv("SW_B200_PLAN_QGROUPS")) h->plan_qgroups = (e[0] != '0');
     if (const char *e = std::getenv("SW_B200_STREAMS")) h->plan_streams = std::max(1, std::min(kStreams, std::atoi(e)));
