@@ -192,6 +192,37 @@ def case_pair(pkg, n=100000):
                reps=2, check=0)
 
 
+def case_pair_overflow(pkg, n=100000):
+    """One long, nearly identical pair (0.5 % substitutions): the score leaves 16 bits, so the pair is
+    recomputed from the overflow list by the 32-bit band-pipelined kernel.  Whole call with host buffers
+    (sw_score_batch + sw_fetch); the expected score is checked against a lower bound only (the oracle
+    would need minutes): >= 5 x n - 9 x substitutions."""
+    import random
+    rng = random.Random(1)
+    a = "".join(rng.choice("ACGT") for _ in range(n))
+    b = list(a)
+    nsub = n // 200
+    for _ in range(nsub):
+        b[rng.randrange(n)] = rng.choice("ACGT")
+    b = "".join(b)
+    with pkg.Engine() as e:
+        e.score([a], [b])
+        t0 = time.perf_counter()
+        got = e.score([a], [b])
+        dt = time.perf_counter() - t0
+        score = int(got[0, 0])
+        assert 5 * n - 9 * nsub <= score <= 5 * n, score
+        return {"config": f"one nearly identical pair {n} x {n} nt, score beyond 16 bits (overflow list -> 32-bit band-pipelined pass)",
+                "kernel": e.last_kernel_name + " + sw_wave32_kernel", "score": score, "call_ms": dt * 1e3, "kernel_ms": e.last_kernel_ms,
+                "cells": n * n, "gcups_call": n * n / dt / 1e9}
+
+
+def case_wave_mid(pkg):
+    """A few hundred long pairs: 256 x 20 kb subjects against one 20 kb query (band-pipelined, 4 columns per step)."""
+    return run(pkg, "1 x 20 kb query vs 256 x 20 kb subjects", pkg.random_packed_db(1, 20000, 8), pkg.random_packed_db(256, 20000, 9),
+               reps=2, check=3, seed=5)
+
+
 def case_penalties(pkg, n=2_000_000):
     """Run-time loadable penalties (ld_penalties, ScoreBank_v2.v:34,161): an arbitrary set with run-time
     operands, the same set specialised at run time (NVRTC), and the compiled-in default set, all on the
@@ -233,6 +264,7 @@ def bench_blocks(pkg, log=lambda *a: None):
     t0 = time.perf_counter()
     for key, fn in (("latency", case_latency), ("config4_full", case_4full), ("config4_200k", case_4),
                     ("config4_2000_subjects", case_4w), ("config5_mixed", case_5), ("single_pair_100kb", case_pair),
+                    ("single_pair_100kb_score_beyond_16_bits", case_pair_overflow), ("long_256_x_20kb", case_wave_mid),
                     ("run_time_penalties", case_penalties)):
         try:
             r = fn(pkg)
@@ -260,6 +292,10 @@ if __name__ == "__main__":
             print(json.dumps(case_4full(pkg)), flush=True)
         elif w == "pair":
             print(json.dumps(case_pair(pkg)), flush=True)
+        elif w == "ovf":
+            print(json.dumps(case_pair_overflow(pkg)), flush=True)
+        elif w == "mid":
+            print(json.dumps(case_wave_mid(pkg)), flush=True)
         elif w == "pen":
             print(json.dumps(case_penalties(pkg)), flush=True)
         elif w in ("4", "4w", "5"):
