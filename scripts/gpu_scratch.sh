@@ -1,2 +1,3 @@
 #!/bin/bash
-for t in 0.9 0.99; do echo "== THR=$t"; SW_B200_TAIL_DEBUG=1 SW_B200_TAIL_THR=$t timeout 600 python scripts/bench_configs.py 4 2>&1 | cut -c1-330 | grep -v "^\[sw_b200\] tail.*\[sw" | sort -u | head -5; done
+timeout 900 python -m pytest tests/test_gpu_round2.py -m gpu -q -x -k "completion_protocols or sharded_and_streaming" --timeout=600 -p no:cacheprovider 2>&1 | tail -15
+SW_B200_LIB=$PWD/smith-waterman-fpga-module_b200/libsw_b200_check.so timeout 900 python -m pytest tests/test_gpu_round2.py -m gpu -q -x -k "completion_protocols or sharded_and_streaming" --timeout=600 -p no:cacheprovider 2>&1 | tail -5

@@ -86,6 +86,49 @@ def test_small_path_golden_and_streaming(golden, oracle_mod, pkg):
     np.testing.assert_array_equal(got2, want2)
 
 
+def test_small_path_completion_protocols_and_reuse(oracle_mod, pkg, monkeypatch):
+    """Latency path: completion read from the sentinel-filled result words (default) or from the flag
+    (SW_B200_SMALL_SENTINEL=0, and whenever a query is empty); staging read in place (default) or
+    copied (SW_B200_SMALL_ZEROCOPY=0); many batches through the same two slots, alternating with
+    regular-path batches that reuse the slots; both strands."""
+    rng = random.Random(91)
+    queries = [_rand(rng, 100), _rand(rng, 37)]
+    batches = [[_rand(rng, rng.choice([0, 1, 3, 64, 128, rng.randint(1, 400)])) for _ in range(rng.randint(1, 90))] for _ in range(12)]
+    big = [_rand(rng, rng.randint(50, 300)) for _ in range(9000)]             # too many subjects: regular path
+    wants = [_oracle_matrix(oracle_mod, pkg, queries, b) for b in batches]
+    want_big = _oracle_matrix(oracle_mod, pkg, queries, big)
+    for sentinel, zero_copy in (("1", "1"), ("0", "1"), ("1", "0"), ("0", "0")):
+        monkeypatch.setenv("SW_B200_SMALL_SENTINEL", sentinel)
+        monkeypatch.setenv("SW_B200_SMALL_ZEROCOPY", zero_copy)
+        with pkg.Engine() as e:
+            e.set_queries(queries)
+            for k, b in enumerate(batches):
+                e.score_batch(b)
+                assert e.last_kernel_name.endswith("+direct")
+                if k % 2:                                  # two in flight, fetched in order
+                    np.testing.assert_array_equal(e.fetch(), wants[k - 1])
+                    np.testing.assert_array_equal(e.fetch(), wants[k])
+                if k == 5:                                 # a regular-path batch reuses the slots
+                    np.testing.assert_array_equal(e.score(queries, big), want_big)
+                    assert "+direct" not in e.last_kernel_name
+                    e.set_queries(queries)
+            assert e.device_error_bits == 0
+    # an empty query (flag protocol by construction) and both strands
+    with pkg.Engine() as e:
+        got = e.score([queries[0], "", queries[1]], batches[3])
+        assert e.last_kernel_name.endswith("+direct")
+        np.testing.assert_array_equal(got[[0, 2]], wants[3])
+        assert not got[1].any()
+    with pkg.Engine() as e:
+        e.set_strands(True)
+        got = e.score(queries, batches[4])
+        comp = {"A": "T", "C": "G", "G": "C", "T": "A"}
+        rc = ["".join(comp[c] for c in reversed(q)) for q in queries]
+        want = _oracle_matrix(oracle_mod, pkg, queries + rc, batches[4])
+        assert got.shape == want.shape
+        np.testing.assert_array_equal(got, want)
+
+
 def _overflow_case(rng):
     s = _rand(rng, 6700)                      # identical pair scores 33500 > 32767
     t = _mutate(rng, s, 0.004, 0.002)         # around the threshold
@@ -395,7 +438,8 @@ def test_bounds_check_build_runs_clean(pkg):
     sel = ("test_random_mixed_lengths_vs_oracle or test_long_query_multi_pass_and_chunks or test_edge_cases or "
            "test_small_path_direct_variants_vs_oracle or test_topk_vs_oracle_argsort or test_output_i16 or "
            "test_very_long_subjects_short_queries or test_query_groups or test_is_check_build or test_wave_kernel or "
-           "test_randomised_modes_stress or test_virtual_multi_shard")
+           "test_randomised_modes_stress or test_virtual_multi_shard or test_overflow_list_scored_by_32bit_bands or "
+           "test_overflow_32bit_bands_sharded or test_small_path_completion_protocols")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-x", "-q", "-m", "gpu", "-k", sel,
                         "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
@@ -535,6 +579,35 @@ def test_overflow_list_scored_by_32bit_bands(oracle_mod, pkg):
         sc, ix = e.fetch_topk()
         order = sorted(range(len(subs)), key=lambda i: (-int(want[0, i]), i))[:5]
         assert ix[0].tolist() == order and sc[0].tolist() == [int(want[0, i]) for i in order]
+
+
+def test_overflow_32bit_bands_sharded_and_streaming(oracle_mod, pkg):
+    """The 32-bit band scorer of the overflow list on a handle with three (virtual) shards, and on
+    streaming batches with two in flight (the scorer's state and boundary rows are per GPU, shared
+    by the slots)."""
+    rng = random.Random(79)
+    big = _rand(rng, 7000)
+    subs, want = [], []
+    for k in range(40):
+        if k % 3 == 0:
+            L = rng.randint(6600, 7000)
+            a0 = rng.randint(0, 7000 - L)
+            subs.append(big[a0:a0 + L]); want.append(5 * L)
+        else:
+            subs.append(_rand(rng, rng.randint(1, 400))); want.append(None)
+    o = oracle_mod.Oracle()
+    want = np.array([[w if w is not None else o.score(big, s) for w, s in zip(want, subs)]], dtype=np.int32)
+    with pkg.Engine(gpu_ids=[0, 0, 0]) as e:
+        np.testing.assert_array_equal(e.score([big], subs), want)
+        assert e.device_error_bits == 0
+    with pkg.Engine() as e:
+        e.set_small_batch_path(False)
+        e.set_queries([big])
+        e.score_batch(subs[:21])
+        e.score_batch(subs[21:])
+        np.testing.assert_array_equal(e.fetch(), want[:, :21])
+        np.testing.assert_array_equal(e.fetch(), want[:, 21:])
+        assert e.device_error_bits == 0
 
 
 def test_overflow_list_mixed_long_and_short_entries(oracle_mod, pkg):
