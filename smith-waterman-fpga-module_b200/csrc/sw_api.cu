@@ -871,6 +871,9 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
             const double tau = std::max(h->plan_tau * t_total, 1.0e-3);      // the longest items start first
             const int nv = sw_strip_variant_count();
             auto pick = [&](const Seg &sg, const uint32_t *ql, size_t nql, uint32_t maxq, double *item_s) {
+                if (const char *e = std::getenv("SW_B200_PLAN_FORCE")) {          // A/B measurements: this variant for every group
+                    for (int i = 0; i < nv; ++i) if (std::strcmp(sw_strip_variant(i)->name, e) == 0) { *item_s = 1.0; return i; }
+                }
                 int best = -1, best_any = -1;
                 double best_thr = 0, best_any_cost = 0, best_item = 0, best_any_item = 0;
                 const double cols_avg = std::max(1.0, (double)sg.sum_len / (2.0 * std::max<uint32_t>(sg.p1 - sg.p0, 1)));
