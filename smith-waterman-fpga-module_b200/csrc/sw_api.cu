@@ -1533,8 +1533,9 @@ int small_submit(sw_handle *h, int si, const uint8_t *packed, const uint32_t *le
     if (h->topk_k > 0 || h->out_mode != SW_OUT_I32 || h->params.score_width != 0) return SW_OK;
     uint64_t bmin = ~0ull, bmax = 0, sum = 0;
     uint32_t maxlen = 0;
+    size_t n_empty = 0;
     for (size_t i = 0; i < ns; ++i) {
-        if (len[i] == 0) continue;
+        if (len[i] == 0) { ++n_empty; continue; }
         bmin = std::min(bmin, off[i]);
         bmax = std::max<uint64_t>(bmax, off[i] + ((len[i] + 3ull) >> 2));
         maxlen = std::max(maxlen, len[i]);
@@ -1607,7 +1608,7 @@ int small_submit(sw_handle *h, int si, const uint8_t *packed, const uint32_t *le
     g.small_by_flag = !h->small_sentinel;
     for (uint32_t l : h->q_len) if (l == 0) g.small_by_flag = true;       // be safe: rows the kernel may not write
     if (!g.small_by_flag) std::fill(hout, hout + (size_t)nq * ns, kSmallSentinel);
-    if (np * 2 != ns)
+    if (n_empty)        // (np * 2 == ns says nothing: one empty subject and an odd number of others pair up to ns / 2 as well)
         for (size_t k = 0; k < ns; ++k) if (len[k] == 0) for (int q = 0; q < nq; ++q) hout[(size_t)q * ns + k] = 0;
 
     // ---- one copy, one kernel
