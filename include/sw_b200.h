@@ -259,7 +259,7 @@ int sw_set_wave_mode(sw_handle_t *h, int mode);
 /* Scores that leave the 16-bit range of the packed kernels (the reference's SCORE_WIDTH is a
  * synthesis parameter, SW_ProcessingElement_v1.0.v:26; here 32 bits are used where needed) are
  * recomputed from the overflow list.  With the default scoring such a pair is at least 6 400 x
- * 6 400 nt, so entries of at least min_cells cells (default 10^6; the first 4 096 of a call) are
+ * 6 400 nt, so entries of at least min_cells cells (default 10^6; the first 16 384 of a call) are
  * scored by 256-row bands on many warps in 32-bit arithmetic, the rest by one thread each.
  * enable = 0 leaves every entry to the one-thread scorer (environment SW_B200_WAVE32=0). */
 int sw_set_overflow_wave(sw_handle_t *h, int enable, unsigned long long min_cells);

@@ -156,6 +156,7 @@ struct GpuCtx {
     DevBuf d_wave_bnd, d_wave_state;  // band-pipelined kernel: boundary rows; progress / best / done words
     int wave_bps[16] = {0};           // resident blocks per SM of its instances (0 = not asked yet)
     DevBuf d_wave32_bnd, d_wave32_state;   // 32-bit band-pipelined scorer of the overflow list
+    DevBuf d_wave_rows;               // top-k mode: one scratch score row per band-pipelined query
     uint32_t wave32_epoch = 0;        // 8-bit tag field: 1 .. 255, boundary rows zeroed when it restarts
     int wave32_bps = 0;
     uint32_t wave_epoch = 0;          // launches so far: the tag of the boundary elements (20 bits)
@@ -265,7 +266,7 @@ SwScoring scoring_of(const sw_handle *h)
 std::vector<DevBuf *> all_devbufs(GpuCtx &g)
 {
     std::vector<DevBuf *> v = {&g.d_qpacked, &g.d_qoff, &g.d_qlen, &g.d_qidx, &g.d_bnd, &g.d_counters, &g.d_scratch32,
-                               &g.d_best_score, &g.d_best_index, &g.d_topk_keys, &g.d_err, &g.d_wave_bnd, &g.d_wave_state, &g.d_wave32_bnd, &g.d_wave32_state,
+                               &g.d_best_score, &g.d_best_index, &g.d_topk_keys, &g.d_err, &g.d_wave_bnd, &g.d_wave_state, &g.d_wave32_bnd, &g.d_wave32_state, &g.d_wave_rows,
                                &g.d_bnd_aux[0], &g.d_bnd_aux[1], &g.d_bnd_aux[2]};
     for (Slot &b : g.slot) {
         DevBuf *bufs[] = {&b.d_raw, &b.d_off, &b.d_len, &b.d_pair_subj, &b.d_pair_len, &b.d_tile_woff, &b.d_tp, &b.d_out,
@@ -539,6 +540,9 @@ double variant_cost(const GpuCtx &gc, const Slot &g, const SwStripVariant *v, co
     return job + 0.5 * item;
 }
 
+// launches of the 32-bit band scorer per call (4 096 overflow-list entries each)
+constexpr unsigned kWave32Parts = 4;
+
 bool variant_forced(const sw_handle *h) { return h->force_variant >= 0 || h->force_R || h->force_G; }
 
 // Picks the strip variant for a set of queries (least estimated time); ranked = all candidates, best first.
@@ -751,7 +755,8 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
     // ---- few, long pairs: the bands of a long query become concurrent work items (sw_wave.cuh) ----
     std::vector<int> wave_q, strip_q;
     {
-        const bool wave_ok = h->wave && !topk && !sc.limit && !h->force32 && !variant_forced(h);
+        // (top-k: the band-pipelined kernel fills a scratch row per query, whose top k then join the key lists)
+        const bool wave_ok = h->wave && !sc.limit && !h->force32 && !variant_forced(h);
         for (int q = 0; q < nq; ++q) {
             const uint32_t ql = h->q_len[q];
             bool w = false;
@@ -1003,7 +1008,13 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
 
     const bool use32 = !have_strip && wave_q.empty();        // forced 32-bit scorer
     if (topk) {
-        if (!have_strip) return SW_EINVAL;                    // the 32-bit scorer has no top-k epilogue
+        if (!have_strip && wave_q.empty()) return SW_EINVAL;  // the 32-bit scorer has no top-k epilogue
+        if (!wave_q.empty()) {
+            max_grid = std::max(max_grid, 1);                 // list 0 also takes the rows of the band-pipelined queries
+            const size_t rb = wave_q.size() * (size_t)n * sizeof(int32_t);
+            SW_CUDA(h, gc.d_wave_rows.reserve(rb));
+            SW_CUDA(h, cudaMemsetAsync(gc.d_wave_rows.p, 0xFF, rb, gc.st_compute));    // -1 = not scored here
+        }
         const size_t bytes = (size_t)max_grid * nq * g.topk_k * sizeof(unsigned long long);
         SW_CUDA(h, gc.d_topk_keys.reserve(bytes));
         SW_CUDA(h, cudaMemsetAsync(gc.d_topk_keys.p, 0, bytes, gc.st_compute));
@@ -1078,7 +1089,9 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
             // state words: best [2 * npairs] | done [npairs]
             const size_t n_state = 3 * (size_t)g.npairs;
             SW_CUDA(h, gc.d_wave_state.reserve(n_state * sizeof(unsigned)));
+            int wave_row = -1;
             for (int q : wave_q) {
+                ++wave_row;
                 SwWaveLaunch W;
                 // pair-bands of 256 rows in this launch: many -> throughput-bound (512-row bands,
                 // four pairs per block); fewer -> one pair per block, four columns per step; a
@@ -1095,8 +1108,9 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 W.db = db; W.q = dq; W.query = q; W.sc = sc;
                 W.npass = (int)((h->q_len[q] + rows - 1) / rows);
                 W.out = g.d_out.p; W.out_stride = n; W.out_mode = g.out_mode;
+                if (topk) { W.out = gc.d_wave_rows.p; W.out_mode = SW_OUT_I32; W.out_row = wave_row; }
                 W.bnd = gc.d_wave_bnd.p; W.cols_stride = cols_stride;
-                W.bnd_elems = (size_t)g.npairs * 2 * cols_stride; W.out_elems = (size_t)nq * n;
+                W.bnd_elems = (size_t)g.npairs * 2 * cols_stride; W.out_elems = topk ? wave_q.size() * (size_t)n : (size_t)nq * n;
                 gc.wave_epoch = (gc.wave_epoch % 0xFFFFEu) + 1u;            // 1 .. 2^20 - 2
                 if (gc.wave_epoch == 1u && gc.counter_next > 0) {
                     // the epoch wrapped (or first use): stale tags must not match again
@@ -1115,6 +1129,13 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 SW_CUDA(h, cudaMemsetAsync(W.counter, 0, sizeof(unsigned), gc.st_compute));
                 SW_CUDA(h, sw_launch_wave(gc.st_compute, W));
                 h->launches++;
+                if (topk) {
+                    // the row's k best scores become list 0 of this query (pairs flagged for the 32-bit
+                    // scorer keep the sentinel here and reach the merge through the overflow list)
+                    SW_CUDA(h, sw_launch_topk_row(gc.st_compute, (const int32_t *)gc.d_wave_rows.p + (size_t)wave_row * n, (uint32_t)n, q,
+                                                  g.topk_k, gc.d_topk_keys.as<unsigned long long>()));
+                    h->launches++;
+                }
                 if (&gc == &h->gpus[0] && label_v < 0)
                     std::snprintf(h->last_kernel, sizeof h->last_kernel, "%s", sw_wave_kernel_name(W.instance));
             }
@@ -1139,16 +1160,9 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                     SW_CUDA(h, gc.d_wave32_bnd.reserve(W.bnd_elems * 16));
                     fresh = true;
                 }
-                gc.wave32_epoch = gc.wave32_epoch % 255u + 1u;
-                if (fresh || gc.wave32_epoch == 1u)          // stale tags must never match
-                    SW_CUDA(h, cudaMemsetAsync(gc.d_wave32_bnd.p, 0, gc.d_wave32_bnd.cap, gc.st_compute));
-                W.bnd = gc.d_wave32_bnd.p; W.epoch = gc.wave32_epoch;
                 const size_t state_bytes = (size_t)3 * SW_WAVE32_MAX_ENTRIES * sizeof(unsigned);
                 SW_CUDA(h, gc.d_wave32_state.reserve(state_bytes));
-                SW_CUDA(h, cudaMemsetAsync(gc.d_wave32_state.p, 0, state_bytes, gc.st_compute));
                 W.state = gc.d_wave32_state.as<unsigned>();
-                W.counter = next_counter(gc);
-                SW_CUDA(h, cudaMemsetAsync(W.counter, 0, sizeof(unsigned), gc.st_compute));
                 W.maxb = (h->q_max_len + SW_WAVE32_ROWS - 1) / SW_WAVE32_ROWS;
                 W.min_cells = h->wave32_min_cells;
                 if (!gc.wave32_bps) SW_CUDA(h, sw_wave32_occupancy(&gc.wave32_bps));
@@ -1157,9 +1171,23 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 // up on a few SMs (measured: 16 blocks per SM = 2.3x slower for one 100 kb entry)
                 W.grid = gc.num_sms * std::min(gc.wave32_bps, 4);
                 W.dev_err = gc.d_err.as<unsigned>();
-                SW_CUDA(h, sw_launch_wave32(gc.st_compute, W));
-                h->launches++;
-                s32.wave32_min_cells = W.min_cells;
+                // 4 096 entries per launch (12 tag bits); a launch that finds no entry costs one
+                // atomic per block
+                W.entry_limit = kWave32Parts * SW_WAVE32_MAX_ENTRIES;
+                for (unsigned part = 0; part < kWave32Parts; ++part) {
+                    gc.wave32_epoch = gc.wave32_epoch % 255u + 1u;
+                    if (fresh || gc.wave32_epoch == 1u)      // stale tags must never match
+                        SW_CUDA(h, cudaMemsetAsync(gc.d_wave32_bnd.p, 0, gc.d_wave32_bnd.cap, gc.st_compute));
+                    fresh = false;
+                    W.bnd = gc.d_wave32_bnd.p; W.epoch = gc.wave32_epoch;
+                    W.entry_base = part * SW_WAVE32_MAX_ENTRIES;
+                    SW_CUDA(h, cudaMemsetAsync(gc.d_wave32_state.p, 0, state_bytes, gc.st_compute));
+                    W.counter = next_counter(gc);
+                    SW_CUDA(h, cudaMemsetAsync(W.counter, 0, sizeof(unsigned), gc.st_compute));
+                    SW_CUDA(h, sw_launch_wave32(gc.st_compute, W));
+                    h->launches++;
+                }
+                s32.wave32_min_cells = W.min_cells; s32.wave32_limit = W.entry_limit;
             }
             SW_CUDA(h, sw_launch_score32(gc.st_compute, s32));
             h->launches++;

@@ -64,6 +64,7 @@ struct Score32Args {
     int match, mismatch, goe, ge, limit, mode;
     const unsigned *list_count; const uint2 *list; unsigned list_cap; int32_t *list_score;
     unsigned long long wave32_min_cells;
+    unsigned wave32_limit;
 };
 
 __device__ __forceinline__ int score32_pair(const uint8_t *rp, int m, const uint8_t *cp, int n, int32_t *Hb,
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(128) score32_kernel(const Score32Args a)
         }
         const int m = (int)a.qlen[q], n = (int)a.len[s];
         // long entries at the head of the list belong to the band-pipelined 32-bit scorer
-        if (a.mode == 2 && a.wave32_min_cells && wave32_takes((unsigned)job, (uint32_t)m, (uint32_t)n, a.wave32_min_cells)) continue;
+        if (a.mode == 2 && a.wave32_min_cells && wave32_takes((unsigned)job, (uint32_t)m, (uint32_t)n, a.wave32_min_cells, a.wave32_limit)) continue;
         const uint8_t *qp = a.qpacked + a.qoff[q];
         const uint8_t *tpk = a.raw + a.off[s];
         const int best = (n <= m) ? score32_pair(qp, m, tpk, n, Hb, Gb, nthreads, a)
@@ -408,6 +409,7 @@ cudaError_t sw_launch_wave(cudaStream_t st, const SwWaveLaunch &L)
     a.tp = L.db.tp; a.tile_woff = L.db.tile_woff; a.pair_len = L.db.pair_len; a.pair_subj = L.db.pair_subj;
     a.npairs = L.db.npairs; a.npb = (L.db.npairs + (uint32_t)(w.bt / 32) - 1u) / (uint32_t)(w.bt / 32);
     a.qpacked = L.q.packed; a.qoff = L.q.off; a.qlen = L.q.len; a.q = L.query; a.npass = L.npass;
+    a.out_row = L.out_row >= 0 ? L.out_row : L.query;
     a.out = L.out; a.out_stride = L.out_stride; a.out_mode = L.out_mode;
     a.bnd = (ulonglong2 *)L.bnd; a.cols_stride = L.cols_stride; a.epoch = L.epoch; a.best = L.best; a.done = L.done; a.counter = L.counter;
     a.match = sc.match; a.mismatch = sc.mismatch; a.goe = sc.goe; a.ge = sc.ge;
@@ -442,6 +444,7 @@ cudaError_t sw_launch_wave32(cudaStream_t st, const SwWave32Launch &L)
     a.raw = L.db.raw; a.off = L.db.off; a.len = L.db.len;
     a.qpacked = L.q.packed; a.qoff = L.q.off; a.qlen = L.q.len;
     a.list_count = L.list_count; a.list = L.list; a.list_cap = L.list_cap; a.list_score = L.list_score;
+    a.entry_base = L.entry_base; a.entry_limit = L.entry_limit;
     a.out = L.out; a.out_stride = L.out_stride; a.out_mode = L.out_mode; a.out_elems = L.out_elems;
     a.bnd = (ulonglong2 *)L.bnd; a.cols_stride = L.cols_stride; a.nslots = L.nslots; a.epoch = L.epoch; a.bnd_elems = L.bnd_elems;
     a.best = (int *)L.state; a.done = L.state + kWave32MaxEntries; a.flag = L.state + 2 * kWave32MaxEntries;
@@ -465,7 +468,7 @@ cudaError_t sw_launch_score32(cudaStream_t st, const SwScore32Launch &L)
     a.scratch = L.scratch; a.max_cols = L.max_cols;
     a.match = L.sc.match; a.mismatch = L.sc.mismatch; a.goe = L.sc.goe; a.ge = L.sc.ge; a.limit = L.sc.limit;
     a.mode = L.mode; a.list_count = L.list_count; a.list = L.list; a.list_cap = L.list_cap; a.list_score = L.list_score;
-    a.wave32_min_cells = L.wave32_min_cells;
+    a.wave32_min_cells = L.wave32_min_cells; a.wave32_limit = L.wave32_limit;
     score32_kernel<<<grid, bt, 0, st>>>(a);
     return cudaGetLastError();
 }
@@ -486,6 +489,47 @@ cudaError_t sw_launch_best(cudaStream_t st, const int32_t *scores, size_t stride
 {
     if (nq <= 0) return cudaSuccess;
     best_kernel<<<nq, 1024, 0, st>>>(scores, stride, ns, best_score, best_index);
+    return cudaGetLastError();
+}
+
+namespace {
+// k rounds of a block-wide max over the unique keys (score << 32 | ~subject) of one score row
+__global__ void __launch_bounds__(256) topk_row_kernel(const int32_t *row, uint32_t n, int k, unsigned long long *out)
+{
+    __shared__ unsigned long long s_red[8];
+    __shared__ unsigned long long s_pick;
+    unsigned long long prev = ~0ull;
+    for (int round = 0; round < k; ++round) {
+        unsigned long long best = 0;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const int32_t v = row[i];
+            if (v < 0) continue;                                   // not scored here (empty subject, overflow sentinel)
+            const unsigned long long key = ((unsigned long long)(uint32_t)v << 32) | (uint32_t)(~i);
+            if (key < prev && key > best) best = key;
+        }
+        for (int o = 16; o >= 1; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, best, o);
+            best = other > best ? other : best;
+        }
+        if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long b = 0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) b = s_red[w] > b ? s_red[w] : b;
+            s_pick = b;
+            out[round] = b;
+        }
+        __syncthreads();
+        prev = s_pick;
+        if (prev == 0) break;                                      // fewer than k entries: the rest stays 0
+    }
+}
+}  // namespace
+
+cudaError_t sw_launch_topk_row(cudaStream_t st, const int32_t *row, uint32_t n, int q, int k, unsigned long long *keys)
+{
+    if (k <= 0) return cudaSuccess;
+    topk_row_kernel<<<1, 256, 0, st>>>(row, n, k, keys + (size_t)q * k);
     return cudaGetLastError();
 }
 

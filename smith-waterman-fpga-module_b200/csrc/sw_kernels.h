@@ -121,6 +121,7 @@ struct SwWaveLaunch {
     SwDevDb db{};
     SwDevQueries q{};
     int query = 0;
+    int out_row = -1;        /* row of out the scores go to; -1 = query */
     int npass = 0;
     SwScoring sc{};
     void *out = nullptr;
@@ -147,8 +148,8 @@ int sw_wave_instance_count(void);
 int sw_wave_pairs_per_block(int instance);
 
 /* 32-bit band-pipelined scorer of the overflow list (sw_wave.cuh, sw_wave32_kernel): the first
- * SW_WAVE32_MAX_ENTRIES entries with at least min_cells cells; score32 (mode 2) with the same
- * wave32_min_cells skips exactly those.  bnd: nslots * 2 * cols_stride 16-byte elements (zeroed once
+ * SW_WAVE32_MAX_ENTRIES entries per launch (entry_base), of those below entry_limit with at least
+ * min_cells cells; score32 (mode 2) with the same wave32_min_cells / wave32_limit skips exactly those.  bnd: nslots * 2 * cols_stride 16-byte elements (zeroed once
  * and whenever epoch restarts at 1); state: 3 * SW_WAVE32_MAX_ENTRIES zeroed words per launch. */
 #define SW_WAVE32_MAX_ENTRIES 4096
 #define SW_WAVE32_ROWS 256
@@ -159,6 +160,7 @@ struct SwWave32Launch {
     const unsigned *list_count = nullptr;
     const uint2 *list = nullptr;
     unsigned list_cap = 0;
+    unsigned entry_base = 0, entry_limit = SW_WAVE32_MAX_ENTRIES;   /* this launch's first list entry; entries all launches take */
     int32_t *list_score = nullptr;
     void *out = nullptr;
     size_t out_stride = 0, out_elems = 0;
@@ -198,6 +200,7 @@ struct SwScore32Launch {
     unsigned list_cap = 0;
     int32_t *list_score = nullptr;
     unsigned long long wave32_min_cells = 0;   /* mode 2: entries sw_wave32_kernel takes are skipped (0 = none) */
+    unsigned wave32_limit = 0;                 /* ... among the first wave32_limit list entries */
 };
 cudaError_t sw_launch_score32(cudaStream_t st, const SwScore32Launch &L);
 
@@ -209,6 +212,9 @@ cudaError_t sw_launch_best(cudaStream_t st, const int32_t *scores, size_t stride
 
 /* Folds the per-block top-k lists (nlists x nq x k keys) and the recomputed overflow entries into
  * out_keys[nq][k] (descending; key = score << 32 | ~subject, 0 = no entry). */
+/* Top-k of one materialised score row (entries < 0 are skipped) written as list 0 of query q in the
+ * per-block key lists that sw_launch_topk_merge folds: the band-pipelined kernel has no top-k epilogue. */
+cudaError_t sw_launch_topk_row(cudaStream_t st, const int32_t *row, uint32_t n, int q, int k, unsigned long long *keys);
 cudaError_t sw_launch_topk_merge(cudaStream_t st, const unsigned long long *keys, int nlists, int nq, int k,
                                  const unsigned *ovf_count, const uint2 *ovf_list, const int32_t *ovf_score,
                                  unsigned ovf_cap, unsigned long long *out_keys);

@@ -50,6 +50,7 @@ struct WaveArgs {
     const uint32_t *qoff;
     const uint32_t *qlen;
     int q;                     // the query of this launch
+    int out_row;               // row of `out` its scores go to (q, or the row of a scratch matrix)
     int npass;                 // bands of that query (of R * 32 rows each), <= 4095
     void *out;
     size_t out_stride;
@@ -502,13 +503,13 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
                     if (ov0) { const unsigned p = atomicAdd(a.ovf_count, 1u); if (p < a.ovf_cap) a.ovf_list[p] = make_uint2((unsigned)q, subj_lo); }
                     if (has1 && ov1) { const unsigned p = atomicAdd(a.ovf_count, 1u); if (p < a.ovf_cap) a.ovf_list[p] = make_uint2((unsigned)q, subj_hi); }
                 }
-                SW_CHECK((unsigned long long)q * a.out_stride + subj_lo < a.out_elems && (!has1 || (unsigned long long)q * a.out_stride + subj_hi < a.out_elems), SW_DEVERR_OUT, a);
+                SW_CHECK((unsigned long long)a.out_row * a.out_stride + subj_lo < a.out_elems && (!has1 || (unsigned long long)a.out_row * a.out_stride + subj_hi < a.out_elems), SW_DEVERR_OUT, a);
                 if (a.out_mode == SW_OUT_I16) {
-                    int16_t *orow = (int16_t *)a.out + (size_t)q * a.out_stride;
+                    int16_t *orow = (int16_t *)a.out + (size_t)a.out_row * a.out_stride;
                     orow[subj_lo] = (int16_t)(ov0 ? SW_OVERFLOW_SENTINEL : f0);
                     if (has1) orow[subj_hi] = (int16_t)(ov1 ? SW_OVERFLOW_SENTINEL : f1);
                 } else {
-                    int32_t *orow = (int32_t *)a.out + (size_t)q * a.out_stride;
+                    int32_t *orow = (int32_t *)a.out + (size_t)a.out_row * a.out_stride;
                     orow[subj_lo] = ov0 ? SW_OVERFLOW_SENTINEL : f0;
                     if (has1) orow[subj_hi] = ov1 ? SW_OVERFLOW_SENTINEL : f1;
                 }
@@ -530,15 +531,16 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
 //   boundary  = bnd[e % nslots][b & 1][column], tag = (epoch : 8, e : 12, b : 12); entry e may only
 //               start when entry e - nslots has finished (flag[e - nslots], set by its last band, or
 //               by band 0 of an entry this kernel leaves to score32_kernel)
-//   entries   = the first kWave32MaxEntries of the list that satisfy wave32_takes(); score32_kernel
-//               (mode 2) skips exactly those.
+//   entries   = kWave32MaxEntries list entries per launch (12 tag bits), a few launches per call:
+//               the first entry_limit entries of the list that satisfy wave32_takes();
+//               score32_kernel (mode 2) skips exactly those.
 // ------------------------------------------------------------------------------------------
 constexpr unsigned kWave32MaxEntries = 4096;
 constexpr int kWave32Rows = 256;
 
-__host__ __device__ inline bool wave32_takes(unsigned e, uint32_t m, uint32_t n, unsigned long long min_cells)
+__host__ __device__ inline bool wave32_takes(unsigned e, uint32_t m, uint32_t n, unsigned long long min_cells, unsigned limit)
 {
-    return e < kWave32MaxEntries && (unsigned long long)m * n >= min_cells && n > 0 &&
+    return e < limit && (unsigned long long)m * n >= min_cells && n > 0 &&
            (m + kWave32Rows - 1) / kWave32Rows <= 4095u;
 }
 
@@ -552,6 +554,7 @@ struct Wave32Args {
     const unsigned *list_count;
     const uint2 *list;             // (query, subject)
     unsigned list_cap;
+    unsigned entry_base, entry_limit;   // this launch: list entries entry_base .. entry_base + kWave32MaxEntries - 1; all launches: < entry_limit
     int32_t *list_score;
     void *out;                     // score matrix (may be null), as for score32_kernel
     size_t out_stride;
@@ -580,7 +583,8 @@ __global__ void __launch_bounds__(32, MINB) sw_wave32_kernel(const Wave32Args a)
     __shared__ __align__(16) uint2 s_top[BLK + kWaveBotSlots];
     __shared__ uint8_t s_qb[P / 4 + 4];
     const int lane = threadIdx.x;
-    const unsigned listed = min(min(*a.list_count, a.list_cap), kWave32MaxEntries);
+    const unsigned total = min(*a.list_count, a.list_cap);
+    const unsigned listed = total > a.entry_base ? min(total - a.entry_base, kWave32MaxEntries) : 0u;
     const uint32_t goe = (uint32_t)a.goe, ge = (uint32_t)a.ge, h0 = goe, gb = 0u;
 
     for (;;) {
@@ -590,12 +594,12 @@ __global__ void __launch_bounds__(32, MINB) sw_wave32_kernel(const Wave32Args a)
         const unsigned e = work / a.maxb;
         const int b = (int)(work % a.maxb);
         if (e >= listed) break;
-        const uint2 ent = a.list[e];
+        const uint2 ent = a.list[a.entry_base + e];
         const int q = (int)ent.x;
         const uint32_t subj = ent.y;
         const int m = (int)a.qlen[q], n = (int)a.len[subj];
         const int npass = (m + P - 1) / P;
-        const bool take = wave32_takes(e, (uint32_t)m, (uint32_t)n, a.min_cells);
+        const bool take = wave32_takes(a.entry_base + e, (uint32_t)m, (uint32_t)n, a.min_cells, a.entry_limit);
         if (e >= a.nslots) {
             // the boundary rows of this slot are free once entry e - nslots has finished (every item
             // of the entry waits here, so that the waits inside a band stay pipeline-short)
@@ -664,7 +668,7 @@ __global__ void __launch_bounds__(32, MINB) sw_wave32_kernel(const Wave32Args a)
             if (atomicAdd(a.done + e, 1u) == (unsigned)npass - 1u) {
                 __threadfence();
                 const int f = atomicMax(a.best + e, 0);
-                if (a.list_score) a.list_score[e] = f;
+                if (a.list_score) a.list_score[a.entry_base + e] = f;
                 if (a.out) {
                     SW_CHECK((unsigned long long)q * a.out_stride + subj < a.out_elems, SW_DEVERR_OUT, a);
                     // a 16-bit matrix keeps the sentinel for scores it cannot hold (they are on the list)

@@ -439,7 +439,8 @@ def test_bounds_check_build_runs_clean(pkg):
            "test_small_path_direct_variants_vs_oracle or test_topk_vs_oracle_argsort or test_output_i16 or "
            "test_very_long_subjects_short_queries or test_query_groups or test_is_check_build or test_wave_kernel or "
            "test_randomised_modes_stress or test_virtual_multi_shard or test_overflow_list_scored_by_32bit_bands or "
-           "test_overflow_32bit_bands_sharded or test_small_path_completion_protocols")
+           "test_overflow_32bit_bands_sharded or test_small_path_completion_protocols or test_overflow_list_more_entries or "
+           "test_topk_of_few_long_pairs")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-x", "-q", "-m", "gpu", "-k", sel,
                         "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
@@ -518,6 +519,35 @@ def test_wave_kernel_every_instance_vs_oracle(oracle_mod, pkg, monkeypatch, inst
         # a second call on the same handle: the boundary tags of the first launches must not match
         got = e.score(queries[::-1], subjects)
         np.testing.assert_array_equal(got, want[::-1])
+
+
+def test_topk_of_few_long_pairs_uses_the_band_pipelined_kernel(oracle_mod, pkg):
+    """Top-k for a handful of long subjects: the long queries run on the band-pipelined kernel (a
+    scratch score row per query, its k best joined to the key lists), the short query on the strip
+    kernel, in the same call; one pair's score is beyond 16 bits (overflow list -> 32-bit bands);
+    empty subjects; a sharded handle merges the lists of its shards."""
+    rng = random.Random(406)
+    q1 = _rand(rng, 7000)
+    q2 = _rand(rng, 2600)
+    q3 = _rand(rng, 90)
+    subjects = [q1[100:6900], _mutate(rng, q1, 0.05, 0.02), _rand(rng, 3000), "", _mutate(rng, q2, 0.1, 0.05), q2[500:2100],
+                _rand(rng, 40), q3 + _rand(rng, 200), "", _rand(rng, 1500), _mutate(rng, q1[2000:5000], 0.02, 0.01)]
+    subjects += [_rand(rng, rng.randint(1, 900)) for _ in range(20)]
+    want = _oracle_matrix(oracle_mod, pkg, [q1, q2, q3], subjects)
+    assert want[0, 0] == 34000
+    for k in (1, 5, 32):
+        wsc, wix = _topk_want(want, k)
+        for gpu_ids in (None, [0, 0]):
+            with pkg.Engine(gpu_ids=gpu_ids) as e:
+                e.set_small_batch_path(False)
+                e.set_topk(k)
+                e.set_queries([q1, q2, q3])
+                e.score_batch(subjects)
+                sc, ix = e.fetch_topk()
+                assert "wave" in e.last_kernel_name, e.last_kernel_name
+                assert e.device_error_bits == 0
+            np.testing.assert_array_equal(sc, wsc, err_msg=str((k, gpu_ids)))
+            np.testing.assert_array_equal(ix, wix, err_msg=str((k, gpu_ids)))
 
 
 def test_wave_kernel_single_long_pair_and_overflow(oracle_mod, pkg):
@@ -631,6 +661,26 @@ def test_overflow_list_mixed_long_and_short_entries(oracle_mod, pkg):
             got = e.score([q1, q2], subs)
             assert e.device_error_bits == 0
             np.testing.assert_array_equal(got, want, err_msg=str((enable, cells)))
+
+
+def test_overflow_list_more_entries_than_one_launch_of_the_band_scorer(pkg):
+    """5 000 overflow entries: the 32-bit band scorer takes 4 096 list entries per launch (12 tag bits)
+    and runs a few launches per call.  match = 100, subjects = exact substrings of the query."""
+    rng = random.Random(80)
+    q = _rand(rng, 700)
+    subs, want = [], []
+    for k in range(5000):
+        L = rng.randint(340, 700)
+        a0 = rng.randint(0, 700 - L)
+        subs.append(q[a0:a0 + L]); want.append(100 * L)
+    want = np.array([want], dtype=np.int32)
+    with pkg.Engine(match=100, mismatch=-40, gap_open=-120, gap_extend=-20) as e:
+        e.set_small_batch_path(False)
+        for cells in (1, 1000000000):                       # all entries by bands / all by one thread each
+            e.set_overflow_wave(True, cells)
+            got = e.score([q], subs)
+            assert e.device_error_bits == 0
+            np.testing.assert_array_equal(got, want, err_msg=str(cells))
 
 
 def test_randomised_modes_stress_vs_oracle(oracle_mod, pkg):
