@@ -254,7 +254,8 @@ int sw_set_small_batch_timing(sw_handle_t *h, int enable);
  * band consuming the bottom row of the band above as it is produced -- the module chaining the
  * reference left "for future use" (ScoringModule_v1.1.v:36-39, 49-54).  mode 0 = never,
  * 1 = automatic (default: <= 1536 subject pairs and a query of >= 1024 rows, or <= 64 pairs and a
- * query of > 512 rows), 2 = whenever the query has more than one band (environment SW_B200_WAVE). */
+ * query of > 512 rows, or every query >= 1024 rows and too few pairs to fill whole rounds of the
+ * strip kernel's work items), 2 = whenever the query has more than one band (environment SW_B200_WAVE). */
 int sw_set_wave_mode(sw_handle_t *h, int mode);
 /* Scores that leave the 16-bit range of the packed kernels (the reference's SCORE_WIDTH is a
  * synthesis parameter, SW_ProcessingElement_v1.0.v:26; here 32 bits are used where needed) are

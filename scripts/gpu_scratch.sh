@@ -1,8 +1,3 @@
 #!/bin/bash
-timeout 900 python scripts/bench_configs.py 4full 4 5 2>&1 | python -c "
-import sys,json
-for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print(d['config'][:50], d['kernel'], round(d['gcups'],1), round(d['kernel_ms'],2))
-    else: print(l.strip()[:200])
-"
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=10 --timeout=900 -p no:cacheprovider 2>&1 | tail -4
+timeout 900 python scripts/shape_ab.py 2>&1 | tail -10 > gpurun_out/shape_ab.jsonl; cat gpurun_out/shape_ab.jsonl

@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -759,12 +760,23 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
     {
         // (top-k: the band-pipelined kernel fills a scratch row per query, whose top k then join the key lists)
         const bool wave_ok = h->wave && !sc.limit && !h->force32 && !variant_forced(h);
+        // Besides "few pairs": whenever the long queries' work items (128 pairs x all passes) would
+        // leave the strip kernel's last round mostly empty.  Measured (profiles/r02_wave_vs_strip_mid.txt):
+        // the band-pipelined kernel holds 7.2-7.5 TCUPS from 3 000 to 100 000 pairs, the strip kernel
+        // 8.1 TCUPS at exactly two full rounds but 4.9-6.9 below and between whole rounds.
+        size_t n_long = 0;
+        for (int q = 0; q < nq; ++q) n_long += (h->q_len[q] >= 2 * SW_WAVE_ROWS_PER_BAND && h->q_len[q] <= 4000u * 256u) ? 1 : 0;
+        const double rounds = (double)((g.npairs + 127) / 128) * (double)n_long / ((double)gc.num_sms * 2.0);
+        // (only when every query is long: shorter ones in the same launch fill the strip kernel's rounds)
+        const bool underfilled = n_long == (size_t)nq && (rounds < 1.05 || (rounds < 4.0 && rounds / std::ceil(rounds) < 0.85));
+        const bool bnd_fits = (double)g.npairs * 2.0 * ((double)g.max_len + 64.0) * 16.0 <= 4.0e9;
         for (int q = 0; q < nq; ++q) {
             const uint32_t ql = h->q_len[q];
             bool w = false;
             if (wave_ok && ql > SW_WAVE_ROWS_PER_BAND && ql <= 4000u * 256u) {
                 if (h->wave >= 2) w = true;
-                else w = (g.npairs <= 1536 && ql >= 2 * SW_WAVE_ROWS_PER_BAND) || g.npairs <= 64;
+                else w = (g.npairs <= 1536 && ql >= 2 * SW_WAVE_ROWS_PER_BAND) || g.npairs <= 64 ||
+                         (ql >= 2 * SW_WAVE_ROWS_PER_BAND && underfilled && bnd_fits);
             }
             (w ? wave_q : strip_q).push_back(q);
         }
@@ -947,7 +959,8 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 }
                 for (auto &kv : by_variant) {
                     std::vector<int> &ql = kv.second;
-                    std::sort(ql.begin(), ql.end());
+                    // longest queries first inside a super-block: the longest work items start earliest
+                    std::sort(ql.begin(), ql.end(), [&](int x, int y) { return h->q_len[x] != h->q_len[y] ? h->q_len[x] > h->q_len[y] : x < y; });
                     uint32_t gmaxq = 0;
                     for (int q : ql) gmaxq = std::max(gmaxq, h->q_len[q]);
                     Planned p{base, 0, 0, 0, item_of[kv.first]};
