@@ -1,4 +1,8 @@
 #!/bin/bash
-mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -k "multi_gpu or sharded or shard" --timeout=600 -p no:cacheprovider 2>&1 | tail -3
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_2gpu.json 2> gpurun_out/bench_2gpu.err; tail -c 900 gpurun_out/bench_2gpu.json
+timeout 1500 python -m pytest tests -m gpu -q --maxfail=10 --timeout=900 -p no:cacheprovider 2>&1 | tail -4
+timeout 900 python scripts/shape_ab.py 2>&1 | grep shape | python -c "
+import sys,json
+for l in sys.stdin:
+    d=json.loads(l); print(f\"{d['shape']:40s} {d['kernel']:28s} {d['gcups']:8.1f}\")
+"
+timeout 600 python scripts/bench_configs.py 4w 2>&1 | cut -c1-200

@@ -1110,9 +1110,11 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 SwWaveLaunch W;
                 // pair-bands of 256 rows in this launch: many -> throughput-bound (512-row bands,
                 // four pairs per block); fewer -> one pair per block, four columns per step; a
-                // handful -> two columns per step (measured crossovers)
+                // handful -> two columns per step; many pairs of long subjects -> 512-row bands with two
+                // columns per step (measured crossovers)
                 const size_t warps256 = (size_t)g.npairs * ((h->q_len[q] + 255) / 256);
-                W.instance = warps256 < 1200 ? 2 : warps256 < 15000 ? 1 : 0;
+                const double mean_len = (double)g.sum_len / (2.0 * std::max<uint32_t>(g.npairs, 1));
+                W.instance = warps256 < 1200 ? 2 : warps256 < 15000 ? 1 : mean_len >= 1000.0 ? 3 : 0;
                 if (const char *e = std::getenv("SW_B200_WAVE_INSTANCE")) {       // A/B measurements
                     const int wi = std::atoi(e);
                     if (wi >= 0 && wi < sw_wave_instance_count() && wi < 16) W.instance = wi;

@@ -358,7 +358,7 @@ cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L)
 }
 
 // ---- band-pipelined kernel ---------------------------------------------------------------------
-// Three instances (measured over few-long-pair shapes, profiles/r02_wave_instance_ab2.txt):
+// Four instances (measured over few-long-pair shapes, profiles/r02_wave_instance_ab2.txt, r02_wave_vs_strip_mid.txt):
 //   0  R8x2        bands of 512 rows, one column per step, four pairs per block: many pairs (the
 //                  GPU is full of pair-bands; throughput-bound)
 //   1  R8x1 C4     bands of 256 rows, four columns per step, ONE pair per block: a few dozen to a
@@ -367,6 +367,9 @@ cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L)
 //                  down to a single one (latency-bound: one warp per band; with one pair per block
 //                  the active warps spread over the four schedulers of an SM instead of all being
 //                  warp 0 of a four-warp block)
+//   3  R8x2 C2     bands of 512 rows, two columns per step, four pairs per block: many pairs of long
+//                  subjects (>= 1 kb on average: +2-6 % over instance 0; the doubled skew of 126
+//                  columns per band costs more than that on shorter ones)
 namespace {
 typedef void (*WaveFn)(const WaveArgs);
 struct WaveInstance { int rows, bt; size_t smem; WaveFn fn, fn_fixed; const char *name; };
@@ -378,6 +381,7 @@ const WaveInstance g_wave[] = {
     SW_WAVE(8, 2, 128, 4, 32, 1, false, "wave_s16x2_R8x2_G32"),
     SW_WAVE(8, 1, 32, 8, 32, 4, false, "wave_s16x2_R8x1_G32_C4"),
     SW_WAVE(8, 1, 32, 16, 32, 2, true, "wave_s16x2_R8x1_G32_C2"),
+    SW_WAVE(8, 2, 128, 3, 32, 2, false, "wave_s16x2_R8x2_G32_C2"),
     // measured and dropped (profiles/r02_wave_instance_ab.jsonl, r02_wave_instance_ab2.txt): 16-column
     // blocks, 128-row bands (R4x1 with 1 / 2 / 4 columns per step, R4x2), R8x1 with one column per
     // step, four-pair blocks for the multi-column instances

@@ -199,7 +199,7 @@ __device__ __forceinline__ uint32_t wave_band(const WaveArgs &a, const uint2 *pr
     return best;
 }
 
-// The same band with C columns per systolic step (S = 1): a lane finishes the C x RS tile of its
+// The same band with C columns per systolic step: a lane finishes the C x RS tile of its (S x RS)
 // rows before it hands (H, G) of its bottom row -- C columns at once -- to the next lane, so the
 // lanes are skewed by C columns, a band needs ncols / C + 31 steps instead of ncols + 31, and the
 // fixed cost of a step (shuffles, selects, the profile address, loop control) is paid once per C
@@ -225,13 +225,13 @@ struct RawCodes {                    // one subject's packed 2-bit record: code 
     }
 };
 
-template <int RS, int C, class AR, int BLK, bool HAS_TOP, bool HAS_BOTTOM, bool LS, class ARGS, class SRC>
+template <int RS, int S, int C, class AR, int BLK, bool HAS_TOP, bool HAS_BOTTOM, bool LS, class ARGS, class SRC>
 __device__ __forceinline__ uint32_t wave_band_c(const ARGS &a, const uint2 *prof_lane, uint2 *s_top, const SRC src,
                                                 int ncols, const ulonglong2 *top, ulonglong2 *bot, uint32_t tag_top, uint32_t tag_bot,
                                                 uint32_t goe2, uint32_t ge2, uint32_t h0, uint32_t gb2, uint32_t zero)
 {
     static_assert(C == 2 || C == 4, "2 or 4 columns per step");
-    constexpr int G = 32, RP = (RS + 1) / 2, TC = 8, U = TC / C;      // a loop trip = 8 columns = U steps
+    constexpr int G = 32, RP = (RS + 1) / 2, VPE = G * S, TC = 8, U = TC / C;   // a loop trip = 8 columns = U steps
     constexpr int PF = 16;                                            // columns between prefetch and use of a boundary block
     constexpr unsigned FULL = 0xFFFFFFFFu;
     constexpr uint32_t PADW = SRC::kPad * 0x01010101u;
@@ -240,9 +240,11 @@ __device__ __forceinline__ uint32_t wave_band_c(const ARGS &a, const uint2 *prof
     const int lane = threadIdx.x & 31;
     const bool head = lane == 0;
     uint32_t best = h0;
-    uint32_t H[1][RS], Gl[1][RS];
+    uint32_t H[S][RS], Gl[S][RS];
 #pragma unroll
-    for (int r = 0; r < RS; ++r) { H[0][r] = h0; Gl[0][r] = gb2; }
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int r = 0; r < RS; ++r) { H[s][r] = h0; Gl[s][r] = gb2; }
 
     // Code words (4 columns each): the warp keeps 2 x 32 of them in one register per lane -- lane i
     // holds word 32 B + i of the current / next block of 128 columns, loaded 128 columns before they
@@ -256,24 +258,34 @@ __device__ __forceinline__ uint32_t wave_band_c(const ARGS &a, const uint2 *prof
     uint32_t tc0 = __shfl_sync(FULL, cw_cur, 0), tc1 = __shfl_sync(FULL, cw_cur, 1);
     uint32_t tn0 = __shfl_sync(FULL, cw_cur, 2), tn1 = __shfl_sync(FULL, cw_cur, 3);
 
-    uint32_t pub_h[C], pub_g[C], pub_t = head ? (tc0 & CMASK) : (PADW & CMASK), hd_carry = h0;
+    // what each sub-strip hands to the next virtual PE (the next sub-strip of the lane, or for
+    // s = S-1 the next lane): bottom H and G of its C columns, and the code word it uses NEXT step
+    uint32_t pub_h[S][C], pub_g[S][C], pub_t[S], hd_carry[S];
 #pragma unroll
-    for (int j = 0; j < C; ++j) { pub_h[j] = h0; pub_g[j] = gb2; }
-    auto load_sv = [&](uint2 (&sv)[C][RP], uint32_t tw) {
+    for (int s = 0; s < S; ++s) {
+        pub_t[s] = PADW & CMASK;
+        hd_carry[s] = h0;
 #pragma unroll
-        for (int j = 0; j < C; ++j) {
-            const uint2 *prow = prof_lane + ((tw >> (8 * j)) & 255u) * G;
+        for (int j = 0; j < C; ++j) { pub_h[s][j] = h0; pub_g[s][j] = gb2; }
+    }
+    if (head) pub_t[0] = tc0 & CMASK;
+    auto load_sv = [&](uint2 (&sv)[S][C][RP], const uint32_t (&tw)[S]) {
 #pragma unroll
-            for (int k = 0; k < RP; ++k) sv[j][k] = prow[k * SRC::kCodes * G];
-        }
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                const uint2 *prow = prof_lane + (s * RP * SRC::kCodes + ((tw[s] >> (8 * j)) & 255u)) * G;
+#pragma unroll
+                for (int k = 0; k < RP; ++k) sv[s][j][k] = prow[k * SRC::kCodes * G];
+            }
     };
-    uint2 sv[C][RP];
+    uint2 sv[S][C][RP];
     load_sv(sv, pub_t);
     ulonglong2 pre = make_ulonglong2(0ull, 0ull);
     uint32_t sto_h[TC], sto_g[TC];
     uint2 *s_bot = s_top + BLK;            // LS: the last lane's bottom-row values of this trip
     const unsigned long long tag_hi = (unsigned long long)tag_bot << 32;
-    const int nsteps = ncols > 0 ? ((ncols + C - 1) / C + (G - 1) + U - 1) / U * U : 0;
+    const int nsteps = ncols > 0 ? ((ncols + C - 1) / C + (VPE - 1) + U - 1) / U * U : 0;
 
 #pragma unroll 1
     for (int k0 = 0; k0 < nsteps; k0 += U) {
@@ -313,13 +325,13 @@ __device__ __forceinline__ uint32_t wave_band_c(const ARGS &a, const uint2 *prof
         const uint2 *stp = s_top + (c0 & (BLK - 1));
 #pragma unroll
         for (int uu = 0; uu < U; ++uu) {
-            uint32_t in_h[C], in_g[C];
+            uint32_t in_h[S][C], in_g[S][C], in_t[S];
 #pragma unroll
             for (int j = 0; j < C; ++j) {
-                in_h[j] = __shfl_up_sync(FULL, pub_h[j], 1, G);
-                in_g[j] = __shfl_up_sync(FULL, pub_g[j], 1, G);
+                in_h[0][j] = __shfl_up_sync(FULL, pub_h[S - 1][j], 1, G);
+                in_g[0][j] = __shfl_up_sync(FULL, pub_g[S - 1][j], 1, G);
             }
-            uint32_t in_t = __shfl_up_sync(FULL, pub_t, 1, G);
+            in_t[0] = __shfl_up_sync(FULL, pub_t[S - 1], 1, G);
             // head lane: the band above (or the matrix edge) and the codes of its NEXT step's columns
             const int nb = C * (uu + 1);                       // first byte of those codes inside this trip's 8
             uint32_t lead;
@@ -330,43 +342,59 @@ __device__ __forceinline__ uint32_t wave_band_c(const ARGS &a, const uint2 *prof
             for (int j = 0; j < C; ++j) {
                 uint2 b = make_uint2(h0, gb2);
                 if constexpr (HAS_TOP) b = stp[uu * C + j];
-                in_h[j] = head ? b.x : in_h[j];
-                in_g[j] = head ? b.y : in_g[j];
+                in_h[0][j] = head ? b.x : in_h[0][j];
+                in_g[0][j] = head ? b.y : in_g[0][j];
             }
-            in_t = head ? (lead & CMASK) : in_t;
+            in_t[0] = head ? (lead & CMASK) : in_t[0];
+            // sub-strip s > 0 of the lane is fed by sub-strip s - 1 as it stood after the previous step
 #pragma unroll
-            for (int j = 0; j < C; ++j) SW_CHECK(((in_t >> (8 * j)) & 255u) <= (uint32_t)SRC::kPad, SW_DEVERR_PROF, a);
-            uint2 sv_next[C][RP];
+            for (int s = 1; s < S; ++s) {
+                in_t[s] = pub_t[s - 1];
+#pragma unroll
+                for (int j = 0; j < C; ++j) { in_h[s][j] = pub_h[s - 1][j]; in_g[s][j] = pub_g[s - 1][j]; }
+            }
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+#pragma unroll
+                for (int j = 0; j < C; ++j) SW_CHECK(((in_t[s] >> (8 * j)) & 255u) <= (uint32_t)SRC::kPad, SW_DEVERR_PROF, a);
+            uint2 sv_next[S][C][RP];
             load_sv(sv_next, in_t);
 #pragma unroll
             for (int j = 0; j < C; ++j) {
-                const uint32_t hd[1] = {j == 0 ? hd_carry : in_h[j - 1]};
-                const uint32_t gt[1] = {in_g[j]};
-                uint2 svj[1][RP];
+                uint32_t hd[S], gt[S];
+                uint2 svj[S][RP];
 #pragma unroll
-                for (int k = 0; k < RP; ++k) svj[0][k] = sv[j][k];
-                column_step_multi<RS, 1, G, AR, false>(H, Gl, best, hd, gt, svj, goe2, ge2, zero, 0u);
-                pub_h[j] = H[0][RS - 1];
-                pub_g[j] = Gl[0][RS - 1];
+                for (int s = 0; s < S; ++s) {
+                    hd[s] = j == 0 ? hd_carry[s] : in_h[s][j - 1];
+                    gt[s] = in_g[s][j];
+#pragma unroll
+                    for (int k = 0; k < RP; ++k) svj[s][k] = sv[s][j][k];
+                }
+                column_step_multi<RS, S, G, AR, false>(H, Gl, best, hd, gt, svj, goe2, ge2, zero, 0u);
+#pragma unroll
+                for (int s = 0; s < S; ++s) { pub_h[s][j] = H[s][RS - 1]; pub_g[s][j] = Gl[s][RS - 1]; }
                 if constexpr (HAS_BOTTOM && LS) {
-                    if (lane == G - 1) s_bot[uu * C + j] = make_uint2(pub_h[j], pub_g[j]);
+                    if (lane == G - 1) s_bot[uu * C + j] = make_uint2(pub_h[S - 1][j], pub_g[S - 1][j]);
                 } else {
-                    sto_h[uu * C + j] = pub_h[j];
-                    sto_g[uu * C + j] = pub_g[j];
+                    sto_h[uu * C + j] = pub_h[S - 1][j];
+                    sto_g[uu * C + j] = pub_g[S - 1][j];
                 }
             }
-            hd_carry = in_h[C - 1];
-            pub_t = in_t;
 #pragma unroll
-            for (int j = 0; j < C; ++j)
+            for (int s = 0; s < S; ++s) {
+                hd_carry[s] = in_h[s][C - 1];
+                pub_t[s] = in_t[s];
 #pragma unroll
-                for (int k = 0; k < RP; ++k) sv[j][k] = sv_next[j][k];
+                for (int j = 0; j < C; ++j)
+#pragma unroll
+                    for (int k = 0; k < RP; ++k) sv[s][j][k] = sv_next[s][j][k];
+            }
         }
         tc0 = tn0; tc1 = tn1; tn0 = tnn0; tn1 = tnn1;
         if constexpr (HAS_BOTTOM) {
-            // the last lane finished columns cl0 .. cl0 + 7 in this trip; columns outside
+            // the last virtual PE finished columns cl0 .. cl0 + 7 in this trip; columns outside
             // 0 .. ncols - 1 land in the row's slack and are never read
-            const int cl0 = c0 - C * (G - 1);
+            const int cl0 = c0 - C * (VPE - 1);
             if constexpr (LS) {
                 // LS (latency-bound instances: one warp per scheduler): stored by TC lanes, one element
                 // each, through shared memory.  A single lane storing TC elements reuses one register
@@ -401,7 +429,6 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
     constexpr int PASS_ENTRIES = VPE * RP * kWaveCodes;
     constexpr int PPB = BT / G;
     constexpr unsigned FULL = 0xFFFFFFFFu;
-    static_assert(C == 1 || S == 1, "several columns per step: one sub-strip");
     __shared__ __align__(16) uint2 s_top[PPB][BLK + kWaveBotSlots];
     __shared__ uint8_t s_qb[P / 4 + 4];                // packed query bytes of the band
 
@@ -477,7 +504,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_wave_kernel(const WaveArgs a)
 #define SW_WAVE_BAND(T, B)                                                                                                   \
         do {                                                                                                                 \
             if constexpr (C > 1)                                                                                             \
-                best = wave_band_c<RS, C, AR, BLK, T, B, LS>(a, prof_lane, s_top[warp], TiledCodes{tpp}, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero); \
+                best = wave_band_c<RS, S, C, AR, BLK, T, B, LS>(a, prof_lane, s_top[warp], TiledCodes{tpp}, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero); \
             else                                                                                                             \
                 best = wave_band<RS, S, AR, BLK, T, B>(a, prof_lane, s_top[warp], tpp, ncols, top, bot, tag_top, tag_bot, goe2, ge2, h0, gb2, zero); \
         } while (0)
@@ -656,7 +683,7 @@ __global__ void __launch_bounds__(32, MINB) sw_wave32_kernel(const Wave32Args a)
         const uint2 *prof_lane = s_prof + lane;
         uint32_t best;
 #define SW_WAVE32_BAND(T, B) \
-        best = wave_band_c<RS, C, ArithS32, BLK, T, B, true>(a, prof_lane, s_top, src, n, top, bot, tag_top, tag_bot, goe, ge, h0, gb, 0u)
+        best = wave_band_c<RS, 1, C, ArithS32, BLK, T, B, true>(a, prof_lane, s_top, src, n, top, bot, tag_top, tag_bot, goe, ge, h0, gb, 0u)
         if (has_top) { if (has_bottom) SW_WAVE32_BAND(true, true); else SW_WAVE32_BAND(true, false); }
         else { if (has_bottom) SW_WAVE32_BAND(false, true); else SW_WAVE32_BAND(false, false); }
 #undef SW_WAVE32_BAND

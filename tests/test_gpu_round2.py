@@ -492,10 +492,11 @@ def test_wave_kernel_few_long_pairs_vs_oracle(oracle_mod, pkg):
         assert "wave" not in e.last_kernel_name
 
 
-@pytest.mark.parametrize("instance", [0, 1, 2])
+@pytest.mark.parametrize("instance", [0, 1, 2, 3])
 def test_wave_kernel_every_instance_vs_oracle(oracle_mod, pkg, monkeypatch, instance):
     """Each instance of the band-pipelined kernel (512-row bands, one column per step; 256-row bands
-    with four / two columns per step and one pair per block) forced in turn over ragged lengths:
+    with four / two columns per step and one pair per block; 512-row bands with two columns per
+    step) forced in turn over ragged lengths:
     subject lengths around the 4- and 8-column trip, the 32-column boundary block and the 128-column
     code-word block; query lengths that leave the last band almost empty or exactly full."""
     monkeypatch.setenv("SW_B200_WAVE_INSTANCE", str(instance))
