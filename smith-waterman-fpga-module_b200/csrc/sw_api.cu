@@ -769,13 +769,14 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
         const double rounds = (double)((g.npairs + 127) / 128) * (double)n_long / ((double)gc.num_sms * 2.0);
         // (only when every query is long: shorter ones in the same launch fill the strip kernel's rounds)
         const bool underfilled = n_long == (size_t)nq && (rounds < 1.05 || (rounds < 4.0 && rounds / std::ceil(rounds) < 0.85));
-        const bool bnd_fits = (double)g.npairs * 2.0 * ((double)g.max_len + 64.0) * 16.0 <= 4.0e9;
+        const double bnd_bytes = (double)g.npairs * 2.0 * ((double)g.max_len + 64.0) * 16.0;      // tagged boundary rows of all pairs
+        const bool bnd_fits = bnd_bytes <= 4.0e9, bnd_fits_few = bnd_bytes <= 16.0e9;
         for (int q = 0; q < nq; ++q) {
             const uint32_t ql = h->q_len[q];
             bool w = false;
             if (wave_ok && ql > SW_WAVE_ROWS_PER_BAND && ql <= 4000u * 256u) {
                 if (h->wave >= 2) w = true;
-                else w = (g.npairs <= 1536 && ql >= 2 * SW_WAVE_ROWS_PER_BAND) || g.npairs <= 64 ||
+                else w = (bnd_fits_few && ((g.npairs <= 1536 && ql >= 2 * SW_WAVE_ROWS_PER_BAND) || g.npairs <= 64)) ||
                          (ql >= 2 * SW_WAVE_ROWS_PER_BAND && underfilled && bnd_fits);
             }
             (w ? wave_q : strip_q).push_back(q);
