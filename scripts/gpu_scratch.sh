@@ -1,8 +1,5 @@
 #!/bin/bash
-timeout 1500 python -m pytest tests -m gpu -q --maxfail=10 --timeout=900 -p no:cacheprovider 2>&1 | tail -4
-timeout 900 python scripts/shape_ab.py 2>&1 | grep shape | python -c "
-import sys,json
-for l in sys.stdin:
-    d=json.loads(l); print(f\"{d['shape']:40s} {d['kernel']:28s} {d['gcups']:8.1f}\")
-"
-timeout 600 python scripts/bench_configs.py 4w 2>&1 | cut -c1-200
+mkdir -p gpurun_out
+SW_B200_LIB=$PWD/smith-waterman-fpga-module_b200/libsw_b200_check.so timeout 3000 python -m pytest tests -m gpu -q --maxfail=15 --timeout=1200 -p no:cacheprovider --deselect tests/test_gpu_round2.py::test_bounds_check_build_runs_clean > gpurun_out/pytest_gpu_checkbuild.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/pytest_gpu_checkbuild.log
+tail -5 gpurun_out/pytest_gpu_checkbuild.log
