@@ -80,8 +80,9 @@ def sass_functions(path):
 
 
 def demangle_params(fn):
-    m = re.search(r"sw_strip_kernelILi(\d+)ELi(\d+)ELi(\d+)ENS\w*8ArithS16ELb([01])ELi(\d+)ELi(\d+)ELi(n?\d+)ELi(n?\d+)ELb([01])ELi(\d+)", fn)
+    m = re.search(r"sw_strip_kernelILi(\d+)ELi(\d+)ELi(\d+)ENS\w*8ArithS16ELb([01])ELi(\d+)ELi(\d+)ELi(n?\d+)ELi(n?\d+)ELb([01])ELi(\d+)(?:ELi(\d+))?", fn)
     U = int(m.group(10)) if m else 4
+    FL = int(m.group(11)) if m and m.group(11) else 0
     if not m:
         m2 = re.search(r"sw_strip_kernelILi(\d+)ELi(\d+)ELi(\d+)ENS\w*8ArithS16ELb([01])ELi(\d+)ELi(\d+)ELi(n?\d+)ELi(n?\d+)ELi", fn)
         if not m2:
@@ -91,7 +92,39 @@ def demangle_params(fn):
         g = m.groups()
     num = lambda s: -int(s[1:]) if s.startswith("n") else int(s)
     return {"RS": int(g[0]), "S": int(g[1]), "G": int(g[2]), "w12": g[3] == "1", "BT": int(g[4]), "MINB": int(g[5]),
-            "goe": num(g[6]), "ge": num(g[7]), "direct": g[8] == "1", "U": U}
+            "goe": num(g[6]), "ge": num(g[7]), "direct": g[8] == "1", "U": U, "FL": FL}
+
+
+def all_loops(rows):
+    """(first index, last index, VIADDMNMX count) of every backward branch with packed DPX work."""
+    addr_index = {a: i for i, (a, _, _, _) in enumerate(rows)}
+    out = []
+    for i, (a, op, text, _p) in enumerate(rows):
+        if not op.startswith("BRA"):
+            continue
+        m = re.search(r"0x([0-9a-f]+)", text)
+        if not m:
+            continue
+        tgt = int(m.group(1), 16)
+        if tgt >= a or tgt not in addr_index:
+            continue
+        j = addr_index[tgt]
+        n = sum(1 for r in rows[j:i + 1] if r[1].startswith("VIADDMNMX"))
+        if n >= 16:
+            out.append((j, i, n))
+    return out
+
+
+def general_loop(rows, hot):
+    """Instances with interior trips (FL bit 0): the loop of the general trips = the smallest other
+    DPX loop that does not overlap the hot (interior) loop."""
+    h0 = rows.index(hot[0])
+    h1 = h0 + len(hot) - 1
+    cand = [(i - j, j, i) for j, i, n in all_loops(rows) if i < h0 or j > h1]
+    if not cand:
+        return None
+    _, j, i = min(cand)
+    return rows[j:i + 1]
 
 
 def hot_loop(rows):
@@ -129,7 +162,8 @@ def analyse(path, pattern):
         p = demangle_params(fn)
         if not p:
             continue
-        name = "strip_s16x2_R%dx%d_G%d" % (p["RS"], p["S"], p["G"]) + ("_U%d" % p["U"] if p["U"] != 4 else "")
+        name = ("strip_s16x2_R%dx%d_G%d" % (p["RS"], p["S"], p["G"]) + ("_U%d" % p["U"] if p["U"] != 4 or p["FL"] else "")
+                + ("_F%d" % p["FL"] if p["FL"] else ""))
         kind = "direct" if p["direct"] else "w12" if p["w12"] else ("fixed(%d,%d)" % (p["goe"], p["ge"])) if p["goe"] else "runtime"
         label = f"{name} [{kind}]"
         if pattern and not re.search(pattern, label):
@@ -148,6 +182,26 @@ def analyse(path, pattern):
                       "fma_pipe_per_cell_pair": pipes["fma"] / pairs,
                       "issue_slots_per_cell_pair": len(body) / pairs,
                       "histogram": dict(sorted(hist.items(), key=lambda kv: -kv[1]))}
+        if p["FL"] & 1:
+            # interior + general trips: weight the two loop bodies by the trips of a 150-column pass
+            # (sw_strip.cuh: interior trips cover [t_int0, t_int), the general loop the rest)
+            gen = general_loop(rows, body)
+            if gen:
+                gpairs = (1 if p["FL"] & 16 else p["U"]) * p["RS"] * p["S"]
+                galu = sum(1 for _a, op, _t, _p in gen if pipe_of(op) == "alu") / gpairs
+                ahead = (5 if p["FL"] & 2 else 9) if p["FL"] & 8 else 9
+                U, cols = p["U"], 150
+                nsteps = (cols + p["S"] - 1 + U - 1) // U * U
+                t_int = (cols - ahead) // U * U
+                n_int = max(0, t_int - (0 if p["FL"] & 8 else U)) // U
+                n_all = nsteps // U
+                r = res[label]
+                r["interior_alu_pipe_per_cell_pair"] = r["alu_pipe_per_cell_pair"]
+                r["general_alu_pipe_per_cell_pair"] = galu
+                r["general_issue_slots_per_cell_pair"] = len(gen) / gpairs
+                r["interior_trips_of_150_columns"] = [n_int, n_all]
+                r["alu_pipe_per_cell_pair"] = (n_int * r["interior_alu_pipe_per_cell_pair"] + (n_all - n_int) * galu) / n_all
+                r["issue_slots_per_cell_pair"] = (n_int * r["issue_slots_per_cell_pair"] + (n_all - n_int) * len(gen) / gpairs) / n_all
     return res
 
 
@@ -167,6 +221,11 @@ def main():
                      f"{r['cell_pairs_per_trip'] // r['columns_per_trip']} rows = {r['cell_pairs_per_trip']} cell pairs")
         lines.append(f"   per cell pair: ALU pipe {r['alu_pipe_per_cell_pair']:.3f}, FMA-side pipe {r['fma_pipe_per_cell_pair']:.3f}, "
                      f"issue slots {r['issue_slots_per_cell_pair']:.3f}")
+        if "general_alu_pipe_per_cell_pair" in r:
+            lines.append(f"   (interior loop shown; ALU pipe {r['interior_alu_pipe_per_cell_pair']:.3f} in the interior trips, "
+                         f"{r['general_alu_pipe_per_cell_pair']:.3f} in the general trips; the per-cell-pair figures above are "
+                         f"weighted {r['interior_trips_of_150_columns'][0]} : {r['interior_trips_of_150_columns'][1] - r['interior_trips_of_150_columns'][0]} "
+                         f"as in a pass over 150 columns)")
         lines.append("   by pipe: " + ", ".join(f"{k} {v}" for k, v in sorted(r["by_pipe"].items(), key=lambda kv: -kv[1])))
         lines.append("   " + ", ".join(f"{k} {v}" for k, v in r["histogram"].items()))
     text = "\n".join(lines)

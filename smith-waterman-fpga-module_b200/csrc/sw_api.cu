@@ -516,6 +516,8 @@ double variant_speed(const SwStripVariant *v)
         // 8 columns per trip: measured +1.6 % on 150-nt reads (profiles/r02_variant_ab_u8.jsonl); the
         // R25x3 / R38x2 counterparts lose 15 % (their loop bodies outgrow the instruction cache)
         {"strip_s16x2_R25x2_G1_U8", 8840}, {"strip_s16x2_R25x3_G1_U8", 7320}, {"strip_s16x2_R38x2_G1_U8", 7390},
+        // interior trips: +1.6 % over the 8-column instance (profiles/r02_variant_ab_interior.jsonl)
+        {"strip_s16x2_R25x2_G1_U4_F31", 8975},
     };
     for (auto &t : tab) if (std::strcmp(t.name, v->name) == 0) return t.gcups;
     return 5000.0;

@@ -100,8 +100,8 @@ void *sw_jit_strip_kernel(const SwStripVariant *v, int goe, int ge, char *msg, s
     if (!v) return nullptr;
     const int rs = v->R / v->S;
     char expr[256];
-    std::snprintf(expr, sizeof expr, "swk::sw_strip_kernel<%d, %d, %d, swk::ArithS16, false, %d, %d, %d, %d, false, %d>", rs, v->S, v->G,
-                  v->block_threads, v->min_blocks, goe, ge, v->U);
+    std::snprintf(expr, sizeof expr, "swk::sw_strip_kernel<%d, %d, %d, swk::ArithS16, false, %d, %d, %d, %d, false, %d, %d>", rs, v->S, v->G,
+                  v->block_threads, v->min_blocks, goe, ge, v->U, v->FL);
     std::lock_guard<std::mutex> lock(g_mu);
     auto it = g_cache.find(expr);
     if (it != g_cache.end()) { set_msg(msg, msg_cap, it->second.why); return it->second.kernel; }

@@ -244,7 +244,7 @@ static const std::vector<VariantEntry> &variants()
         std::vector<VariantEntry> v;
         const VariantPart parts[] = {sw_variants_part_a(), sw_variants_part_b(), sw_variants_part_c(),
                                      sw_variants_part_d(), sw_variants_part_e(), sw_variants_part_f(),
-                                     sw_variants_part_g()};
+                                     sw_variants_part_g(), sw_variants_part_h()};
         for (const VariantPart &p : parts) v.insert(v.end(), p.v, p.v + p.n);
         return v;
     }();

@@ -62,6 +62,7 @@ struct SwStripVariant {
     const char *name;
     int has_direct;   /* a DIRECT instance exists (codes formed on the fly: small-batch path) */
     int U;            /* columns per trip of the step loop */
+    int FL;           /* interior-trip flags of the instance (sw_strip.cuh, SW_FAST_LOOP) */
 };
 
 int sw_strip_variant_count(void);

@@ -41,6 +41,11 @@
 #define SW_STEP_UNROLL 4      /* columns per trip of the step loop; nsteps is rounded up to a multiple */
 #endif
 
+#ifndef SW_FAST_LOOP
+#define SW_FAST_LOOP 0        /* bit 0: G = 1 instances run predicate-free trips over the interior columns of a
+                                 warp; bits 1 / 2 (A/B): no L1 prefetch of the code stream / boundary row there */
+#endif
+
 #define SW_NO_SUBJECT 0xFFFFFFFFu
 #define SW_OVERFLOW_SENTINEL (-1)   /* 16-bit range possibly exceeded: the pair is on the overflow list */
 
@@ -59,6 +64,8 @@
 #define SW_DEVERR_TOPK  32u
 
 namespace swk {
+
+template <bool B> struct BoolTag { static constexpr bool value = B; };
 
 constexpr int kPadScoreS16 = -8192;   // profile value of padding rows: M becomes 0, nothing can grow
 
@@ -350,7 +357,7 @@ __device__ __forceinline__ void topk_insert_warp(unsigned long long *list, int K
 // DIRECT: the column codes are formed on the fly from the uploaded 2-bit records instead of being
 // read from the code stream -- no build_tp launch: the small-batch (latency) path.
 template <int RS, int S, int G, class AR, bool W12, int BT, int MINB, int CGOE = 0, int CGE = 0, bool DIRECT = false,
-          int U = SW_STEP_UNROLL>
+          int U = SW_STEP_UNROLL, int FL = SW_FAST_LOOP>
 __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
 {
     extern __shared__ uint2 s_prof[];
@@ -477,6 +484,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
         };
         // rounded up: the step loop is unrolled (extra steps are PAD columns)
         const int nsteps = (__reduce_max_sync(FULL, ncols) + (VPE - 1) + U - 1) / U * U;
+        const int ncols_min = __reduce_min_sync(FULL, ncols);     // shortest pair of the warp (interior trips)
 
         uint32_t best = h0;
         {
@@ -563,11 +571,13 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                     load_scores<RS, S, G>(sv, prof_lane, pub_t);
                 }
 
-#pragma unroll 1
-                for (int t2 = 0; t2 < nsteps; t2 += U) {
-#pragma unroll
-                  for (int uu = 0; uu < U; ++uu) {
-                    const int t = t2 + uu;
+                // One column step of every virtual PE of the lane.  INTERIOR trips (G = 1 only): every
+                // lane of the warp has a column at each step of the trip, a code word two words ahead and
+                // (t + 4 < ncols), so the head's predicates, selects and the divergent region around the
+                // boundary loads disappear from the loop body (about 7 of 10 ALU-pipe bookkeeping
+                // instructions per column; the general body handles the first trip and the last few).
+                auto step = [&](auto interior_tag, const int t, const int uu) {
+                    constexpr bool INTERIOR = decltype(interior_tag)::value;
                     const int u = uu & 3;                 // column inside the current 4-column code word
                     // in_t: the code of THIS step (of the NEXT step in EARLY mode) of each virtual PE
                     uint32_t in_h[S], in_g[S], in_t[S];
@@ -600,6 +610,21 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                                 }
                                 if (t + 4 < ncols) prefetch_l1(bnd + (size_t)(t + 4) * PPB);
                             }
+                        }
+                    } else if constexpr (INTERIOR) {
+                        in_h[0] = bcur.x;
+                        in_g[0] = bcur.y;
+                        in_t[0] = (wcur >> (8 * u)) & 255u;
+                        if (u == 3) {
+                            wcur = wnext;
+                            const int k = (t >> 2) + 2;
+                            wnext = code_word(k);
+                            if (!DIRECT && !(FL & 2)) prefetch_l1(tpp + (k + 1) * 32);
+                        }
+                        if (has_top) {
+                            SW_CHECK((unsigned long long)(bnd - a.bnd) + (unsigned long long)(t + 1) * PPB < a.bnd_elems, SW_DEVERR_BND, a);
+                            bcur = bnd_load(bnd + (size_t)(t + 1) * PPB, bnd_pol);
+                            if (!(FL & 4)) prefetch_l1(bnd + (size_t)(t + 4) * PPB);
                         }
                     } else if (G == 1 || gl == 0) {
                         // head of the systolic group: column t comes from the code stream, the row
@@ -652,12 +677,41 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
                     }
                     if (MULTIPASS && has_bottom && gl == G - 1) {
                         const int cl = t - (VPE - 1);          // column the last virtual PE just finished
-                        if (cl >= 0 && cl < ncols) {
+                        // (an interior trip that starts at column 0 -- FL bit 3 -- skips the stores of the fill steps)
+                        if (INTERIOR ? (!(FL & 8) || uu >= VPE - 1 || t > uu) : (cl >= 0 && cl < ncols)) {
                             SW_CHECK((unsigned long long)(bnd - a.bnd) + (unsigned long long)cl * PPB < a.bnd_elems, SW_DEVERR_BND, a);
                             bnd_store(bnd + (size_t)cl * PPB, make_uint2(pub_h[S - 1], pub_g[S - 1]), bnd_pol);
                         }
                     }
-                  }
+                };
+                // interior trips: t2 in [t_int0, t_int).  The last column touched ahead of a trip is
+                // t2 + U + 8 (L1 prefetch of the code stream), t2 + U + 4 without that prefetch (next
+                // code word); the first trip holds the pipeline fill (no boundary store before column 0)
+                // and is interior only with FL bit 3.  FL bit 4: the general trips run one column per
+                // loop trip (small code: both loop bodies stay in the instruction cache).
+                constexpr bool kInt = (FL & 1) && G == 1 && !EARLY && MULTIPASS;
+                constexpr int kAhead = (FL & 8) ? ((FL & 2) ? 5 : 9) : 9;
+                const int t_int0 = (FL & 8) ? 0 : U;
+                const int t_int = kInt ? ((ncols_min - kAhead) / U * U) : 0;
+                static_assert(!kInt || U >= S - 1, "interior trips start behind the pipeline fill");
+#pragma unroll 1
+                for (int t2 = 0; t2 < nsteps;) {
+                    if (kInt && t2 >= t_int0 && t2 < t_int) {
+#pragma unroll 1
+                        do {
+#pragma unroll
+                            for (int uu = 0; uu < U; ++uu) step(BoolTag<true>{}, t2 + uu, uu);
+                            t2 += U;
+                        } while (t2 < t_int);
+                    } else if constexpr (kInt && (FL & 16)) {
+#pragma unroll 1
+                        for (int uu = 0; uu < U; ++uu) step(BoolTag<false>{}, t2 + uu, uu);
+                        t2 += U;
+                    } else {
+#pragma unroll
+                        for (int uu = 0; uu < U; ++uu) step(BoolTag<false>{}, t2 + uu, uu);
+                        t2 += U;
+                    }
                 }
                 if (has_bottom) __syncwarp();   // bottom row written by lane G-1, read by lane 0
             }

@@ -28,7 +28,7 @@ constexpr int kFixedGoe = -16, kFixedGe = -4;
 constexpr int kFixed2Goe = -12, kFixed2Ge = -4;
 
 #define SW_K(RS, S, G, W12, MINB, ...) sw_strip_kernel<RS, S, G, ArithS16, W12, kBT, MINB, ##__VA_ARGS__>
-#define SW_INFO(RS, S, G, MINB, D) {RS * S, G, kBT, S, MINB, "strip_s16x2_R" #RS "x" #S "_G" #G, D, 4}
+#define SW_INFO(RS, S, G, MINB, D) {RS * S, G, kBT, S, MINB, "strip_s16x2_R" #RS "x" #S "_G" #G, D, 4, 0}
 // run-time penalties + W-bit
 #define SW_VARIANT_S16(RS, S, G, MINB) \
     { SW_INFO(RS, S, G, MINB, 0), SW_K(RS, S, G, false, MINB), SW_K(RS, S, G, true, MINB), nullptr, nullptr, nullptr }
@@ -51,9 +51,15 @@ constexpr int kFixed2Goe = -12, kFixed2Ge = -4;
 // experimental: U columns per trip of the step loop (the register fix-up moves at the loop's back
 // edge are amortised over more columns); selectable by name for A/B measurements
 #define SW_VARIANT_S16F_U(RS, S, G, MINB, U) \
-    { {RS * S, G, kBT, S, MINB, "strip_s16x2_R" #RS "x" #S "_G" #G "_U" #U, 0, U}, \
+    { {RS * S, G, kBT, S, MINB, "strip_s16x2_R" #RS "x" #S "_G" #G "_U" #U, 0, U, 0}, \
       SW_K(RS, S, G, false, MINB, 0, 0, false, U), SW_K(RS, S, G, true, MINB, 0, 0, false, U), \
       SW_K(RS, S, G, false, MINB, kFixedGoe, kFixedGe, false, U), nullptr, nullptr }
+
+// interior-trip flags FL (sw_strip.cuh, SW_FAST_LOOP) on top of U
+#define SW_VARIANT_S16F_UF(RS, S, G, MINB, U, FL) \
+    { {RS * S, G, kBT, S, MINB, "strip_s16x2_R" #RS "x" #S "_G" #G "_U" #U "_F" #FL, 0, U, FL}, \
+      SW_K(RS, S, G, false, MINB, 0, 0, false, U, FL), SW_K(RS, S, G, true, MINB, 0, 0, false, U, FL), \
+      SW_K(RS, S, G, false, MINB, kFixedGoe, kFixedGe, false, U, FL), nullptr, nullptr }
 
 struct VariantPart { const VariantEntry *v; int n; };
 VariantPart sw_variants_part_a();
@@ -63,6 +69,7 @@ VariantPart sw_variants_part_d();
 VariantPart sw_variants_part_e();
 VariantPart sw_variants_part_f();
 VariantPart sw_variants_part_g();
+VariantPart sw_variants_part_h();
 
 }  // namespace swk
 #endif

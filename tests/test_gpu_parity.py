@@ -51,6 +51,8 @@ STRIP_VARIANTS = [
     "strip_s16x2_R8x1_G16", "strip_s16x2_R16x1_G8", "strip_s16x2_R2x2_G32",
     # experimental: 8 columns per trip of the step loop (A/B against the 4-column instances)
     "strip_s16x2_R25x2_G1_U8", "strip_s16x2_R25x3_G1_U8", "strip_s16x2_R38x2_G1_U8",
+    # interior (predicate-free) trips over the columns every lane of a warp has
+    "strip_s16x2_R25x2_G1_U4_F31",
 ]
 # variants that also exist as DIRECT instances (column codes formed on the fly: the small-batch path)
 DIRECT_VARIANTS = ["strip_s16x2_R16x1_G32", "strip_s16x2_R1x1_G32", "strip_s16x2_R2x1_G32", "strip_s16x2_R4x1_G32",
