@@ -523,6 +523,20 @@ double variant_speed(const SwStripVariant *v)
     return 5000.0;
 }
 
+// Instances whose interior trips drop the L1 prefetch of the boundary row (FL bit 2) are only fast while
+// the pass-boundary scratch of all resident blocks stays in L2 (150-nt reads: 68 MB, 8 973 vs 8 833 GCUPS);
+// with 1 kb subjects (454 MB of scratch) they lose 5 % to the prefetching instances
+// (profiles/r02_variant_ab_interior.jsonl).
+double variant_speed_at(const GpuCtx &gc, const SwStripVariant *v, uint32_t max_len)
+{
+    double sp = variant_speed(v);
+    if (v->FL & 4) {
+        const double scratch = (double)gc.num_sms * v->min_blocks * (v->block_threads / v->G) * (double)max_len * sizeof(uint2);
+        if (scratch > 96.0e6) sp *= 0.9;
+    }
+    return sp;
+}
+
 // Estimated time (arbitrary units) of scoring queries of the given lengths against the shard with
 // variant v = padded rows x (columns + pipeline fill) / measured speed / fraction of the GPU the
 // pairs can keep busy, plus half the time of the longest work item running at its share of an SM:
@@ -538,10 +552,11 @@ double variant_cost(const GpuCtx &gc, const Slot &g, const SwStripVariant *v, co
     const double fill = (double)gc.num_sms * v->min_blocks * v->block_threads;
     const double util = std::min(1.0, lanes / fill);
     const double cols = (double)std::max<uint32_t>(g.max_len, 1);
-    const double job = rows * (cols + v->G * v->S - 1) / cols * (double)g.sum_len / variant_speed(v) / util;
+    const double speed = variant_speed_at(gc, v, g.max_len);
+    const double job = rows * (cols + v->G * v->S - 1) / cols * (double)g.sum_len / speed / util;
     const int ppb = v->block_threads / v->G;
     const double qrows = (double)((maxq + P - 1) / P) * P;
-    const double item = qrows * cols * 2.0 * ppb * ((double)gc.num_sms * v->min_blocks) / variant_speed(v);
+    const double item = qrows * cols * 2.0 * ppb * ((double)gc.num_sms * v->min_blocks) / speed;
     return job + 0.5 * item;
 }
 
@@ -905,7 +920,7 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                     const int P = v->R * v->G, vpe = v->G * v->S;
                     double rows = 0;
                     for (size_t k = 0; k < nql; ++k) rows += (double)((ql[k] + P - 1) / P) * P;
-                    const double speed = variant_speed(v) * 1e9;
+                    const double speed = variant_speed_at(gc, v, sg.max_len) * 1e9;
                     const double thr = rows * (double)sg.sum_len * (cols_avg + vpe - 1) / cols_avg / speed;
                     const double qrows = (double)((maxq + P - 1) / P) * P;
                     const int ppb = v->block_threads / v->G;
