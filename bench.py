@@ -286,7 +286,7 @@ def main():
     ap.add_argument("--queries", type=int, default=100)
     ap.add_argument("--ref-subjects", type=int, default=4000, help="subjects per step of the CPU arm")
     ap.add_argument("--cpu-subjects", type=int, default=20000, help="subjects of the cpu_baseline sample")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--rows", type=int, default=0, help="force rows-per-lane of the strip kernel")
     ap.add_argument("--lanes", type=int, default=0, help="force lanes-per-pair of the strip kernel")
     ap.add_argument("--arith", type=int, default=-1, help="-1 auto, 0 s16x2")

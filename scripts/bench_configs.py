@@ -230,12 +230,15 @@ def case_penalties(pkg, n=2_000_000):
     q = pkg.random_packed_db(100, 150, 11)
     db = pkg.random_packed_db(n, 150, 12)
     custom = dict(match=5, mismatch=-4, gap_open=-10, gap_extend=-3)
-    out = {"workload": f"{n} x 150 nt subjects vs 100 x 150 nt queries, strip_s16x2_R25x2_G1"}
+    name = "strip_s16x2_R25x2_G1_U4_F31"
+    out = {"workload": f"{n} x 150 nt subjects vs 100 x 150 nt queries, {name}"}
+    ok, msg = pkg.jit_compile_check(name, custom["gap_open"], custom["gap_extend"])
+    out["nvrtc_specialisation"] = "ok" if ok == 1 else msg[:200]
     for label, params, jit in (("default_set_compiled_in", {}, 0), ("custom_set_runtime_operands", custom, 0),
                                ("custom_set_specialised_at_run_time", custom, 2)):
         with pkg.Engine(**params) as e:
             e.set_jit(jit)
-            e.set_kernel_name("strip_s16x2_R25x2_G1")
+            e.set_kernel_name(name)
             e.set_queries(q)
             e.load_db(db)
             ms = []

@@ -653,8 +653,9 @@ uint32_t superblock_for(const SwStripVariant *v, uint32_t npairs, uint64_t tp_wo
     const uint32_t npb = (npairs + ppb - 1) / ppb;
     if (npb == 0 || tp_words == 0) return 0;
     const double bytes_per_block = (double)tp_words * 4.0 / (double)npb;
-    uint32_t b = (uint32_t)std::max(1.0, (24.0 * 1024 * 1024) / std::max(bytes_per_block, 1.0));
-    b = std::max<uint32_t>(b, 2u * (uint32_t)std::max(grid, 1));
+    static const double sb_mb = std::getenv("SW_B200_SUPERBLOCK_MB") ? std::atof(std::getenv("SW_B200_SUPERBLOCK_MB")) : 24.0;   // A/B
+    uint32_t b = (uint32_t)std::max(1.0, (sb_mb * 1024 * 1024) / std::max(bytes_per_block, 1.0));
+    if (sb_mb >= 8.0) b = std::max<uint32_t>(b, 2u * (uint32_t)std::max(grid, 1));
     b = std::min<uint32_t>(b, std::max<uint32_t>(1u, npb >> 3));
     return std::max<uint32_t>(b, 1u);
 }
@@ -666,11 +667,41 @@ unsigned *next_counter(GpuCtx &gc)
     return c;
 }
 
+// Work queue(s) of one strip launch, zeroed on `st`: one counter per query of the launch ("sticky"
+// order, sw_strip.cuh) when the launch has 2 .. kMaxStickyQueries queries, else one counter.
+const int kMaxStickyQueries = 256;
+int sticky_default()
+{
+    // 0 = super-block order; > 0 = sticky order with this drift bound in pair blocks; -1 (default) = sticky
+    // order, drift bound of about 1 MB of code stream (4 .. 32 pair blocks).  Measured on config 3
+    // (profiles/r02_traffic.json): bound 32: 9 000 GCUPS, 3.7 GB of DRAM traffic per launch; 96: 8 998,
+    // 4.4 GB; none: 9 001, 14.9 GB; super-block order: 8 971, 19.2 GB.
+    static const int v = std::getenv("SW_B200_STICKY") ? std::atoi(std::getenv("SW_B200_STICKY")) : -1;   // A/B switch
+    return v;
+}
+cudaError_t assign_counters(GpuCtx &gc, SwStripLaunch &L, cudaStream_t st, bool equal_queries, uint64_t tp_words)
+{
+    // (queries of different lengths: the blocks of the short ones finish early and pile onto the long
+    // ones' queues -- config 5: 7 799 vs 8 302 GCUPS -- so only launches of equally long queries)
+    const bool sticky = sticky_default() && equal_queries && L.nql >= 2 && L.nql <= kMaxStickyQueries;
+    const unsigned n = sticky ? (unsigned)L.nql : 1u;
+    if (gc.counter_next % kMaxCounters + n > (unsigned)kMaxCounters) gc.counter_next += kMaxCounters - gc.counter_next % kMaxCounters;
+    L.counter = gc.d_counters.as<unsigned>() + (gc.counter_next % kMaxCounters);
+    gc.counter_next += n;
+    if (sticky && sticky_default() < 0) {
+        const double bytes_per_block = L.db.npairs ? (double)tp_words * 4.0 * 128.0 / (double)L.db.npairs : 1.0;
+        L.sticky = (int)std::min(32.0, std::max(4.0, 1048576.0 / std::max(bytes_per_block, 1.0)));
+    } else {
+        L.sticky = sticky ? sticky_default() : 0;
+    }
+    return cudaMemsetAsync(L.counter, 0, n * sizeof(unsigned), st);
+}
+
 // Times the model's best candidates on a window of the pair list (middle of the length order)
 // and a few queries; *choice = the fastest.  Every variant produces identical scores, so the
 // sample launches may write into the real output buffer.  Returns a status; the events live in
 // the GpuCtx, so no exit path leaks them.
-int autotune_variant(sw_handle *h, GpuCtx &gc, Slot &g, SwStripLaunch base, const std::vector<int> &ranked, int nq, int *choice)
+int autotune_variant(sw_handle *h, GpuCtx &gc, Slot &g, SwStripLaunch base, const std::vector<int> &ranked, int nq, bool equal_queries, int *choice)
 {
     *choice = ranked[0];
     const int ncand = std::min<int>(3, (int)ranked.size());
@@ -699,8 +730,7 @@ int autotune_variant(sw_handle *h, GpuCtx &gc, Slot &g, SwStripLaunch base, cons
         base.bnd = gc.d_bnd.as<uint2>();
         float ms = 0.f;
         for (int rep = 0; rep < 2; ++rep) {  // first run warms caches and the instruction cache
-            base.counter = next_counter(gc);
-            SW_CUDA(h, cudaMemsetAsync(base.counter, 0, sizeof(unsigned), gc.st_compute));
+            SW_CUDA(h, assign_counters(gc, base, gc.st_compute, equal_queries, g.tp_words * (uint64_t)base.db.npairs / std::max<uint32_t>(g.npairs, 1)));
             SW_CUDA(h, cudaEventRecord(gc.ev_tune0, gc.st_compute));
             SW_CUDA(h, sw_launch_strip(gc.st_compute, base));
             h->launches++;
@@ -812,7 +842,7 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
     qidx_host.clear();
     std::vector<int> ranked;
     int max_grid = 0;
-    bool simple = false, jit_used = false;
+    bool simple = false, jit_used = false, sticky_ok = false;
     int label_v = -1;
     size_t n_groups_total = 0;
 
@@ -845,6 +875,7 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
         }
         if (segs.empty() || variant_forced(h) || !use_segs) segs.assign(1, Seg{0, g.npairs, g.max_len, g.sum_len});
         simple = all_strip && segs.size() == 1 && (variant_forced(h) || same_len || strip_q.size() == 1);
+        sticky_ok = same_len;
 
         if (simple) {
             int vidx = choose_variant(h, gc, g, sl.data(), sl.size(), smaxq, &ranked);
@@ -862,7 +893,7 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 for (uint64_t x : parts) { key ^= x; key *= 1099511628211ull; }
                 if (gc.tune_key != key || gc.tune_choice < 0) {
                     int choice = vidx;
-                    rc = autotune_variant(h, gc, g, base, ranked, nq, &choice);
+                    rc = autotune_variant(h, gc, g, base, ranked, nq, same_len, &choice);
                     if (rc != SW_OK) return rc;
                     gc.tune_choice = choice;
                     gc.tune_key = key;
@@ -1086,8 +1117,7 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 }
             }
             p.L.bnd = (p.stream == 0 ? gc.d_bnd : gc.d_bnd_aux[p.stream - 1]).as<uint2>();
-            p.L.counter = next_counter(gc);
-            SW_CUDA(h, cudaMemsetAsync(p.L.counter, 0, sizeof(unsigned), st));
+            SW_CUDA(h, assign_counters(gc, p.L, st, simple && sticky_ok, g.tp_words));
             if (topk) { p.L.topk_keys = gc.d_topk_keys.as<unsigned long long>(); p.L.topk_k = g.topk_k; p.L.topk_nq = nq; }
             SW_CUDA(h, sw_launch_strip(st, p.L));
             h->launches++;

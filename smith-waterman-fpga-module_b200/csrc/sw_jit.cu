@@ -145,7 +145,9 @@ void *sw_jit_strip_kernel(const SwStripVariant *v, int goe, int ge, char *msg, s
             ent.why = "nvrtcCreateProgram failed"; set_msg(msg, msg_cap, ent.why); return nullptr;
         }
         n.AddNameExpression(prog, expr);
-        const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DSW_JIT_BUILD=1",
+        // -default-device: NVRTC takes the kernel's generic lambda (no execution-space annotation, as
+        // nvcc wants it inside device code) for a host function otherwise
+        const char *opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DSW_JIT_BUILD=1", "-default-device",
 #ifdef SW_BOUNDS_CHECK
                               "-DSW_BOUNDS_CHECK=1",
 #endif

@@ -324,7 +324,7 @@ cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L)
     a.npairs = L.db.npairs; a.npb = (L.db.npairs + ppb - 1) / ppb; a.superblock = L.superblock;
     a.qpacked = L.q.packed; a.qoff = L.q.off; a.qlen = L.q.len; a.qidx = L.qidx; a.q0 = L.q0; a.nql = L.nql;
     a.out = L.out; a.out_stride = L.out_stride; a.out_mode = L.out_mode;
-    a.bnd = L.bnd; a.bnd_cols = L.bnd_cols; a.counter = L.counter;
+    a.bnd = L.bnd; a.bnd_cols = L.bnd_cols; a.counter = L.counter; a.sticky = (L.counter && L.sticky > 0 && L.nql > 1) ? L.sticky : 0;
     a.chunk_passes = L.chunk_passes;
     a.match = sc.match; a.mismatch = sc.mismatch; a.goe = sc.goe; a.ge = sc.ge; a.limit = sc.limit;
     a.goe2 = ((uint32_t)sc.goe & 0xFFFFu) * 0x10001u; a.ge2 = ((uint32_t)sc.ge & 0xFFFFu) * 0x10001u;

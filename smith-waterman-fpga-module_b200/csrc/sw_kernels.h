@@ -95,6 +95,8 @@ struct SwStripLaunch {
     uint32_t bnd_cols = 0;
     size_t bnd_elems = 0;
     unsigned *counter = nullptr;
+    int sticky = 0;               /* > 0: counter points to nql zeroed words, one work queue per query (sw_strip.cuh);
+                                     the value bounds the drift between the queues (pair blocks) */
     int grid = 0, chunk_passes = 1;
     uint32_t superblock = 0;      /* pair blocks per super-block of the work order (0 = a tenth... npb / 8) */
     unsigned *ovf_count = nullptr;

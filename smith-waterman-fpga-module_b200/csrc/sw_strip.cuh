@@ -164,6 +164,8 @@ struct StripArgs {
     uint2 *bnd;
     uint32_t bnd_cols;
     unsigned *counter;         // work queue; null = static schedule (item = blockIdx.x + k * gridDim.x)
+    int sticky;                // > 0: counter[0 .. nql) = one work queue per query of the launch (see "work order");
+                               // the value = how many pair blocks the queues may drift apart
     int chunk_passes;          // passes whose query profile is resident in shared memory at once
     int match, mismatch, goe, ge, limit;
     uint32_t goe2, ge2;        // goe / ge packed in both 16-bit lanes (host side: uniform operands)
@@ -409,7 +411,21 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
     // small the order degenerates to longest-first over everything, which is what short launches
     // need for their tail.  (Decoded twice per item -- before the column loops and again in the epilogue --
     // so that nothing but s_work has to stay live across the hot loop.)
+    // Sticky order (a.sticky, launches with several queries): one queue of pair blocks PER QUERY, every
+    // thread block stays with "its" query (blockIdx.x mod queries) until that queue is empty and then
+    // moves on to the next one.  The profile in shared memory is rebuilt about once per launch instead
+    // of every few items, and the queries sweep the pair blocks side by side, so a code-stream line is
+    // read from HBM once and from L2 by the other queries (DRAM traffic of a config-3 launch: 19.2 GB in
+    // super-block order, 3.7 GB in this one -- profiles/r02_traffic.json; algorithmic 1.3 GB; and
+    // 9 000 vs 8 970 GCUPS).  work = query slot * npb + block.
     auto decode = [&](unsigned work, unsigned &pair, int &q) {
+        if (a.sticky) {
+            const unsigned qk = work / a.npb;
+            const unsigned pb = a.npb - 1u - (work - qk * a.npb);      // longest pair blocks first
+            q = a.qidx ? a.qidx[qk] : a.q0 + (int)qk;
+            pair = pb * PPB + pslot;
+            return;
+        }
         const unsigned nql = (unsigned)a.nql;
         const unsigned B = a.superblock ? a.superblock : max(1u, a.npb >> 3);
         const unsigned sb = work / (nql * B);
@@ -422,12 +438,34 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
     };
 
     int prof_q = -1, prof_pass = -1;     // which (query, first pass) the shared-memory profile holds
-    if (threadIdx.x == 0) s_iter = 0;
+    if (threadIdx.x == 0) s_iter = a.sticky ? blockIdx.x % (unsigned)a.nql : 0u;     // sticky: the block's query slot
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) {
             // work queue (atomic counter) or, for small launches, a static schedule
-            if (a.counter) s_work = atomicAdd(a.counter, 1u);
+            if (a.sticky) {
+                unsigned qk = s_iter, w = 0xFFFFFFFFu;
+                // bounded drift: the queries' sweeps over the code stream stay within a.sticky pair blocks
+                // of each other (the window the L2 keeps) -- a block whose queue is further ahead than
+                // that of the slowest queue joins that one (one profile rebuild)
+                if (a.nql <= 32) {
+                    const unsigned mine = *(volatile const unsigned *)(a.counter + qk);
+                    unsigned lo = mine, lo_k = qk;
+                    for (int k = 0; k < a.nql; ++k) {
+                        const unsigned c = *(volatile const unsigned *)(a.counter + k);
+                        if (c < lo) { lo = c; lo_k = (unsigned)k; }
+                    }
+                    if (mine > lo + (unsigned)a.sticky) qk = lo_k;
+                }
+                for (int tries = 0; tries < a.nql; ++tries) {
+                    const unsigned pb = atomicAdd(a.counter + qk, 1u);
+                    if (pb < a.npb) { w = qk * a.npb + pb; break; }
+                    qk = (qk + 1u == (unsigned)a.nql) ? 0u : qk + 1u;
+                }
+                s_iter = qk;
+                s_work = w;
+            }
+            else if (a.counter) s_work = atomicAdd(a.counter, 1u);
             else { s_work = blockIdx.x + s_iter * gridDim.x; s_iter++; }
         }
         __syncthreads();
