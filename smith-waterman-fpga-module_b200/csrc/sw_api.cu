@@ -216,6 +216,10 @@ struct sw_handle {
     bool plan_qgroups = false;        // per-query variant choice (measured: the extra launches cost more than they gain)
     int plan_streams = kStreams;
     double plan_tau = 0.5;
+    // work order of a strip launch (sw_strip.cuh; environment SW_B200_STICKY / SW_B200_SUPERBLOCK_MB)
+    int sticky = -1;                  // 0 = super-block order; > 0 = sticky order with this drift bound in pair blocks;
+                                      // -1 = sticky order, drift bound of about 1 MB of code stream (4 .. 32 pair blocks)
+    double superblock_mb = 24.0;      // code-stream bytes of one super-block
     // bookkeeping
     std::atomic<int> last_cuda{0};    // written by the per-GPU worker threads as well
     std::atomic<uint64_t> launches{0};
@@ -647,13 +651,12 @@ int strip_setup(sw_handle *h, GpuCtx &gc, DevBuf &bnd_buf, uint32_t npairs, uint
 // over the same pair blocks one after the other, so its code stream should stay in L2 (about a
 // quarter of it: the pass-boundary scratch and the scores live there too) -- but not fewer blocks
 // than two full grids, or consecutive items of a thread block stop sharing the query profile.
-uint32_t superblock_for(const SwStripVariant *v, uint32_t npairs, uint64_t tp_words, int grid)
+uint32_t superblock_for(const SwStripVariant *v, uint32_t npairs, uint64_t tp_words, int grid, double sb_mb)
 {
     const uint32_t ppb = (uint32_t)(v->block_threads / v->G);
     const uint32_t npb = (npairs + ppb - 1) / ppb;
     if (npb == 0 || tp_words == 0) return 0;
     const double bytes_per_block = (double)tp_words * 4.0 / (double)npb;
-    static const double sb_mb = std::getenv("SW_B200_SUPERBLOCK_MB") ? std::atof(std::getenv("SW_B200_SUPERBLOCK_MB")) : 24.0;   // A/B
     uint32_t b = (uint32_t)std::max(1.0, (sb_mb * 1024 * 1024) / std::max(bytes_per_block, 1.0));
     if (sb_mb >= 8.0) b = std::max<uint32_t>(b, 2u * (uint32_t)std::max(grid, 1));
     b = std::min<uint32_t>(b, std::max<uint32_t>(1u, npb >> 3));
@@ -670,29 +673,22 @@ unsigned *next_counter(GpuCtx &gc)
 // Work queue(s) of one strip launch, zeroed on `st`: one counter per query of the launch ("sticky"
 // order, sw_strip.cuh) when the launch has 2 .. kMaxStickyQueries queries, else one counter.
 const int kMaxStickyQueries = 256;
-int sticky_default()
-{
-    // 0 = super-block order; > 0 = sticky order with this drift bound in pair blocks; -1 (default) = sticky
-    // order, drift bound of about 1 MB of code stream (4 .. 32 pair blocks).  Measured on config 3
-    // (profiles/r02_traffic.json): bound 32: 9 000 GCUPS, 3.7 GB of DRAM traffic per launch; 96: 8 998,
-    // 4.4 GB; none: 9 001, 14.9 GB; super-block order: 8 971, 19.2 GB.
-    static const int v = std::getenv("SW_B200_STICKY") ? std::atoi(std::getenv("SW_B200_STICKY")) : -1;   // A/B switch
-    return v;
-}
-cudaError_t assign_counters(GpuCtx &gc, SwStripLaunch &L, cudaStream_t st, bool equal_queries, uint64_t tp_words)
+// Drift bound `sticky` (sw_handle::sticky), measured on config 3 (profiles/r02_traffic.json): 32: 9 000 GCUPS,
+// 3.7 GB of DRAM traffic per launch; 96: 8 998, 4.4 GB; none: 9 001, 14.9 GB; super-block order: 8 971, 19.2 GB.
+cudaError_t assign_counters(GpuCtx &gc, SwStripLaunch &L, cudaStream_t st, int sticky_mode, bool equal_queries, uint64_t tp_words)
 {
     // (queries of different lengths: the blocks of the short ones finish early and pile onto the long
     // ones' queues -- config 5: 7 799 vs 8 302 GCUPS -- so only launches of equally long queries)
-    const bool sticky = sticky_default() && equal_queries && L.nql >= 2 && L.nql <= kMaxStickyQueries;
+    const bool sticky = sticky_mode && equal_queries && L.nql >= 2 && L.nql <= kMaxStickyQueries;
     const unsigned n = sticky ? (unsigned)L.nql : 1u;
     if (gc.counter_next % kMaxCounters + n > (unsigned)kMaxCounters) gc.counter_next += kMaxCounters - gc.counter_next % kMaxCounters;
     L.counter = gc.d_counters.as<unsigned>() + (gc.counter_next % kMaxCounters);
     gc.counter_next += n;
-    if (sticky && sticky_default() < 0) {
+    if (sticky && sticky_mode < 0) {
         const double bytes_per_block = L.db.npairs ? (double)tp_words * 4.0 * 128.0 / (double)L.db.npairs : 1.0;
         L.sticky = (int)std::min(32.0, std::max(4.0, 1048576.0 / std::max(bytes_per_block, 1.0)));
     } else {
-        L.sticky = sticky ? sticky_default() : 0;
+        L.sticky = sticky ? sticky_mode : 0;
     }
     return cudaMemsetAsync(L.counter, 0, n * sizeof(unsigned), st);
 }
@@ -730,7 +726,7 @@ int autotune_variant(sw_handle *h, GpuCtx &gc, Slot &g, SwStripLaunch base, cons
         base.bnd = gc.d_bnd.as<uint2>();
         float ms = 0.f;
         for (int rep = 0; rep < 2; ++rep) {  // first run warms caches and the instruction cache
-            SW_CUDA(h, assign_counters(gc, base, gc.st_compute, equal_queries, g.tp_words * (uint64_t)base.db.npairs / std::max<uint32_t>(g.npairs, 1)));
+            SW_CUDA(h, assign_counters(gc, base, gc.st_compute, h->sticky, equal_queries, g.tp_words * (uint64_t)base.db.npairs / std::max<uint32_t>(g.npairs, 1)));
             SW_CUDA(h, cudaEventRecord(gc.ev_tune0, gc.st_compute));
             SW_CUDA(h, sw_launch_strip(gc.st_compute, base));
             h->launches++;
@@ -911,7 +907,7 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
             L.vidx = vidx;
             rc = strip_setup(h, gc, gc.d_bnd, g.npairs, g.max_len, smaxq, nq / nchunks, vidx, &L.grid, &L.chunk_passes, &L.bnd_elems);
             if (rc != SW_OK) return rc;
-            L.superblock = superblock_for(sw_strip_variant(vidx), g.npairs, g.tp_words, L.grid);
+            L.superblock = superblock_for(sw_strip_variant(vidx), g.npairs, g.tp_words, L.grid, h->superblock_mb);
             max_grid = L.grid;
             label_v = vidx;
             n_groups_total = 1;
@@ -1117,7 +1113,7 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 }
             }
             p.L.bnd = (p.stream == 0 ? gc.d_bnd : gc.d_bnd_aux[p.stream - 1]).as<uint2>();
-            SW_CUDA(h, assign_counters(gc, p.L, st, simple && sticky_ok, g.tp_words));
+            SW_CUDA(h, assign_counters(gc, p.L, st, h->sticky, simple && sticky_ok, g.tp_words));
             if (topk) { p.L.topk_keys = gc.d_topk_keys.as<unsigned long long>(); p.L.topk_k = g.topk_k; p.L.topk_nq = nq; }
             SW_CUDA(h, sw_launch_strip(st, p.L));
             h->launches++;
@@ -1873,6 +1869,8 @@ int sw_init(sw_handle_t **out, const sw_params_t *p, const int *gpu_ids, int n_g
     if (const char *e = std::getenv("SW_B200_PLAN_QGROUPS")) h->plan_qgroups = (e[0] != '0');
     if (const char *e = std::getenv("SW_B200_STREAMS")) h->plan_streams = std::max(1, std::min(kStreams, std::atoi(e)));
     if (const char *e = std::getenv("SW_B200_TAU")) h->plan_tau = std::atof(e);
+    if (const char *e = std::getenv("SW_B200_STICKY")) h->sticky = std::atoi(e);
+    if (const char *e = std::getenv("SW_B200_SUPERBLOCK_MB")) h->superblock_mb = std::max(0.01, std::atof(e));
     h->gpus.resize(ids.size());
     for (size_t i = 0; i < ids.size(); ++i) {
         GpuCtx &g = h->gpus[i];

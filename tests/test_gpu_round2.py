@@ -425,6 +425,41 @@ def test_mixed_one_very_long_subject_with_many_short(oracle_mod, pkg):
     assert int(got[0, 100000]) == o.score(query, genome) > 1500
 
 
+@pytest.mark.parametrize("sticky", ["-1", "0", "2", "1000000"])
+@pytest.mark.parametrize("nq,ns", [(3, 20000), (40, 8000), (300, 3000)])
+def test_work_order_switch_vs_oracle(oracle_mod, pkg, monkeypatch, sticky, nq, ns):
+    """The work order of a strip launch (one queue per query with a drift bound, or super-blocks) only
+    changes who scores what when: every order gives the oracle's matrix.  3 and 40 equally long queries
+    take the per-query queues (with / without the drift check, which covers at most 32 queries), 300
+    queries exceed the per-launch limit of the sticky order; ragged subjects so that the warps run
+    general and interior trips; SW_B200_STICKY: -1 automatic bound, 0 super-block order, 2 a tight
+    bound (blocks keep moving to the slowest queue), 10^6 no bound."""
+    monkeypatch.setenv("SW_B200_STICKY", sticky)
+    monkeypatch.setenv("SW_B200_SUPERBLOCK_MB", "0.05" if sticky == "0" else "24")
+    rng = np.random.default_rng(700 + nq)
+    qp, ql, qo = pkg.random_packed_db(nq, 150, seed=70 + nq)
+    packed, ln, off = pkg.random_packed_db(ns, 150, seed=71 + nq)
+    nb = 38
+    rows = packed[:ns * nb].reshape(ns, nb).copy()
+    for k in range(0, ns, 37):                      # planted near-copies of a query: gaps and high scores
+        rows[k] = qp[(k % nq) * nb:(k % nq + 1) * nb]
+        rows[k, rng.integers(0, nb)] ^= np.uint8(rng.integers(1, 255))
+    ln = rng.integers(1, 151, size=ns).astype(np.uint32)
+    ln[::5] = 150
+    flat = np.concatenate([rows.reshape(-1), np.zeros(16, np.uint8)])
+    o = oracle_mod.Oracle()
+    want, _ = o.score_batch_packed(qp, ql, qo, flat, ln, off)
+    with pkg.Engine() as e:
+        e.set_small_batch_path(False)
+        got = e.score((qp, ql, qo), (flat, ln, off))
+        assert e.device_error_bits == 0
+        e.set_output(pkg.SW_OUTPUT_I16)
+        got16 = e.score((qp, ql, qo), (flat, ln, off))
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(got16.astype(np.int32), want)
+    assert want.max() > 500
+
+
 def test_bounds_check_build_runs_clean(pkg):
     """Stand-in for compute-sanitizer (closed on this pool): the same sources built with
     -DSW_BOUNDS_CHECK (device-side index checks on tp / bnd / profile / out, canaries around every
