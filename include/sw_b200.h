@@ -274,6 +274,18 @@ int sw_set_overflow_wave(sw_handle_t *h, int enable, unsigned long long min_cell
  * off: on the mixed-length config the extra launches cost more than the better fit gains --
  * measured 7.3 vs 8.2 TCUPS). */
 int sw_set_launch_plan(sw_handle_t *h, int length_groups, int query_groups);
+/* Pass split.  A free module of the bank is handed the next target at once, whatever it is
+ * (ScoreBank_v2.v:78-139), so the bank idles only at the very end of a database.  A strip-kernel work item
+ * is (block of pairs, query) for ALL passes of the query: with a long query and a database of a few
+ * rounds of such items (200 k x 1 kb subjects against one 10 kb query = 2.64 rounds) the last, partly
+ * filled round leaves much of the GPU idle for the length of a whole item.  The split cuts the passes
+ * of an item into parts that are handed out as separate items, part-major; the chain's boundary row and
+ * running maximum wait in device scratch between parts.  mode: 0 = never, -1 = automatic (default: one
+ * launch of 1 .. 16 rounds of multi-chunk items), n >= 2 = about n parts whenever the query spans at
+ * least two profile chunks (environment SW_B200_PASS_SPLIT).  sw_last_pass_parts: parts per item of
+ * the last scoring call's plan on the handle's first GPU (1 = not split). */
+int sw_set_pass_split(sw_handle_t *h, int mode);
+int sw_last_pass_parts(const sw_handle_t *h);
 int sw_kernel_variant_count(void);
 const char *sw_kernel_variant_name(int idx);
 int sw_set_kernel_name(sw_handle_t *h, const char *name);

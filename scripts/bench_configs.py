@@ -73,7 +73,8 @@ def run(pkg, name, queries, db, reps=3, kernel=None, check=0, seed=0):
             ms.append(e.last_kernel_ms)
         best = min(ms[1:])
         res = {"config": name, "kernel": e.last_kernel_name, "cells": e.last_cells, "kernel_ms": best,
-               "gcups": e.last_cells / best / 1e6, "pipe_frac": e.last_cells / best / 1e6 / PIPE_BOUND_GCUPS}
+               "gcups": e.last_cells / best / 1e6, "pipe_frac": e.last_cells / best / 1e6 / PIPE_BOUND_GCUPS,
+               "pass_parts": e.last_pass_parts}
         if check:
             got = e.fetch_db()
             ns = len(db[1])

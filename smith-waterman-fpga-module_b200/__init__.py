@@ -114,6 +114,8 @@ def load_library():
     L.sw_set_wave_mode.argtypes = [vp, i32]
     L.sw_set_overflow_wave.argtypes = [vp, i32, C.c_ulonglong]
     L.sw_set_launch_plan.argtypes = [vp, i32, i32]
+    L.sw_set_pass_split.argtypes = [vp, i32]
+    L.sw_last_pass_parts.argtypes = [vp]
     L.sw_get_stats.argtypes = [vp, C.POINTER(SwStats)]
     L.sw_params_in_exact_domain.argtypes = [C.POINTER(SwParams)]
     L.sw_device_count.restype = i32
@@ -265,6 +267,15 @@ class Engine:
     def set_launch_plan(self, length_groups=2, query_groups=False):
         """length_groups: 0 one launch, 1 one launch per length group, 2 automatic; query_groups: variant per query length."""
         self._check(self.lib.sw_set_launch_plan(self.h, length_groups, int(bool(query_groups))))
+
+    def set_pass_split(self, mode=-1):
+        """Pass split of long queries: 0 never, -1 automatic, n >= 2 about n parts per work item."""
+        self._check(self.lib.sw_set_pass_split(self.h, mode))
+
+    @property
+    def last_pass_parts(self):
+        """Parts per work item of the last scoring call's plan (1 = not split)."""
+        return int(self.lib.sw_last_pass_parts(self.h))
 
     def set_small_batch_path(self, enable):
         self._check(self.lib.sw_set_small_batch_path(self.h, int(bool(enable))))

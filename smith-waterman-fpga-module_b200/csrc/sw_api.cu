@@ -154,6 +154,7 @@ struct GpuCtx {
     Slot slot[2];
     // scratch shared by both slots (kernels of one GPU run in stream order)
     DevBuf d_bnd, d_counters, d_scratch32, d_best_score, d_best_index, d_topk_keys, d_err;
+    DevBuf d_part_done, d_part_best;  // pass split: progress words and parked running maxima per (pair block, query) chain
     DevBuf d_wave_bnd, d_wave_state;  // band-pipelined kernel: boundary rows; progress / best / done words
     int wave_bps[16] = {0};           // resident blocks per SM of its instances (0 = not asked yet)
     DevBuf d_wave32_bnd, d_wave32_state;   // 32-bit band-pipelined scorer of the overflow list
@@ -220,7 +221,10 @@ struct sw_handle {
     int sticky = -1;                  // 0 = super-block order; > 0 = sticky order with this drift bound in pair blocks;
                                       // -1 = sticky order, drift bound of about 1 MB of code stream (4 .. 32 pair blocks)
     double superblock_mb = 24.0;      // code-stream bytes of one super-block
+    int pass_split = -1;              // pass split of long queries with few work items: 0 never, -1 automatic,
+                                      // n > 1 = about n parts whenever the query has that many profile chunks (A/B, tests)
     // bookkeeping
+    int last_parts = 1;               // parts per work item of the last strip plan (pass split), 1 = not split
     std::atomic<int> last_cuda{0};    // written by the per-GPU worker threads as well
     std::atomic<uint64_t> launches{0};
     uint64_t last_cells = 0;
@@ -272,7 +276,7 @@ std::vector<DevBuf *> all_devbufs(GpuCtx &g)
 {
     std::vector<DevBuf *> v = {&g.d_qpacked, &g.d_qoff, &g.d_qlen, &g.d_qidx, &g.d_bnd, &g.d_counters, &g.d_scratch32,
                                &g.d_best_score, &g.d_best_index, &g.d_topk_keys, &g.d_err, &g.d_wave_bnd, &g.d_wave_state, &g.d_wave32_bnd, &g.d_wave32_state, &g.d_wave_rows,
-                               &g.d_bnd_aux[0], &g.d_bnd_aux[1], &g.d_bnd_aux[2]};
+                               &g.d_bnd_aux[0], &g.d_bnd_aux[1], &g.d_bnd_aux[2], &g.d_part_done, &g.d_part_best};
     for (Slot &b : g.slot) {
         DevBuf *bufs[] = {&b.d_raw, &b.d_off, &b.d_len, &b.d_pair_subj, &b.d_pair_len, &b.d_tile_woff, &b.d_tp, &b.d_out,
                           &b.d_ovf_count, &b.d_ovf_list, &b.d_ovf_score, &b.d_topk_out, &b.d_small_in, &b.d_small_done};
@@ -647,6 +651,52 @@ int strip_setup(sw_handle *h, GpuCtx &gc, DevBuf &bnd_buf, uint32_t npairs, uint
     return SW_OK;
 }
 
+// Pass split (sw_strip.cuh) of a one-launch plan: decides the number of parts, grows the per-chain scratch
+// and fills L.nparts / part_passes / part_done / part_best.  Used when the launch is a few rounds of long,
+// equally long work items -- rounds = items / resident blocks < 16 -- so that the last, partly filled
+// round costs a fraction of a part instead of a whole item: 200 k x 1 kb subjects x one 10 kb query is
+// 781 items on 296 blocks = 2.64 rounds (12 % of the GPU-time idle), 8 parts make it 21.1 rounds.
+int plan_pass_split(sw_handle *h, GpuCtx &gc, SwStripLaunch &L, uint32_t npairs, uint32_t max_len, uint32_t maxq, int nql_max)
+{
+    L.nparts = 0; L.part_passes = 0; L.part_done = nullptr; L.part_best = nullptr;
+    if (h->pass_split == 0 || L.direct) return SW_OK;
+    const SwStripVariant *v = sw_strip_variant(L.vidx);
+    const int P = v->R * v->G;
+    const int npass = (int)((maxq + P - 1) / P);
+    const int chunks = (npass + L.chunk_passes - 1) / L.chunk_passes;       // a part is whole profile chunks
+    if (chunks < 2) return SW_OK;
+    const int ppb = v->block_threads / v->G;
+    const uint64_t npb = (npairs + ppb - 1) / ppb;
+    const uint64_t chains = npb * (uint64_t)std::max(nql_max, 1);
+    int want = 0;
+    if (h->pass_split > 1) {
+        want = h->pass_split;
+    } else {
+        const double rounds = (double)chains / (double)std::max(L.grid, 1);
+        if (rounds < 1.0 || rounds >= 16.0) return SW_OK;                   // under-filled GPU (other kernels' job) / tail already short
+        want = (int)std::ceil(20.0 / rounds);
+    }
+    const int chunks_per_part = std::max(1, chunks / std::max(1, std::min(want, chunks)));
+    const int part_passes = chunks_per_part * L.chunk_passes;
+    const int nparts = (npass + part_passes - 1) / part_passes;
+    if (nparts < 2 || chains * (uint64_t)nparts >= (1ull << 31)) return SW_OK;
+    const size_t bnd_bytes = (size_t)chains * (size_t)max_len * ppb * sizeof(uint2);
+    size_t free_b = 0, total_b = 0;
+    SW_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
+    if (bnd_bytes > ((size_t)16 << 30) || (gc.d_bnd.cap < bnd_bytes && bnd_bytes - gc.d_bnd.cap > free_b / 2)) return SW_OK;
+    if (gc.d_bnd.cap < bnd_bytes || gc.d_part_done.cap < chains * sizeof(unsigned) || gc.d_part_best.cap < chains * v->block_threads * sizeof(uint32_t)) {
+        SW_CUDA(h, cudaStreamSynchronize(gc.st_compute));
+        for (cudaStream_t st : gc.st_aux) if (st) SW_CUDA(h, cudaStreamSynchronize(st));
+        SW_CUDA(h, gc.d_bnd.reserve(bnd_bytes));
+        SW_CUDA(h, gc.d_part_done.reserve(chains * sizeof(unsigned)));
+        SW_CUDA(h, gc.d_part_best.reserve(chains * v->block_threads * sizeof(uint32_t)));
+    }
+    L.nparts = nparts; L.part_passes = part_passes;
+    L.part_done = gc.d_part_done.as<unsigned>(); L.part_best = gc.d_part_best.as<uint32_t>();
+    L.bnd_elems = bnd_bytes / sizeof(uint2);
+    return SW_OK;
+}
+
 // Pair blocks per super-block of the work order: inside a super-block the queries of a launch pass
 // over the same pair blocks one after the other, so its code stream should stay in L2 (about a
 // quarter of it: the pass-boundary scratch and the scores live there too) -- but not fewer blocks
@@ -756,6 +806,7 @@ struct QueryGroup { int vidx; std::vector<int> q; uint64_t rows; };
 
 int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
 {
+    if (&gc == &h->gpus[0]) h->last_parts = 1;
     SW_CUDA(h, cudaSetDevice(gc.dev));
     const int nq = (int)h->q_len.size();
     const size_t n = g.s1 - g.s0;
@@ -908,6 +959,9 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
             rc = strip_setup(h, gc, gc.d_bnd, g.npairs, g.max_len, smaxq, nq / nchunks, vidx, &L.grid, &L.chunk_passes, &L.bnd_elems);
             if (rc != SW_OK) return rc;
             L.superblock = superblock_for(sw_strip_variant(vidx), g.npairs, g.tp_words, L.grid, h->superblock_mb);
+            rc = plan_pass_split(h, gc, L, g.npairs, g.max_len, smaxq, (nq + nchunks - 1) / nchunks);
+            if (rc != SW_OK) return rc;
+            if (&gc == &h->gpus[0]) h->last_parts = std::max(1, L.nparts);
             max_grid = L.grid;
             label_v = vidx;
             n_groups_total = 1;
@@ -1113,7 +1167,12 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
                 }
             }
             p.L.bnd = (p.stream == 0 ? gc.d_bnd : gc.d_bnd_aux[p.stream - 1]).as<uint2>();
-            SW_CUDA(h, assign_counters(gc, p.L, st, h->sticky, simple && sticky_ok, g.tp_words));
+            SW_CUDA(h, assign_counters(gc, p.L, st, p.L.nparts > 1 ? 0 : h->sticky, simple && sticky_ok, g.tp_words));
+            if (p.L.nparts > 1) {
+                const SwStripVariant *pv = sw_strip_variant(p.L.vidx);
+                const size_t chains = (size_t)((p.L.db.npairs + pv->block_threads / pv->G - 1) / (pv->block_threads / pv->G)) * (size_t)p.L.nql;
+                SW_CUDA(h, cudaMemsetAsync(p.L.part_done, 0, chains * sizeof(unsigned), st));
+            }
             if (topk) { p.L.topk_keys = gc.d_topk_keys.as<unsigned long long>(); p.L.topk_k = g.topk_k; p.L.topk_nq = nq; }
             SW_CUDA(h, sw_launch_strip(st, p.L));
             h->launches++;
@@ -1870,6 +1929,7 @@ int sw_init(sw_handle_t **out, const sw_params_t *p, const int *gpu_ids, int n_g
     if (const char *e = std::getenv("SW_B200_STREAMS")) h->plan_streams = std::max(1, std::min(kStreams, std::atoi(e)));
     if (const char *e = std::getenv("SW_B200_TAU")) h->plan_tau = std::atof(e);
     if (const char *e = std::getenv("SW_B200_STICKY")) h->sticky = std::atoi(e);
+    if (const char *e = std::getenv("SW_B200_PASS_SPLIT")) h->pass_split = std::atoi(e);
     if (const char *e = std::getenv("SW_B200_SUPERBLOCK_MB")) h->superblock_mb = std::max(0.01, std::atof(e));
     h->gpus.resize(ids.size());
     for (size_t i = 0; i < ids.size(); ++i) {
@@ -2214,6 +2274,18 @@ int sw_set_launch_plan(sw_handle_t *h, int length_groups, int query_groups)
     h->plan_segs = length_groups;
     h->plan_qgroups = query_groups != 0;
     return SW_OK;
+}
+
+int sw_set_pass_split(sw_handle_t *h, int mode)
+{
+    if (!h || mode < -1 || mode == 1) return SW_EINVAL;
+    h->pass_split = mode;
+    return SW_OK;
+}
+
+int sw_last_pass_parts(const sw_handle_t *h)
+{
+    return h ? std::max(1, h->last_parts) : SW_EINVAL;
 }
 
 int sw_set_wave_mode(sw_handle_t *h, int mode)

@@ -326,6 +326,10 @@ cudaError_t sw_launch_strip(cudaStream_t st, const SwStripLaunch &L)
     a.out = L.out; a.out_stride = L.out_stride; a.out_mode = L.out_mode;
     a.bnd = L.bnd; a.bnd_cols = L.bnd_cols; a.counter = L.counter; a.sticky = (L.counter && L.sticky > 0 && L.nql > 1) ? L.sticky : 0;
     a.chunk_passes = L.chunk_passes;
+    const bool split = L.nparts > 1 && L.part_done && L.part_best && L.part_passes > 0 && L.part_passes % L.chunk_passes == 0 && !L.direct;
+    a.nparts = split ? L.nparts : 0; a.part_passes = split ? L.part_passes : 0;
+    a.part_done = split ? L.part_done : nullptr; a.part_best = split ? L.part_best : nullptr;
+    if (L.nparts > 1 && !split) return cudaErrorInvalidValue;
     a.match = sc.match; a.mismatch = sc.mismatch; a.goe = sc.goe; a.ge = sc.ge; a.limit = sc.limit;
     a.goe2 = ((uint32_t)sc.goe & 0xFFFFu) * 0x10001u; a.ge2 = ((uint32_t)sc.ge & 0xFFFFu) * 0x10001u;
     a.ovf_limit = 32767 - sc.match - 1;

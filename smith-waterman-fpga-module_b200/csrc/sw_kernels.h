@@ -98,6 +98,12 @@ struct SwStripLaunch {
     int sticky = 0;               /* > 0: counter points to nql zeroed words, one work queue per query (sw_strip.cuh);
                                      the value bounds the drift between the queues (pair blocks) */
     int grid = 0, chunk_passes = 1;
+    /* pass split (sw_strip.cuh): nparts > 1 = an item covers part_passes passes (a multiple of chunk_passes)
+       of its (pair block, query) chain; bnd then holds one boundary row per CHAIN (nql * pair blocks),
+       part_done = zeroed progress words [chains], part_best = parked running maxima [chains * block threads] */
+    int nparts = 0, part_passes = 0;
+    unsigned *part_done = nullptr;
+    uint32_t *part_best = nullptr;
     uint32_t superblock = 0;      /* pair blocks per super-block of the work order (0 = a tenth... npb / 8) */
     unsigned *ovf_count = nullptr;
     uint2 *ovf_list = nullptr;

@@ -136,6 +136,18 @@ __device__ __forceinline__ uint2 bnd_load(const uint2 *p, uint64_t pol)
     asm volatile("ld.global.ca.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
     return v;
 }
+// Progress word of a pass-split chain (gpu scope): the acquire load also drops the SM's L1 lines, so the
+// L1-cached boundary loads that follow it see the rows another SM released.
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void prefetch_l1(const void *p)
 {
     asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
@@ -167,6 +179,12 @@ struct StripArgs {
     int sticky;                // > 0: counter[0 .. nql) = one work queue per query of the launch (see "work order");
                                // the value = how many pair blocks the queues may drift apart
     int chunk_passes;          // passes whose query profile is resident in shared memory at once
+    // Pass split (nparts > 1, multi-pass queries with few work items, see "pass split"): an item covers
+    // part_passes passes of its (pair block, query) chain; the boundary row and the running maximum of a
+    // chain live in per-CHAIN scratch between parts, part_done[chain] counts the finished parts.
+    int nparts, part_passes;
+    unsigned *part_done;       // [nql * npb], zeroed before the launch
+    uint32_t *part_best;       // [nql * npb * block threads]
     int match, mismatch, goe, ge, limit;
     uint32_t goe2, ge2;        // goe / ge packed in both 16-bit lanes (host side: uniform operands)
     int ovf_limit;             // 32767 - match - 1: a larger final maximum means a possible wrap
@@ -400,7 +418,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
     const uint32_t lim2 = AR::pack(a.limit, a.limit);
     // value of "H = 0" in the strip's representation (K = H + goe in the clamped form)
     const uint32_t h0 = !W12 ? goe2 : zero;
-    uint2 *bnd = a.bnd + (size_t)blockIdx.x * a.bnd_cols * PPB + pslot;
+    uint2 *bnd = a.bnd + (size_t)blockIdx.x * a.bnd_cols * PPB + pslot;     // (pass split: per chain, set per item)
     const uint64_t bnd_pol = l2_evict_last_policy();
 
     // work item -> (pair block, query).  Pairs are sorted by ascending length: the longest blocks go
@@ -418,12 +436,26 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
     // read from HBM once and from L2 by the other queries (DRAM traffic of a config-3 launch: 19.2 GB in
     // super-block order, 3.7 GB in this one -- profiles/r02_traffic.json; algorithmic 1.3 GB; and
     // 9 000 vs 8 970 GCUPS).  work = query slot * npb + block.
-    auto decode = [&](unsigned work, unsigned &pair, int &q) {
+    // Pass split (a.nparts > 1): the passes of a long query are cut into parts of a.part_passes passes and
+    // an item is (part, pair block, query), handed out PART-MAJOR: work = part * items_per_part + the index
+    // above.  Items get shorter in time without losing lanes, so a launch of few long items (200 k x 1 kb
+    // subjects against one 10 kb query: 781 items on 296 resident blocks = 2.64 rounds, a third of the GPU
+    // idle in the last one) ends on a short tail.  Part p of a chain starts from the boundary row and the
+    // running maximum that part p - 1 left in the chain's scratch; it waits for part_done[chain] >= p
+    // (acquire; the producer releases after a block barrier).  The item it waits for has a smaller work
+    // index, so it was claimed earlier by a block that is resident and running: no deadlock (and a
+    // watchdog raises SW_DEVERR_SPIN instead of hanging).  ScoreBank_v2.v:78-139 keeps its modules busy
+    // the same way: a module is handed the next target as soon as it is free, whatever that target is.
+    const unsigned items_per_part = a.npb * (unsigned)a.nql;
+    auto decode = [&](unsigned work, unsigned &pair, int &q, unsigned &chain, int &part) {
+        part = 0;
+        if (a.nparts > 1) { part = (int)(work / items_per_part); work -= (unsigned)part * items_per_part; }
         if (a.sticky) {
             const unsigned qk = work / a.npb;
             const unsigned pb = a.npb - 1u - (work - qk * a.npb);      // longest pair blocks first
             q = a.qidx ? a.qidx[qk] : a.q0 + (int)qk;
             pair = pb * PPB + pslot;
+            chain = qk * a.npb + pb;
             return;
         }
         const unsigned nql = (unsigned)a.nql;
@@ -435,6 +467,7 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
         const int qk = (int)(rem / bcur);
         q = a.qidx ? a.qidx[qk] : a.q0 + qk;
         pair = pb * PPB + pslot;
+        chain = (unsigned)qk * a.npb + pb;
     };
 
     int prof_q = -1, prof_pass = -1;     // which (query, first pass) the shared-memory profile holds
@@ -469,10 +502,26 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
             else { s_work = blockIdx.x + s_iter * gridDim.x; s_iter++; }
         }
         __syncthreads();
-        if (s_work >= a.npb * (unsigned)a.nql) break;
-        unsigned pair;
-        int q;
-        decode(s_work, pair, q);
+        if (s_work >= items_per_part * (unsigned)max(a.nparts, 1)) break;
+        unsigned pair, chain;
+        int q, part;
+        decode(s_work, pair, q, chain, part);
+        if (MULTIPASS && a.nparts > 1) {
+            bnd = a.bnd + (size_t)chain * a.bnd_cols * PPB + pslot;
+            if (part > 0) {
+                if (threadIdx.x == 0) {
+                    unsigned spins = 0;
+                    while (ld_acquire_gpu(a.part_done + chain) < (unsigned)part) {
+                        __nanosleep(128);
+                        if (++spins > (1u << 26)) {                    // watchdog: never hang the GPU
+                            if (a.dev_err) atomicOr(a.dev_err, SW_DEVERR_SPIN);
+                            break;
+                        }
+                    }
+                }
+                __syncthreads();      // the acquire above orders the whole block behind the producer's release
+            }
+        }
 
         const bool valid = pair < a.npairs;
         int ncols_v = 0;                                                   // longer member (low lane)
@@ -527,8 +576,14 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
         uint32_t best = h0;
         {
             const int npass = (m + P - 1) / P;
+            int pass_lo = 0, pass_hi = npass;
+            if (MULTIPASS && a.nparts > 1) {
+                pass_lo = min(npass, part * a.part_passes);
+                pass_hi = (part + 1 == a.nparts) ? npass : min(npass, pass_lo + a.part_passes);
+                if (part > 0) best = __ldcg(a.part_best + (size_t)chain * BT + threadIdx.x);
+            }
 
-            for (int pass = 0; pass < npass; ++pass) {
+            for (int pass = pass_lo; pass < pass_hi; ++pass) {
                 const int pass_in_chunk = pass % a.chunk_passes;
                 if (pass_in_chunk == 0 && (prof_q != q || prof_pass != pass)) {
                     prof_q = q;
@@ -755,6 +810,17 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
             }
         }
 
+        unsigned epair, echain;          // (decoded again: nothing but s_work stays live across the hot loop)
+        int eq, epart;
+        decode(s_work, epair, eq, echain, epart);
+        if (MULTIPASS && a.nparts > 1 && epart + 1 < a.nparts) {
+            // pass split, not the last part: park the running maximum, publish the part (the boundary row
+            // went to the chain's scratch in the step loop) and take the next item
+            __stcg(a.part_best + (size_t)echain * BT + threadIdx.x, best);
+            __syncthreads();
+            if (threadIdx.x == 0) st_release_gpu(a.part_done + echain, (unsigned)epart + 1u);
+            continue;
+        }
 #pragma unroll
         for (int o = G / 2; o >= 1; o >>= 1) best = AR::max2(best, __shfl_xor_sync(FULL, best, o));
         // While every value so far is <= 32767 - match the next cell cannot wrap, and the running
@@ -762,9 +828,6 @@ __global__ void __launch_bounds__(BT, MINB) sw_strip_kernel(const StripArgs a)
         // can have happened.  Such pairs get a sentinel, are appended to the overflow list and are
         // recomputed in 32 bit (fix32_list_kernel).
         const int shift = !W12 ? a.goe : 0;
-        unsigned epair;
-        int eq;
-        decode(s_work, epair, eq);
         const bool owner = gl == 0 && epair < a.npairs;
         uint32_t subj_lo = SW_NO_SUBJECT, subj_hi = SW_NO_SUBJECT;
         if (owner) {

@@ -460,6 +460,85 @@ def test_work_order_switch_vs_oracle(oracle_mod, pkg, monkeypatch, sticky, nq, n
     assert want.max() > 500
 
 
+@pytest.mark.parametrize("variant", ["strip_s16x2_R25x2_G1", "strip_s16x2_R25x2_G1_U4_F31", "strip_s16x2_R38x2_G1", "strip_s16x2_R32x2_G1",
+                                     "strip_s16x2_R25x3_G2", "strip_s16x2_R19x2_G4", "strip_s16x2_R16x1_G32"])
+@pytest.mark.parametrize("parts", [3, 64])
+def test_pass_split_forced_vs_oracle(oracle_mod, pkg, variant, parts):
+    """Pass split (sw_set_pass_split): the passes of a work item are handed out as separate items whose
+    boundary row and running maximum wait in per-chain scratch.  Forced here for multi-chunk queries of
+    DIFFERENT lengths (one of them single-pass: its later parts are empty and only carry the maximum),
+    ragged subjects with planted homologs, in every output mode; 64 parts = one profile chunk per part."""
+    rng = random.Random(4100 + parts)
+    queries = [_rand(rng, n) for n in (1500, 700, 64, 1501, 2304)]
+    subjects = []
+    for i in range(2500):
+        r = rng.random()
+        if r < 0.2:
+            q = rng.choice(queries)
+            a = rng.randint(0, max(0, len(q) - 80))
+            subjects.append(_mutate(rng, q[a:a + rng.randint(40, 500)], 0.06, 0.04) or "A")
+        elif r < 0.22:
+            subjects.append("")
+        else:
+            subjects.append(_rand(rng, rng.randint(1, 420)))
+    want = _oracle_matrix(oracle_mod, pkg, queries, subjects)
+    assert want.max() > 1200
+    with pkg.Engine() as e:
+        e.set_small_batch_path(False)
+        e.set_wave_mode(0)
+        e.set_kernel_name(variant)
+        e.set_pass_split(parts)
+        got = e.score(queries, subjects)
+        assert e.last_pass_parts >= 2, e.last_kernel_name
+        assert e.device_error_bits == 0
+        e.set_output(pkg.SW_OUTPUT_I16)
+        got16 = e.score(queries, subjects)
+        e.set_output(pkg.SW_OUTPUT_I32)
+        e.set_topk(7)
+        e.score_batch(subjects)
+        tsc, tix = e.fetch_topk()
+        e.set_topk(0)
+        e.set_pass_split(0)
+        plain = e.score(queries, subjects)
+        assert e.last_pass_parts == 1
+    np.testing.assert_array_equal(got, want)
+    np.testing.assert_array_equal(got16.astype(np.int32), want)
+    np.testing.assert_array_equal(plain, want)
+    wsc, wix = _topk_want(want, 7)
+    np.testing.assert_array_equal(tsc, wsc)
+    np.testing.assert_array_equal(tix, wix)
+
+
+def test_pass_split_automatic_on_few_rounds_of_long_items(oracle_mod, pkg):
+    """The automatic rule: one 3 000-nt query against 200 000 short subjects is a few rounds of multi-chunk
+    work items -> split; the same database against 150-nt queries (single pass) is not.  Scores of a
+    sample of subjects equal the oracle's, and the split and unsplit matrices are identical."""
+    rng = random.Random(77)
+    query = _rand(rng, 3000)
+    db = pkg.random_packed_db(200000, 100, seed=78)
+    qp = pkg.pack_sequences([query])
+    with pkg.Engine() as e:
+        e.set_wave_mode(0)
+        got = e.score(qp, db)
+        parts = e.last_pass_parts
+        assert e.device_error_bits == 0
+        e.set_pass_split(0)
+        plain = e.score(qp, db)
+        assert e.last_pass_parts == 1
+        e.set_pass_split(-1)
+        short = e.score(pkg.random_packed_db(4, 150, seed=79), db)
+        assert e.last_pass_parts == 1 and short.shape == (4, 200000)
+    assert parts >= 2
+    np.testing.assert_array_equal(got, plain)
+    nb = 25
+    idx = np.arange(0, 200000, 100)
+    sub = (np.concatenate([db[0][i * nb:(i + 1) * nb] for i in idx] + [np.zeros(16, np.uint8)]),
+           db[1][idx], (np.arange(len(idx), dtype=np.uint64) * nb))
+    o = oracle_mod.Oracle()
+    want, _ = o.score_batch_packed(qp[0], qp[1], qp[2], sub[0], sub[1], sub[2])
+    np.testing.assert_array_equal(got[:, idx], want)
+
+
 def test_bounds_check_build_runs_clean(pkg):
     """Stand-in for compute-sanitizer (closed on this pool): the same sources built with
     -DSW_BOUNDS_CHECK (device-side index checks on tp / bnd / profile / out, canaries around every
@@ -475,7 +554,7 @@ def test_bounds_check_build_runs_clean(pkg):
            "test_very_long_subjects_short_queries or test_query_groups or test_is_check_build or test_wave_kernel or "
            "test_randomised_modes_stress or test_virtual_multi_shard or test_overflow_list_scored_by_32bit_bands or "
            "test_overflow_32bit_bands_sharded or test_small_path_completion_protocols or test_overflow_list_more_entries or "
-           "test_topk_of_few_long_pairs")
+           "test_topk_of_few_long_pairs or test_pass_split or test_work_order_switch")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests"), "-x", "-q", "-m", "gpu", "-k", sel,
                         "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
