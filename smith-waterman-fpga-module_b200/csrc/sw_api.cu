@@ -510,13 +510,15 @@ double variant_speed(const SwStripVariant *v)
         {"strip_s16x2_R30x1_G1", 8220}, {"strip_s16x2_R38x1_G1", 8310}, {"strip_s16x2_R75x1_G1", 8040},
         {"strip_s16x2_R32x1_G1", 8230}, {"strip_s16x2_R50x1_G1", 8180}, {"strip_s16x2_R25x2_G1", 8700},
         {"strip_s16x2_R19x2_G1", 7810}, {"strip_s16x2_R15x3_G1", 7590}, {"strip_s16x2_R30x2_G1", 8040},
-        {"strip_s16x2_R64x1_G1", 7910}, {"strip_s16x2_R32x2_G1", 8650}, {"strip_s16x2_R25x3_G1", 8620},
+        {"strip_s16x2_R64x1_G1", 7910}, {"strip_s16x2_R32x2_G1", 8320}, {"strip_s16x2_R25x3_G1", 8620},
         {"strip_s16x2_R38x2_G1", 8600}, {"strip_s16x2_R25x4_G1", 7200}, {"strip_s16x2_R25x1_G2", 7345},
         {"strip_s16x2_R75x1_G2", 7380}, {"strip_s16x2_R25x3_G2", 7480}, {"strip_s16x2_R38x1_G4", 7325},
         {"strip_s16x2_R19x2_G4", 7220}, {"strip_s16x2_R32x1_G4", 7180}, {"strip_s16x2_R16x1_G32", 5980},
         {"strip_s16x2_R8x2_G32", 6320},
         // (R32x2: re-measured on long queries, where its 64-row passes leave no padding: 7 655 vs R38x2 7 653 GCUPS on
-        // 200 k x 1 kb x 10 kb, 8 310 vs 8 199 on the mixed-length config 5 -- profiles/r02_variant_ab_long_queries.txt)
+        // 200 k x 1 kb x 10 kb, 8 310 vs 8 199 on the mixed-length config 5 -- profiles/r02_variant_ab_long_queries.txt;
+        // on the final build ptxas' schedule of R32x2 is the slower one: 8 146 vs R38x2 8 276 on config 5,
+        // profiles/r02_pass_split_ab.txt -- launches of one length group still time both, see autotune_variant)
         // small-R latency variants: estimates (shuffle-bound), they are chosen for latency, not throughput
         {"strip_s16x2_R1x1_G32", 900}, {"strip_s16x2_R2x1_G32", 1700}, {"strip_s16x2_R4x1_G32", 3000},
         {"strip_s16x2_R8x1_G32", 4500}, {"strip_s16x2_R8x1_G16", 4600}, {"strip_s16x2_R16x1_G8", 5900},
@@ -549,7 +551,9 @@ double variant_speed_at(const GpuCtx &gc, const SwStripVariant *v, uint32_t max_
 // variant v = padded rows x (columns + pipeline fill) / measured speed / fraction of the GPU the
 // pairs can keep busy, plus half the time of the longest work item running at its share of an SM:
 // with few, long items the tail of the launch is what matters.
-double variant_cost(const GpuCtx &gc, const Slot &g, const SwStripVariant *v, const uint32_t *qlens, size_t nql, uint32_t maxq)
+// split: the launch may use the pass split (plan_pass_split), which cuts the item -- and the tail -- into parts.
+double variant_cost(const GpuCtx &gc, const Slot &g, const SwStripVariant *v, const uint32_t *qlens, size_t nql, uint32_t maxq,
+                    bool split = false)
 {
     const int P = v->R * v->G;
     double rows = 0;                      // padded rows over all queries
@@ -564,7 +568,15 @@ double variant_cost(const GpuCtx &gc, const Slot &g, const SwStripVariant *v, co
     const double job = rows * (cols + v->G * v->S - 1) / cols * (double)g.sum_len / speed / util;
     const int ppb = v->block_threads / v->G;
     const double qrows = (double)((maxq + P - 1) / P) * P;
-    const double item = qrows * cols * 2.0 * ppb * ((double)gc.num_sms * v->min_blocks) / speed;
+    double item = qrows * cols * 2.0 * ppb * ((double)gc.num_sms * v->min_blocks) / speed;
+    if (split) {
+        // the same arithmetic as plan_pass_split: parts of whole profile chunks, about 20 rounds of items
+        const size_t pass_bytes = (size_t)v->G * v->S * ((v->R / v->S + 1) / 2) * 32 * sizeof(uint2);
+        const double chunk_rows = (double)std::max<size_t>(1, (48 * 1024) / pass_bytes) * P;
+        const double chunks = std::ceil(qrows / chunk_rows);
+        const double rounds = std::ceil((double)g.npairs / ppb) * (double)std::max<size_t>(nql, 1) / ((double)gc.num_sms * v->min_blocks);
+        if (chunks >= 2.0 && rounds >= 1.0 && rounds < 16.0) item /= std::min(chunks, std::ceil(20.0 / rounds));
+    }
     return job + 0.5 * item;
 }
 
@@ -575,7 +587,7 @@ bool variant_forced(const sw_handle *h) { return h->force_variant >= 0 || h->for
 
 // Picks the strip variant for a set of queries (least estimated time); ranked = all candidates, best first.
 int choose_variant(const sw_handle *h, const GpuCtx &gc, const Slot &g, const uint32_t *qlens, size_t nql, uint32_t maxq,
-                   std::vector<int> *ranked = nullptr)
+                   std::vector<int> *ranked = nullptr, bool split = false)
 {
     const int nv = sw_strip_variant_count();
     if (h->force_variant >= 0) return h->force_variant;
@@ -591,7 +603,7 @@ int choose_variant(const sw_handle *h, const GpuCtx &gc, const Slot &g, const ui
     double best_cost = 0;
     std::vector<std::pair<double, int>> costs;
     for (int i = 0; i < nv; ++i) {
-        const double cost = variant_cost(gc, g, sw_strip_variant(i), qlens, nql, maxq);
+        const double cost = variant_cost(gc, g, sw_strip_variant(i), qlens, nql, maxq, split);
         if (best < 0 || cost < best_cost) { best = i; best_cost = cost; }
         costs.emplace_back(cost, i);
     }
@@ -862,7 +874,18 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
         for (int q = 0; q < nq; ++q) n_long += (h->q_len[q] >= 2 * SW_WAVE_ROWS_PER_BAND && h->q_len[q] <= 4000u * 256u) ? 1 : 0;
         const double rounds = (double)((g.npairs + 127) / 128) * (double)n_long / ((double)gc.num_sms * 2.0);
         // (only when every query is long: shorter ones in the same launch fill the strip kernel's rounds)
-        const bool underfilled = n_long == (size_t)nq && (rounds < 1.05 || (rounds < 4.0 && rounds / std::ceil(rounds) < 0.85));
+        // With the pass split (one launch, equally long queries) the strip kernel no longer pays for a
+        // partly filled last round, so from one full round on it is the faster one
+        // (profiles/r02_pass_split_ab.txt: 8.4-8.8 TCUPS against the band-pipelined 7.2-7.6).
+        // -- when ONE query's items fill 2.2 rounds: the queries of a call may go out as separate launches
+        // (query chunks), and below about two rounds the variant model prefers a 4-lane variant, which the
+        // band-pipelined kernel beats (scripts/split_ab.py, profiles/r02_pass_split_ab.txt: 10 kb x 120 000 x 1 kb,
+        // 1.58 rounds: R38x1_G4 7 014 vs 7 340 GCUPS; 3 x 4 kb queries x 60 000 x 2 kb, 0.79 rounds per query:
+        // 6 160 vs 7 794; from 2.0 rounds on R38x2_G1 with the split: 8 752-8 780).
+        bool split_possible = h->pass_split != 0 && n_long > 0 && rounds / (double)std::max<size_t>(n_long, 1) >= 2.2;
+        for (int q = 1; q < nq; ++q) split_possible = split_possible && h->q_len[q] == h->q_len[0];
+        const bool underfilled = n_long == (size_t)nq &&
+                                 (rounds < 1.05 || (!split_possible && rounds < 4.0 && rounds / std::ceil(rounds) < 0.85));
         const double bnd_bytes = (double)g.npairs * 2.0 * ((double)g.max_len + 64.0) * 16.0;      // tagged boundary rows of all pairs
         const bool bnd_fits = bnd_bytes <= 4.0e9, bnd_fits_few = bnd_bytes <= 16.0e9;
         for (int q = 0; q < nq; ++q) {
@@ -925,7 +948,10 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
         sticky_ok = same_len;
 
         if (simple) {
-            int vidx = choose_variant(h, gc, g, sl.data(), sl.size(), smaxq, &ranked);
+            // (the split-aware tail term of variant_cost stays off: with it the model prefers the 3-blocks-per-SM
+            // R25x2 instances for 10 kb queries, whose table speed was measured on single-chunk 150-nt reads --
+            // scripts/split_ab.py: 8 059 vs 8 752 GCUPS with R38x2 at two rounds, 8 362 vs 8 780 on 200 k x 1 kb)
+            int vidx = choose_variant(h, gc, g, sl.data(), sl.size(), smaxq, &ranked, false);
             if (vidx < 0) return SW_EINVAL;
             // large jobs: let the GPU pick among the model's top candidates (decision cached per workload shape)
             const double est_ms_all = (double)g.sum_len * (double)srows / 6.0e9;
