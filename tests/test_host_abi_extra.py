@@ -29,3 +29,12 @@ def test_strip_kernel_source_compiles_under_nvrtc(pkg, tmp_path, monkeypatch):
             pytest.skip("NVRTC is not installed here")
         assert ok == 1 or "loading the specialised cubin failed" in msg, (variant, msg)
         assert "NVRTC compile failed" not in msg
+
+
+def test_switch_setters_reject_a_null_handle(pkg):
+    """The plan / work-order switches validate their handle without touching a device."""
+    lib = pkg.load_library()
+    assert lib.sw_set_pass_split(None, 0) == pkg.SW_EINVAL
+    assert lib.sw_last_pass_parts(None) == pkg.SW_EINVAL
+    assert lib.sw_set_launch_plan(None, 2, 0) == pkg.SW_EINVAL
+    assert lib.sw_set_wave_mode(None, 1) == pkg.SW_EINVAL
