@@ -580,6 +580,10 @@ double variant_cost(const GpuCtx &gc, const Slot &g, const SwStripVariant *v, co
     return job + 0.5 * item;
 }
 
+// From this many rounds of ONE query's 128-pair items on (2 x SMs) resident blocks the strip kernel with the
+// pass split takes partly filled rounds; below it the band-pipelined kernel keeps them.
+constexpr double kSplitMinRounds = 1.1;
+
 // launches of the 32-bit band scorer per call (4 096 overflow-list entries each)
 constexpr unsigned kWave32Parts = 4;
 
@@ -877,12 +881,11 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
         // With the pass split (one launch, equally long queries) the strip kernel no longer pays for a
         // partly filled last round, so from one full round on it is the faster one
         // (profiles/r02_pass_split_ab.txt: 8.4-8.8 TCUPS against the band-pipelined 7.2-7.6).
-        // -- when ONE query's items fill 2.2 rounds: the queries of a call may go out as separate launches
-        // (query chunks), and below about two rounds the variant model prefers a 4-lane variant, which the
-        // band-pipelined kernel beats (scripts/split_ab.py, profiles/r02_pass_split_ab.txt: 10 kb x 120 000 x 1 kb,
-        // 1.58 rounds: R38x1_G4 7 014 vs 7 340 GCUPS; 3 x 4 kb queries x 60 000 x 2 kb, 0.79 rounds per query:
-        // 6 160 vs 7 794; from 2.0 rounds on R38x2_G1 with the split: 8 752-8 780).
-        bool split_possible = h->pass_split != 0 && n_long > 0 && rounds / (double)std::max<size_t>(n_long, 1) >= 2.2;
+        // -- when ONE query's items fill kSplitMinRounds rounds (the queries of a call may go out as separate
+        // launches: 3 x 4 kb queries x 60 000 x 2 kb, 0.79 rounds per query, strip + split 6 160 vs 7 794 GCUPS).
+        // scripts/split_ab.py, profiles/r02_pass_split_ab.txt: 10 kb x 100 000 x 1 kb (1.32 rounds) 7 340 -> 8 492,
+        // x 120 000 (1.58) 7 343 -> 8 660, x 151 552 (2.00) 8 327 -> 8 758, x 260 000 (3.43) 8 417 -> 8 756.
+        bool split_possible = h->pass_split != 0 && n_long > 0 && rounds / (double)std::max<size_t>(n_long, 1) >= kSplitMinRounds;
         for (int q = 1; q < nq; ++q) split_possible = split_possible && h->q_len[q] == h->q_len[0];
         const bool underfilled = n_long == (size_t)nq &&
                                  (rounds < 1.05 || (!split_possible && rounds < 4.0 && rounds / std::ceil(rounds) < 0.85));
@@ -953,8 +956,25 @@ int score_gpu(sw_handle *h, GpuCtx &gc, Slot &g)
             // scripts/split_ab.py: 8 059 vs 8 752 GCUPS with R38x2 at two rounds, 8 362 vs 8 780 on 200 k x 1 kb)
             int vidx = choose_variant(h, gc, g, sl.data(), sl.size(), smaxq, &ranked, false);
             if (vidx < 0) return SW_EINVAL;
-            // large jobs: let the GPU pick among the model's top candidates (decision cached per workload shape)
             const double est_ms_all = (double)g.sum_len * (double)srows / 6.0e9;
+            if (h->pass_split != 0 && !variant_forced(h) && sw_strip_variant(vidx)->G > 1) {
+                // The model asks for more lanes per pair because whole items of a one-lane variant would leave
+                // the last round partly empty.  With the pass split that round costs a fraction of a part, so a
+                // one-lane variant is the faster one as soon as its chains fill the GPU once
+                // (scripts/split_ab.py: 10 kb x 120 000 x 1 kb: R38x1_G4 7 014, band-pipelined 7 340, R32x2_G1 8 390 GCUPS).
+                const int nchunks_est = (topk || may_overflow || !wave_q.empty()) ? 1 : std::max(1, std::min(std::min(nq, 8), (int)(est_ms_all / 50.0)));
+                const uint64_t nql_launch = (uint64_t)std::max(1, nq / nchunks_est);
+                for (int cand : ranked) {
+                    const SwStripVariant *cv = sw_strip_variant(cand);
+                    if (cv->G != 1) continue;
+                    const int P = cv->R;
+                    const int npass = (int)((smaxq + P - 1) / P);
+                    const int cp = std::max(1, std::min<int>(npass, (int)((48 * 1024) / sw_strip_smem_bytes(cand, 1))));
+                    const uint64_t chains = (uint64_t)((g.npairs + cv->block_threads - 1) / cv->block_threads) * nql_launch;
+                    if ((npass + cp - 1) / cp >= 2 && (double)chains >= 1.05 * (double)gc.num_sms * cv->min_blocks) { vidx = cand; break; }
+                }
+            }
+            // large jobs: let the GPU pick among the model's top candidates (decision cached per workload shape)
             base.bnd_cols = g.max_len;
             if (!topk && h->autotune && !variant_forced(h) && est_ms_all >= 400.0 && ranked.size() > 1) {
                 uint64_t key = 1469598103934665603ull;
