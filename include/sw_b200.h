@@ -286,6 +286,10 @@ int sw_set_launch_plan(sw_handle_t *h, int length_groups, int query_groups);
  * the last scoring call's plan on the handle's first GPU (1 = not split). */
 int sw_set_pass_split(sw_handle_t *h, int mode);
 int sw_last_pass_parts(const sw_handle_t *h);
+/* The split's arithmetic, without a device (what the automatic rule would do for npass passes in profile
+ * chunks of chunk_passes, `chains` = pair blocks x queries of the launch, on `grid` resident blocks).
+ * Returns 1 and the number of parts / passes per part, or 0 = not split (nparts = 1). */
+int sw_plan_pass_parts(int npass, int chunk_passes, unsigned long long chains, int grid, int mode, int *nparts, int *part_passes);
 int sw_kernel_variant_count(void);
 const char *sw_kernel_variant_name(int idx);
 int sw_set_kernel_name(sw_handle_t *h, const char *name);

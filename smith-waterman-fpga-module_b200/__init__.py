@@ -116,6 +116,7 @@ def load_library():
     L.sw_set_launch_plan.argtypes = [vp, i32, i32]
     L.sw_set_pass_split.argtypes = [vp, i32]
     L.sw_last_pass_parts.argtypes = [vp]
+    L.sw_plan_pass_parts.argtypes = [i32, i32, C.c_ulonglong, i32, i32, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.sw_get_stats.argtypes = [vp, C.POINTER(SwStats)]
     L.sw_params_in_exact_domain.argtypes = [C.POINTER(SwParams)]
     L.sw_device_count.restype = i32
@@ -364,6 +365,13 @@ class Engine:
 def kernel_variants():
     L = load_library()
     return [L.sw_kernel_variant_name(i).decode() for i in range(L.sw_kernel_variant_count())]
+
+
+def plan_pass_parts(npass, chunk_passes, chains, grid, mode=-1):
+    """(split?, parts, passes per part) of the pass split for a launch of that shape (pure host arithmetic)."""
+    n, pp = C.c_int(0), C.c_int(0)
+    ok = load_library().sw_plan_pass_parts(npass, chunk_passes, chains, grid, mode, C.byref(n), C.byref(pp))
+    return bool(ok), int(n.value), int(pp.value)
 
 
 def plan_shards(lengths, n_shards):

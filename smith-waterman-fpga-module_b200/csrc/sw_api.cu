@@ -667,6 +667,32 @@ int strip_setup(sw_handle *h, GpuCtx &gc, DevBuf &bnd_buf, uint32_t npairs, uint
     return SW_OK;
 }
 
+// The arithmetic of the pass split, free of any device state (exported for the CPU tests): npass passes in
+// profile chunks of chunk_passes, `chains` (pair block, query) chains on `grid` resident blocks (ABI: sw_plan_pass_parts).  mode -1:
+// only for 1 <= chains / grid < 16 rounds, aiming at about 20 rounds of part-items; mode n >= 2: about n
+// parts.  A part is a whole number of profile chunks.  Returns 1 and the plan, or 0 = do not split.
+int plan_pass_parts(int npass, int chunk_passes, unsigned long long chains, int grid, int mode, int *nparts, int *part_passes)
+{
+    if (nparts) *nparts = 1;
+    if (part_passes) *part_passes = npass;
+    if (mode == 0 || mode == 1 || mode < -1 || npass < 1 || chunk_passes < 1 || chains < 1) return 0;
+    const int chunks = (npass + chunk_passes - 1) / chunk_passes;
+    if (chunks < 2) return 0;
+    int want = mode;
+    if (mode < 0) {
+        const double rounds = (double)chains / (double)std::max(grid, 1);
+        if (rounds < 1.0 || rounds >= 16.0) return 0;          // under-filled GPU (other kernels' job) / tail already short
+        want = (int)std::ceil(20.0 / rounds);
+    }
+    const int chunks_per_part = std::max(1, chunks / std::max(1, std::min(want, chunks)));
+    const int pp = chunks_per_part * chunk_passes;
+    const int np = (npass + pp - 1) / pp;
+    if (np < 2 || chains * (unsigned long long)np >= (1ull << 31)) return 0;
+    if (nparts) *nparts = np;
+    if (part_passes) *part_passes = pp;
+    return 1;
+}
+
 // Pass split (sw_strip.cuh) of a one-launch plan: decides the number of parts, grows the per-chain scratch
 // and fills L.nparts / part_passes / part_done / part_best.  Used when the launch is a few rounds of long,
 // equally long work items -- rounds = items / resident blocks < 16 -- so that the last, partly filled
@@ -684,18 +710,8 @@ int plan_pass_split(sw_handle *h, GpuCtx &gc, SwStripLaunch &L, uint32_t npairs,
     const int ppb = v->block_threads / v->G;
     const uint64_t npb = (npairs + ppb - 1) / ppb;
     const uint64_t chains = npb * (uint64_t)std::max(nql_max, 1);
-    int want = 0;
-    if (h->pass_split > 1) {
-        want = h->pass_split;
-    } else {
-        const double rounds = (double)chains / (double)std::max(L.grid, 1);
-        if (rounds < 1.0 || rounds >= 16.0) return SW_OK;                   // under-filled GPU (other kernels' job) / tail already short
-        want = (int)std::ceil(20.0 / rounds);
-    }
-    const int chunks_per_part = std::max(1, chunks / std::max(1, std::min(want, chunks)));
-    const int part_passes = chunks_per_part * L.chunk_passes;
-    const int nparts = (npass + part_passes - 1) / part_passes;
-    if (nparts < 2 || chains * (uint64_t)nparts >= (1ull << 31)) return SW_OK;
+    int nparts = 0, part_passes = 0;
+    if (!plan_pass_parts(npass, L.chunk_passes, chains, L.grid, h->pass_split, &nparts, &part_passes)) return SW_OK;
     const size_t bnd_bytes = (size_t)chains * (size_t)max_len * ppb * sizeof(uint2);
     size_t free_b = 0, total_b = 0;
     SW_CUDA(h, cudaMemGetInfo(&free_b, &total_b));
@@ -2327,6 +2343,11 @@ int sw_set_pass_split(sw_handle_t *h, int mode)
     if (!h || mode < -1 || mode == 1) return SW_EINVAL;
     h->pass_split = mode;
     return SW_OK;
+}
+
+int sw_plan_pass_parts(int npass, int chunk_passes, unsigned long long chains, int grid, int mode, int *nparts, int *part_passes)
+{
+    return plan_pass_parts(npass, chunk_passes, chains, grid, mode, nparts, part_passes);
 }
 
 int sw_last_pass_parts(const sw_handle_t *h)

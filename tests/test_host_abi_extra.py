@@ -38,3 +38,28 @@ def test_switch_setters_reject_a_null_handle(pkg):
     assert lib.sw_last_pass_parts(None) == pkg.SW_EINVAL
     assert lib.sw_set_launch_plan(None, 2, 0) == pkg.SW_EINVAL
     assert lib.sw_set_wave_mode(None, 1) == pkg.SW_EINVAL
+
+
+def test_pass_split_arithmetic(pkg):
+    """sw_plan_pass_parts: the host arithmetic of the pass split (csrc/sw_api.cu plan_pass_split).  Parts are
+    whole profile chunks; the automatic rule splits launches of 1 .. 16 rounds of multi-chunk items into
+    about 20 rounds of part-items; shapes as measured in profiles/r02_pass_split_ab.txt."""
+    # 200 k x 1 kb subjects x one 10 kb query on R38x2_G1: 132 passes in chunks of 5, 782 chains, 296 blocks
+    ok, parts, pp = pkg.plan_pass_parts(132, 5, 782, 296)
+    assert ok and pp % 5 == 0 and parts == -(-132 // pp) and parts == 9
+    assert 782 * parts / 296 >= 20
+    # 1 M subjects: 13.2 rounds -> a few parts only
+    ok, parts, pp = pkg.plan_pass_parts(132, 5, 3907, 296)
+    assert ok and parts == 3 and pp == 65
+    # many rounds already / under-filled GPU / single profile chunk / switched off: not split
+    assert pkg.plan_pass_parts(132, 5, 296 * 16, 296) == (False, 1, 132)
+    assert pkg.plan_pass_parts(132, 5, 200, 296) == (False, 1, 132)
+    assert pkg.plan_pass_parts(3, 7, 39063, 444) == (False, 1, 3)
+    assert pkg.plan_pass_parts(132, 5, 782, 296, mode=0) == (False, 1, 132)
+    # forced: about n parts, never finer than one chunk per part, every pass covered exactly once
+    for npass, cp, want in ((60, 7, 3), (60, 7, 64), (5, 1, 2), (31, 4, 5)):
+        ok, parts, pp = pkg.plan_pass_parts(npass, cp, 10, 296, mode=want)
+        assert ok and pp % cp == 0 and (parts - 1) * pp < npass <= parts * pp
+        assert parts <= -(-npass // cp)
+    # the 32-bit work counter: parts x chains must stay below 2^31
+    assert pkg.plan_pass_parts(1000, 1, 1 << 30, 296, mode=8)[0] is False
